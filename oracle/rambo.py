@@ -1,0 +1,196 @@
+"""Oracle: RAMBO-on-diet flat phase space 2 -> n with pT / deltaR / rapidity cuts — CPU, float64.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Restates the ``pdf_active=False`` path of
+  /root/reference/nisrep/PhaseSpace/flat_phase_space_generator.py:81-113,139-441
+  /root/reference/nisrep/PhaseSpace/utils.py:5-81,134-187
+as straight-line tensor code (one formula per reference step, cited inline).  The root of the
+mass-generation polynomial is found with the reference's own integer-lattice bisection (:313-359) so
+that the oracle tracks the reference to rounding; the CUDA kernel uses a Newton iteration instead and
+is compared with a tolerance.
+"""
+import math
+
+import torch
+
+EPS_SQRT = float(torch.finfo(torch.float64).eps) ** 0.5     # utils.py:151 eps=np.finfo(float).eps**0.5
+HUGE = float(torch.finfo(torch.float64).max)                 # utils.py:151 huge
+
+
+class PhaseSpaceGeneratorError(Exception):
+    pass
+
+
+def n_dim_phase_space(n_final):
+    """flat_phase_space_generator.py:48-54."""
+    return 0 if n_final == 1 else 3 * n_final - 4
+
+
+def flat_weight(E_cm, n):
+    """flat_phase_space_generator.py:81-97 — massless n-body volume."""
+    if n == 1:
+        return 1.0
+    return math.pow(2 * math.pi, 4 - 3 * n) * math.pow(math.pi / 2.0, n - 1) * \
+        (math.pow(E_cm ** 2, n - 2) / (math.factorial(n - 1) * math.factorial(n - 2)))
+
+
+def rho(M, N, m):
+    """flat_phase_space_generator.py:107-113."""
+    Msqr = M ** 2
+    return ((Msqr - (N + m) ** 2) * (Msqr - (N - m) ** 2)) ** 0.5 / (8.0 * Msqr)
+
+
+def massless_map(x, e):
+    """flat_phase_space_generator.py:101-103."""
+    return (x ** e) * ((e + 1) - e * x)
+
+
+def bisect(v, n_final, target=1e-16, max_level=600):
+    """flat_phase_space_generator.py:313-359, verbatim control flow (batch-max stopping rule)."""
+    if v.shape[1] == 0:
+        return v
+    e = torch.arange(n_final - 2, 0, step=-1, dtype=torch.float64).unsqueeze(0).repeat(v.shape[0], 1)
+    level = 0
+    left = torch.zeros_like(v)
+    right = torch.ones_like(v)
+    check = -torch.ones_like(v)
+    u = -torch.ones_like(v)
+    error = torch.ones_like(v)
+    step = max_level / 10
+    ml = step
+    old = 100
+    while torch.max(error) > target and ml < 10 * step:
+        while level < ml:
+            u = (left + right) * (0.5 ** (level + 1))
+            check = massless_map(u, e)
+            left = left * 2.0
+            right = right * 2.0
+            adder = torch.where(v <= check, torch.full_like(v, -0.5), torch.full_like(v, 0.5))
+            left = left + (adder + 0.5)
+            right = right + (adder - 0.5)
+            level += 1
+        error = torch.abs(1.0 - check / v)
+        ml = ml + step
+        new = torch.max(error)
+        if new >= old:
+            break
+        old = new
+    return u
+
+
+def _pseudorap(p):
+    """utils.py:151-166.  p: [..., 4] -> [...]."""
+    pt = torch.sqrt(p[..., 1] ** 2 + p[..., 2] ** 2)
+    th = torch.atan2(pt, p[..., 3])
+    eta = -torch.log(torch.tan(th / 2.0))
+    return torch.where((pt < EPS_SQRT) & (p[..., 3].abs() < EPS_SQRT), torch.full_like(eta, HUGE), eta)
+
+
+def _delphi(p1, p2):
+    """utils.py:170-180."""
+    pt1 = torch.sqrt(p1[:, 1] ** 2 + p1[:, 2] ** 2)
+    pt2 = torch.sqrt(p2[:, 1] ** 2 + p2[:, 2] ** 2)
+    tmp = (p1[:, 1] * p2[:, 1] + p1[:, 2] * p2[:, 2]) / (pt1 * pt2)
+    r = torch.where(tmp.abs() > 1, torch.acos(tmp / tmp.abs()), torch.acos(tmp))
+    return torch.where((pt1 == 0.0) | (pt2 == 0.0), torch.full_like(r, HUGE), r)
+
+
+def delta_r(p1, p2):
+    """utils.py:182-187."""
+    return torch.sqrt((_pseudorap(p1) - _pseudorap(p2)) ** 2 + _delphi(p1, p2) ** 2)
+
+
+def generate_kinematics(E_cm, r, initial_masses, final_masses,
+                        pT_mincut=-1, delR_mincut=-1, rap_maxcut=-1, return_parts=False):
+    """flat_phase_space_generator.py:139-308 with pdf inactive.
+
+    r: [B, 3n-4] float64.  Returns (momenta [B, 2+n, 4] (E,px,py,pz; CM frame), weight [B]); with
+    ``return_parts`` also (flat*massive weight before cuts, cut factor in {0,1})."""
+    r = torch.as_tensor(r, dtype=torch.float64)
+    n = len(final_masses)
+    if len(initial_masses) != 2:                                    # :76-79
+        raise PhaseSpaceGeneratorError("only 2 incoming particles")
+    if torch.isnan(r).any():                                        # :147-149
+        raise PhaseSpaceGeneratorError("NaN random variables")
+    assert r.shape[1] == n_dim_phase_space(n)                       # :191
+    B = r.shape[0]
+    m = torch.tensor(final_masses, dtype=torch.float64)
+
+    # (1) massless intermediate masses K_j, :204-210,:384,:363-370
+    K = torch.zeros(B, n - 1, dtype=torch.float64)
+    K[:, 0] = E_cm - m.sum()
+    u = bisect(r[:, :n - 2], n)
+    for i in range(2, n):
+        K[:, i - 1] = torch.sqrt(u[:, i - 2] * K[:, i - 2] ** 2)
+    # (2) flat weight, :372
+    w = torch.full((B,), flat_weight(E_cm, n), dtype=torch.float64)
+    # (3) massive intermediates and reweighting, :389-403
+    msum = torch.flip(torch.cumsum(torch.flip(m, (-1,)), -1), (-1,))
+    M = K + msum[:-1]
+    w = w * 8.0 * rho(M[:, n - 2], m[n - 1], m[n - 2])
+    if n > 2:
+        w = w * torch.prod(rho(M[:, :n - 2], M[:, 1:], m[:n - 2]) / rho(K[:, :n - 2], K[:, 1:], 0.0)
+                           * (M[:, 1:n - 1] / K[:, 1:n - 1]), -1)
+    w = w * torch.pow(K[:, 0] / M[:, 0], 2 * n - 4)
+    # (4) decay momenta, :226-228
+    Mx = torch.cat((M, m[-1:].unsqueeze(0).repeat(B, 1)), -1)       # M_{n-1} = m_{n-1}
+    q = 4.0 * Mx[:, :-1] * rho(Mx[:, :-1], Mx[:, 1:], m[:-1])
+    # (5) angles, :230-243
+    rnd = r[:, n - 2:3 * n - 4]
+    ct = 2.0 * rnd[:, 0::2] - 1.0
+    st = torch.sqrt(1.0 - ct ** 2)
+    phi = 2 * math.pi * rnd[:, 1::2]
+    cp = torch.cos(phi)
+    sp0 = torch.sqrt(1.0 - cp ** 2)
+    sp = torch.where(phi > math.pi, -sp0, sp0)
+    # (6) sequential two-body decays, :250-278
+    out = torch.zeros(B, 2 + n, 4, dtype=torch.float64)
+    Q = torch.zeros(B, 4, dtype=torch.float64)
+    Q[:, 0] = Mx[:, 0]
+    for j in range(n - 1):
+        p = torch.stack((torch.zeros(B, dtype=torch.float64),
+                         q[:, j] * st[:, j] * cp[:, j], q[:, j] * st[:, j] * sp[:, j],
+                         q[:, j] * ct[:, j]), -1)
+        p[:, 0] = torch.sqrt((p[:, 1:] ** 2).sum(-1) + m[j] ** 2)   # set_square_t utils.py:5-19
+        bv = Q[:, 1:] / Q[:, 0:1]                                    # boostVector_t utils.py:31-36
+        b2 = (bv * bv).sum(-1)                                       # boost_t utils.py:58-81
+        gamma = 1.0 / torch.sqrt(1.0 - b2)
+        bp = (p[:, 1:] * bv).sum(-1)
+        gamma2 = torch.where(b2 > 0, (gamma - 1.0) / b2, torch.zeros_like(b2))
+        fac = gamma2 * bp + gamma * p[:, 0]
+        ps = p[:, 1:] + fac.unsqueeze(1) * bv
+        p = torch.cat((torch.sqrt((ps ** 2).sum(-1) + m[j] ** 2).unsqueeze(1), ps), -1)   # :265
+        out[:, 2 + j] = p
+        Qs = Q[:, 1:] - p[:, 1:]
+        Q = torch.cat((torch.sqrt((Qs ** 2).sum(-1) + Mx[:, j + 1] ** 2).unsqueeze(1), Qs), -1)  # :271-275
+    out[:, -1] = Q                                                   # :278
+    # (7) beams, :408-441
+    m1, m2 = float(initial_masses[0]), float(initial_masses[1])
+    if m1 == 0.0 or m2 == 0.0:
+        out[:, 0] = torch.tensor([E_cm / 2.0, 0.0, 0.0, +E_cm / 2.0], dtype=torch.float64)
+        out[:, 1] = torch.tensor([E_cm / 2.0, 0.0, 0.0, -E_cm / 2.0], dtype=torch.float64)
+    else:
+        M1, M2 = m1 ** 2, m2 ** 2
+        E1 = (E_cm ** 2 + M1 - M2) / E_cm
+        E2 = (E_cm ** 2 - M1 + M2) / E_cm
+        Z = math.sqrt(E_cm ** 4 - 2 * E_cm ** 2 * M1 - 2 * E_cm ** 2 * M2 + M1 ** 2 - 2 * M1 * M2 + M2 ** 2) / E_cm
+        out[:, 0] = torch.tensor([E1 / 2.0, 0.0, 0.0, +Z / 2.0], dtype=torch.float64)
+        out[:, 1] = torch.tensor([E2 / 2.0, 0.0, 0.0, -Z / 2.0], dtype=torch.float64)
+    # (8) cuts on the final state (x1=x2=1: boost_to_lab_frame is the identity, utils.py:134-146)
+    fin = out[:, 2:]
+    ptmin = torch.sqrt(fin[:, :, 1] ** 2 + fin[:, :, 2] ** 2).abs().min(1).values
+    cut = torch.where(ptmin < pT_mincut, torch.zeros_like(w), torch.ones_like(w))     # :285-288
+    for i in range(n):
+        for j in range(n):
+            if i > j:                                                                  # :290-296
+                cut = cut * torch.where(delta_r(fin[:, i], fin[:, j]).abs() < delR_mincut,
+                                        torch.zeros_like(w), torch.ones_like(w))
+    if rap_maxcut > 0:                                                                 # :298-301
+        cut = cut * torch.where(rap_maxcut < _pseudorap(fin).max(1).values.abs(),
+                                torch.zeros_like(w), torch.ones_like(w))
+    # (9) :304-308
+    weight = w * cut / (2.0 * E_cm ** 2)
+    if return_parts:
+        return out, weight, w, cut
+    return out, weight
