@@ -1,0 +1,158 @@
+/*
+ * nis_b200.h — C ABI of libnisb200.so: the B200 (sm_100a) kernels under the NIS hot path of NGoetz/NF.
+ *
+ * The reference (`nisrep`, pure Python/PyTorch) has no FFI; its boundary is the Python class surface
+ * (SURVEY.md §8b).  Each entry point below replaces the body of one reference method and is what a
+ * binding from that method would call (see INTEGRATION.md for the ctypes stub):
+ *
+ *   nis_flow_forward      <- torch.nn.Sequential.__call__ over AddJacobian/PWLin/PWQuad/RectNN/
+ *                            RollLayer/MaskLayer/DeMaskLayer
+ *                            (nisrep/normalizing_flows/layers/coupling_cells.py:107-142,159-228,230-254;
+ *                             layers/layers.py:27-32,43-51,75-77,90-91; called at manager.py:174,225,341,397)
+ *   nis_flow_backward     <- loss.backward() through the same modules (manager.py:278)
+ *   nis_reduce_moments    <- torch.var / torch.mean of f*J (manager.py:255,399-400)
+ *   nis_rambo_generate    <- FlatInvertiblePhasespace.generateKinematics_batch, pdf inactive
+ *                            (nisrep/PhaseSpace/flat_phase_space_generator.py:139-308, 313-441;
+ *                             PhaseSpace/utils.py:5-81,134-187)
+ *   nis_uniform_fill      <- torch.nn.init.uniform_(w) (manager.py:222,395)
+ *
+ * Conventions: plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ * unless marked host; work is enqueued on `stream` and the call returns without synchronising; no
+ * allocation; no global state (re-entrant).  Return value: 0 on success, a negative NIS_E* code
+ * otherwise (nis_strerror() gives text).  `stream` is a cudaStream_t passed as void*.
+ */
+#ifndef NIS_B200_H
+#define NIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NIS_MAX_DIM 32     /* max n_flow */
+#define NIS_MAX_CELLS 32   /* max coupling cells */
+#define NIS_MAX_HIDDEN 8   /* max hidden layers of the conditioner */
+#define NIS_MAX_WIDTH 512  /* max hidden width */
+#define NIS_MAX_FINAL 8    /* max final-state particles of the phase-space generator */
+
+enum { NIS_KIND_PWLIN = 0, NIS_KIND_PWQUAD = 1 };
+enum { NIS_F32 = 0, NIS_F64 = 1 };
+enum { NIS_BN_EVAL = 0, NIS_BN_TRAIN = 1 };
+
+enum {
+    NIS_OK = 0,
+    NIS_EINVAL = -1,     /* bad descriptor / argument */
+    NIS_EWORKSPACE = -2, /* workspace too small */
+    NIS_ECUDA = -3,      /* CUDA launch error (cudaGetLastError) */
+    NIS_EUNSUPPORTED = -4
+};
+
+/* One coupling cell.  Roll / Mask / DeMask layers are folded into column tables over a state whose
+ * columns never move (layers.py:27-32,43-51,90-91): the cell conditions on physical columns
+ * feed_idx[0..n_pass) and transforms physical columns trafo_idx[0..n_flow-n_pass), in the order the
+ * reference cell sees them. */
+typedef struct NisCellDesc {
+    int32_t n_pass;
+    int32_t feed_idx[NIS_MAX_DIM];
+    int32_t trafo_idx[NIS_MAX_DIM];
+    int64_t param_off; /* float offset of this cell's parameter block in `params` */
+    int64_t bn_off;    /* float offset of this cell's running-statistics block in `bn_running` */
+} NisCellDesc;
+
+/* Parameter block of a cell (float32, torch-native layouts, same order as the reference state_dict
+ * "{cell}.NN.{idx}.*"):
+ *   bn0.weight[P] bn0.bias[P]
+ *   for l in 0..depth-1:  lin_l.weight[H_l][in_l]  bn_{l+1}.weight[H_l]  bn_{l+1}.bias[H_l]
+ *   out.weight[OUT][H_last]  out.bias[OUT]            OUT = T*n_bins (PWLIN) or T*(2*n_bins+1) (PWQUAD)
+ * Running-statistics block: for l in 0..depth: running_mean[W_l] running_var[W_l], W_0=P, W_l=H_{l-1}. */
+typedef struct NisFlowDesc {
+    int32_t n_flow;
+    int32_t n_cells;
+    int32_t kind;   /* NIS_KIND_* */
+    int32_t n_bins;
+    int32_t depth;  /* hidden layers */
+    int32_t widths[NIS_MAX_HIDDEN];
+    int32_t out_perm[NIS_MAX_DIM]; /* reference's final column i = physical column out_perm[i] */
+    float bn_eps;
+    float bn_momentum;
+    NisCellDesc cells[NIS_MAX_CELLS];
+} NisFlowDesc;
+
+/* floats in one cell's parameter / running-stat block (host helpers, no CUDA) */
+int64_t nis_flow_cell_param_count(const NisFlowDesc* desc, int32_t cell);
+int64_t nis_flow_cell_bn_count(const NisFlowDesc* desc, int32_t cell);
+/* floats in the saved-batch-statistics buffer written by a TRAIN forward and read by backward */
+int64_t nis_flow_bn_saved_count(const NisFlowDesc* desc);
+/* bytes of scratch needed by forward / backward for a batch of B points */
+size_t nis_flow_workspace_bytes(const NisFlowDesc* desc, int64_t B);
+
+/* Forward of the whole flow: xj_out[B, n_flow+1] = flow(xj_in), last column = accumulated Jacobian.
+ *   params      float32 parameter pack (see above)
+ *   bn_running  float32 running statistics; read in EVAL mode, updated in TRAIN mode (may be NULL in
+ *               TRAIN mode to skip the update)
+ *   xj_in       [B, in_cols] row-major, in_cols = n_flow (J=1 implied) or n_flow+1; dtype in_dtype
+ *   xj_out      [B, n_flow+1] row-major, dtype out_dtype, reference column order
+ *   bins_out    optional int32 [n_cells, B, n_flow]: bin index of transformed dim t of cell c at
+ *               [c, i, t] (entries t >= T_c are left untouched)
+ *   saved       optional float32 [n_cells+1, B, n_flow+1]: state before each cell and after the last
+ *               (physical column order); required by nis_flow_backward
+ *   bn_saved    optional float32 [nis_flow_bn_saved_count]: batch mean / inverse std of every BN layer
+ *               (TRAIN mode); required by nis_flow_backward in TRAIN mode
+ */
+int nis_flow_forward(const NisFlowDesc* desc, const float* params, float* bn_running,
+                     const void* xj_in, int32_t in_dtype, int32_t in_cols,
+                     void* xj_out, int32_t out_dtype, int32_t* bins_out,
+                     float* saved, float* bn_saved, int32_t bn_mode,
+                     void* workspace, size_t workspace_bytes, int64_t B, void* stream);
+
+/* Backward: given dL/d(xj_out) computes dL/d(params) (accumulated into grad_params, which the caller
+ * zeroes when it wants a fresh gradient) and optionally dL/d(xj_in).
+ *   grad_out    [B, n_flow+1] dtype grad_dtype, reference column order
+ *   grad_in     optional [B, n_flow+1] same dtype (column n_flow = dL/dJ_in)
+ */
+int nis_flow_backward(const NisFlowDesc* desc, const float* params, const float* saved,
+                      const float* bn_saved, const void* grad_out, int32_t grad_dtype,
+                      float* grad_params, void* grad_in, int32_t bn_mode,
+                      void* workspace, size_t workspace_bytes, int64_t B, void* stream);
+
+/* out[0..3) = { sum v, sum v^2, n } in float64 over v[0..n) (dtype NIS_F32/NIS_F64), accumulated onto
+ * the existing contents of `out` when accumulate != 0.  Deterministic (fixed reduction order).
+ * workspace: at least nis_reduce_workspace_bytes(). */
+size_t nis_reduce_workspace_bytes(void);
+int nis_reduce_moments(const void* v, int32_t dtype, int64_t n, double* out, int32_t accumulate,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Phase-space generator descriptor (flat_phase_space_generator.py:25-39). */
+typedef struct NisRamboDesc {
+    int32_t n_final;
+    double initial_masses[2];
+    double final_masses[NIS_MAX_FINAL];
+    double E_cm;
+    double pT_mincut;   /* event weight -> 0 if min_j pT_j < pT_mincut      (:285-288) */
+    double delR_mincut; /* ... if any pair |deltaR| < delR_mincut           (:290-296) */
+    double rap_maxcut;  /* ... if rap_maxcut > 0 and rap_maxcut < |max eta| (:298-301) */
+} NisRamboDesc;
+
+/* r[B, 3n-4] (dtype r_dtype) -> momenta[B, 2+n, 4] float64 (E,px,py,pz; CM frame; optional),
+ * weight[B] float64 (cuts applied, divided by 2 s), cutmask[B] uint8 (1 = passed; optional). */
+int nis_rambo_generate(const NisRamboDesc* desc, const void* r, int32_t r_dtype, double* momenta,
+                       double* weight, uint8_t* cutmask, int64_t B, void* stream);
+
+/* Philox4x32-10 uniforms in [0,1): out[n] of dtype; element i is a pure function of (seed, offset+i),
+ * so ranks draw disjoint streams by offsetting. */
+int nis_uniform_fill(void* out, int32_t dtype, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* sizeof(NisFlowDesc) / sizeof(NisRamboDesc) as compiled, so a foreign-language binding can verify its
+ * struct layout at load time. */
+size_t nis_sizeof_flow_desc(void);
+size_t nis_sizeof_rambo_desc(void);
+
+const char* nis_strerror(int code);
+const char* nis_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NIS_B200_H */

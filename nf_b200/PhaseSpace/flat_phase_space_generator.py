@@ -1,0 +1,123 @@
+"""RAMBO-on-diet flat phase-space generator — the public surface of
+nisrep/PhaseSpace/flat_phase_space_generator.py (VirtualPhaseSpaceGenerator, FlatInvertiblePhasespace,
+PhaseSpaceGeneratorError) on top of the fused sm_100a kernel ``nis_rambo_generate``: intermediate
+masses, massive reweighting, sequential two-body decays with boosts, the pT / deltaR / rapidity cuts and
+the 1/(2 s) flux factor in ONE pass per event (the reference: a 120-180 level batched bisection plus
+~600 ATen launches).
+
+Scope: the ``pdf_active=False`` path (what BASELINE.json names).  ``pdf_active=True`` needs LHAPDF,
+which is neither in this image nor under /root/reference; it raises NotImplementedError.
+"""
+import ctypes
+import math
+
+import torch
+
+from .. import _cabi
+
+
+class PhaseSpaceGeneratorError(Exception):
+    pass
+
+
+class VirtualPhaseSpaceGenerator(object):
+    """flat_phase_space_generator.py:23-54."""
+
+    def __init__(self, initial_masses, final_masses, pdf=None, pdf_active=False, tau=True):
+        dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
+        self.initial_masses = initial_masses
+        self.masses_t = torch.tensor(final_masses, requires_grad=False, dtype=torch.double, device=dev)
+        self.n_initial = len(initial_masses)
+        self.n_final = len(final_masses)
+        self.pdf = pdf
+        self.pdf_active = pdf_active
+        self.tau = tau
+        if pdf_active:
+            raise NotImplementedError("pdf_active=True needs LHAPDF; only the pdf-inactive path is built")
+
+    def generateKinematics(self, E_cm, random_variables):
+        raise NotImplementedError
+
+    def nDimPhaseSpace(self):
+        """Number of uniforms per event: 3 n_final - 4 (0 for a single final particle)."""
+        return 0 if self.n_final == 1 else 3 * self.n_final - 4
+
+
+class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
+    """Implementation following S. Platzer, arXiv:1308.2922 (flat_phase_space_generator.py:57-441)."""
+
+    epsilon_border = 1e-10
+    absolute_Ecm_min = 1.
+    check_nan = True      # the reference scans the uniforms for NaN on every call (:147-149)
+
+    def __init__(self, *args, **opts):
+        super(FlatInvertiblePhasespace, self).__init__(*args, **opts)
+        if self.n_initial == 1:
+            raise PhaseSpaceGeneratorError("This basic generator does not support decay topologies.")
+        if self.n_initial > 2:
+            raise PhaseSpaceGeneratorError("This basic generator does not support more than 2 incoming particles.")
+        if not 2 <= self.n_final <= _cabi.NIS_MAX_FINAL:
+            raise PhaseSpaceGeneratorError("This build supports 2 to %d final-state particles." % _cabi.NIS_MAX_FINAL)
+
+    @staticmethod
+    def get_flatWeights(E_cm, n):
+        """Massless n-body phase-space volume (2 pi)^(4-3n) (pi/2)^(n-1) s^(n-2) / ((n-1)! (n-2)!)
+        (flat_phase_space_generator.py:81-97)."""
+        if n == 1:
+            return 1.
+        norm = math.pow(2 * math.pi, 4 - 3 * n) * math.pow(math.pi / 2.0, n - 1) / \
+            (math.factorial(n - 1) * math.factorial(n - 2))
+        if torch.is_tensor(E_cm):
+            return norm * torch.pow(E_cm ** 2, n - 2)
+        return norm * math.pow(E_cm ** 2, n - 2)
+
+    def _desc(self, E_cm, pT_mincut, delR_mincut, rap_maxcut):
+        d = _cabi.NisRamboDesc()
+        d.n_final = self.n_final
+        d.initial_masses[0], d.initial_masses[1] = float(self.initial_masses[0]), float(self.initial_masses[1])
+        for i, m in enumerate(self.masses_t.tolist()):
+            d.final_masses[i] = m
+        d.E_cm = float(E_cm)
+        d.pT_mincut, d.delR_mincut, d.rap_maxcut = float(pT_mincut), float(delR_mincut), float(rap_maxcut)
+        return d
+
+    def generateKinematics_batch(self, E_cm, random_variables_full, pT_mincut=-1, delR_mincut=-1, rap_maxcut=-1,
+                                 pdgs=[0, 0], return_cutmask=False, momenta=True):
+        """r[B, 3 n_final - 4] uniforms -> (momenta[B, 2+n_final, 4] float64 in the CM frame, weight[B]
+        float64 = flat weight x massive Jacobian x cuts / (2 s))  (flat_phase_space_generator.py:139-308).
+
+        Extras over the reference signature: ``return_cutmask`` appends the uint8 pass mask,
+        ``momenta=False`` skips writing the momenta (weight-only mode) and returns None for them.
+        Results come back on the device of ``random_variables_full`` (the kernel always runs on CUDA).
+        """
+        r = random_variables_full
+        if not torch.is_tensor(r):
+            r = torch.as_tensor(r, dtype=torch.double)
+        self.collider_energy = E_cm
+        if self.check_nan and torch.isnan(r).any():
+            raise PhaseSpaceGeneratorError("Some of the random variables passed to the phase-space generator are NaN")
+        assert r.dim() == 2 and r.shape[1] == self.nDimPhaseSpace()
+        if torch.is_tensor(E_cm):
+            raise NotImplementedError("per-event E_cm belongs to the PDF path, which is not built")
+        lib = _cabi.lib()
+        home = r.device
+        dev = home if home.type == "cuda" else self.masses_t.device
+        rd = r.detach().to(dev).contiguous()
+        if rd.dtype not in (torch.float32, torch.float64):
+            rd = rd.double()
+        B = rd.shape[0]
+        desc = self._desc(E_cm, pT_mincut, delR_mincut, rap_maxcut)
+        with torch.cuda.device(dev):
+            mom = torch.empty(B, 2 + self.n_final, 4, dtype=torch.double, device=dev) if momenta else None
+            weight = torch.empty(B, dtype=torch.double, device=dev)
+            mask = torch.empty(B, dtype=torch.uint8, device=dev) if return_cutmask else None
+            rc = lib.nis_rambo_generate(ctypes.byref(desc), _cabi.ptr(rd), _cabi.dtype_code(rd), _cabi.ptr(mom),
+                                        _cabi.ptr(weight), _cabi.ptr(mask), B, _cabi.stream_ptr(dev))
+            _cabi.check(rc, "nis_rambo_generate")
+        if home != dev:
+            mom = mom.to(home) if mom is not None else None
+            weight = weight.to(home)
+            mask = mask.to(home) if mask is not None else None
+        if return_cutmask:
+            return mom, weight, mask
+        return mom, weight

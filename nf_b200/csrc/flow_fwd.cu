@@ -1,0 +1,388 @@
+// Fused coupling-cell flow, forward — shape-generic kernel (any n_flow / widths / bins).
+//
+// One thread owns one point for the whole flow: its state row, every conditioner activation and the
+// per-dimension logits live in a private shared-memory column (stride NT, conflict-free), the weights
+// are read as warp-uniform 128-bit loads from the repacked, transposed, zero-padded arena `wpack`
+// (L1-resident), and the bin search / CDF / Jacobian product run in registers.  Eval-mode BN is one
+// launch for all cells.  Train-mode BN (batch statistics, which is what the reference runs both in
+// training and in integrate(): manager.py:225,397) needs one grid-wide reduction per BN layer; each
+// is a "statistics pass" of the same kernel that stops at that layer, accumulates sum / sum-of-squares
+// per feature in float64 and lets the last CTA to finish fold them into the layer's scale/shift.
+//
+// Reference semantics: coupling_cells.py:107-142 (PWLin), :159-228 (PWQuad), :230-254 (RectNN),
+// layers.py:27-32,43-51,75-77,90-91 (Mask/DeMask/AddJacobian/Roll, folded into column tables).
+#include "common.cuh"
+#include "spline.cuh"
+
+struct FwdArgs {
+    const void* in; int in_dtype; int in_cols;   // external input rows (first cell, !from_state)
+    const float* state_in;                       // fp32 [B][d+1] (from_state)
+    float* state_out;                            // fp32 [B][d+1] or null
+    void* out; int out_dtype;                    // external output (to_out)
+    int from_state, to_out;
+    float* saved;                                // [n_cells+1][B][d+1] or null
+    int32_t* bins;
+    const float* params; float* wpack; float* bn_running; float* bn_saved;
+    double* partials; unsigned* counter;
+    long long B; int c_begin, c_end, stats_layer;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// repack: torch-layout params -> transposed zero-padded weights (+ eval-mode BN scale/shift)
+// grid = (blocks, n_cells)
+// ---------------------------------------------------------------------------------------------------
+__global__ void flow_pack_kernel(DevFlow F, const float* __restrict__ params, const float* __restrict__ bn_running,
+                                 float* __restrict__ wpack, int bn_mode) {
+    const int c = blockIdx.y;
+    const DevCell& q = F.cells[c];
+    const float* p = params + q.param_off;
+    float* pk = wpack + q.pk_off;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (bn_mode == NIS_BN_EVAL) {
+        const float* rs = bn_running + q.bn_off;
+        for (int l = 0; l <= F.depth; ++l) {
+            const int W = F.W(c, l), Wp = F.Wp(c, l);
+            const long long g = F.p_bn_gamma(c, l), r = F.r_mean(c, l);
+            for (int j = tid; j < Wp; j += nth) {
+                float sc = 0.f, sh = 0.f;
+                if (j < W) {
+                    sc = p[g + j] / sqrtf(rs[r + W + j] + F.eps);
+                    sh = p[g + W + j] - rs[r + j] * sc;
+                }
+                pk[q.aff_off[l] + j] = sc;
+                pk[q.aff_off[l] + Wp + j] = sh;
+            }
+        }
+    }
+    int in = q.P;
+    for (int l = 0; l < F.depth; ++l) {
+        const int H = F.widths[l], Hp = pad8(H);
+        const float* w = p + F.p_lin(c, l);
+        float* wt = pk + q.wt_off[l];
+        for (int i = tid; i < in * Hp; i += nth) {
+            const int k = i / Hp, j = i - k * Hp;
+            wt[i] = j < H ? w[(long long)j * in + k] : 0.f;
+        }
+        in = H;
+    }
+    const float* wo = p + F.p_out_w(c);
+    const float* bo = p + F.p_out_b(c);
+    const int K = F.K, Kp = F.Kpad;
+    for (int i = tid; i < q.T * in * Kp; i += nth) {
+        const int t = i / (in * Kp), r = i - t * in * Kp, k = r / Kp, j = r - k * Kp;
+        pk[q.wo_off + i] = j < K ? wo[((long long)t * K + j) * in + k] : 0.f;
+    }
+    for (int i = tid; i < q.T * Kp; i += nth) {
+        const int t = i / Kp, j = i - t * Kp;
+        pk[q.bo_off + i] = j < K ? bo[t * K + j] : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dense layer for one point: out[j] = sum_k a[k] * Wt[k][j], 8 outputs per sweep
+// ---------------------------------------------------------------------------------------------------
+template <int NT, typename Epi>
+__device__ __forceinline__ void dense8(const float* __restrict__ Wt, int in, int outp, const float* a_col, Epi epi) {
+    for (int jb = 0; jb < outp; jb += 8) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        const float* wrow = Wt + jb;
+#pragma unroll 4
+        for (int k = 0; k < in; ++k) {
+            const float a = a_col[k * NT];
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)k * outp));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)k * outp + 4));
+            acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]);
+            acc[2] = fmaf(a, w0.z, acc[2]); acc[3] = fmaf(a, w0.w, acc[3]);
+            acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]);
+            acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) epi(jb + i, acc[i]);
+    }
+}
+
+// per-feature sum / sum of squares of a [W][NT] tile into the CTA's float64 accumulators
+template <int NT>
+__device__ __forceinline__ void reduce_rows(const float* buf, int W, double* sacc, int maxW) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < W; j += NT) {
+        double s = 0.0, q = 0.0;
+        for (int i = 0; i < NT; ++i) {
+            const double v = (double)buf[j * NT + ((i + threadIdx.x) & (NT - 1))];
+            s += v; q += v * v;
+        }
+        sacc[j] += s; sacc[maxW + j] += q;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float load_io(const void* p, int dtype, long long idx) {
+    return dtype == NIS_F64 ? (float)reinterpret_cast<const double*>(p)[idx] : reinterpret_cast<const float*>(p)[idx];
+}
+__device__ __forceinline__ void store_io(void* p, int dtype, long long idx, float v) {
+    if (dtype == NIS_F64) reinterpret_cast<double*>(p)[idx] = (double)v; else reinterpret_cast<float*>(p)[idx] = v;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) flow_fwd_generic_kernel(const __grid_constant__ DevFlow F, const FwdArgs A) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    const int d = F.d, maxW = F.maxW;
+    const int bw = maxW > F.Kpad ? maxW : F.Kpad;
+    float* st = sm + tid;                         // [(d+1)][NT]
+    float* bufA = sm + (d + 1) * NT + tid;        // [maxW][NT]
+    float* bufB = bufA + maxW * NT;               // [bw][NT]
+    double* sacc = reinterpret_cast<double*>(sm + ((d + 1) + maxW + bw) * NT + (((d + 1) + maxW + bw) * NT & 1));
+    const bool stats = A.stats_layer >= 0;
+    if (stats) {
+        for (int i = tid; i < 2 * maxW; i += NT) sacc[i] = 0.0;
+        __syncthreads();
+    }
+    const long long ntiles = (A.B + NT - 1) / NT;
+    const long long rowlen = d + 1;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long pt = tile * NT + tid;
+        const bool valid = pt < A.B;
+        // ---- load the state row -------------------------------------------------------------
+        if (valid) {
+            if (A.from_state) {
+                for (int i = 0; i <= d; ++i) st[i * NT] = A.state_in[pt * rowlen + i];
+            } else {
+                for (int i = 0; i < d; ++i) st[i * NT] = load_io(A.in, A.in_dtype, pt * A.in_cols + i);
+                st[d * NT] = A.in_cols > d ? load_io(A.in, A.in_dtype, pt * A.in_cols + d) : 1.f;
+            }
+        } else {
+            for (int i = 0; i < d; ++i) st[i * NT] = 0.5f;
+            st[d * NT] = 1.f;
+        }
+        bool tile_done = false;
+        for (int c = A.c_begin; c < A.c_end && !tile_done; ++c) {
+            const DevCell& q = F.cells[c];
+            const float* pk = A.wpack + q.pk_off;
+            if (!stats && A.saved && valid && (!A.from_state || c > A.c_begin)) {
+                float* sv = A.saved + ((long long)c * A.B + pt) * rowlen;
+                for (int i = 0; i <= d; ++i) sv[i] = st[i * NT];
+            }
+            // ---- BN0 on the pass-through columns ----------------------------------------------
+            if (A.stats_layer == 0) {
+                for (int k = 0; k < q.P; ++k) bufA[k * NT] = valid ? st[q.feed[k] * NT] : 0.f;
+                reduce_rows<NT>(bufA - tid, q.P, sacc, maxW);
+                tile_done = true;
+                break;
+            }
+            {
+                const float* sc = pk + q.aff_off[0];
+                const float* sh = sc + pad8(q.P);
+                for (int k = 0; k < q.P; ++k) bufA[k * NT] = fmaf(st[q.feed[k] * NT], sc[k], sh[k]);
+            }
+            float* cur = bufA;
+            float* nxt = bufB;
+            int in = q.P;
+            // ---- hidden layers: Linear(no bias) -> BN -> ReLU ----------------------------------
+            for (int l = 0; l < F.depth; ++l) {
+                const int H = F.widths[l], Hp = pad8(H);
+                const float* Wt = pk + q.wt_off[l];
+                if (A.stats_layer == l + 1) {
+                    dense8<NT>(Wt, in, Hp, cur, [&](int j, float z) { nxt[j * NT] = valid ? z : 0.f; });
+                    reduce_rows<NT>(nxt - tid, H, sacc, maxW);
+                    tile_done = true;
+                    break;
+                }
+                const float* sc = pk + q.aff_off[l + 1];
+                const float* sh = sc + Hp;
+                dense8<NT>(Wt, in, Hp, cur, [&](int j, float z) { nxt[j * NT] = fmaxf(fmaf(z, sc[j], sh[j]), 0.f); });
+                float* t_ = cur; cur = nxt; nxt = t_;
+                in = H;
+            }
+            if (tile_done) break;
+            // ---- output layer + spline, one transformed dimension at a time --------------------
+            float jfac = 1.f;
+            for (int t = 0; t < q.T; ++t) {
+                const float* Wt = pk + q.wo_off + (size_t)t * in * F.Kpad;
+                const float* bo = pk + q.bo_off + t * F.Kpad;
+                dense8<NT>(Wt, in, F.Kpad, cur, [&](int j, float z) { nxt[j * NT] = z + bo[j]; });
+                const int col = q.trafo[t];
+                const float x = st[col * NT];
+                float y, f;
+                int k;
+                if (F.kind == NIS_KIND_PWLIN) {
+                    float S, al;
+                    y = pwlin_fwd(nxt, NT, F.nb, x, f, k, S, al);
+                } else {
+                    QuadCtx qc;
+                    pwquad_fwd(nxt, NT, F.nb, x, qc);
+                    y = qc.y; f = qc.f; k = qc.k;
+                }
+                st[col * NT] = y;
+                jfac *= f;
+                if (A.bins && valid) A.bins[((long long)c * A.B + pt) * d + t] = k;
+            }
+            st[d * NT] *= jfac;
+        }
+        if (stats || !valid) continue;
+        // ---- store ------------------------------------------------------------------------------
+        if (A.saved && A.c_end == F.n_cells) {
+            float* sv = A.saved + ((long long)F.n_cells * A.B + pt) * rowlen;
+            for (int i = 0; i <= d; ++i) sv[i] = st[i * NT];
+        }
+        if (A.state_out) {
+            float* so = A.state_out + pt * rowlen;
+            for (int i = 0; i <= d; ++i) so[i] = st[i * NT];
+        }
+        if (A.to_out) {
+            for (int i = 0; i < d; ++i) store_io(A.out, A.out_dtype, pt * rowlen + i, st[F.out_perm[i] * NT]);
+            store_io(A.out, A.out_dtype, pt * rowlen + d, st[d * NT]);
+        }
+    }
+    if (!stats) return;
+    // ---- fold this CTA's sums; the last CTA to arrive finalises the layer ------------------------
+    __syncthreads();
+    const int c = A.c_begin, l = A.stats_layer;
+    const DevCell& q = F.cells[c];
+    const int W = F.W(c, l), Wp = F.Wp(c, l);
+    double* mine = A.partials + (size_t)blockIdx.x * 2 * maxW;
+    for (int i = tid; i < 2 * maxW; i += NT) mine[i] = sacc[i];
+    __threadfence();
+    __syncthreads();
+    __shared__ bool s_last;
+    if (tid == 0) s_last = atomicAdd(A.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float* p = A.params + q.param_off + F.p_bn_gamma(c, l);
+    float* aff = A.wpack + q.pk_off + q.aff_off[l];
+    for (int j = tid; j < Wp; j += NT) {
+        float sc = 0.f, sh = 0.f;
+        if (j < W) {
+            double s = 0.0, s2 = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) {
+                s += __ldcg(A.partials + (size_t)b * 2 * maxW + j);
+                s2 += __ldcg(A.partials + (size_t)b * 2 * maxW + maxW + j);
+            }
+            const double n = (double)A.B;
+            const double mean = s / n;
+            double var = s2 / n - mean * mean;
+            var = var > 0.0 ? var : 0.0;
+            const double invstd = 1.0 / sqrt(var + (double)F.eps);
+            sc = (float)((double)p[j] * invstd);
+            sh = (float)((double)p[W + j] - mean * (double)p[j] * invstd);
+            if (A.bn_saved) {
+                A.bn_saved[q.sv_off + l * 2 * maxW + j] = (float)mean;
+                A.bn_saved[q.sv_off + l * 2 * maxW + maxW + j] = (float)invstd;
+            }
+            if (A.bn_running) {
+                float* rs = A.bn_running + q.bn_off + F.r_mean(c, l);
+                const double m = (double)F.momentum;
+                const double unb = A.B > 1 ? var * n / (n - 1.0) : var;
+                rs[j] = (float)((1.0 - m) * (double)rs[j] + m * mean);
+                rs[W + j] = (float)((1.0 - m) * (double)rs[W + j] + m * unb);
+            }
+        }
+        aff[j] = sc;
+        aff[Wp + j] = sh;
+    }
+    if (tid == 0) *A.counter = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launcher
+// ---------------------------------------------------------------------------------------------------
+size_t nis_flow_bwd_scratch_floats(const DevFlow& F, int64_t B);
+
+static size_t fwd_smem_bytes(const DevFlow& F, int NT) {
+    const int bw = F.maxW > F.Kpad ? F.maxW : F.Kpad;
+    size_t fl = (size_t)((F.d + 1) + F.maxW + bw) * NT;
+    fl += fl & 1;
+    return fl * sizeof(float) + sizeof(double) * 2 * F.maxW;
+}
+
+extern "C" size_t nis_flow_workspace_bytes(const NisFlowDesc* desc, int64_t B) {
+    DevFlow F;
+    if (nis_build_dev_flow(desc, &F) != NIS_OK || B < 0) return 0;
+    FlowWorkspace ws;
+    size_t fwd = nis_flow_carve(F, B, nullptr, &ws);
+    return fwd + sizeof(float) * nis_flow_bwd_scratch_floats(F, B) + 256;
+}
+
+template <int NT>
+static int launch_fwd(const DevFlow& F, const FwdArgs& A, cudaStream_t s) {
+    const size_t smem = fwd_smem_bytes(F, NT);
+    cudaFuncSetAttribute(flow_fwd_generic_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long long ntiles = (A.B + NT - 1) / NT;
+    int grid = (int)(ntiles < NIS_MAX_GRID ? ntiles : NIS_MAX_GRID);
+    flow_fwd_generic_kernel<NT><<<grid, NT, smem, s>>>(F, A);
+    NIS_CUDA_CHECK_LAUNCH();
+    return NIS_OK;
+}
+
+static int launch_fwd_any(const DevFlow& F, const FwdArgs& A, cudaStream_t s) {
+    const size_t lim = 200 * 1024;
+    if (fwd_smem_bytes(F, 128) <= lim / 2) return launch_fwd<128>(F, A, s);   // >= 2 CTAs per SM
+    if (fwd_smem_bytes(F, 64) <= lim) return launch_fwd<64>(F, A, s);
+    if (fwd_smem_bytes(F, 32) <= lim) return launch_fwd<32>(F, A, s);
+    return NIS_EUNSUPPORTED;
+}
+
+extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, float* bn_running,
+                                const void* xj_in, int32_t in_dtype, int32_t in_cols,
+                                void* xj_out, int32_t out_dtype, int32_t* bins_out,
+                                float* saved, float* bn_saved, int32_t bn_mode,
+                                void* workspace, size_t workspace_bytes, int64_t B, void* stream) {
+    DevFlow F;
+    int rc = nis_build_dev_flow(desc, &F);
+    if (rc) return rc;
+    if (!params || !xj_in || !xj_out || !workspace || B < 0) return NIS_EINVAL;
+    if (in_cols != F.d && in_cols != F.d + 1) return NIS_EINVAL;
+    if ((in_dtype != NIS_F32 && in_dtype != NIS_F64) || (out_dtype != NIS_F32 && out_dtype != NIS_F64)) return NIS_EINVAL;
+    if (bn_mode == NIS_BN_EVAL && !bn_running) return NIS_EINVAL;
+    if (workspace_bytes < nis_flow_workspace_bytes(desc, B)) return NIS_EWORKSPACE;
+    if (B == 0) return NIS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    FlowWorkspace ws;
+    nis_flow_carve(F, B, workspace, &ws);
+    cudaMemsetAsync(ws.counter, 0, 256, s);
+    {
+        int mx = 0;
+        for (int c = 0; c < F.n_cells; ++c) {
+            int sz = (c + 1 < F.n_cells ? F.cells[c + 1].pk_off : F.pack_total) - F.cells[c].pk_off;
+            if (sz > mx) mx = sz;
+        }
+        int bx = (mx + 255) / 256;
+        if (bx > 64) bx = 64;
+        flow_pack_kernel<<<dim3(bx, F.n_cells), 256, 0, s>>>(F, params, bn_running, ws.wpack, bn_mode);
+        NIS_CUDA_CHECK_LAUNCH();
+    }
+    FwdArgs A;
+    A.in = xj_in; A.in_dtype = in_dtype; A.in_cols = in_cols;
+    A.out = xj_out; A.out_dtype = out_dtype;
+    A.saved = saved; A.bins = bins_out;
+    A.params = params; A.wpack = ws.wpack; A.bn_running = bn_running; A.bn_saved = bn_saved;
+    A.partials = ws.partials; A.counter = ws.counter; A.B = B;
+    if (bn_mode == NIS_BN_EVAL) {
+        A.state_in = nullptr; A.state_out = nullptr; A.from_state = 0; A.to_out = 1;
+        A.c_begin = 0; A.c_end = F.n_cells; A.stats_layer = -1;
+        return launch_fwd_any(F, A, s);
+    }
+    // TRAIN: per cell, one statistics pass per BN layer, then the full pass
+    const long long rows = (long long)B * (F.d + 1);
+    for (int c = 0; c < F.n_cells; ++c) {
+        A.c_begin = c; A.c_end = c + 1;
+        A.from_state = c > 0;
+        A.state_in = c > 0 ? (saved ? saved + (long long)c * rows : ws.state) : nullptr;
+        A.state_out = nullptr; A.to_out = 0;
+        for (int l = 0; l <= F.depth; ++l) {
+            A.stats_layer = l;
+            rc = launch_fwd_any(F, A, s);
+            if (rc) return rc;
+        }
+        A.stats_layer = -1;
+        const bool last = c == F.n_cells - 1;
+        A.to_out = last;
+        A.state_out = last ? nullptr : (saved ? saved + (long long)(c + 1) * rows : ws.state);
+        rc = launch_fwd_any(F, A, s);
+        if (rc) return rc;
+    }
+    return NIS_OK;
+}

@@ -1,0 +1,90 @@
+// RAMBO-on-diet 2 -> n: momenta + Jacobian weight + pT / deltaR / rapidity cuts in one pass.
+// One thread per event, float64.  The uniforms of a 128-event tile are staged through shared memory
+// with coalesced 16-byte loads and the momenta tile is written back the same way; rows are padded to
+// an odd number of doubles so the per-thread row accesses are bank-conflict free.
+// Reference: nisrep/PhaseSpace/flat_phase_space_generator.py:139-308 (see rambo_core.cuh).
+#include <math.h>
+#include "common.cuh"
+#include "rambo_core.cuh"
+
+#define RAMBO_NT 128
+
+template <int N, typename RT>
+__global__ void __launch_bounds__(RAMBO_NT) rambo_kernel(const __grid_constant__ RamboConst C, const RT* __restrict__ r,
+                                                         double* __restrict__ momenta, double* __restrict__ weight,
+                                                         uint8_t* __restrict__ cutmask, long long B) {
+    constexpr int ND = 3 * N - 4;           // uniforms per event
+    constexpr int NDP = ND | 1;             // odd row stride (doubles)
+    constexpr int NM = (N + 2) * 4;         // momentum components per event
+    constexpr int NMP = NM | 1;
+    extern __shared__ __align__(16) double smd[];
+    double* rs = smd;                       // [NT][NDP]
+    double* mo = smd + RAMBO_NT * NDP;      // [NT][NMP]
+    const int tid = threadIdx.x;
+    const long long ntiles = (B + RAMBO_NT - 1) / RAMBO_NT;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * RAMBO_NT;
+        const int cnt = (int)((B - base) < RAMBO_NT ? (B - base) : RAMBO_NT);
+        const RT* src = r + base * ND;
+        for (int i = tid; i < cnt * ND; i += RAMBO_NT) {
+            const int ev = i / ND, c = i - ev * ND;
+            rs[ev * NDP + c] = (double)src[i];
+        }
+        __syncthreads();
+        if (tid < cnt) {
+            double w;
+            uint8_t pass;
+            rambo_event<N>(C, rs + tid * NDP, 1, momenta ? mo + tid * NMP : nullptr, 1, w, pass);
+            weight[base + tid] = w;
+            if (cutmask) cutmask[base + tid] = pass;
+        }
+        __syncthreads();
+        if (momenta) {
+            double* dst = momenta + base * NM;
+            for (int i = tid; i < cnt * NM; i += RAMBO_NT) {
+                const int ev = i / NM, c = i - ev * NM;
+                dst[i] = mo[ev * NMP + c];
+            }
+        }
+    }
+}
+
+template <int N, typename RT>
+static int rambo_launch(const RamboConst& C, const void* r, double* momenta, double* weight, uint8_t* cutmask,
+                        long long B, cudaStream_t s) {
+    constexpr int NDP = (3 * N - 4) | 1, NMP = ((N + 2) * 4) | 1;
+    const size_t smem = sizeof(double) * RAMBO_NT * (NDP + NMP);
+    cudaFuncSetAttribute(rambo_kernel<N, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long long ntiles = (B + RAMBO_NT - 1) / RAMBO_NT;
+    int grid = (int)(ntiles < 148 * 16 ? ntiles : 148 * 16);
+    rambo_kernel<N, RT><<<grid, RAMBO_NT, smem, s>>>(C, (const RT*)r, momenta, weight, cutmask, B);
+    NIS_CUDA_CHECK_LAUNCH();
+    return NIS_OK;
+}
+
+template <int N>
+static int rambo_launch_dt(const RamboConst& C, const void* r, int dt, double* m, double* w, uint8_t* cm, long long B,
+                           cudaStream_t s) {
+    return dt == NIS_F64 ? rambo_launch<N, double>(C, r, m, w, cm, B, s) : rambo_launch<N, float>(C, r, m, w, cm, B, s);
+}
+
+extern "C" int nis_rambo_generate(const NisRamboDesc* desc, const void* r, int32_t r_dtype, double* momenta,
+                                  double* weight, uint8_t* cutmask, int64_t B, void* stream) {
+    if (!desc || !r || !weight || B < 0) return NIS_EINVAL;
+    if (r_dtype != NIS_F32 && r_dtype != NIS_F64) return NIS_EINVAL;
+    RamboConst C;
+    int rc = rambo_fill_const(desc, &C);
+    if (rc) return rc;
+    if (B == 0) return NIS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (desc->n_final) {
+        case 2: return rambo_launch_dt<2>(C, r, r_dtype, momenta, weight, cutmask, B, s);
+        case 3: return rambo_launch_dt<3>(C, r, r_dtype, momenta, weight, cutmask, B, s);
+        case 4: return rambo_launch_dt<4>(C, r, r_dtype, momenta, weight, cutmask, B, s);
+        case 5: return rambo_launch_dt<5>(C, r, r_dtype, momenta, weight, cutmask, B, s);
+        case 6: return rambo_launch_dt<6>(C, r, r_dtype, momenta, weight, cutmask, B, s);
+        case 7: return rambo_launch_dt<7>(C, r, r_dtype, momenta, weight, cutmask, B, s);
+        case 8: return rambo_launch_dt<8>(C, r, r_dtype, momenta, weight, cutmask, B, s);
+    }
+    return NIS_EUNSUPPORTED;
+}

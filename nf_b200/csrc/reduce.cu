@@ -1,0 +1,128 @@
+// Moments of the Monte Carlo weights and the Philox uniform generator.
+//   nis_reduce_moments <- torch.var / torch.mean of f*J (manager.py:255,399-400)
+//   nis_uniform_fill   <- torch.nn.init.uniform_(w)      (manager.py:222,395)
+#include "common.cuh"
+
+#define RED_NT 256
+#define RED_GRID 592   // 148 SMs x 4
+
+// Two-stage deterministic reduction: every CTA writes (sum, sum of squares) of its grid-stride slice
+// in float64; the last CTA to finish adds the partials in index order.
+template <typename T>
+__global__ void __launch_bounds__(RED_NT) moments_kernel(const T* __restrict__ v, long long n, double* __restrict__ out,
+                                                         int accumulate, double* __restrict__ partials,
+                                                         unsigned* __restrict__ counter) {
+    double s = 0.0, q = 0.0;
+    for (long long i = (long long)blockIdx.x * RED_NT + threadIdx.x; i < n; i += (long long)gridDim.x * RED_NT) {
+        const double x = (double)v[i];
+        s += x; q += x * x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    __shared__ double ws[RED_NT / 32], wq[RED_NT / 32];
+    __shared__ bool last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { ws[warp] = s; wq[warp] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s = 0.0; q = 0.0;
+        for (int i = 0; i < RED_NT / 32; ++i) { s += ws[i]; q += wq[i]; }
+        partials[2 * blockIdx.x] = s;
+        partials[2 * blockIdx.x + 1] = q;
+        __threadfence();
+        last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last || threadIdx.x != 0) return;
+    __threadfence();
+    s = 0.0; q = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) { s += __ldcg(partials + 2 * b); q += __ldcg(partials + 2 * b + 1); }
+    if (accumulate) { out[0] += s; out[1] += q; out[2] += (double)n; }
+    else { out[0] = s; out[1] = q; out[2] = (double)n; }
+    *counter = 0u;
+}
+
+extern "C" size_t nis_reduce_workspace_bytes(void) { return sizeof(double) * 2 * RED_GRID + 256; }
+
+extern "C" int nis_reduce_moments(const void* v, int32_t dtype, int64_t n, double* out, int32_t accumulate,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    if (!v || !out || !workspace || n < 0) return NIS_EINVAL;
+    if (workspace_bytes < nis_reduce_workspace_bytes()) return NIS_EWORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    double* partials = (double*)workspace;
+    unsigned* counter = (unsigned*)((char*)workspace + sizeof(double) * 2 * RED_GRID);
+    cudaMemsetAsync(counter, 0, 4, s);
+    long long blocks = (n + RED_NT - 1) / RED_NT;
+    int grid = (int)(blocks < 1 ? 1 : (blocks < RED_GRID ? blocks : RED_GRID));
+    if (dtype == NIS_F64) moments_kernel<double><<<grid, RED_NT, 0, s>>>((const double*)v, n, out, accumulate, partials, counter);
+    else if (dtype == NIS_F32) moments_kernel<float><<<grid, RED_NT, 0, s>>>((const float*)v, n, out, accumulate, partials, counter);
+    else return NIS_EINVAL;
+    NIS_CUDA_CHECK_LAUNCH();
+    return NIS_OK;
+}
+
+// ---- Philox4x32-10 ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+// element i <- word (i & 3) of Philox(counter = (offset + i) >> 2, key = seed); [0,1) with 24 (f32) or
+// 32+21 (f64 from two words of the same block: elements are then 2 per block) bits
+template <typename T>
+__global__ void uniform_kernel(T* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset) {
+    const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long e = offset + (unsigned long long)i;
+        if (sizeof(T) == 4) {
+            const unsigned long long blk = e >> 2;
+            const uint4 rnd = philox4x32_10(make_uint4((unsigned)blk, (unsigned)(blk >> 32), 0u, 0u), key);
+            const unsigned w = (e & 3) == 0 ? rnd.x : ((e & 3) == 1 ? rnd.y : ((e & 3) == 2 ? rnd.z : rnd.w));
+            out[i] = (T)((float)(w >> 8) * (1.0f / 16777216.0f));
+        } else {
+            const unsigned long long blk = e >> 1;
+            const uint4 rnd = philox4x32_10(make_uint4((unsigned)blk, (unsigned)(blk >> 32), 1u, 0u), key);
+            const unsigned a = (e & 1) ? rnd.z : rnd.x, b = (e & 1) ? rnd.w : rnd.y;
+            const unsigned long long m = ((unsigned long long)a << 21) | (b >> 11);     // 53 bits
+            out[i] = (T)((double)m * (1.0 / 9007199254740992.0));
+        }
+    }
+}
+
+extern "C" int nis_uniform_fill(void* out, int32_t dtype, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+    if (!out || n < 0) return NIS_EINVAL;
+    if (n == 0) return NIS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    long long blocks = (n + 255) / 256;
+    int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+    if (dtype == NIS_F32) uniform_kernel<float><<<grid, 256, 0, s>>>((float*)out, n, seed, offset);
+    else if (dtype == NIS_F64) uniform_kernel<double><<<grid, 256, 0, s>>>((double*)out, n, seed, offset);
+    else return NIS_EINVAL;
+    NIS_CUDA_CHECK_LAUNCH();
+    return NIS_OK;
+}
+
+extern "C" const char* nis_strerror(int code) {
+    switch (code) {
+        case NIS_OK: return "ok";
+        case NIS_EINVAL: return "invalid descriptor or argument";
+        case NIS_EWORKSPACE: return "workspace too small (see nis_flow_workspace_bytes)";
+        case NIS_ECUDA: return "CUDA launch failed";
+        case NIS_EUNSUPPORTED: return "configuration not supported by this build";
+    }
+    return "unknown error";
+}
+
+extern "C" size_t nis_sizeof_flow_desc(void) { return sizeof(NisFlowDesc); }
+extern "C" size_t nis_sizeof_rambo_desc(void) { return sizeof(NisRamboDesc); }
+
+extern "C" const char* nis_version(void) { return "nis_b200 0.1 (sm_100a)"; }

@@ -1,0 +1,439 @@
+"""Model factories, variance-loss training and Monte Carlo integration — the public surface of
+nisrep/normalizing_flows/manager.py (ModelAPI, BasicManager, PWLinManager, PWQuadManager) on top of the
+fused sm_100a kernels.
+
+Same method names, positional argument order, attributes (``_model``, ``best_model``, ``format_input``,
+``best_loss``, ``best_loss_rel``, ``best_func_count``, ``varJ``, ``DKL``, ``best_var``, ``best_epoch``,
+``int_loss``, ``history``, ``integ_tot``, ``err_tot``) and return conventions as the reference
+(manager.py:66-70, 380, 474-480, 518-523).  What differs, on purpose:
+
+* the flow forward/backward is one fused C-ABI call per (mini)batch instead of ~40 ATen launches per cell;
+* no ``gc.collect()`` per minibatch (manager.py:270 — 90 % of the reference's wall time, no effect on results);
+* when ``torch.distributed`` is initialised the minibatches of an epoch are dealt round-robin to the
+  ranks, gradients and the epoch loss are sum-allreduced (the reference objective is a mean over
+  minibatches with per-minibatch BN statistics, so this is the same objective), ``maxf`` is
+  max-allreduced and ``integrate`` sum-allreduces (sum w, sum w^2, n) per iteration;
+* parameters are float32 (the kernels compute in fp32); tensors handed to the user integrand ``f`` are
+  float64 like the reference's.
+"""
+import copy
+import datetime
+import math
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from tqdm.autonotebook import tqdm
+
+from .. import _cabi
+from ..flowspec import FlowSequential
+from .layers.coupling_cells import PWLin, PWQuad
+from .layers.layers import AddJacobian, DeMaskLayer, MaskLayer, RollLayer
+from .misc import tqdm_recycled
+
+
+def get_bin(x, n=0):
+    """Binary digits of x, most significant first, left-padded with zeros to n digits (manager.py:20-36)."""
+    return [int(ch) for ch in format(x, "b").zfill(n)]
+
+
+def normal(x, mu, sigma, n_flow):
+    """Isotropic Gaussian density helper (manager.py:39-40)."""
+    return torch.exp(-torch.sum((x - mu) ** 2 / (2 * sigma ** 2), -1)) / (sigma * np.sqrt((2 * np.pi) ** n_flow))
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _device(dev):
+    if not torch.cuda.is_available():
+        raise _cabi.NisBackendError("nf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if isinstance(dev, torch.device):
+        return dev
+    return torch.device("cuda:" + str(0 if dev is None else dev))
+
+
+class ModelAPI():
+
+    @property
+    def model(self):
+        if self._model is not None:
+            return self._model
+        raise AttributeError("No model was instantiated")
+
+
+class EpochState:
+    """Best-model bookkeeping, preburn switch and early stopping of the training loop
+    (manager.py:205-210, 291-327) as a pure host state machine over the epoch losses."""
+
+    def __init__(self, int_loss, preburn_time, kill_counter, impr_ratio):
+        self.check_time = preburn_time if preburn_time > 10 else 50
+        self.preburn_time, self.kill_counter, self.impr_ratio = preburn_time, kill_counter, impr_ratio
+        self.int_loss = int_loss
+        self.best_loss = int_loss
+        self.stale_save = 1000
+        self.preburner = preburn_time > 0
+        self.counter = 0
+        self.last_loss = 1000
+
+    def improved(self, loss, track):
+        """True when this epoch's model must be snapshotted as best_model (manager.py:293)."""
+        if track and loss < self.best_loss and not self.preburner:
+            self.best_loss = loss
+            return True
+        return False
+
+    def advance(self, i, loss):
+        """Update counters after epoch i; True = stop training (manager.py:307-327)."""
+        if loss < self.last_loss:
+            self.counter = 0
+        else:
+            self.counter += 1
+            if self.counter > self.kill_counter:
+                if not self.preburner:
+                    return True
+                self.counter = 0
+                self.preburner = False
+        self.last_loss = loss
+        on_check = i % self.check_time == 0
+        if on_check and i > self.preburn_time + 1 and not self.preburner and \
+                float(self.best_loss / self.stale_save) > 1 - self.impr_ratio:
+            return True
+        if on_check and not self.preburner and (self.best_loss < self.int_loss or i > 300):
+            self.stale_save = self.best_loss
+        if self.preburner and (loss < 0.25 * self.best_loss or i > self.preburn_time):
+            self.preburner = False
+        return False
+
+
+class BasicManager(ModelAPI):
+    """Training (variance loss, Jacobian from the forward pass) and integration."""
+
+    format_input = AddJacobian()
+
+    def __init__(self, n_flow=2, *args):
+        self.n_flow = n_flow
+        self._model = None
+        self._inverse_model = None
+        self.optimizer_object = None
+        self.best_model = None
+
+    # ------------------------------------------------------------------------------------------
+    def _uniform(self, n, dev, dtype=torch.double):
+        """Latent points: torch's device generator, so ``torch.manual_seed`` controls the stream."""
+        return torch.rand(n, self.n_flow, device=dev, dtype=dtype)
+
+    def _train_variance_forward_seq(self, f, optimizer_object, log=True, logdir=None, batch_size=10000, epochs=10,
+                                    epoch_start=0, pretty_progressbar=True, save_best=True, run=None, dev=0,
+                                    mini_batch_size=2000, integrate=False, preburn_time=75, kill_counter=7,
+                                    impr_ratio=1e-2, loss_mode="var"):
+        """Train on the variance of f(x) J(x) / maxf over fresh uniform minibatches (manager.py:66-378)."""
+        dev = _device(dev)
+        rank, world = _world()
+        if mini_batch_size > batch_size:
+            mini_batch_size = batch_size
+        n_minibatches = int(batch_size / mini_batch_size)
+        batch_size = batch_size - (batch_size % mini_batch_size)
+        my_minibatches = [j for j in range(n_minibatches) if j % world == rank]
+
+        filename = None
+        if log and rank == 0:
+            base = os.path.join(logdir, str(run._id)) if run is not None else logdir
+            filename = os.path.join(base, "torch")
+            try:
+                os.makedirs(base, exist_ok=True)
+                torch.save({'model_state_dict': self.best_model.state_dict()}, filename + "_int")
+            except Exception:
+                print("Torch save not possible")
+
+        integ = torch.zeros((epochs + 1,), device=dev)
+        err = torch.zeros((epochs + 1,), device=dev)
+        if pretty_progressbar and rank == 0:
+            epoch_progress = tqdm(range(epoch_start, epoch_start + epochs), leave=False,
+                                  desc="Loss: {0:.3e} | Epoch".format(0.))
+            minibatch_progress = tqdm_recycled(my_minibatches, leave=False, desc="Step") \
+                if len(my_minibatches) > 1 else my_minibatches
+        else:
+            epoch_progress = range(epoch_start, epoch_start + epochs)
+            minibatch_progress = my_minibatches
+
+        self.model.to(dev)
+        if world > 1:
+            self._sync_model()
+        if loss_mode not in ("var", "est"):
+            print("Unknown loss function")
+            return
+
+        # ---- initial loss of the untransformed integrand, maxf (manager.py:139-165) ---------------
+        self.best_loss = 0
+        self.best_var = 0
+        maxf = torch.zeros((), device=dev, dtype=torch.double)
+        w = None
+        for _ in range(self.n_flow):
+            w = self._uniform(2 * mini_batch_size, dev)
+            fres = f(w)
+            integ[0] += torch.sum(fres) / (self.n_flow * 2 * mini_batch_size)
+            err[0] += torch.var(fres) / self.n_flow
+            maxf = torch.maximum(maxf, torch.max(fres).to(maxf.dtype))
+            if world > 1:
+                dist.all_reduce(maxf, op=dist.ReduceOp.MAX)
+            if loss_mode == "var":
+                self.best_loss = self.best_loss + torch.var(fres / maxf).detach() / self.n_flow
+            else:
+                self.best_loss = self.best_loss + torch.mean(fres ** 2).detach() / self.n_flow
+            self.best_var += float((torch.var((fres / maxf) ** 2) / 2 * mini_batch_size).detach())
+
+        if world > 1:                       # every rank must take the same early-stopping decisions
+            init = torch.stack((torch.as_tensor(self.best_loss, device=dev).double(), integ[0].double(), err[0].double()))
+            dist.all_reduce(init)
+            init /= world
+            self.best_loss, integ[0], err[0] = init[0], init[1], init[2]
+        if save_best or log:
+            XJ = self.model(self.format_input(w, dev))
+            X, J = XJ[:, :-1], XJ[:, -1]
+            self.varJ = torch.mean(J ** 2).detach()
+            self.DKL = torch.nn.KLDivLoss(reduction='batchmean')(torch.log(X + 1e-45), w).detach()
+            self.best_model = copy.deepcopy(self.model)
+            self.best_epoch = 0
+            self.best_time = 0
+            self.best_loss_rel = torch.ones_like(self.best_loss)
+            self.best_func_count = 2 * batch_size * self.n_flow
+            self.history = []
+            del XJ, X, J
+        if run is not None and log:
+            run.log_scalar("training.int_loss", self.best_loss.tolist(), 0)
+        self.int_loss = self.best_loss
+
+        state = EpochState(self.int_loss, preburn_time, kill_counter, impr_ratio)
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        i = epoch_start - 1
+        for i in epoch_progress:
+            loss = 0
+            var = 0
+            optimizer_object.zero_grad()
+            for j in minibatch_progress:
+                w = self._uniform(mini_batch_size, dev)
+                XJ = self.model(self.format_input(w, dev))
+                X = XJ[:, :-1].detach()                 # the sample is fixed, the Jacobian is optimised
+                if state.preburner:
+                    fres = f(w)
+                    fXJ = torch.mul(fres, XJ[:, -1]) / maxf
+                    integ[i + 1] += torch.mean(fres) / n_minibatches
+                    err[i + 1] += torch.var(fres) / n_minibatches
+                else:
+                    fres = torch.mul(f(X), XJ[:, -1])
+                    fXJ = fres / maxf
+                    integ[i + 1] += torch.mean(fres.detach()) / n_minibatches
+                    err[i + 1] += torch.var(fres.detach()) / n_minibatches
+                if loss_mode == "var":
+                    loss = loss + torch.var(fXJ)
+                else:
+                    loss = loss + torch.mean((fXJ * maxf) ** 2)
+                var = var + (torch.var(fXJ.detach() ** 2) / mini_batch_size)
+                del X, fXJ, XJ
+            if not torch.is_tensor(loss):              # a rank without minibatches this epoch
+                loss = sum(p.sum() for p in params) * 0.0
+                var = torch.zeros((), device=dev, dtype=torch.double)
+            loss = loss / n_minibatches
+            loss.backward()
+            if world > 1:
+                self._allreduce_grads(params)
+                stats = torch.stack((loss.detach().double(), var.double(), integ[i + 1].double(), err[i + 1].double()))
+                dist.all_reduce(stats)
+                loss = stats[0].to(loss.dtype)
+                var = stats[1]
+                integ[i + 1], err[i + 1] = stats[2], stats[3]
+            optimizer_object.step()
+            loss = loss.detach()
+            var = float(var)
+
+            self.history.append(loss) if hasattr(self, "history") else None
+            if pretty_progressbar and rank == 0:
+                epoch_progress.set_description("Loss: {0:.3e} | Epoch".format(loss))
+            if run is not None and log:
+                run.log_scalar("training.loss", loss.tolist(), i)
+                run.log_scalar("training.loss_rel", (loss / self.int_loss).tolist(), i)
+
+            if save_best or log:
+                self.best_func_count = self.best_func_count + batch_size
+            if state.improved(loss, save_best or log):
+                self.best_loss = loss
+                self.best_var = var
+                self.best_loss_rel = loss / self.int_loss
+                self.best_model = copy.deepcopy(self.model)
+                self.best_epoch = i
+                self.best_time = (datetime.datetime.utcnow() - run.start_time).total_seconds() if run is not None else 0
+            if state.advance(i, loss):
+                break
+
+        # ---- optional tail integration with the best model in eval mode (manager.py:332-350) -------
+        endpoint = i + 1
+        with torch.no_grad():
+            if integrate and endpoint < epochs - 1:
+                model = self.best_model.eval()
+                for s in range(endpoint, epochs):
+                    for t in my_minibatches:
+                        w = self._uniform(mini_batch_size, dev)
+                        XJ = model(self.format_input(w, dev)).detach()
+                        fres = torch.mul(f(XJ[:, :-1]), XJ[:, -1])
+                        integ[s + 1] += torch.mean(fres) / (n_minibatches * math.sqrt(mini_batch_size))
+                        err[s + 1] += torch.std(fres) / n_minibatches
+                    self.best_func_count = self.best_func_count + batch_size
+                if world > 1:
+                    tail = torch.stack((integ[endpoint + 1:], err[endpoint + 1:]))
+                    dist.all_reduce(tail)
+                    integ[endpoint + 1:], err[endpoint + 1:] = tail[0], tail[1]
+        self.integ_tot = torch.sum(integ / err) / torch.sum(1 / err)
+        self.err_tot = torch.sqrt(1 / torch.sum(1 / err))
+
+        if run is not None and integrate:
+            run.log_scalar("training.integ", self.integ_tot.tolist(), 0)
+            run.log_scalar("training.err", self.err_tot.tolist(), 0)
+        if log and rank == 0:
+            try:
+                torch.save({'best_epoch': self.best_epoch, 'best_loss': self.best_loss, 'int_loss': self.int_loss,
+                            'best_loss_rel': self.best_loss_rel, 'best_func_count': self.best_func_count,
+                            'model_state_dict': self.best_model.state_dict(), 'integ': self.integ_tot,
+                            'err': self.err_tot}, filename)
+            except Exception:
+                print("Torch save not possible")
+        if integrate:
+            return (self.integ_tot.detach().tolist(), self.err_tot.detach().tolist())
+        return (0, 0)
+
+    @staticmethod
+    def _allreduce_grads(params):
+        """One flat sum-allreduce of all gradients (NCCL over NVLink when launched one rank per GPU)."""
+        for p in params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        dist.all_reduce(flat)
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p))
+            off += n
+
+    def _sync_model(self):
+        """Ranks must start from identical weights: broadcast parameters and BN buffers from rank 0."""
+        tensors = list(self.model.parameters()) + [b for b in self.model.buffers() if b.dtype.is_floating_point]
+        flat = torch.cat([t.detach().reshape(-1).float() for t in tensors])
+        dist.broadcast(flat, 0)
+        off = 0
+        with torch.no_grad():
+            for t in tensors:
+                n = t.numel()
+                t.copy_(flat[off:off + n].view_as(t))
+                off += n
+
+    # ------------------------------------------------------------------------------------------
+    def integrate(self, f, nitn, neval, dev=None):
+        """nitn independent estimates of neval points through ``best_model``, combined by inverse
+        variance (manager.py:380-405, including its error formula).  With torch.distributed the neval
+        points of every iteration are split over the ranks and (sum, sum of squares, n) are allreduced."""
+        if self.best_model is None:
+            print("No model has been trained")
+            return (0, 0)
+        dev = _device(0 if dev is None else dev)
+        rank, world = _world()
+        neval, nitn = int(neval), int(nitn)
+        share = neval // world + (1 if rank < neval % world else 0)
+        lib = _cabi.lib()
+        moments = torch.zeros(nitn, 3, dtype=torch.double, device=dev)
+        rws = torch.empty(lib.nis_reduce_workspace_bytes(), dtype=torch.uint8, device=dev)
+        w = torch.empty(share, self.n_flow, device=dev)                     # float32 like manager.py:390
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())     # drawn from torch's CPU generator
+        if world > 1:
+            s = torch.tensor([seed], device=dev)
+            dist.broadcast(s, 0)
+            seed = int(s.item())
+        first = (neval // world) * rank + min(rank, neval % world)
+        with torch.no_grad(), torch.cuda.device(dev):
+            for i in range(nitn):
+                _cabi.check(lib.nis_uniform_fill(_cabi.ptr(w), _cabi.F32, w.numel(), seed,
+                                                 (i * neval + first) * self.n_flow, _cabi.stream_ptr(dev)),
+                            "nis_uniform_fill")
+                X = self.best_model(self.format_input(w, dev)).detach()
+                fres = (f(X[:, :-1]) * X[:, -1]).contiguous()
+                _cabi.check(lib.nis_reduce_moments(_cabi.ptr(fres), _cabi.dtype_code(fres), fres.numel(),
+                                                   _cabi.ptr(moments[i]), 0, _cabi.ptr(rws), rws.numel(),
+                                                   _cabi.stream_ptr(dev)), "nis_reduce_moments")
+        if world > 1:
+            dist.all_reduce(moments)
+        moments = moments.cpu()
+        n = moments[:, 2]
+        mean = moments[:, 0] / n
+        var = (moments[:, 1] - n * mean ** 2) / (n - 1)                      # unbiased, like torch.var
+        mean, var = mean.float(), var.float()                                # manager.py:391-392 holds float32
+        sig = torch.sum(mean / var) / torch.sum(1 / var)
+        sig_err = torch.sqrt(1 / torch.sum(1 / var)) / np.sqrt(neval * nitn)
+        return (sig, sig_err)
+
+
+def _finish_model(manager, model, dev):
+    manager._model = model
+    if torch.cuda.is_available():
+        model.to(_device(dev))
+    manager.best_model = manager.model
+    if torch.cuda.is_available():                        # one pass forward, like the reference factories
+        w = torch.rand(5, manager.n_flow, dtype=torch.double)
+        with torch.no_grad():
+            model(manager.format_input(w, _device(dev)))
+
+
+class PWLinManager(BasicManager):
+    """Piecewise-linear coupling cells with cyclic roll layers (manager.py:456-499).
+
+    Hyperparameters: n_pass_through, n_cells, n_bins, NN (hidden widths), roll_step.
+    """
+
+    def create_model(self, n_pass_through, n_cells, n_bins, NN, roll_step):
+        model = FlowSequential(self.n_flow)
+        for i_cell in range(n_cells):
+            model.add_module(str(i_cell), PWLin(flow_size=self.n_flow, pass_through_size=n_pass_through,
+                                                n_bins=n_bins, NN_layers=NN))
+            # The reference registers every roll under the one name "roll" (manager.py:492): add_module
+            # replaces it in place, so a single roll survives, right after cell 0.  Reproduced as is.
+            model.add_module("roll", RollLayer(roll_step))
+        _finish_model(self, model, 0)
+
+
+class PWQuadManager(BasicManager):
+    """Piecewise-quadratic coupling cells; roll layout for n_flow <= 7, binary-mask layout above
+    (manager.py:502-600).  Hyperparameters: n_cells, n_bins, NN (hidden widths)."""
+
+    def create_model(self, n_cells, n_bins, NN, dev=0):
+        d = self.n_flow
+        if n_cells < 2 * np.ceil(np.log2(d)) and n_cells < d:            # manager.py:526-534
+            n_cells = d if d <= 6 else (6 if d == 7 else int(2 * np.ceil(np.log2(d))))
+            print("Adjusted # coupling cells to " + str(n_cells))
+        model = FlowSequential(d)
+
+        def roll_cells(first, count, n_pass_through):
+            # `count` cells, each followed by a unit roll; the last roll restores the original order
+            for k in range(count):
+                name = str(first + k)
+                model.add_module(name, PWQuad(flow_size=d, pass_through_size=n_pass_through, n_bins=n_bins,
+                                              NN_layers=NN))
+                shift = 1 if k < count - 1 else d - ((count - 1) % d)
+                model.add_module("roll" + name, RollLayer(shift))
+
+        if d <= 7:
+            roll_cells(0, n_cells, 1 if d <= 6 else 2)
+        else:
+            nbits = len(get_bin(d - 1, 0))
+            dims_bin = torch.IntTensor([get_bin(i, nbits) for i in range(d)])
+            for c in range(2 * nbits):
+                masker = MaskLayer(dims_bin, c, "cpu")
+                model.add_module("mask" + str(c), masker)
+                model.add_module(str(c), PWQuad(flow_size=d, pass_through_size=masker.pass_through,
+                                                n_bins=n_bins, NN_layers=NN))
+                model.add_module("demask" + str(c), DeMaskLayer(masker.feeder, masker.trafoer))
+            roll_cells(2 * nbits, n_cells - 2 * nbits, int(d / 2))
+        _finish_model(self, model, dev)
+        return

@@ -1,0 +1,57 @@
+// Host build of the product's scalar device code (nf_b200/csrc/spline.cuh, rambo_core.cuh) so that the
+// CPU test-suite can check the very same source the kernels run against the oracle.  Test harness only.
+#include <math.h>
+#include <stdint.h>
+#include "../../nf_b200/csrc/spline.cuh"
+#include "../../nf_b200/csrc/rambo_core.cuh"
+
+template <int N>
+static void rambo_n(const RamboConst& C, long long B, const double* r, double* mom, double* w, uint8_t* pass) {
+    const int nd = 3 * N - 4, nm = (N + 2) * 4;
+    for (long long i = 0; i < B; ++i) rambo_event<N>(C, r + i * nd, 1, mom ? mom + i * nm : nullptr, 1, w[i], pass[i]);
+}
+
+extern "C" {
+
+// z: [n][K] logits (K = nb), overwritten with dL/dz.  gy, gJJ per point.
+void host_pwlin(int n, int nb, float* z, const float* x, const float* gy, const float* gJJ, float* y, float* f,
+                int* k, float* dx) {
+    for (int i = 0; i < n; ++i) {
+        float S, al;
+        float* zi = z + (size_t)i * nb;
+        y[i] = pwlin_fwd(zi, 1, nb, x[i], f[i], k[i], S, al);
+        dx[i] = pwlin_bwd(zi, 1, nb, k[i], S, al, y[i], f[i], gy[i], gJJ[i]);
+    }
+}
+
+// z: [n][2nb+1] logits, overwritten with dL/dz.  gy, gf per point.
+void host_pwquad(int n, int nb, float* z, const float* x, const float* gy, const float* gf, float* y, float* f,
+                 int* k, float* dx) {
+    for (int i = 0; i < n; ++i) {
+        QuadCtx c;
+        float* zi = z + (size_t)i * (2 * nb + 1);
+        pwquad_fwd(zi, 1, nb, x[i], c);
+        y[i] = c.y; f[i] = c.f; k[i] = c.k;
+        dx[i] = pwquad_bwd(zi, 1, nb, c, gy[i], gf[i]);
+    }
+}
+
+int host_rambo(const NisRamboDesc* d, long long B, const double* r, double* mom, double* w, uint8_t* pass) {
+    RamboConst C;
+    int rc = rambo_fill_const(d, &C);
+    if (rc) return rc;
+    switch (d->n_final) {
+        case 2: rambo_n<2>(C, B, r, mom, w, pass); break;
+        case 3: rambo_n<3>(C, B, r, mom, w, pass); break;
+        case 4: rambo_n<4>(C, B, r, mom, w, pass); break;
+        case 5: rambo_n<5>(C, B, r, mom, w, pass); break;
+        case 6: rambo_n<6>(C, B, r, mom, w, pass); break;
+        case 7: rambo_n<7>(C, B, r, mom, w, pass); break;
+        case 8: rambo_n<8>(C, B, r, mom, w, pass); break;
+        default: return -4;
+    }
+    return 0;
+}
+
+double host_rambo_root(int e, double r) { return rambo_root_dyn(e, r); }
+}

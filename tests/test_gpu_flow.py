@@ -1,0 +1,100 @@
+"""GPU parity of the fused flow forward (through FlowSequential -> nis_flow_forward) against
+(a) the golden vectors dumped from the reference and (b) the oracle at larger sizes."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import FLOW_CASES
+from gpu_util import compare_flow, make_manager, oracle_layers
+from oracle import flow as oflow
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", FLOW_CASES)
+@pytest.mark.parametrize("mode", ["eval", "train"])
+@pytest.mark.parametrize("io", [torch.float64, torch.float32])
+def test_forward_matches_reference_golden(golden, case, mode, io):
+    g = golden("flow_" + case)
+    NF = make_manager(g.meta)
+    model = NF._model
+    model.load_state_dict(g.state_dict())
+    model.train(mode == "train")
+    xj = g.t("xj").to(io).cuda()
+    XJ, bins = model.forward_with_bins(xj)
+    assert XJ.dtype == io and XJ.shape == xj.shape
+    ref_bins = [g["%s/bins/%d" % (mode, i)] for i in range(model.spec().n_cells)]
+    compare_flow(XJ.cpu(), bins.cpu(), g.t(mode + "/XJ"), ref_bins, "%s/%s" % (case, mode))
+    if mode == "train":                      # running statistics updated like torch BatchNorm1d
+        sd = model.state_dict()
+        for k in g.keys("train/stats/"):
+            name = k[len("train/stats/"):]
+            ref = g.t(k)
+            if name.endswith("num_batches_tracked"):
+                assert int(sd[name]) == int(ref)
+            else:
+                assert torch.allclose(sd[name].double().cpu(), ref, rtol=2e-5, atol=1e-6), name
+
+
+@pytest.mark.parametrize("case", ["quad2d", "lin4d", "quad8d_small"])
+def test_autograd_entry_equals_plain_forward_and_accepts_d_columns(golden, case):
+    g = golden("flow_" + case)
+    NF = make_manager(g.meta)
+    model = NF._model
+    model.load_state_dict(g.state_dict())
+    model.eval()
+    xj = g.t("xj").cuda()
+    a = model(xj)
+    b, _ = model.forward_with_bins(xj)
+    assert torch.equal(a, b)
+    x_only = xj[:, :-1].contiguous()
+    c, _ = model.forward_with_bins(x_only)                       # J = 1 implied
+    assert torch.allclose(c[:, -1] * xj[:, -1], a[:, -1], rtol=1e-6)
+    assert torch.equal(c[:, :-1], a[:, :-1])
+
+
+BIG = [
+    dict(name="cfg2", kind="lin", n_flow=8, n_pass_through=4, n_cells=6, n_bins=32, NN=[64] * 3, roll_step=4, B=1 << 15),
+    dict(name="cfg4", kind="quad", n_flow=8, n_cells=6, n_bins=32, NN=[64] * 3, B=1 << 14),
+    dict(name="cfg1", kind="quad", n_flow=2, n_cells=2, n_bins=4, NN=[3] * 3, B=10000),
+    dict(name="cfg5_small", kind="quad", n_flow=16, n_cells=8, n_bins=64, NN=[256] * 2, B=1 << 11),
+]
+
+
+@pytest.mark.parametrize("cfg", BIG, ids=[c["name"] for c in BIG])
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_forward_matches_oracle_at_size(cfg, mode):
+    torch.manual_seed(5)
+    NF = make_manager(cfg)
+    model = NF._model
+    cells, out_perm = oflow.compile_layers(oracle_layers(cfg), cfg["n_flow"])
+    sd = oflow.init_state_dict(cells, cfg["n_flow"], cfg["kind"], cfg["n_bins"], cfg["NN"], seed=7,
+                               dtype=torch.float32, bn_jitter=0.2)
+    model.load_state_dict(sd)
+    model.train(mode == "train")
+    gen = torch.Generator().manual_seed(2026)
+    x = torch.rand(cfg["B"], cfg["n_flow"], generator=gen, dtype=torch.float32).double()
+    xj = NF.format_input(x, torch.device("cuda"))
+    XJ, bins = model.forward_with_bins(xj)
+    sd64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    with torch.no_grad():
+        ref, ref_bins = oflow.flow_forward(oracle_layers(cfg), sd64, xj.cpu(), cfg["kind"], cfg["n_bins"],
+                                           train=(mode == "train"))
+    compare_flow(XJ.cpu(), bins.cpu(), ref, [b.numpy() for b in ref_bins], "%s/%s" % (cfg["name"], mode))
+
+
+def test_flow_is_a_bijection_of_the_unit_cube_at_full_size():
+    """Size-independent properties at cfg2's full batch (2^22 points): <J> = 1 within Monte Carlo error,
+    outputs stay in [0,1], pass-through columns of the last cell are bit-identical to its input."""
+    torch.manual_seed(11)
+    cfg = BIG[0]
+    NF = make_manager(cfg)
+    model = NF._model.eval()
+    B = 1 << 22
+    x = torch.rand(B, 8, device="cuda", dtype=torch.float32)
+    XJ = model(x)
+    J = XJ[:, -1].double()
+    assert abs(float(J.mean()) - 1.0) < 6 * float(J.std()) / np.sqrt(B)
+    assert float(XJ[:, :-1].min()) >= 0.0 and float(XJ[:, :-1].max()) <= 1.0 + 1e-6
+    # determinism: same input, same bits
+    assert torch.equal(model(x), XJ)

@@ -1,0 +1,86 @@
+"""GPU parity of the fused RAMBO kernel (FlatInvertiblePhasespace -> nis_rambo_generate)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import RAMBO_CASES
+from oracle import rambo as orambo
+
+from nf_b200.PhaseSpace.flat_phase_space_generator import FlatInvertiblePhasespace
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", RAMBO_CASES)
+@pytest.mark.parametrize("where", ["cuda", "cpu"])
+def test_matches_reference_golden(golden, case, where):
+    g = golden("rambo_" + case)
+    m = g.meta
+    ps = FlatInvertiblePhasespace(m["initial"], m["final"], pdf=None, pdf_active=False)
+    r = g.t("r").to(where)
+    mom, w, mask = ps.generateKinematics_batch(m["E_cm"], r, return_cutmask=True, **m["cuts"])
+    assert mom.device.type == where and w.dtype == torch.float64
+    ref_w, ref_mom = g.t("weight"), g.t("momenta")
+    assert np.array_equal(mask.cpu().numpy().astype(bool), (ref_w != 0).numpy()), "cut mask must be bit-exact"
+    assert np.array_equal((w.cpu() != 0).numpy(), (ref_w != 0).numpy())
+    assert torch.allclose(w.cpu(), ref_w, rtol=1e-9, atol=0)
+    assert torch.allclose(mom.cpu(), ref_mom, rtol=1e-9, atol=1e-9 * m["E_cm"])
+
+
+def test_float32_uniforms_and_weight_only_mode():
+    ps = FlatInvertiblePhasespace([100.0] * 2, [100.0] * 4)
+    r32 = torch.rand(4096, 8, device="cuda", dtype=torch.float32)
+    mom, w = ps.generateKinematics_batch(1000.0, r32, pT_mincut=20, delR_mincut=0.4, rap_maxcut=2.5)
+    mom2, w2 = ps.generateKinematics_batch(1000.0, r32.double(), pT_mincut=20, delR_mincut=0.4, rap_maxcut=2.5)
+    assert torch.equal(w, w2) and torch.equal(mom, mom2)
+    none, w3 = ps.generateKinematics_batch(1000.0, r32, pT_mincut=20, delR_mincut=0.4, rap_maxcut=2.5, momenta=False)
+    assert none is None and torch.equal(w3, w)
+
+
+@pytest.mark.parametrize("n,masses", [(4, 100.0), (4, 0.0), (3, 50.0), (6, 10.0)])
+def test_matches_oracle_at_size(n, masses):
+    B = 1 << 15
+    r = torch.rand(B, 3 * n - 4, generator=torch.Generator().manual_seed(n), dtype=torch.float64)
+    cuts = dict(pT_mincut=20, delR_mincut=0.4, rap_maxcut=2.5)
+    ps = FlatInvertiblePhasespace([masses] * 2, [masses] * n)
+    mom, w, mask = ps.generateKinematics_batch(1000.0, r.cuda(), return_cutmask=True, **cuts)
+    rmom, rw = orambo.generate_kinematics(1000.0, r, [masses] * 2, [masses] * n, **cuts)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), (rw != 0).numpy())
+    assert torch.allclose(w.cpu(), rw, rtol=1e-8)
+    assert torch.allclose(mom.cpu(), rmom, rtol=1e-8, atol=1e-6)
+
+
+def test_physics_invariants_at_full_size():
+    """cfg3 size (2^24 events would need 3 GiB of momenta; 2^22 keeps the check light): 4-momentum
+    conservation, on-shell masses, constant massless weight, empty and ragged batches."""
+    B = 1 << 22
+    r = torch.rand(B, 8, device="cuda", dtype=torch.float64)
+    ps = FlatInvertiblePhasespace([100.0] * 2, [100.0] * 4)
+    mom, w = ps.generateKinematics_batch(1000.0, r)
+    assert float((mom[:, :2].sum(1) - mom[:, 2:].sum(1)).abs().max()) < 5e-9
+    mass = torch.sqrt(mom[:, 2:, 0] ** 2 - (mom[:, 2:, 1:] ** 2).sum(-1))
+    assert float((mass - 100.0).abs().max()) < 1e-6
+    assert bool((w > 0).all())
+    ps0 = FlatInvertiblePhasespace([0.0] * 2, [0.0] * 4)
+    _, w0 = ps0.generateKinematics_batch(1000.0, r[: 1 << 20])
+    assert torch.allclose(w0, torch.full_like(w0, 0.06648282151394422), rtol=1e-12)
+    for b in (0, 1, 127, 129):
+        m_, w_ = ps.generateKinematics_batch(1000.0, r[:b])
+        assert m_.shape == (b, 6, 4) and torch.equal(w_, w[:b])
+
+
+def test_cut_quirks_of_the_reference():
+    """strict '<' comparisons: defaults (-1) and 0 disable the cuts; |max eta| not max |eta|."""
+    r = torch.rand(1 << 14, 8, device="cuda", dtype=torch.float64)
+    ps = FlatInvertiblePhasespace([0.0] * 2, [0.0] * 4)
+    _, w_def = ps.generateKinematics_batch(1000.0, r)
+    _, w_zero = ps.generateKinematics_batch(1000.0, r, pT_mincut=0, delR_mincut=0, rap_maxcut=-1)
+    assert torch.equal(w_def, w_zero) and bool((w_def > 0).all())
+    mom, w_rap = ps.generateKinematics_batch(1000.0, r, rap_maxcut=1.0)
+    p = mom[:, 2:]
+    eta = torch.asinh(p[..., 3] / torch.sqrt(p[..., 1] ** 2 + p[..., 2] ** 2))
+    expect = ~(1.0 < eta.max(1).values.abs())
+    assert torch.equal(w_rap != 0, expect)
+    assert bool(((eta.abs().max(1).values > 1.0) & (w_rap != 0)).any())     # very negative eta passes, like the reference

@@ -1,0 +1,163 @@
+"""CPU tests of the host layer: the reference-facing API mirror, topology folding, state_dict schema,
+the epoch state machine and the C-ABI library's symbols (no compute: this box has no GPU)."""
+import ctypes
+import math
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import FLOW_CASES, ROOT
+from oracle import flow as oflow
+from oracle import nis as onis
+
+from nf_b200 import _cabi
+from nf_b200.flowspec import FlowSequential
+from nf_b200.normalizing_flows.manager import EpochState, PWLinManager, PWQuadManager, get_bin
+from nf_b200.PhaseSpace.flat_phase_space_generator import FlatInvertiblePhasespace, PhaseSpaceGeneratorError
+
+
+def make_manager(meta):
+    torch.manual_seed(0)
+    if meta["kind"] == "quad":
+        NF = PWQuadManager(n_flow=meta["n_flow"])
+        NF.create_model(meta["n_cells"], meta["n_bins"], meta["NN"])
+    else:
+        NF = PWLinManager(n_flow=meta["n_flow"])
+        NF.create_model(meta["n_pass_through"], meta["n_cells"], meta["n_bins"], meta["NN"], meta["roll_step"])
+    return NF
+
+
+@pytest.mark.parametrize("case", FLOW_CASES)
+def test_create_model_reproduces_reference_topology_and_schema(golden, case):
+    g = golden("flow_" + case)
+    NF = make_manager(g.meta)
+    model = NF._model
+    assert isinstance(model, torch.nn.Sequential) and isinstance(model, FlowSequential)
+    assert [n for n, _ in model.named_children()] == g.meta["children"]
+    ref_sd = g.state_dict()
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(ref_sd.keys())
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(ref_sd[k].shape), k
+    model.load_state_dict(ref_sd)            # reference checkpoints load unchanged (float64 -> float32)
+    assert NF.best_model is NF.model
+    assert sum(p.numel() for p in model.parameters()) == model.spec().n_params
+
+
+@pytest.mark.parametrize("case", FLOW_CASES)
+def test_flowspec_tables_equal_oracle_compile(golden, case):
+    g = golden("flow_" + case)
+    meta = g.meta
+    spec = make_manager(meta)._model.spec()
+    if meta["kind"] == "quad":
+        layers = oflow.pwquad_layers(meta["n_flow"], meta["n_cells"])
+    else:
+        layers = oflow.pwlin_layers(meta["n_flow"], meta["n_pass_through"], meta["n_cells"], meta["roll_step"])
+    cells, out_perm = oflow.compile_layers(layers, meta["n_flow"])
+    assert spec.out_perm == out_perm
+    assert [(n, f, t) for n, _, f, t in spec.cells] == [(c["name"], c["feed_idx"], c["trafo_idx"]) for c in cells]
+    d = spec.desc
+    assert d.n_cells == len(cells) and d.n_bins == meta["n_bins"] and d.depth == len(meta["NN"])
+    lib = _cabi.load()
+    off = 0
+    for i in range(d.n_cells):
+        assert d.cells[i].param_off == off
+        off += lib.nis_flow_cell_param_count(ctypes.byref(d), i)
+    assert off == spec.n_params
+    assert lib.nis_flow_workspace_bytes(ctypes.byref(d), 1 << 16) > 0
+    assert lib.nis_flow_bn_saved_count(ctypes.byref(d)) > 0
+
+
+def test_parameters_are_views_of_one_arena_and_survive_optimizer_and_deepcopy():
+    import copy
+    NF = PWQuadManager(n_flow=3)
+    NF.create_model(3, 4, [8, 8])
+    spec = NF._model.spec()
+    flat = spec.param_arena.get(torch.device("cpu"))
+    assert flat.numel() == spec.n_params
+    p0 = spec.params[3]
+    assert p0.data_ptr() == flat.data_ptr() + 4 * spec.param_arena.offsets[3]
+    opt = torch.optim.Adamax(NF._model.parameters(), lr=1e-2)
+    for p in NF._model.parameters():
+        p.grad = torch.ones_like(p)
+    before = flat.clone()
+    opt.step()
+    assert spec.param_arena.get(torch.device("cpu")) is flat and not torch.equal(flat, before)
+    twin = copy.deepcopy(NF._model)
+    f2 = twin.spec().param_arena.get(torch.device("cpu"))
+    assert torch.equal(f2, flat) and f2.data_ptr() != flat.data_ptr()
+    NF._model.double()                                   # user-side dtype change: slow path, still consistent
+    f3 = spec.param_arena.get(torch.device("cpu"))
+    assert f3.dtype == torch.float32 and torch.allclose(f3, flat)
+
+
+def test_model_property_and_errors():
+    NF = PWQuadManager(n_flow=2)
+    with pytest.raises(AttributeError, match="No model was instantiated"):
+        NF.model
+    assert NF.integrate(lambda x: x[:, 0], 2, 10) == (0, 0)          # "No model has been trained"
+    assert get_bin(5, 4) == [0, 1, 0, 1] and get_bin(7) == [1, 1, 1]
+    NF.create_model(2, 4, [3] * 3)
+    if not torch.cuda.is_available():
+        with pytest.raises(_cabi.NisBackendError):                    # no silent CPU fallback
+            NF._model(NF.format_input(torch.rand(4, 2)))
+    out = NF.format_input(torch.rand(4, 2))
+    assert out.shape == (4, 3) and out.dtype == torch.float64 and torch.all(out[:, -1] == 1)
+
+
+def test_phase_space_host_surface():
+    with pytest.raises(PhaseSpaceGeneratorError):
+        FlatInvertiblePhasespace([100.0], [100.0] * 3)
+    with pytest.raises(PhaseSpaceGeneratorError):
+        FlatInvertiblePhasespace([1.0, 1.0, 1.0], [100.0] * 3)
+    ps = FlatInvertiblePhasespace([100.0] * 2, [100.0] * 4, pdf=None, pdf_active=False)
+    assert ps.nDimPhaseSpace() == 8
+    assert math.isclose(FlatInvertiblePhasespace.get_flatWeights(1000.0, 4) / 2e6, 0.06648282151394422, rel_tol=1e-13)
+    assert FlatInvertiblePhasespace.get_flatWeights(1000.0, 1) == 1.0
+    with pytest.raises(PhaseSpaceGeneratorError):
+        ps.generateKinematics_batch(1000.0, torch.full((4, 8), float("nan"), dtype=torch.double))
+    if not torch.cuda.is_available():
+        with pytest.raises(_cabi.NisBackendError):
+            ps.generateKinematics_batch(1000.0, torch.rand(4, 8, dtype=torch.double))
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_epoch_state_equals_oracle_state_machine_on_reference_traces(golden, case):
+    g = golden("train_" + case)
+    m = g.meta
+    losses = [float(x) for x in g["losses"]]
+    # extend the trace with synthetic tails to drive every branch
+    rng = np.random.default_rng(3)
+    tails = [losses, losses + list(losses[-1] * (1 + 0.2 * rng.random(40))), [1.0] * 30, list(np.linspace(1, 0.1, 400))]
+    for seq in tails:
+        ours = EpochState(float(g["int_loss"]), m["preburn_time"], m["kill_counter"], 1e-2)
+        ref = onis.EpochStateMachine(float(g["int_loss"]), preburn_time=m["preburn_time"], kill_counter=m["kill_counter"])
+        best_epoch = 0
+        for i, loss in enumerate(seq):
+            if ours.improved(loss, True):
+                best_epoch = i
+            stop_o = ours.advance(i, loss)
+            stop_r = ref.step(i, loss)
+            assert stop_o == stop_r and ours.preburner == ref.preburner and ours.counter == ref.counter, (case, i)
+            if stop_o:
+                break
+        assert best_epoch == ref.best_epoch and ours.best_loss == ref.best_loss
+    assert best_epoch >= 0
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    lib = _cabi.load()
+    header = open(ROOT + "/include/nis_b200.h").read()
+    declared = set(re.findall(r"\b(nis_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_cabi.EXPORTS)
+    assert lib.nis_sizeof_flow_desc() == ctypes.sizeof(_cabi.NisFlowDesc)
+    assert lib.nis_sizeof_rambo_desc() == ctypes.sizeof(_cabi.NisRamboDesc)
+    assert lib.nis_strerror(-2).decode().startswith("workspace")
+    bad = _cabi.NisFlowDesc()
+    assert lib.nis_flow_workspace_bytes(ctypes.byref(bad), 10) == 0       # invalid descriptor rejected on the host
+    assert lib.nis_flow_cell_param_count(ctypes.byref(bad), 0) == -1
