@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the NIS hot path (BASELINE.json): fused flow forward + log-det, points/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (N=1 and per GPU for N>1, weak scaling): BASELINE.json configs[1] — 8D, PWLinear coupling,
+6 cells, 32 bins, conditioner [64]*3, forward + Jacobian on 2^22 synthetic uniform points per step,
+BatchNorm in train mode (batch statistics) exactly as the reference's integrate() runs it
+(manager.py:397).  A step = one pass of the flow over the 2^22-point batch (+ for N>1 the moment
+reduction and its NCCL all-reduce, the path's only exchange).  One JSON line is printed by rank 0.
+
+Extra objects on the line: ``roofline`` (dominant kernel vs the measured FP32-FMA peak — this path is
+compute-bound on the FP32 pipe, SURVEY.md §8d — plus its HBM view), ``cpu_baseline`` (the oracle port of
+the reference timed on the host cores on a bounded sample), ``e2e`` (same metric through the public API
+from pinned host buffers, H2D/D2H inside the timed region), ``eval_mode`` (BN folded: one launch),
+``rambo`` (BASELINE.json configs[2]: events/s of the fused RAMBO+cuts kernel against the HBM roofline).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+CFG2 = dict(kind="lin", n_flow=8, n_pass_through=4, n_cells=6, n_bins=32, NN=[64] * 3, roll_step=4)
+N_POINTS = 1 << 22
+FLOP_PER_POINT = 199680          # 6 cells x 2 x 16 640 MAC
+IO_BYTES_PER_POINT = 68          # fp32 in 32 B + out 36 B
+RAMBO_EVENTS = 1 << 24
+RAMBO_BYTES_PER_EVENT = 264      # fp64: 8 uniforms in + (6x4 momenta + weight) out
+METRIC = "nis_flow_fwd_logdet_points_per_sec"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_flow(seed=1234):
+    from nf_b200.normalizing_flows.manager import PWLinManager
+    torch.manual_seed(seed)
+    NF = PWLinManager(n_flow=CFG2["n_flow"])
+    NF.create_model(CFG2["n_pass_through"], CFG2["n_cells"], CFG2["n_bins"], CFG2["NN"], CFG2["roll_step"])
+    return NF
+
+
+def time_steps(fn, steps, warmup, world):
+    """W untimed + exactly K timed steps, barrier + synchronize on both sides, CUDA events, max over ranks."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()) / steps
+
+
+def fma_peak_tflops():
+    from nf_b200 import _cabi
+    lib = _cabi.lib()
+    out = torch.zeros(4, device="cuda")
+    best = 0.0
+    for it in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        flop = lib.nis_probe_fp32_fma(_cabi.ptr(out), 1 << 15, _cabi.stream_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        if it:
+            best = max(best, flop / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def reference_flow(threads):
+    """The reference's CPU path for this workload as a callable [B,9] float64 -> [B,9] (train-mode BN like
+    the reference's integrate).  kind "reference": the UNMODIFIED reference package installed under
+    baseline/_ref (pip --target from /root/reference; git-ignored, travels with the repo snapshot), built
+    through its own PWLinManager.create_model (plus the documented .double() shim).
+    kind "port": the oracle restatement, used when baseline/_ref is absent."""
+    torch.set_num_threads(threads)
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref, "nisrep")):
+        sys.path.insert(0, ref)
+        try:
+            from nisrep.normalizing_flows.manager import PWLinManager as RefPWLin
+            torch.manual_seed(1234)
+            NF = RefPWLin(n_flow=CFG2["n_flow"])
+            try:
+                NF.create_model(CFG2["n_pass_through"], CFG2["n_cells"], CFG2["n_bins"], CFG2["NN"], CFG2["roll_step"])
+            except RuntimeError:
+                pass                     # mixed-dtype trial forward, raised after _model is built (manager.py:493-499)
+            model = NF._model.to("cpu").double()
+            model.train()
+            return (lambda xj: model(xj)), "reference"
+        except Exception as e:           # fall through to the port, but say why
+            print("reference import failed, using the oracle port: %r" % (e,), file=sys.stderr)
+    from oracle import flow as oflow
+    layers = oflow.pwlin_layers(CFG2["n_flow"], CFG2["n_pass_through"], CFG2["n_cells"], CFG2["roll_step"])
+    cells, _ = oflow.compile_layers(layers, CFG2["n_flow"])
+    sd = oflow.init_state_dict(cells, CFG2["n_flow"], "lin", CFG2["n_bins"], CFG2["NN"], seed=1234)
+    return (lambda xj: oflow.flow_forward(layers, sd, xj, "lin", CFG2["n_bins"], train=True)[0]), "port"
+
+
+def cpu_reference_flow(n_points, reps, threads):
+    fn, kind = reference_flow(threads)
+    x = torch.rand(n_points, CFG2["n_flow"], dtype=torch.float64)
+    xj = torch.cat((x, torch.ones(n_points, 1, dtype=torch.float64)), 1)
+    best = None
+    with torch.no_grad():
+        for i in range(reps + 1):
+            t0 = time.perf_counter()
+            fn(xj)
+            dt = time.perf_counter() - t0
+            if i and (best is None or dt < best):
+                best = dt
+    return n_points / best, best, kind
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, same
+    metric/config; each step is a bounded sample of the workload.  Rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 1 << 17
+    fn, kind = reference_flow(threads)
+    x = torch.rand(sample, CFG2["n_flow"], dtype=torch.float64)
+    xj = torch.cat((x, torch.ones(sample, 1, dtype=torch.float64)), 1)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            fn(xj)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn(xj)
+        dt = (time.perf_counter() - t0) / args.steps
+    value = sample / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(sample),
+            "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": kind,
+                             "sample": "%d points per step (of the 2^22-point workload), float64, train-mode BN" % sample},
+            "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(points):
+    return {"workload": "cfg2: 8D PWLinear flow, 6 cells, 32 bins, MLP [64]*3, forward + log-det, "
+                        "train-mode BatchNorm (batch statistics, as the reference's integrate runs it)",
+            "points_per_step_per_gpu": points, "n_flow": 8, "cells": 6, "bins": 32, "hidden": [64, 64, 64],
+            "l2": "inputs larger than L2 (134 MB fp32 points per step > 126 MB)"}
+
+
+def bench_rambo(steps, warmup, world, hbm_peak, peak_kind):
+    from nf_b200.PhaseSpace.flat_phase_space_generator import FlatInvertiblePhasespace
+    ps = FlatInvertiblePhasespace([100.0] * 2, [100.0] * 4, pdf=None, pdf_active=False)
+    ps.check_nan = False
+    r = torch.rand(RAMBO_EVENTS, 8, device="cuda", dtype=torch.float64)
+
+    def step():
+        ps.generateKinematics_batch(1000.0, r, pT_mincut=20, delR_mincut=0.4, rap_maxcut=2.5)
+
+    ms = time_steps(step, steps, warmup, world)
+
+    def step_w():
+        ps.generateKinematics_batch(1000.0, r, pT_mincut=20, delR_mincut=0.4, rap_maxcut=2.5, momenta=False)
+
+    ms_w = time_steps(step_w, steps, warmup, world)
+    ev = world * RAMBO_EVENTS / (ms * 1e-3)
+    gbs = RAMBO_EVENTS * RAMBO_BYTES_PER_EVENT / (ms * 1e-3) / 1e9
+    del r
+    return {"metric": "rambo_events_per_sec", "value": ev, "unit": "events/s", "ms_per_step": ms,
+            "config": {"workload": "cfg3: FlatInvertiblePhasespace 2->4 massive (m=100), E_cm=1000, pdf inactive, "
+                                   "pT>20, dR>0.4, |eta|<2.5 cuts", "events_per_step_per_gpu": RAMBO_EVENTS},
+            "dtype": "f64",
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes_per_event": RAMBO_BYTES_PER_EVENT},
+            "weight_only": {"value": world * RAMBO_EVENTS / (ms_w * 1e-3), "unit": "events/s", "ms_per_step": ms_w}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu baseline / rambo / eval-mode extras")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from nf_b200 import _cabi
+    lib = _cabi.lib()
+    pk, peak_kind = peaks()
+    dev = torch.device("cuda", local)
+
+    NF = build_flow()
+    model = NF._model
+    model.train()
+    x = torch.rand(N_POINTS, 8, device=dev, dtype=torch.float32,
+                   generator=torch.Generator(device=dev).manual_seed(2026 + rank))
+    moments = torch.zeros(3, dtype=torch.double, device=dev)
+    rws = torch.empty(lib.nis_reduce_workspace_bytes(), dtype=torch.uint8, device=dev)
+
+    def step():
+        with torch.no_grad():
+            XJ = model(x)
+        if world > 1:      # the path's only exchange: sum-allreduce of (sum J, sum J^2, n)
+            J = XJ[:, -1].contiguous()
+            lib.nis_reduce_moments(_cabi.ptr(J), _cabi.F32, J.numel(), _cabi.ptr(moments), 0, _cabi.ptr(rws),
+                                   rws.numel(), _cabi.stream_ptr(dev))
+            dist.all_reduce(moments)
+        return XJ
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = time_steps(step, args.steps, args.warmup, world)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * N_POINTS / (ms * 1e-3)
+    n_cells, depth = 6, 3
+    launches_per_step = 1 + n_cells * (depth + 2) + (1 if world > 1 else 0)     # pack + per cell (depth+1 stats + 1 full)
+
+    # ---- end to end through the public API from pinned host buffers ---------------------------------
+    xh = torch.rand(N_POINTS, 8, dtype=torch.float32).pin_memory()
+    oh = torch.empty(N_POINTS, 9, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        xd = xh.to(dev, non_blocking=True)
+        with torch.no_grad():
+            out = model(xd)
+        oh.copy_(out, non_blocking=True)
+        if world > 1:
+            J = out[:, -1].contiguous()
+            lib.nis_reduce_moments(_cabi.ptr(J), _cabi.F32, J.numel(), _cabi.ptr(moments), 0, _cabi.ptr(rws),
+                                   rws.numel(), _cabi.stream_ptr(dev))
+            dist.all_reduce(moments)
+
+    ms_e2e = time_steps(step_e2e, args.steps, args.warmup, world)
+    e2e = {"value": world * N_POINTS / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": xh.numel() * 4, "d2h_bytes_per_step": oh.numel() * 4,
+           "api": "FlowSequential.__call__ (PWLinManager._model) on pinned host float32 points"}
+    del xh, oh
+
+    line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(N_POINTS),
+            "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks}
+
+    if rank == 0 or world > 1:
+        fma = fma_peak_tflops()
+        tfl = N_POINTS * FLOP_PER_POINT / (ms * 1e-3) / 1e12
+        gbs = N_POINTS * IO_BYTES_PER_POINT / (ms * 1e-3) / 1e9
+        line["roofline"] = {"bound": "fp32_fma", "achieved": tfl, "peak": fma, "unit": "TFLOP/s", "frac": tfl / fma,
+                            "traffic": None, "peak_kind": "measured in this run (nis_probe_fp32_fma)",
+                            "kernel": "flow_fwd_generic_kernel (%d launches per step: %d statistics passes + %d full "
+                                      "passes; algorithmic flop exclude the re-computation of the statistics passes)"
+                                      % (n_cells * (depth + 2), n_cells * (depth + 1), n_cells),
+                            "algorithmic_flop_per_point": FLOP_PER_POINT,
+                            "hbm": {"achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                                    "peak_kind": peak_kind, "algorithmic_bytes_per_point": IO_BYTES_PER_POINT}}
+
+    if not args.no_extras:
+        model.eval()
+        ms_eval = time_steps(step, args.steps, args.warmup, world)
+        tfl_e = N_POINTS * FLOP_PER_POINT / (ms_eval * 1e-3) / 1e12
+        line["eval_mode"] = {"value": world * N_POINTS / (ms_eval * 1e-3), "unit": "points/s", "ms_per_step": ms_eval,
+                             "launches_per_step": 2,
+                             "roofline": {"bound": "fp32_fma", "achieved": tfl_e, "peak": line.get("roofline", {}).get("peak"),
+                                          "unit": "TFLOP/s",
+                                          "frac": tfl_e / line["roofline"]["peak"] if "roofline" in line else None}}
+        model.train()
+        del x
+        torch.cuda.empty_cache()
+        line["rambo"] = bench_rambo(max(3, args.steps // 2), args.warmup, world, pk["hbm_gbs"], peak_kind)
+        if rank == 0 and world == 1:
+            threads = os.cpu_count() or 1
+            sample = 1 << 17
+            v, dt, kind = cpu_reference_flow(sample, 2, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": threads, "kind": kind,
+                                    "sample": "%d points (of 2^22), best of 2 after 1 warm-up, float64, train-mode BN, "
+                                              "torch CPU ops as the reference uses" % sample}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

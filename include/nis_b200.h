@@ -109,11 +109,13 @@ int nis_flow_forward(const NisFlowDesc* desc, const float* params, float* bn_run
 
 /* Backward: given dL/d(xj_out) computes dL/d(params) (accumulated into grad_params, which the caller
  * zeroes when it wants a fresh gradient) and optionally dL/d(xj_in).
+ *   bn_running  running statistics (EVAL mode; may be NULL in TRAIN mode)
+ *   saved / bn_saved  as written by the matching nis_flow_forward
  *   grad_out    [B, n_flow+1] dtype grad_dtype, reference column order
  *   grad_in     optional [B, n_flow+1] same dtype (column n_flow = dL/dJ_in)
  */
-int nis_flow_backward(const NisFlowDesc* desc, const float* params, const float* saved,
-                      const float* bn_saved, const void* grad_out, int32_t grad_dtype,
+int nis_flow_backward(const NisFlowDesc* desc, const float* params, const float* bn_running,
+                      const float* saved, const float* bn_saved, const void* grad_out, int32_t grad_dtype,
                       float* grad_params, void* grad_in, int32_t bn_mode,
                       void* workspace, size_t workspace_bytes, int64_t B, void* stream);
 
@@ -143,6 +145,11 @@ int nis_rambo_generate(const NisRamboDesc* desc, const void* r, int32_t r_dtype,
 /* Philox4x32-10 uniforms in [0,1): out[n] of dtype; element i is a pure function of (seed, offset+i),
  * so ranks draw disjoint streams by offsetting. */
 int nis_uniform_fill(void* out, int32_t dtype, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* Measurement aid for bench.py: launches a kernel of pure FP32 FMA chains on `stream` and returns the
+ * number of floating-point operations it performs (or a negative error).  Timing it with CUDA events
+ * gives the measured FP32-pipe peak the compute-bound flow kernels are quoted against. */
+int64_t nis_probe_fp32_fma(float* out, int32_t iters, void* stream);
 
 /* sizeof(NisFlowDesc) / sizeof(NisRamboDesc) as compiled, so a foreign-language binding can verify its
  * struct layout at load time. */

@@ -59,7 +59,7 @@ _PROTOS = {
     "nis_flow_forward": (ctypes.c_int, [ctypes.POINTER(NisFlowDesc), _P, _P, _P, ctypes.c_int32, ctypes.c_int32,
                                         _P, ctypes.c_int32, _P, _P, _P, ctypes.c_int32, _P, ctypes.c_size_t,
                                         ctypes.c_int64, _P]),
-    "nis_flow_backward": (ctypes.c_int, [ctypes.POINTER(NisFlowDesc), _P, _P, _P, _P, ctypes.c_int32, _P, _P,
+    "nis_flow_backward": (ctypes.c_int, [ctypes.POINTER(NisFlowDesc), _P, _P, _P, _P, _P, ctypes.c_int32, _P, _P,
                                          ctypes.c_int32, _P, ctypes.c_size_t, ctypes.c_int64, _P]),
     "nis_reduce_workspace_bytes": (ctypes.c_size_t, []),
     "nis_reduce_moments": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int64, _P, ctypes.c_int32, _P,
@@ -67,6 +67,7 @@ _PROTOS = {
     "nis_rambo_generate": (ctypes.c_int, [ctypes.POINTER(NisRamboDesc), _P, ctypes.c_int32, _P, _P, _P,
                                           ctypes.c_int64, _P]),
     "nis_uniform_fill": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, _P]),
+    "nis_probe_fp32_fma": (ctypes.c_int64, [_P, ctypes.c_int32, _P]),
     "nis_sizeof_flow_desc": (ctypes.c_size_t, []),
     "nis_sizeof_rambo_desc": (ctypes.c_size_t, []),
     "nis_strerror": (ctypes.c_char_p, [ctypes.c_int]),

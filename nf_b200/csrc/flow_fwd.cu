@@ -132,9 +132,9 @@ __global__ void __launch_bounds__(NT) flow_fwd_generic_kernel(const __grid_const
     const int d = F.d, maxW = F.maxW;
     const int bw = maxW > F.Kpad ? maxW : F.Kpad;
     float* st = sm + tid;                         // [(d+1)][NT]
-    float* bufA = sm + (d + 1) * NT + tid;        // [maxW][NT]
-    float* bufB = bufA + maxW * NT;               // [bw][NT]
-    double* sacc = reinterpret_cast<double*>(sm + ((d + 1) + maxW + bw) * NT + (((d + 1) + maxW + bw) * NT & 1));
+    float* bufA = sm + (d + 1) * NT + tid;        // [bw][NT]  (either buffer may receive the logits)
+    float* bufB = bufA + bw * NT;                 // [bw][NT]
+    double* sacc = reinterpret_cast<double*>(sm + ((d + 1) + 2 * bw) * NT + (((d + 1) + 2 * bw) * NT & 1));
     const bool stats = A.stats_layer >= 0;
     if (stats) {
         for (int i = tid; i < 2 * maxW; i += NT) sacc[i] = 0.0;
@@ -293,7 +293,7 @@ size_t nis_flow_bwd_scratch_floats(const DevFlow& F, int64_t B);
 
 static size_t fwd_smem_bytes(const DevFlow& F, int NT) {
     const int bw = F.maxW > F.Kpad ? F.maxW : F.Kpad;
-    size_t fl = (size_t)((F.d + 1) + F.maxW + bw) * NT;
+    size_t fl = (size_t)((F.d + 1) + 2 * bw) * NT;
     fl += fl & 1;
     return fl * sizeof(float) + sizeof(double) * 2 * F.maxW;
 }
@@ -333,7 +333,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     DevFlow F;
     int rc = nis_build_dev_flow(desc, &F);
     if (rc) return rc;
-    if (!params || !xj_in || !xj_out || !workspace || B < 0) return NIS_EINVAL;
+    if (!params || !workspace || B < 0 || (B > 0 && (!xj_in || !xj_out))) return NIS_EINVAL;
     if (in_cols != F.d && in_cols != F.d + 1) return NIS_EINVAL;
     if ((in_dtype != NIS_F32 && in_dtype != NIS_F64) || (out_dtype != NIS_F32 && out_dtype != NIS_F64)) return NIS_EINVAL;
     if (bn_mode == NIS_BN_EVAL && !bn_running) return NIS_EINVAL;

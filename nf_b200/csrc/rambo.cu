@@ -70,7 +70,7 @@ static int rambo_launch_dt(const RamboConst& C, const void* r, int dt, double* m
 
 extern "C" int nis_rambo_generate(const NisRamboDesc* desc, const void* r, int32_t r_dtype, double* momenta,
                                   double* weight, uint8_t* cutmask, int64_t B, void* stream) {
-    if (!desc || !r || !weight || B < 0) return NIS_EINVAL;
+    if (!desc || B < 0 || (B > 0 && (!r || !weight))) return NIS_EINVAL;
     if (r_dtype != NIS_F32 && r_dtype != NIS_F64) return NIS_EINVAL;
     RamboConst C;
     int rc = rambo_fill_const(desc, &C);

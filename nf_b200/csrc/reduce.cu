@@ -49,7 +49,7 @@ extern "C" size_t nis_reduce_workspace_bytes(void) { return sizeof(double) * 2 *
 
 extern "C" int nis_reduce_moments(const void* v, int32_t dtype, int64_t n, double* out, int32_t accumulate,
                                   void* workspace, size_t workspace_bytes, void* stream) {
-    if (!v || !out || !workspace || n < 0) return NIS_EINVAL;
+    if ((!v && n > 0) || !out || !workspace || n < 0) return NIS_EINVAL;
     if (workspace_bytes < nis_reduce_workspace_bytes()) return NIS_EWORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
     double* partials = (double*)workspace;
@@ -109,6 +109,30 @@ extern "C" int nis_uniform_fill(void* out, int32_t dtype, int64_t n, uint64_t se
     else return NIS_EINVAL;
     NIS_CUDA_CHECK_LAUNCH();
     return NIS_OK;
+}
+
+// ---- FP32 FMA pipe probe (roofline denominator for the compute-bound flow kernels) -------------------
+// Every thread runs 16 independent FMA chains for `iters` rounds: 32 * iters flop per thread.
+__global__ void __launch_bounds__(256) fma_probe_kernel(float* __restrict__ out, int iters, float a, float b) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 123.456f) out[0] = s;      // never true in practice; keeps the chains alive
+}
+
+extern "C" int64_t nis_probe_fp32_fma(float* out, int32_t iters, void* stream) {
+    if (!out || iters <= 0) return NIS_EINVAL;
+    const int grid = 148 * 8;
+    fma_probe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.999f, 0.001f);
+    NIS_CUDA_CHECK_LAUNCH();
+    return (int64_t)grid * 256 * 32 * (int64_t)iters;
 }
 
 extern "C" const char* nis_strerror(int code) {

@@ -229,10 +229,11 @@ class FlowSpec:
             grad_out = grad_out.double()
         with torch.cuda.device(dev):
             params = self.param_arena.get(dev)
+            bn = self.bn_arena.get(dev)
             gparams = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
             gin = torch.empty(B, d + 1, dtype=grad_out.dtype, device=dev) if need_grad_in else None
             ws = self.workspace(lib, B, dev)
-            rc = lib.nis_flow_backward(ctypes.byref(self.desc), _cabi.ptr(params), _cabi.ptr(saved),
+            rc = lib.nis_flow_backward(ctypes.byref(self.desc), _cabi.ptr(params), _cabi.ptr(bn), _cabi.ptr(saved),
                                        _cabi.ptr(bn_saved), _cabi.ptr(grad_out), _cabi.dtype_code(grad_out),
                                        _cabi.ptr(gparams), _cabi.ptr(gin),
                                        _cabi.BN_TRAIN if train else _cabi.BN_EVAL, _cabi.ptr(ws), ws.numel(), B,

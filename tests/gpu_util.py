@@ -25,10 +25,16 @@ def oracle_layers(meta):
     return oflow.pwlin_layers(meta["n_flow"], meta["n_pass_through"], meta["n_cells"], meta["roll_step"])
 
 
-def compare_flow(XJ, bins, ref_XJ, ref_bins, what=""):
+def compare_flow(XJ, bins, ref_XJ, ref_bins, what="", fp32_yardstick=None):
     """XJ [B,d+1] (ours, any float dtype, cpu), bins [C,B,d] int32 (ours); ref_bins: list of [B,T_c].
     Bin indices must be identical except where fp32 rounding puts x on the other side of an edge
-    (|delta| == 1, at most a handful); points and log-Jacobians within 1e-5 relative."""
+    (|delta| == 1, at most a handful); points and log-Jacobians within 1e-5 relative.
+
+    ``fp32_yardstick`` (the oracle itself evaluated in float32, [B,d+1]) switches the log-Jacobian
+    check to the large-batch form: the Jacobian of a point inside a narrow bin is ill-conditioned
+    (d log f / d logit ~ 1/W_k), so over 10^5 spline evaluations the worst point of ANY float32
+    evaluation exceeds 1e-5; there we require the 99.9 % quantile <= 1e-5 and the maximum to be no
+    worse than twice what the float32 oracle itself loses (and the median <= 3e-6)."""
     XJ = XJ.double()
     B = XJ.shape[0]
     flipped = np.zeros(B, bool)
@@ -48,5 +54,17 @@ def compare_flow(XJ, bins, ref_XJ, ref_bins, what=""):
     assert torch.allclose(y, ry, rtol=RTOL, atol=ATOL_Y), "%s: points, max abs err %g" % (what, float((y - ry).abs().max()))
     lj, rlj = torch.log(XJ[keep, -1]), torch.log(ref_XJ[keep, -1])
     err = (lj - rlj).abs() / rlj.abs().clamp_min(1.0)
-    assert float(err.max()) <= RTOL, "%s: log-Jacobian rel err %g" % (what, float(err.max()))
+    if fp32_yardstick is None:
+        assert float(err.max()) <= RTOL, "%s: log-Jacobian rel err %g" % (what, float(err.max()))
+    else:
+        ylj = torch.log(fp32_yardstick.double()[keep, -1])
+        yerr = (ylj - rlj).abs() / rlj.abs().clamp_min(1.0)
+        yerr = yerr[torch.isfinite(yerr)]
+        q999, yq999 = float(torch.quantile(err, 0.999)), float(torch.quantile(yerr, 0.999))
+        msg = "%s: log-Jacobian rel err: ours median %.2e q99.9 %.2e max %.2e | float32 oracle median %.2e q99.9 %.2e max %.2e" % (
+            what, float(err.median()), q999, float(err.max()), float(yerr.median()), yq999, float(yerr.max()))
+        print(msg)
+        assert float(err.median()) <= 0.3 * RTOL, msg
+        assert q999 <= max(RTOL, 2 * yq999), msg
+        assert float(err.max()) <= max(RTOL, 2 * float(yerr.max())), msg
     return nflip

@@ -1,0 +1,109 @@
+"""GPU parity of the fused backward (autograd.Function -> nis_flow_backward) against the reference's
+autograd gradients (golden) and torch.autograd of the oracle at larger sizes.
+
+Tolerance: gradients are float32 sums over the batch; each tensor must match the float64 reference to
+2e-4 of that tensor's largest entry plus 1e-5 of the largest gradient entry of the whole model (some
+gradients are identically zero by symmetry — e.g. a BatchNorm shift that the next train-mode BatchNorm
+removes — and only rounding noise is left there)."""
+import pytest
+import torch
+
+from conftest import GRAD_CASES
+from gpu_util import make_manager, oracle_layers
+from oracle import flow as oflow
+from oracle import nis as onis
+
+pytestmark = pytest.mark.gpu
+GTOL = 2e-4
+
+
+def close(a, ref, name, gscale):
+    scale = float(ref.abs().max())
+    err = float((a.double().cpu() - ref).abs().max())
+    assert err <= GTOL * scale + 1e-5 * gscale, "%s: err %g vs scale %g (model scale %g)" % (name, err, scale, gscale)
+
+
+@pytest.mark.parametrize("case", GRAD_CASES)
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_variance_loss_gradients_match_reference(golden, case, mode):
+    g = golden("flow_" + case)
+    NF = make_manager(g.meta)
+    model = NF._model
+    model.load_state_dict(g.state_dict())
+    model.train(mode == "train")
+    xj = g.t("xj").cuda()
+    model.zero_grad()
+    XJ = model(xj)
+    fres = g.t(mode + "/grad_var/fres").cuda()
+    loss = torch.var(fres * XJ[:, -1] / fres.max())             # manager.py:245-255
+    assert abs(float(loss) - float(g[mode + "/grad_var/loss"])) <= 1e-5 * abs(float(g[mode + "/grad_var/loss"]))
+    loss.backward()
+    gscale = max(float(g.t("%s/grad_var/%s" % (mode, k)).abs().max()) for k, _ in model.named_parameters())
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        close(p.grad, g.t("%s/grad_var/%s" % (mode, k)), k, gscale)
+
+
+@pytest.mark.parametrize("case", GRAD_CASES)
+@pytest.mark.parametrize("mode", ["eval", "train"])
+@pytest.mark.parametrize("io", [torch.float64, torch.float32])
+def test_generic_upstream_gradient_matches_reference(golden, case, mode, io):
+    g = golden("flow_" + case)
+    NF = make_manager(g.meta)
+    model = NF._model
+    model.load_state_dict(g.state_dict())
+    model.train(mode == "train")
+    xin = g.t("xj").to(io).cuda().requires_grad_(True)
+    G = g.t(mode + "/grad_lin/G").to(io).cuda()
+    model.zero_grad()
+    (model(xin) * G).sum().backward()
+    assert xin.grad.dtype == io
+    gscale = max(float(g.t("%s/grad_lin/%s" % (mode, k)).abs().max()) for k, _ in model.named_parameters())
+    close(xin.grad, g.t(mode + "/grad_lin/dxj"), "dxj", float(g.t(mode + "/grad_lin/dxj").abs().max()))
+    for k, p in model.named_parameters():
+        close(p.grad, g.t("%s/grad_lin/%s" % (mode, k)), k, gscale)
+
+
+BIG = [
+    dict(name="cfg2", kind="lin", n_flow=8, n_pass_through=4, n_cells=6, n_bins=32, NN=[64] * 3, roll_step=4, B=5000),
+    dict(name="cfg4", kind="quad", n_flow=8, n_cells=6, n_bins=32, NN=[64] * 3, B=3000),
+    dict(name="cfg1", kind="quad", n_flow=2, n_cells=2, n_bins=4, NN=[3] * 3, B=2000),
+    dict(name="cfg5_small", kind="quad", n_flow=16, n_cells=8, n_bins=16, NN=[128] * 2, B=1500),
+]
+
+
+@pytest.mark.parametrize("cfg", BIG, ids=[c["name"] for c in BIG])
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_gradients_match_oracle_autograd_at_size(cfg, mode):
+    torch.manual_seed(3)
+    NF = make_manager(cfg)
+    model = NF._model
+    layers = oracle_layers(cfg)
+    cells, _ = oflow.compile_layers(layers, cfg["n_flow"])
+    sd = oflow.init_state_dict(cells, cfg["n_flow"], cfg["kind"], cfg["n_bins"], cfg["NN"], seed=9,
+                               dtype=torch.float32, bn_jitter=0.2)
+    model.load_state_dict(sd)
+    model.train(mode == "train")
+    gen = torch.Generator().manual_seed(77)
+    x = torch.rand(cfg["B"], cfg["n_flow"], generator=gen, dtype=torch.float32).double()
+    fres = torch.exp(-((x - 0.5) ** 2).sum(-1) / 0.2)
+    # two minibatches accumulated before one backward, like the training loop (manager.py:219-278)
+    halves = [slice(0, cfg["B"] // 2), slice(cfg["B"] // 2, cfg["B"])]
+    model.zero_grad()
+    loss = 0
+    for h in halves:
+        XJ = model(NF.format_input(x[h], torch.device("cuda")))
+        loss = loss + torch.var(fres[h].cuda() * XJ[:, -1] / fres.max())
+    (loss / 2).backward()
+    sd64 = {k: (v.double().requires_grad_(k.endswith("weight") or k.endswith("bias")) if v.dtype.is_floating_point else v)
+            for k, v in sd.items()}
+    ref = 0
+    for h in halves:
+        xj = torch.cat((x[h], torch.ones(x[h].shape[0], 1, dtype=torch.float64)), 1)
+        XJr, _ = oflow.flow_forward(layers, sd64, xj, cfg["kind"], cfg["n_bins"], train=(mode == "train"))
+        ref = ref + onis.minibatch_loss(fres[h], XJr[:, -1], fres.max(), "var")
+    (ref / 2).backward()
+    assert abs(float(loss) - float(ref)) <= 2e-5 * abs(float(ref))
+    gscale = max(float(sd64[k].grad.abs().max()) for k, _ in model.named_parameters())
+    for k, p in model.named_parameters():
+        close(p.grad, sd64[k].grad, k, gscale)

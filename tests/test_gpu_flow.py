@@ -80,7 +80,11 @@ def test_forward_matches_oracle_at_size(cfg, mode):
     with torch.no_grad():
         ref, ref_bins = oflow.flow_forward(oracle_layers(cfg), sd64, xj.cpu(), cfg["kind"], cfg["n_bins"],
                                            train=(mode == "train"))
-    compare_flow(XJ.cpu(), bins.cpu(), ref, [b.numpy() for b in ref_bins], "%s/%s" % (cfg["name"], mode))
+        sd32 = {k: (v.float() if v.dtype.is_floating_point else v) for k, v in sd.items()}
+        ref32, _ = oflow.flow_forward(oracle_layers(cfg), sd32, xj.cpu().float(), cfg["kind"], cfg["n_bins"],
+                                      train=(mode == "train"))
+    compare_flow(XJ.cpu(), bins.cpu(), ref, [b.numpy() for b in ref_bins], "%s/%s" % (cfg["name"], mode),
+                 fp32_yardstick=ref32)
 
 
 def test_flow_is_a_bijection_of_the_unit_cube_at_full_size():
