@@ -13,19 +13,7 @@
 // layers.py:27-32,43-51,75-77,90-91 (Mask/DeMask/AddJacobian/Roll, folded into column tables).
 #include "common.cuh"
 #include "spline.cuh"
-
-struct FwdArgs {
-    const void* in; int in_dtype; int in_cols;   // external input rows (first cell, !from_state)
-    const float* state_in;                       // fp32 [B][d+1] (from_state)
-    float* state_out;                            // fp32 [B][d+1] or null
-    void* out; int out_dtype;                    // external output (to_out)
-    int from_state, to_out;
-    float* saved;                                // [n_cells+1][B][d+1] or null
-    int32_t* bins;
-    const float* params; float* wpack; float* bn_running; float* bn_saved;
-    double* partials; unsigned* counter;
-    long long B; int c_begin, c_end, stats_layer;
-};
+#include "flow_fwd_common.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // repack: torch-layout params -> transposed zero-padded weights (+ eval-mode BN scale/shift)
@@ -116,13 +104,6 @@ __device__ __forceinline__ void reduce_rows(const float* buf, int W, double* sac
         sacc[j] += s; sacc[maxW + j] += q;
     }
     __syncthreads();
-}
-
-__device__ __forceinline__ float load_io(const void* p, int dtype, long long idx) {
-    return dtype == NIS_F64 ? (float)reinterpret_cast<const double*>(p)[idx] : reinterpret_cast<const float*>(p)[idx];
-}
-__device__ __forceinline__ void store_io(void* p, int dtype, long long idx, float v) {
-    if (dtype == NIS_F64) reinterpret_cast<double*>(p)[idx] = (double)v; else reinterpret_cast<float*>(p)[idx] = v;
 }
 
 template <int NT>
@@ -237,59 +218,15 @@ __global__ void __launch_bounds__(NT) flow_fwd_generic_kernel(const __grid_const
         }
     }
     if (!stats) return;
-    // ---- fold this CTA's sums; the last CTA to arrive finalises the layer ------------------------
-    __syncthreads();
-    const int c = A.c_begin, l = A.stats_layer;
-    const DevCell& q = F.cells[c];
-    const int W = F.W(c, l), Wp = F.Wp(c, l);
-    double* mine = A.partials + (size_t)blockIdx.x * 2 * maxW;
-    for (int i = tid; i < 2 * maxW; i += NT) mine[i] = sacc[i];
-    __threadfence();
-    __syncthreads();
-    __shared__ bool s_last;
-    if (tid == 0) s_last = atomicAdd(A.counter, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const float* p = A.params + q.param_off + F.p_bn_gamma(c, l);
-    float* aff = A.wpack + q.pk_off + q.aff_off[l];
-    for (int j = tid; j < Wp; j += NT) {
-        float sc = 0.f, sh = 0.f;
-        if (j < W) {
-            double s = 0.0, s2 = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) {
-                s += __ldcg(A.partials + (size_t)b * 2 * maxW + j);
-                s2 += __ldcg(A.partials + (size_t)b * 2 * maxW + maxW + j);
-            }
-            const double n = (double)A.B;
-            const double mean = s / n;
-            double var = s2 / n - mean * mean;
-            var = var > 0.0 ? var : 0.0;
-            const double invstd = 1.0 / sqrt(var + (double)F.eps);
-            sc = (float)((double)p[j] * invstd);
-            sh = (float)((double)p[W + j] - mean * (double)p[j] * invstd);
-            if (A.bn_saved) {
-                A.bn_saved[q.sv_off + l * 2 * maxW + j] = (float)mean;
-                A.bn_saved[q.sv_off + l * 2 * maxW + maxW + j] = (float)invstd;
-            }
-            if (A.bn_running) {
-                float* rs = A.bn_running + q.bn_off + F.r_mean(c, l);
-                const double m = (double)F.momentum;
-                const double unb = A.B > 1 ? var * n / (n - 1.0) : var;
-                rs[j] = (float)((1.0 - m) * (double)rs[j] + m * mean);
-                rs[W + j] = (float)((1.0 - m) * (double)rs[W + j] + m * unb);
-            }
-        }
-        aff[j] = sc;
-        aff[Wp + j] = sh;
-    }
-    if (tid == 0) *A.counter = 0u;
+    bn_stats_finalize(F, A, sacc, NT);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // launcher
 // ---------------------------------------------------------------------------------------------------
 size_t nis_flow_bwd_scratch_floats(const DevFlow& F, int64_t B);
+bool nis_tiled_supported(const DevFlow& F, int64_t B);
+int nis_launch_tiled(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 
 static size_t fwd_smem_bytes(const DevFlow& F, int NT) {
     const int bw = F.maxW > F.Kpad ? F.maxW : F.Kpad;
@@ -360,28 +297,32 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     A.saved = saved; A.bins = bins_out;
     A.params = params; A.wpack = ws.wpack; A.bn_running = bn_running; A.bn_saved = bn_saved;
     A.partials = ws.partials; A.counter = ws.counter; A.B = B;
-    if (bn_mode == NIS_BN_EVAL) {
+    const bool tiled = nis_tiled_supported(F, B);
+    const long long rows = (long long)B * (F.d + 1);
+    if (bn_mode == NIS_BN_EVAL && !tiled) {
         A.state_in = nullptr; A.state_out = nullptr; A.from_state = 0; A.to_out = 1;
         A.c_begin = 0; A.c_end = F.n_cells; A.stats_layer = -1;
         return launch_fwd_any(F, A, s);
     }
-    // TRAIN: per cell, one statistics pass per BN layer, then the full pass
-    const long long rows = (long long)B * (F.d + 1);
+    // One launch sequence per cell.  TRAIN: a statistics pass per BN layer, then the full pass.
+    // (EVAL reaches here only on the register-tiled path, whose launches are per cell.)
     for (int c = 0; c < F.n_cells; ++c) {
         A.c_begin = c; A.c_end = c + 1;
         A.from_state = c > 0;
         A.state_in = c > 0 ? (saved ? saved + (long long)c * rows : ws.state) : nullptr;
         A.state_out = nullptr; A.to_out = 0;
-        for (int l = 0; l <= F.depth; ++l) {
-            A.stats_layer = l;
-            rc = launch_fwd_any(F, A, s);
-            if (rc) return rc;
+        if (bn_mode == NIS_BN_TRAIN) {
+            for (int l = 0; l <= F.depth; ++l) {
+                A.stats_layer = l;
+                rc = (tiled && l >= 1) ? nis_launch_tiled(F, A, s) : launch_fwd_any(F, A, s);
+                if (rc) return rc;
+            }
         }
         A.stats_layer = -1;
         const bool last = c == F.n_cells - 1;
         A.to_out = last;
-        A.state_out = last ? nullptr : (saved ? saved + (long long)(c + 1) * rows : ws.state);
-        rc = launch_fwd_any(F, A, s);
+        A.state_out = saved ? saved + (long long)(c + 1) * rows : (last ? nullptr : ws.state);
+        rc = tiled ? nis_launch_tiled(F, A, s) : launch_fwd_any(F, A, s);
         if (rc) return rc;
     }
     return NIS_OK;

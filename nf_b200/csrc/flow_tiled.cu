@@ -1,0 +1,312 @@
+// Fused coupling-cell forward, register-tiled FP32 path for width-64 conditioners (BASELINE cfg2).
+//
+// One launch = one coupling cell over the whole batch (or one train-mode statistics pass of it).
+// Persistent CTAs (one per SM) loop over tiles of M points.  The cell's weights are staged ONCE per CTA
+// into shared memory (k-major, 64-wide rows); a tile's activations live in shared memory as [feature][M]
+// so that every conditioner layer is an (M x in) x (in x 64) product computed with a 4x8 (points x
+// outputs) register tile per thread: per k-step one 128-bit LDS of activations + two 128-bit LDS of
+// weights feed 32 FFMA (the FP32 pipe is the roofline of this path).  The output layer is
+// produced 64 logits at a time (two transformed dimensions of 32 bins), each followed in place by the
+// per-bin softmax, CDF, bin lookup and Jacobian factor, so logits never leave shared memory.
+//
+// Reference semantics: coupling_cells.py:107-142 (PWLin) with the conditioner of :84-104.
+#include <stdlib.h>
+#include "common.cuh"
+#include "spline.cuh"
+#include "flow_fwd_common.cuh"
+
+#define TH 64            // hidden width handled by this path
+#define TCH 64           // logits per output-layer chunk
+
+struct TiledSmem {
+    int st, A0, A1, W, aff, bias, fbuf, total;   // float offsets
+    int wl[NIS_MAX_HIDDEN + 1];                  // per-layer weight offsets inside W (last = output layer)
+};
+
+__host__ __device__ static inline TiledSmem tiled_layout(const DevFlow& F, int c, int M) {
+    TiledSmem s;
+    const DevCell& q = F.cells[c];
+    int o = 0;
+    s.st = o; o += (F.d + 1) * M;
+    s.A0 = o; o += TH * M;
+    s.A1 = o; o += TH * M;
+    s.W = o;
+    int w = 0, in = q.P;
+    for (int l = 0; l < F.depth; ++l) { s.wl[l] = w; w += in * TH; in = TH; }
+    const int nch = (q.T * F.K + TCH - 1) / TCH;
+    s.wl[F.depth] = w; w += nch * TH * TCH;
+    o += w;
+    s.aff = o; o += (F.depth + 1) * 2 * TH;
+    s.bias = o; o += nch * TCH;
+    s.fbuf = o; o += (TCH / F.K) * M;
+    s.total = o;
+    return s;
+}
+
+template <int M>
+__global__ void __launch_bounds__(2 * M, 1) flow_cell_tiled_kernel(const __grid_constant__ DevFlow F, const FwdArgs A) {
+    constexpr int NT = 2 * M;
+    constexpr int TM = 4;
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    const int c = A.c_begin;
+    const DevCell& q = F.cells[c];
+    const int d = F.d, depth = F.depth, K = F.K, nb = F.nb;
+    const TiledSmem L = tiled_layout(F, c, M);
+    float* st = sm + L.st;
+    float* Ws = sm + L.W;
+    float* affs = sm + L.aff;
+    float* biass = sm + L.bias;
+    float* fbuf = sm + L.fbuf;
+    const float* pk = A.wpack + q.pk_off;
+    const int tpc = TCH / K;                                  // transformed dims per chunk
+    const int nch = (q.T * K + TCH - 1) / TCH;
+    const bool stats = A.stats_layer >= 1;
+    const int last_layer = stats ? A.stats_layer : depth;     // hidden layers to run (1-based count)
+
+    // ---- stage the cell's weights / BN scale+shift / bias once ---------------------------------------
+    {
+        int in = q.P;
+        for (int l = 0; l < last_layer; ++l) {
+            const float* src = pk + q.wt_off[l];               // [in][64]
+            for (int i = tid; i < in * TH; i += NT) Ws[L.wl[l] + i] = src[i];
+            in = TH;
+        }
+        for (int l = 0; l <= depth; ++l) {
+            const int W = l == 0 ? q.P : TH, Wp = pad8(W);
+            const float* src = pk + q.aff_off[l];
+            for (int i = tid; i < W; i += NT) { affs[l * 2 * TH + i] = src[i]; affs[l * 2 * TH + TH + i] = src[Wp + i]; }
+        }
+        if (!stats) {
+            // output layer: per-t [in][Kpad] in wpack -> chunked [chunk][k][64]
+            for (int i = tid; i < nch * TH * TCH; i += NT) {
+                const int ch = i / (TH * TCH), r = i - ch * TH * TCH, k = r / TCH, j = r - k * TCH;
+                const int t = ch * tpc + j / K, jj = j % K;
+                Ws[L.wl[depth] + i] = t < q.T ? pk[q.wo_off + ((size_t)t * TH + k) * F.Kpad + jj] : 0.f;
+            }
+            for (int i = tid; i < nch * TCH; i += NT) {
+                const int t = i / K, jj = i % K;
+                biass[i] = t < q.T ? pk[q.bo_off + t * F.Kpad + jj] : 0.f;
+            }
+        }
+    }
+    const int tc = tid & 7, tr = tid >> 3;                     // thread column (outputs), row (points)
+    double dsum[8], dsq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dsum[j] = 0.0; dsq[j] = 0.0; }
+    __syncthreads();
+
+    const long long ntiles = (A.B + M - 1) / M;
+    const long long rowlen = d + 1;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * M;
+        const int cnt = (int)((A.B - base) < M ? (A.B - base) : M);
+        // ---- state tile -> shared memory, transposed to [col][M] ------------------------------------
+        if (A.from_state) {
+            const float* src = A.state_in + base * rowlen;
+            for (int i = tid; i < M * (d + 1); i += NT) {
+                const int pt = i / (d + 1), col = i - pt * (d + 1);
+                st[col * M + pt] = pt < cnt ? src[i] : (col == d ? 1.f : 0.5f);
+            }
+        } else {
+            for (int i = tid; i < M * (d + 1); i += NT) {
+                const int pt = i / (d + 1), col = i - pt * (d + 1);
+                float v = col == d ? 1.f : 0.5f;
+                if (pt < cnt && col < A.in_cols) v = load_io(A.in, A.in_dtype, (base + pt) * A.in_cols + col);
+                st[col * M + pt] = v;
+            }
+        }
+        __syncthreads();
+        if (!stats && A.saved && !A.from_state) {
+            float* sv = A.saved + ((long long)c * A.B + base) * rowlen;
+            for (int i = tid; i < cnt * (d + 1); i += NT) { const int pt = i / (d + 1), col = i - pt * (d + 1); sv[i] = st[col * M + pt]; }
+        }
+        // ---- BN0 of the pass-through columns -> a0 --------------------------------------------------
+        float* cur = sm + L.A0;
+        float* nxt = sm + L.A1;
+        for (int i = tid; i < q.P * M; i += NT) {
+            const int k = i / M, pt = i - k * M;
+            cur[i] = fmaf(st[q.feed[k] * M + pt], affs[k], affs[TH + k]);
+        }
+        __syncthreads();
+        // ---- hidden layers ---------------------------------------------------------------------------
+        int in = q.P;
+        for (int l = 0; l < last_layer; ++l) {
+            float acc[TM][8];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+            const float* ap = cur + tr * TM;
+            const float* wp = Ws + L.wl[l] + tc * 4;
+#pragma unroll 8
+            for (int k = 0; k < in; ++k) {
+                const float4 a = *reinterpret_cast<const float4*>(ap + k * M);
+                const float4 w0 = *reinterpret_cast<const float4*>(wp + k * TH);
+                const float4 w1 = *reinterpret_cast<const float4*>(wp + k * TH + 32);
+                const float av[4] = {a.x, a.y, a.z, a.w};
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+            }
+            if (stats && l + 1 == A.stats_layer) {
+                // per-feature sums of the pre-BN activations of this tile (points beyond the batch masked)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float s = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < TM; ++i) {
+                        const float v = (tr * TM + i) < cnt ? acc[i][j] : 0.f;
+                        s += v; s2 = fmaf(v, v, s2);
+                    }
+                    dsum[j] += (double)s; dsq[j] += (double)s2;
+                }
+                break;
+            }
+            const float* sc = affs + (l + 1) * 2 * TH;
+            const float* sh = sc + TH;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int o = (j < 4 ? 0 : 28) + tc * 4 + j;
+                float4 v;
+                v.x = fmaxf(fmaf(acc[0][j], sc[o], sh[o]), 0.f);
+                v.y = fmaxf(fmaf(acc[1][j], sc[o], sh[o]), 0.f);
+                v.z = fmaxf(fmaf(acc[2][j], sc[o], sh[o]), 0.f);
+                v.w = fmaxf(fmaf(acc[3][j], sc[o], sh[o]), 0.f);
+                *reinterpret_cast<float4*>(nxt + o * M + tr * TM) = v;
+            }
+            __syncthreads();
+            float* t_ = cur; cur = nxt; nxt = t_;
+            in = TH;
+        }
+        if (stats) { __syncthreads(); continue; }
+        // ---- output layer in chunks of 64 logits, spline in place ------------------------------------
+        for (int ch = 0; ch < nch; ++ch) {
+            float acc[TM][8];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+            const float* ap = cur + tr * TM;
+            const float* wp = Ws + L.wl[depth] + ch * TH * TCH + tc * 4;
+#pragma unroll 8
+            for (int k = 0; k < TH; ++k) {
+                const float4 a = *reinterpret_cast<const float4*>(ap + k * M);
+                const float4 w0 = *reinterpret_cast<const float4*>(wp + k * TCH);
+                const float4 w1 = *reinterpret_cast<const float4*>(wp + k * TCH + 32);
+                const float av[4] = {a.x, a.y, a.z, a.w};
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int o = (j < 4 ? 0 : 28) + tc * 4 + j;
+                const float b = biass[ch * TCH + o];
+                float4 v;
+                v.x = acc[0][j] + b; v.y = acc[1][j] + b; v.z = acc[2][j] + b; v.w = acc[3][j] + b;
+                *reinterpret_cast<float4*>(nxt + o * M + tr * TM) = v;
+            }
+            __syncthreads();
+            for (int pair = tid; pair < tpc * M; pair += NT) {
+                const int tt = pair / M, pt = pair - tt * M;
+                const int t = ch * tpc + tt;
+                if (t < q.T) {
+                    const int col = q.trafo[t];
+                    const float x = st[col * M + pt];
+                    float f, S, al;
+                    int k;
+                    const float y = pwlin_fwd(nxt + tt * K * M + pt, M, nb, x, f, k, S, al);
+                    st[col * M + pt] = y;
+                    fbuf[tt * M + pt] = f;
+                    if (A.bins && pt < cnt) A.bins[((long long)c * A.B + base + pt) * d + t] = k;
+                } else {
+                    fbuf[tt * M + pt] = 1.f;
+                }
+            }
+            __syncthreads();
+            for (int pt = tid; pt < M; pt += NT) {
+                float f = 1.f;
+                for (int tt = 0; tt < tpc; ++tt) f *= fbuf[tt * M + pt];
+                st[d * M + pt] *= f;
+            }
+        }
+        __syncthreads();
+        // ---- store the tile ---------------------------------------------------------------------------
+        if (A.state_out) {
+            float* dst = A.state_out + base * rowlen;
+            for (int i = tid; i < cnt * (d + 1); i += NT) { const int pt = i / (d + 1), col = i - pt * (d + 1); dst[i] = st[col * M + pt]; }
+        }
+        if (A.to_out) {
+            for (int i = tid; i < cnt * (d + 1); i += NT) {
+                const int pt = i / (d + 1), col = i - pt * (d + 1);
+                const int src = col == d ? d : F.out_perm[col];
+                store_io(A.out, A.out_dtype, base * rowlen + i, st[src * M + pt]);
+            }
+        }
+        __syncthreads();
+    }
+    if (!stats) return;
+    // ---- statistics pass: fold rows -> per-feature sums, then the shared finalisation -----------------
+    double* red = reinterpret_cast<double*>(sm + L.A0);        // [2][M/TM rows][64]  (A0/A1 are free now)
+    double* sacc = red + 2 * (M / TM) * TH;                    // [2*maxW]
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int o = (j < 4 ? 0 : 28) + tc * 4 + j;
+        red[tr * TH + o] = dsum[j];
+        red[(M / TM) * TH + tr * TH + o] = dsq[j];
+    }
+    __syncthreads();
+    for (int o = tid; o < 2 * F.maxW; o += NT) sacc[o] = 0.0;
+    __syncthreads();
+    if (tid < TH) {
+        double s = 0.0, s2 = 0.0;
+        for (int r = 0; r < M / TM; ++r) { s += red[r * TH + tid]; s2 += red[(M / TM) * TH + r * TH + tid]; }
+        sacc[tid] = s; sacc[F.maxW + tid] = s2;
+    }
+    bn_stats_finalize(F, A, sacc, NT);
+}
+
+// ---------------------------------------------------------------------------------------------------
+bool nis_tiled_supported(const DevFlow& F, int64_t B) {
+    const char* off = getenv("NIS_DISABLE_TILED");        // test knob: force the shape-generic kernel
+    if (off && off[0] == '1') return false;
+    if (F.kind != NIS_KIND_PWLIN || F.depth < 1 || B < 2048) return false;
+    for (int l = 0; l < F.depth; ++l) if (F.widths[l] != TH) return false;
+    if (F.K != 8 && F.K != 16 && F.K != 32 && F.K != 64) return false;
+    if (F.maxW != TH) return false;
+    for (int c = 0; c < F.n_cells; ++c) {
+        TiledSmem s = tiled_layout(F, c, 128);
+        size_t bytes = (size_t)s.total * 4;
+        size_t red = (size_t)(2 * 32 * TH + 2 * F.maxW) * 8;
+        if (bytes > 220 * 1024 || red > (size_t)2 * TH * 128 * 4) return false;
+    }
+    return true;
+}
+
+template <int M>
+static int launch_tiled_m(const DevFlow& F, const FwdArgs& A, int sms, cudaStream_t s) {
+    TiledSmem L = tiled_layout(F, A.c_begin, M);
+    const size_t smem = (size_t)L.total * sizeof(float);
+    cudaFuncSetAttribute(flow_cell_tiled_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long long ntiles = (A.B + M - 1) / M;
+    int grid = (int)(ntiles < sms ? ntiles : sms);
+    flow_cell_tiled_kernel<M><<<grid, 2 * M, smem, s>>>(F, A);
+    NIS_CUDA_CHECK_LAUNCH();
+    return NIS_OK;
+}
+
+int nis_launch_tiled(const DevFlow& F, const FwdArgs& A, cudaStream_t s) {
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    TiledSmem L256 = tiled_layout(F, A.c_begin, 256);
+    if ((size_t)L256.total * 4 <= 225 * 1024 && A.B >= (long long)sms * 256) return launch_tiled_m<256>(F, A, sms, s);
+    return launch_tiled_m<128>(F, A, sms, s);
+}
