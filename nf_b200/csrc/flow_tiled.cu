@@ -43,10 +43,15 @@ __host__ __device__ static inline TiledSmem tiled_layout(const DevFlow& F, int c
     return s;
 }
 
+// Activation rows are XOR-swizzled at 4-float granularity so that both the k-major GEMM reads and the
+// epilogue's 128-bit stores of one output row per lane are bank-conflict free.
 template <int M>
-__global__ void __launch_bounds__(2 * M, 1) flow_cell_tiled_kernel(const __grid_constant__ DevFlow F, const FwdArgs A) {
-    constexpr int NT = 2 * M;
-    constexpr int TM = 4;
+__device__ __forceinline__ int swz(int row, int pt) { return row * M + ((((pt >> 2) ^ ((row >> 2) & 7)) << 2) | (pt & 3)); }
+
+template <int M, int TM>
+__global__ void __launch_bounds__(M * 8 / TM, 1) flow_cell_tiled_kernel(const __grid_constant__ DevFlow F, const FwdArgs A) {
+    constexpr int NT = M * 8 / TM;
+    constexpr int NV = TM / 4;            // float4 per thread row
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x;
     const int c = A.c_begin;
@@ -126,7 +131,7 @@ __global__ void __launch_bounds__(2 * M, 1) flow_cell_tiled_kernel(const __grid_
         float* nxt = sm + L.A1;
         for (int i = tid; i < q.P * M; i += NT) {
             const int k = i / M, pt = i - k * M;
-            cur[i] = fmaf(st[q.feed[k] * M + pt], affs[k], affs[TH + k]);
+            cur[swz<M>(k, pt)] = fmaf(st[q.feed[k] * M + pt], affs[k], affs[TH + k]);
         }
         __syncthreads();
         // ---- hidden layers ---------------------------------------------------------------------------
@@ -137,14 +142,17 @@ __global__ void __launch_bounds__(2 * M, 1) flow_cell_tiled_kernel(const __grid_
             for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-            const float* ap = cur + tr * TM;
             const float* wp = Ws + L.wl[l] + tc * 4;
-#pragma unroll 8
+#pragma unroll 4
             for (int k = 0; k < in; ++k) {
-                const float4 a = *reinterpret_cast<const float4*>(ap + k * M);
+                float av[TM];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const float4 a = *reinterpret_cast<const float4*>(cur + swz<M>(k, tr * TM + 4 * v));
+                    av[4 * v] = a.x; av[4 * v + 1] = a.y; av[4 * v + 2] = a.z; av[4 * v + 3] = a.w;
+                }
                 const float4 w0 = *reinterpret_cast<const float4*>(wp + k * TH);
                 const float4 w1 = *reinterpret_cast<const float4*>(wp + k * TH + 32);
-                const float av[4] = {a.x, a.y, a.z, a.w};
                 const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
                 for (int i = 0; i < TM; ++i)
@@ -170,12 +178,15 @@ __global__ void __launch_bounds__(2 * M, 1) flow_cell_tiled_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int o = (j < 4 ? 0 : 28) + tc * 4 + j;
-                float4 v;
-                v.x = fmaxf(fmaf(acc[0][j], sc[o], sh[o]), 0.f);
-                v.y = fmaxf(fmaf(acc[1][j], sc[o], sh[o]), 0.f);
-                v.z = fmaxf(fmaf(acc[2][j], sc[o], sh[o]), 0.f);
-                v.w = fmaxf(fmaf(acc[3][j], sc[o], sh[o]), 0.f);
-                *reinterpret_cast<float4*>(nxt + o * M + tr * TM) = v;
+#pragma unroll
+                for (int v4 = 0; v4 < NV; ++v4) {
+                    float4 v;
+                    v.x = fmaxf(fmaf(acc[4 * v4][j], sc[o], sh[o]), 0.f);
+                    v.y = fmaxf(fmaf(acc[4 * v4 + 1][j], sc[o], sh[o]), 0.f);
+                    v.z = fmaxf(fmaf(acc[4 * v4 + 2][j], sc[o], sh[o]), 0.f);
+                    v.w = fmaxf(fmaf(acc[4 * v4 + 3][j], sc[o], sh[o]), 0.f);
+                    *reinterpret_cast<float4*>(nxt + swz<M>(o, tr * TM + 4 * v4)) = v;
+                }
             }
             __syncthreads();
             float* t_ = cur; cur = nxt; nxt = t_;
@@ -189,14 +200,17 @@ __global__ void __launch_bounds__(2 * M, 1) flow_cell_tiled_kernel(const __grid_
             for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-            const float* ap = cur + tr * TM;
             const float* wp = Ws + L.wl[depth] + ch * TH * TCH + tc * 4;
-#pragma unroll 8
+#pragma unroll 4
             for (int k = 0; k < TH; ++k) {
-                const float4 a = *reinterpret_cast<const float4*>(ap + k * M);
+                float av[TM];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const float4 a = *reinterpret_cast<const float4*>(cur + swz<M>(k, tr * TM + 4 * v));
+                    av[4 * v] = a.x; av[4 * v + 1] = a.y; av[4 * v + 2] = a.z; av[4 * v + 3] = a.w;
+                }
                 const float4 w0 = *reinterpret_cast<const float4*>(wp + k * TCH);
                 const float4 w1 = *reinterpret_cast<const float4*>(wp + k * TCH + 32);
-                const float av[4] = {a.x, a.y, a.z, a.w};
                 const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
                 for (int i = 0; i < TM; ++i)
@@ -207,9 +221,12 @@ __global__ void __launch_bounds__(2 * M, 1) flow_cell_tiled_kernel(const __grid_
             for (int j = 0; j < 8; ++j) {
                 const int o = (j < 4 ? 0 : 28) + tc * 4 + j;
                 const float b = biass[ch * TCH + o];
-                float4 v;
-                v.x = acc[0][j] + b; v.y = acc[1][j] + b; v.z = acc[2][j] + b; v.w = acc[3][j] + b;
-                *reinterpret_cast<float4*>(nxt + o * M + tr * TM) = v;
+#pragma unroll
+                for (int v4 = 0; v4 < NV; ++v4) {
+                    float4 v;
+                    v.x = acc[4 * v4][j] + b; v.y = acc[4 * v4 + 1][j] + b; v.z = acc[4 * v4 + 2][j] + b; v.w = acc[4 * v4 + 3][j] + b;
+                    *reinterpret_cast<float4*>(nxt + swz<M>(o, tr * TM + 4 * v4)) = v;
+                }
             }
             __syncthreads();
             for (int pair = tid; pair < tpc * M; pair += NT) {
@@ -220,7 +237,9 @@ __global__ void __launch_bounds__(2 * M, 1) flow_cell_tiled_kernel(const __grid_
                     const float x = st[col * M + pt];
                     float f, S, al;
                     int k;
-                    const float y = pwlin_fwd(nxt + tt * K * M + pt, M, nb, x, f, k, S, al);
+                    const int r0 = tt * K;
+                    auto zacc = [&](int j) -> float& { return nxt[swz<M>(r0 + j, pt)]; };
+                    const float y = pwlin_fwd_z(zacc, nb, x, f, k, S, al);
                     st[col * M + pt] = y;
                     fbuf[tt * M + pt] = f;
                     if (A.bins && pt < cnt) A.bins[((long long)c * A.B + base + pt) * d + t] = k;
@@ -252,7 +271,7 @@ __global__ void __launch_bounds__(2 * M, 1) flow_cell_tiled_kernel(const __grid_
     }
     if (!stats) return;
     // ---- statistics pass: fold rows -> per-feature sums, then the shared finalisation -----------------
-    double* red = reinterpret_cast<double*>(sm + L.A0);        // [2][M/TM rows][64]  (A0/A1 are free now)
+    double* red = reinterpret_cast<double*>(sm + L.A0 + (L.A0 & 1));   // [2][M/TM rows][64]  (A0/A1 are free now)
     double* sacc = red + 2 * (M / TM) * TH;                    // [2*maxW]
     __syncthreads();
 #pragma unroll
@@ -289,14 +308,14 @@ bool nis_tiled_supported(const DevFlow& F, int64_t B) {
     return true;
 }
 
-template <int M>
+template <int M, int TM>
 static int launch_tiled_m(const DevFlow& F, const FwdArgs& A, int sms, cudaStream_t s) {
     TiledSmem L = tiled_layout(F, A.c_begin, M);
     const size_t smem = (size_t)L.total * sizeof(float);
-    cudaFuncSetAttribute(flow_cell_tiled_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flow_cell_tiled_kernel<M, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long long ntiles = (A.B + M - 1) / M;
     int grid = (int)(ntiles < sms ? ntiles : sms);
-    flow_cell_tiled_kernel<M><<<grid, 2 * M, smem, s>>>(F, A);
+    flow_cell_tiled_kernel<M, TM><<<grid, M * 8 / TM, smem, s>>>(F, A);
     NIS_CUDA_CHECK_LAUNCH();
     return NIS_OK;
 }
@@ -307,6 +326,11 @@ int nis_launch_tiled(const DevFlow& F, const FwdArgs& A, cudaStream_t s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
     TiledSmem L256 = tiled_layout(F, A.c_begin, 256);
-    if ((size_t)L256.total * 4 <= 225 * 1024 && A.B >= (long long)sms * 256) return launch_tiled_m<256>(F, A, sms, s);
-    return launch_tiled_m<128>(F, A, sms, s);
+    // 4x8 register tiles (16 warps/SM) measured faster than 8x8 (8 warps/SM) on B200: 26.0 vs 29.0 ms for
+    // cfg2 eval at 2^22 points; NIS_TILED_VARIANT=8 selects the 8x8 variant for experiments.
+    const char* v = getenv("NIS_TILED_VARIANT");
+    const bool tm4 = !(v && v[0] == '8');
+    if ((size_t)L256.total * 4 <= 225 * 1024 && A.B >= (long long)sms * 256)
+        return tm4 ? launch_tiled_m<256, 4>(F, A, sms, s) : launch_tiled_m<256, 8>(F, A, sms, s);
+    return tm4 ? launch_tiled_m<128, 4>(F, A, sms, s) : launch_tiled_m<128, 8>(F, A, sms, s);
 }

@@ -10,34 +10,47 @@
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define NIS_DEV __device__ __forceinline__
+#define NIS_DEV_MEMBER __device__ __forceinline__
 #else
 #include <math.h>
 #define NIS_DEV static inline
+#define NIS_DEV_MEMBER inline
 #endif
 
 #define NIS_QUAD_CLAMP 0.999999f   // float(1 - 1e-6), coupling_cells.py:167
 
 // ---- PWLin --------------------------------------------------------------------------------------
-// Overwrites z[j] with e_j = exp(z_j - max).  Returns y; f = bin height (Jacobian factor); k = bin.
-NIS_DEV float pwlin_fwd(float* z, int zs, int nb, float x, float& f, int& k,
-                                           float& S_out, float& alpha_out) {
-    float m = z[0];
-    for (int j = 1; j < nb; ++j) m = fmaxf(m, z[j * zs]);
+// Overwrites z(j) with e_j = exp(z_j - max).  Returns y; f = bin height (Jacobian factor); k = bin.
+// `z` is any accessor: z(j) -> float& (strided column, swizzled shared-memory row, ...).
+template <typename Z>
+NIS_DEV float pwlin_fwd_z(Z z, int nb, float x, float& f, int& k, float& S_out, float& alpha_out) {
+    float m = z(0);
+    for (int j = 1; j < nb; ++j) m = fmaxf(m, z(j));
     float S = 0.f;
-    for (int j = 0; j < nb; ++j) { float e = expf(z[j * zs] - m); z[j * zs] = e; S += e; }
+    for (int j = 0; j < nb; ++j) { float e = expf(z(j) - m); z(j) = e; S += e; }
     float a = x * (float)nb;
     float fl = floorf(a);
     k = (int)fl;
     k = k < 0 ? 0 : (k > nb - 1 ? nb - 1 : k);       // reference: unclamped gather (x==1 raises)
     float alpha = a - (float)k;                      // in [0,1): fraction of the bin
     float C = 0.f;
-    for (int j = 0; j < k; ++j) C += z[j * zs];
-    float ek = z[k * zs];
+    for (int j = 0; j < k; ++j) C += z(j);
+    float ek = z(k);
     float inv = 1.f / S;
     f = ek * inv * (float)nb;
     S_out = S;
     alpha_out = alpha;
     return (ek * alpha + C) * inv;
+}
+
+struct StridedCol {
+    float* p; int s;
+    NIS_DEV_MEMBER float& operator()(int j) const { return p[j * s]; }
+};
+
+NIS_DEV float pwlin_fwd(float* z, int zs, int nb, float x, float& f, int& k, float& S_out, float& alpha_out) {
+    StridedCol c{z, zs};
+    return pwlin_fwd_z(c, nb, x, f, k, S_out, alpha_out);
 }
 
 // z holds e_j (after pwlin_fwd).  Overwrites z[j] with dL/dz_j.  Returns dL/dx.
