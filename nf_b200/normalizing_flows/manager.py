@@ -49,6 +49,13 @@ def _world():
     return 0, 1
 
 
+def shard_bounds(n, rank, world):
+    """[first, first+count) of rank's share when n Monte Carlo points are dealt to `world` ranks."""
+    count = n // world + (1 if rank < n % world else 0)
+    first = (n // world) * rank + min(rank, n % world)
+    return first, count
+
+
 def _device(dev):
     if not torch.cuda.is_available():
         raise _cabi.NisBackendError("nf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -342,7 +349,7 @@ class BasicManager(ModelAPI):
         dev = _device(0 if dev is None else dev)
         rank, world = _world()
         neval, nitn = int(neval), int(nitn)
-        share = neval // world + (1 if rank < neval % world else 0)
+        first, share = shard_bounds(neval, rank, world)
         lib = _cabi.lib()
         moments = torch.zeros(nitn, 3, dtype=torch.double, device=dev)
         rws = torch.empty(lib.nis_reduce_workspace_bytes(), dtype=torch.uint8, device=dev)
@@ -352,7 +359,6 @@ class BasicManager(ModelAPI):
             s = torch.tensor([seed], device=dev)
             dist.broadcast(s, 0)
             seed = int(s.item())
-        first = (neval // world) * rank + min(rank, neval % world)
         with torch.no_grad(), torch.cuda.device(dev):
             for i in range(nitn):
                 _cabi.check(lib.nis_uniform_fill(_cabi.ptr(w), _cabi.F32, w.numel(), seed,

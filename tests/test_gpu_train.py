@@ -1,0 +1,76 @@
+"""GPU end-to-end checks of the manager surface: the README training example (manager.py:66-378 of the
+reference), integrate(), checkpoints and the returned attributes."""
+import math
+import os
+
+import pytest
+import torch
+
+from nf_b200.normalizing_flows.manager import PWLinManager, PWQuadManager
+
+pytestmark = pytest.mark.gpu
+ANALYTIC = 2 * (0.5 * math.sqrt(0.04 * math.pi) * (math.erf(3.75) + math.erf(1.25))) ** 2      # 0.232322
+
+
+def camel(x):
+    return torch.exp(-((x[:, 0] - 0.75) ** 2 + (x[:, 1] - 0.75) ** 2) / (0.2 ** 2)) + \
+        torch.exp(-((x[:, 0] - 0.25) ** 2 + (x[:, 1] - 0.25) ** 2) / (0.2 ** 2))
+
+
+def test_readme_example_trains_and_integrates(tmp_path):
+    """README.md:31-46 of the reference, verbatim call order (9 positional arguments)."""
+    torch.manual_seed(0)
+    n_flow = 2
+    NF = PWQuadManager(n_flow=n_flow)
+    NF.create_model(2, 4, [3] * 3)
+    optim = torch.optim.Adamax(NF._model.parameters(), lr=2e-3, weight_decay=1e-04)
+    logdir = str(tmp_path / "logs")
+    ret = NF._train_variance_forward_seq(camel, optim, True, logdir, 10000, 300, 0, False, True, preburn_time=50)
+    assert ret == (0, 0)
+    # the reference reaches best_loss 0.024 from int_loss 0.071 on this example; require a
+    # clear variance reduction, not a particular number (different RNG stream)
+    assert float(NF.best_loss) < 0.6 * float(NF.int_loss)
+    assert 0 < NF.best_epoch < 300 and len(NF.history) > 50
+    for attr in ("best_loss_rel", "best_func_count", "varJ", "DKL", "best_var", "int_loss", "integ_tot", "err_tot"):
+        assert hasattr(NF, attr), attr
+    assert NF.best_func_count == 2 * 10000 * n_flow + 10000 * len(NF.history)
+    ck = torch.load(os.path.join(logdir, "torch"), weights_only=False)
+    assert set(ck) == {"best_epoch", "best_loss", "int_loss", "best_loss_rel", "best_func_count",
+                       "model_state_dict", "integ", "err"}
+    assert os.path.exists(os.path.join(logdir, "torch_int"))
+    assert list(ck["model_state_dict"])[:3] == ["0.NN.0.weight", "0.NN.0.bias", "0.NN.0.running_mean"]
+    # integrate with the trained flow (train-mode BN exactly like manager.py:397) and in eval mode
+    sig, err = NF.integrate(camel, 10, 10000, 0)
+    honest = float(err) * math.sqrt(10)
+    assert abs(float(sig) - ANALYTIC) < 5 * honest, (float(sig), honest)
+    untrained = PWQuadManager(n_flow=2)
+    untrained.create_model(2, 4, [3] * 3)
+    _, err0 = untrained.integrate(camel, 10, 10000, 0)
+    assert float(err) < 0.8 * float(err0)            # the trained flow integrates with a smaller error
+
+
+def test_tail_integration_est_loss_and_unknown_loss(tmp_path, capsys):
+    torch.manual_seed(1)
+    NF = PWLinManager(n_flow=2)
+    NF.create_model(1, 2, 8, [8, 8], 1)
+    optim = torch.optim.Adam(NF._model.parameters(), lr=1e-3)
+    ret = NF._train_variance_forward_seq(camel, optim, False, str(tmp_path), 4000, 12, 0, False, True,
+                                         mini_batch_size=1000, integrate=True, preburn_time=2, kill_counter=0,
+                                         loss_mode="est")
+    assert isinstance(ret, tuple) and len(ret) == 2 and all(isinstance(v, float) for v in ret)
+    assert NF._train_variance_forward_seq(camel, optim, False, str(tmp_path), 1000, 2, loss_mode="nope") is None
+    assert "Unknown loss function" in capsys.readouterr().out
+
+
+def test_single_cell_modules_run_standalone(golden):
+    """PWQuad / PWLin modules are callable on their own like the reference's (one-cell fused flow)."""
+    from oracle import flow as oflow
+    from nf_b200.normalizing_flows.layers.coupling_cells import PWLin, PWQuad
+    torch.manual_seed(2)
+    for cls, kind in ((PWQuad, "quad"), (PWLin, "lin")):
+        cell = cls(flow_size=5, pass_through_size=2, n_bins=6, NN_layers=[16, 16]).eval()
+        x = torch.rand(300, 6, dtype=torch.float64)
+        y = cell(x.cuda())
+        sd = {"0." + k: (v.double().cpu() if v.dtype.is_floating_point else v.cpu()) for k, v in cell.state_dict().items()}
+        ref, _ = oflow.flow_forward([dict(type="cell", name="0", P=2)], sd, x, kind, 6, train=False)
+        assert torch.allclose(y.cpu(), ref, rtol=1e-5, atol=1e-6)
