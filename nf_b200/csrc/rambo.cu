@@ -9,17 +9,17 @@
 
 #define RAMBO_NT 128
 
-template <int N, typename RT>
+template <typename RT>
 __global__ void __launch_bounds__(RAMBO_NT) rambo_kernel(const __grid_constant__ RamboConst C, const RT* __restrict__ r,
                                                          double* __restrict__ momenta, double* __restrict__ weight,
                                                          uint8_t* __restrict__ cutmask, long long B) {
-    constexpr int ND = 3 * N - 4;           // uniforms per event
-    constexpr int NDP = ND | 1;             // odd row stride (doubles)
-    constexpr int NM = (N + 2) * 4;         // momentum components per event
-    constexpr int NMP = NM | 1;
+    const int ND = 3 * C.n - 4;             // uniforms per event
+    const int NDP = ND | 1;                 // odd row stride (doubles): conflict-free per-thread rows
+    const int NM = (C.n + 2) * 4;           // momentum components per event
+    const int NMP = NM | 1;
     extern __shared__ __align__(16) double smd[];
     double* rs = smd;                       // [NT][NDP]
-    double* mo = smd + RAMBO_NT * NDP;      // [NT][NMP]
+    double* mo = smd + RAMBO_NT * NDP;      // [NT][NMP]  (scratch even when momenta are not requested)
     const int tid = threadIdx.x;
     const long long ntiles = (B + RAMBO_NT - 1) / RAMBO_NT;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(RAMBO_NT) rambo_kernel(const __grid_constant__
         if (tid < cnt) {
             double w;
             uint8_t pass;
-            rambo_event<N>(C, rs + tid * NDP, 1, momenta ? mo + tid * NMP : nullptr, 1, w, pass);
+            rambo_event(C, rs + tid * NDP, 1, mo + tid * NMP, 1, w, pass);
             weight[base + tid] = w;
             if (cutmask) cutmask[base + tid] = pass;
         }
@@ -49,23 +49,17 @@ __global__ void __launch_bounds__(RAMBO_NT) rambo_kernel(const __grid_constant__
     }
 }
 
-template <int N, typename RT>
+template <typename RT>
 static int rambo_launch(const RamboConst& C, const void* r, double* momenta, double* weight, uint8_t* cutmask,
                         long long B, cudaStream_t s) {
-    constexpr int NDP = (3 * N - 4) | 1, NMP = ((N + 2) * 4) | 1;
+    const int NDP = (3 * C.n - 4) | 1, NMP = ((C.n + 2) * 4) | 1;
     const size_t smem = sizeof(double) * RAMBO_NT * (NDP + NMP);
-    cudaFuncSetAttribute(rambo_kernel<N, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(rambo_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long long ntiles = (B + RAMBO_NT - 1) / RAMBO_NT;
     int grid = (int)(ntiles < 148 * 16 ? ntiles : 148 * 16);
-    rambo_kernel<N, RT><<<grid, RAMBO_NT, smem, s>>>(C, (const RT*)r, momenta, weight, cutmask, B);
+    rambo_kernel<RT><<<grid, RAMBO_NT, smem, s>>>(C, (const RT*)r, momenta, weight, cutmask, B);
     NIS_CUDA_CHECK_LAUNCH();
     return NIS_OK;
-}
-
-template <int N>
-static int rambo_launch_dt(const RamboConst& C, const void* r, int dt, double* m, double* w, uint8_t* cm, long long B,
-                           cudaStream_t s) {
-    return dt == NIS_F64 ? rambo_launch<N, double>(C, r, m, w, cm, B, s) : rambo_launch<N, float>(C, r, m, w, cm, B, s);
 }
 
 extern "C" int nis_rambo_generate(const NisRamboDesc* desc, const void* r, int32_t r_dtype, double* momenta,
@@ -77,14 +71,6 @@ extern "C" int nis_rambo_generate(const NisRamboDesc* desc, const void* r, int32
     if (rc) return rc;
     if (B == 0) return NIS_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    switch (desc->n_final) {
-        case 2: return rambo_launch_dt<2>(C, r, r_dtype, momenta, weight, cutmask, B, s);
-        case 3: return rambo_launch_dt<3>(C, r, r_dtype, momenta, weight, cutmask, B, s);
-        case 4: return rambo_launch_dt<4>(C, r, r_dtype, momenta, weight, cutmask, B, s);
-        case 5: return rambo_launch_dt<5>(C, r, r_dtype, momenta, weight, cutmask, B, s);
-        case 6: return rambo_launch_dt<6>(C, r, r_dtype, momenta, weight, cutmask, B, s);
-        case 7: return rambo_launch_dt<7>(C, r, r_dtype, momenta, weight, cutmask, B, s);
-        case 8: return rambo_launch_dt<8>(C, r, r_dtype, momenta, weight, cutmask, B, s);
-    }
-    return NIS_EUNSUPPORTED;
+    return r_dtype == NIS_F64 ? rambo_launch<double>(C, r, momenta, weight, cutmask, B, s)
+                              : rambo_launch<float>(C, r, momenta, weight, cutmask, B, s);
 }

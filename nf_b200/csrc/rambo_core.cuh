@@ -17,6 +17,45 @@
 #include <stdint.h>
 #include "../../include/nis_b200.h"
 
+#ifndef __CUDACC__
+// host build (tests only): glibc has no sincospi
+static inline void sincospi(double x, double* s, double* c) { *s = sin(3.141592653589793 * x); *c = cos(3.141592653589793 * x); }
+#endif
+
+// Float64 division / square root without the IEEE corner-case sequences: the hardware's 20-bit
+// rcp / rsqrt seed + two / three Newton steps + one residual correction (<= 1 ulp).  The IEEE sequences
+// cost ~35 / ~30 instructions (a third of them integer exponent handling); these cost 8 / 11.
+#ifdef __CUDACC__
+NIS_DEV double nis_rcp(double b) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    double e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+NIS_DEV double nis_div(double a, double b) {
+    const double y = nis_rcp(b);
+    const double q = a * y;
+    return fma(fma(-b, q, a), y, q);
+}
+NIS_DEV double nis_sqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    const double s = x * y;
+    const double rs_ = fma(fma(-s, s, x), 0.5 * y, s);
+    return x > 0.0 ? rs_ : 0.0;
+}
+#else
+static inline double nis_div(double a, double b) { return a / b; }
+static inline double nis_sqrt(double x) { return x > 0.0 ? sqrt(x) : 0.0; }
+#endif
+
 #define NIS_TWO_PI 6.283185307179586
 #define NIS_PI 3.141592653589793
 #define NIS_SQRT_EPS 1.4901161193847656e-08   /* np.finfo(float).eps**0.5, utils.py:151 */
@@ -30,6 +69,10 @@ struct RamboConst {
     double wconst;                // flat volume * (K0/M0)^(2n-4) / (2 E_cm^2)
     double beam[2][4];
     double pT_min, dR_min, rap_max;
+    double e2_rap, e2_rap_inv;    // exp(+-2 rap_max)
+    double e2_dR;                 // exp(2 dR_min)
+    double cos_dR;                // cos(min(dR_min, pi))
+    int dR_ge_pi;                 // dR_min >= pi: the d-phi quick reject never fires
 };
 
 // Host: fold the descriptor into per-launch constants.
@@ -60,159 +103,210 @@ static inline int rambo_fill_const(const NisRamboDesc* d, RamboConst* C) {
         for (int i = 0; i < 8; ++i) C->beam[i / 4][i % 4] = b[i / 4][i % 4];
     }
     C->pT_min = d->pT_mincut; C->dR_min = d->delR_mincut; C->rap_max = d->rap_maxcut;
+    C->e2_rap = exp(2.0 * d->rap_maxcut); C->e2_rap_inv = exp(-2.0 * d->rap_maxcut);
+    C->e2_dR = exp(2.0 * d->delR_mincut);
+    C->dR_ge_pi = d->delR_mincut >= NIS_PI;
+    C->cos_dR = cos(d->delR_mincut < NIS_PI ? d->delR_mincut : NIS_PI);
     return NIS_OK;
 }
 
 
 // Root in [0,1] of  r = (e+1) u^e - e u^(e+1)  (flat_phase_space_generator.py:101-103,313-359; the
-// reference bisects 120-180 levels).  Safeguarded Newton: the bracket [lo,hi] always contains the
-// root, a Newton step leaving it is replaced by bisection.
-template <int E>
-NIS_DEV double rambo_root(double r) {
-    if (E == 1) return r / (1.0 + sqrt(1.0 - r));             // u = 1 - sqrt(1-r), stable form
+// reference bisects 120-180 levels to float64 resolution).  Here: float32 start from the small-r /
+// large-r asymptote, five float32 Newton steps (FP32 pipe, no float64 division), then float64 Newton
+// until the step is below 1e-15 relative — three iterations for essentially every lane, so warps do not
+// diverge.  The bracket [lo,hi] always contains the root; a step leaving it is replaced by bisection.
+NIS_DEV double rambo_root(int e, double r) {
+    if (e == 1) return nis_div(r, 1.0 + nis_sqrt(1.0 - r));             // u = 1 - sqrt(1-r), stable form
     if (r <= 0.0) return 0.0;
     if (r >= 1.0) return 1.0;
-    const double e = (double)E;
-    double lo = 0.0, hi = 1.0;
-    // start: small-r asymptote u ~ (r/(e+1))^(1/e) (a lower bound of the root) or, past the inflection
-    // point (e-1)/e, the large-r asymptote 1 - sqrt(2(1-r)/(e(e+1))) (an upper bound)
-    const double ustar = (e - 1.0) / e;
-    double us = 1.0;
-    for (int i = 0; i < E; ++i) us *= ustar;
-    const double rstar = us * ((e + 1.0) - e * ustar);
-    double x;
-    if (r < rstar) { x = pow(r / (e + 1.0), 1.0 / e); lo = x; hi = ustar; }
-    else { x = 1.0 - sqrt(2.0 * (1.0 - r) / (e * (e + 1.0))); hi = x; lo = ustar; if (x < ustar) { x = ustar; hi = 1.0; } }
-    for (int it = 0; it < 64; ++it) {
-        double xe1 = 1.0;                                     // x^(e-1)
-        for (int i = 0; i < E - 1; ++i) xe1 *= x;
-        const double g = xe1 * x * ((e + 1.0) - e * x) - r;
-        const double dg = e * (e + 1.0) * xe1 * (1.0 - x);
-        if (g > 0.0) hi = x; else lo = x;
-        double xn = x - g / dg;
-        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-        const double dx = fabs(xn - x);
+    const float ef = (float)e;
+    const float ustar = (ef - 1.f) / ef;                      // inflection point of the map
+    float us = 1.f;
+    for (int i = 0; i < e; ++i) us *= ustar;
+    const float rstar = us * ((ef + 1.f) - ef * ustar);
+    const float rf = (float)r;
+    float lo, hi, x;
+    if (rf < rstar) { lo = 0.f; hi = ustar; x = exp2f(log2f(fmaxf(rf, 1e-37f) / (ef + 1.f)) / ef); }
+    else { lo = ustar; hi = 1.f; x = 1.f - sqrtf(2.f * fmaxf(1.f - rf, 0.f) / (ef * (ef + 1.f))); }
+    x = fminf(fmaxf(x, lo), hi);
+    for (int it = 0; it < 5; ++it) {
+        float xe1 = 1.f;
+        for (int i = 0; i < e - 1; ++i) xe1 *= x;
+        const float g = xe1 * x * ((ef + 1.f) - ef * x) - rf;
+        const float dg = ef * (ef + 1.f) * xe1 * (1.f - x);
+        float xn = x - g / dg;
+        if (!(xn > lo && xn < hi)) xn = 0.5f * (lo + hi);
+        if (g > 0.f) hi = fminf(hi, x); else lo = fmaxf(lo, x);
         x = xn;
-        if (dx <= 4.5e-16 * x) break;
     }
-    return x;
-}
-
-NIS_DEV double rambo_root_dyn(int e, double r) {
-    switch (e) {
-        case 1: return rambo_root<1>(r);
-        case 2: return rambo_root<2>(r);
-        case 3: return rambo_root<3>(r);
-        case 4: return rambo_root<4>(r);
-        case 5: return rambo_root<5>(r);
-        default: return rambo_root<6>(r);
+    const double ed = (double)e;
+    double X = (double)x, LO = 0.0, HI = 1.0;
+    for (int it = 0; it < 60; ++it) {
+        double xe1 = 1.0;
+        for (int i = 0; i < e - 1; ++i) xe1 *= X;
+        const double g = xe1 * X * ((ed + 1.0) - ed * X) - r;
+        const double dg = ed * (ed + 1.0) * xe1 * (1.0 - X);
+        if (g > 0.0) HI = X; else LO = X;
+        double xn = X - nis_div(g, dg);
+        if (!(xn > LO && xn < HI)) xn = 0.5 * (LO + HI);
+        const double dx = fabs(xn - X);
+        X = xn;
+        if (dx <= 4.5e-16 * X) break;
     }
+    return X;
 }
 
-NIS_DEV double rambo_rho(double M, double N, double m) {     // :107-113
-    const double M2 = M * M;
-    return sqrt((M2 - (N + m) * (N + m)) * (M2 - (N - m) * (N - m))) / (8.0 * M2);
-}
+NIS_DEV double rambo_root_dyn(int e, double r) { return rambo_root(e, r); }
 
-NIS_DEV double rambo_pseudorap(double px, double py, double pz) {   // utils.py:151-157
-    const double pt = sqrt(px * px + py * py);
-    if (pt < NIS_SQRT_EPS && fabs(pz) < NIS_SQRT_EPS) return NIS_HUGE;
-    const double th = atan2(pt, pz);
-    return -log(tan(th / 2.0));
-}
-
-// One event.  r: 3n-4 uniforms at stride rs.  mom: (n+2)*4 doubles at stride ms, or null.
-template <int N>
-NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* mom, int ms, double& weight,
+// One event, runtime multiplicity n = C.n.  r: 3n-4 uniforms at stride rs.  mo: scratch AND output row of
+// (n+2)*4 doubles at stride ms (beams, final-state momenta; the two beam slots double as scratch for
+// exp(2 eta_j) until the end).
+//
+// Same map as the reference, arranged for the FP64 pipe and a small instruction footprint (every loop is
+// rolled: the first version, fully unrolled per multiplicity, was 72 KB of SASS for n=4 and spent 36 % of
+// its issue slots waiting for instructions):
+//   * q_j = sqrt(lambda_j)/(2 M_j) and rho_j = sqrt(lambda_j)/(8 M_j^2) share one square root; the
+//     massive reweighting (:394-403) is accumulated as numerator / denominator products, one division;
+//   * the decay energy in the parent rest frame is (M_j^2 + m_j^2 - M_{j+1}^2)/(2 M_j) (= sqrt(q^2+m^2), :262);
+//   * the boost by Q (utils.py:58-81, gamma = Q0/M_j because Q is on shell) is
+//     p' = p + [(p.Q)/(Q0+M_j) + p0]/M_j * Q,  E' = (Q0 p0 + p.Q)/M_j  — no square root;
+//   * sin/cos of phi = 2 pi r from one sincospi (the reference takes cos and restores |sin| by a root);
+//   * cuts are decided on squared quantities: pT^2, exp(2 eta) = (|p|+pz)/(|p|-pz); for deltaR two exact
+//     quick rejects (|d eta| >= cut, d phi >= cut), then rigorous series bounds on atanh / asin decide
+//     all but a ~1e-4-wide shell around deltaR = cut, where the reference's log/acos formula runs.
+// All differences to the reference are at float64 rounding level (tests: momenta / weights rtol 1e-9,
+// cut masks bit-exact on the golden vectors).
+NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* mo, int ms, double& weight,
                          uint8_t& pass) {
-    double K[N > 1 ? N - 1 : 1], M[N];
-    K[0] = C.K0;
-#pragma unroll
-    for (int j = 0; j < N - 2; ++j) {                          // :363-370
-        const double u = rambo_root_dyn(N - 2 - j, r[j * rs]);
-        K[j + 1] = sqrt(u * (K[j] * K[j]));
-    }
-#pragma unroll
-    for (int j = 0; j < N - 1; ++j) M[j] = K[j] + C.msum[j];   // :391-392
-    M[N - 1] = C.m[N - 1];
-    double w = C.wconst * 8.0 * rambo_rho(M[N - 2], C.m[N - 1], C.m[N - 2]);   // :394-397
-#pragma unroll
-    for (int j = 0; j < N - 2; ++j)                            // :400-401
-        w *= rambo_rho(M[j], M[j + 1], C.m[j]) / rambo_rho(K[j], K[j + 1], 0.0) * (M[j + 1] / K[j + 1]);
-
-    double Q0 = M[0], Q1 = 0.0, Q2 = 0.0, Q3 = 0.0;
-    double fx[N], fy[N], fz[N];
-    double E_last = 0.0;
-#pragma unroll
-    for (int j = 0; j < N - 1; ++j) {
-        const double q = 4.0 * M[j] * rambo_rho(M[j], M[j + 1], C.m[j]);   // :228
-        const double ct = 2.0 * r[(N - 2 + 2 * j) * rs] - 1.0;             // :233-243
-        const double st = sqrt(1.0 - ct * ct);
-        const double phi = NIS_TWO_PI * r[(N - 1 + 2 * j) * rs];
-        const double cp = cos(phi);
-        const double sp0 = sqrt(1.0 - cp * cp);
-        const double sp = phi > NIS_PI ? -sp0 : sp0;
+    const int n = C.n;
+    double Kj = C.K0, Mj = Kj + C.msum[0];
+    double num = 1.0, den = 1.0;
+    double Q0 = Mj, Q1 = 0.0, Q2 = 0.0, Q3 = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < n - 1; ++j) {
+        double Kn = 0.0, Mn = C.m[n - 1];
+        const double mj = C.m[j];
+        if (j < n - 2) {                                        // :363-370, :391-392
+            const double u = rambo_root(n - 2 - j, r[j * rs]);
+            Kn = nis_sqrt(u) * Kj;
+            Mn = Kn + C.msum[j + 1];
+        }
+        const double M2 = Mj * Mj, sm_ = Mn + mj, dm = Mn - mj;
+        const double sl = nis_sqrt((M2 - sm_ * sm_) * (M2 - dm * dm));   // sqrt(lambda(M_j^2, M_{j+1}^2, m_j^2)), :107-113
+        if (j < n - 2) {                                        // :400-401
+            const double K2 = Kj * Kj;
+            num *= sl * K2 * Mn;
+            den *= M2 * (K2 - Kn * Kn) * Kn;
+        } else {                                                // 8 rho(M_{n-2}, m_{n-1}, m_{n-2}), :394-397
+            num *= sl;
+            den *= M2;
+        }
+        const double i2M = nis_div(0.5, Mj);
+        const double q = sl * i2M;                              // :228
+        const double ct = 2.0 * r[(n - 2 + 2 * j) * rs] - 1.0;  // :233-243
+        const double st = nis_sqrt(1.0 - ct * ct);
+        double sp, cp;
+        sincospi(2.0 * r[(n - 1 + 2 * j) * rs], &sp, &cp);
         double p1 = q * st * cp, p2 = q * st * sp, p3 = q * ct;
-        const double m2 = C.m[j] * C.m[j];
-        const double p0 = sqrt(p1 * p1 + p2 * p2 + p3 * p3 + m2);          // set_square_t utils.py:5-19
-        const double b1 = Q1 / Q0, b2_ = Q2 / Q0, b3 = Q3 / Q0;            // boostVector_t :31-36
-        const double bb = b1 * b1 + b2_ * b2_ + b3 * b3;                   // boost_t :58-81
-        const double gamma = 1.0 / sqrt(1.0 - bb);
-        const double bp = p1 * b1 + p2 * b2_ + p3 * b3;
-        const double gamma2 = bb > 0.0 ? (gamma - 1.0) / bb : 0.0;
-        const double fac = gamma2 * bp + gamma * p0;
-        p1 += fac * b1; p2 += fac * b2_; p3 += fac * b3;
-        const double e = sqrt(p1 * p1 + p2 * p2 + p3 * p3 + m2);           // :265
-        fx[j] = p1; fy[j] = p2; fz[j] = p3;
-        if (mom) { double* o = mom + (2 + j) * 4 * ms; o[0] = e; o[ms] = p1; o[2 * ms] = p2; o[3 * ms] = p3; }
-        Q1 -= p1; Q2 -= p2; Q3 -= p3;                                       // :271-275
-        Q0 = sqrt(Q1 * Q1 + Q2 * Q2 + Q3 * Q3 + M[j + 1] * M[j + 1]);
-        E_last = Q0;
+        const double p0 = (M2 + mj * mj - Mn * Mn) * i2M;
+        const double pQ = p1 * Q1 + p2 * Q2 + p3 * Q3;
+        const double iM = 2.0 * i2M;
+        const double coef = (nis_div(pQ, Q0 + Mj) + p0) * iM;
+        p1 += coef * Q1; p2 += coef * Q2; p3 += coef * Q3;
+        const double e = (Q0 * p0 + pQ) * iM;
+        double* o = mo + (2 + j) * 4 * ms;
+        o[0] = e; o[ms] = p1; o[2 * ms] = p2; o[3 * ms] = p3;
+        Q1 -= p1; Q2 -= p2; Q3 -= p3; Q0 -= e;                  // :271-275
+        Kj = Kn; Mj = Mn;
     }
-    fx[N - 1] = Q1; fy[N - 1] = Q2; fz[N - 1] = Q3;                         // :278
-    if (mom) {
-        double* o = mom + (N + 1) * 4 * ms;
-        o[0] = E_last; o[ms] = Q1; o[2 * ms] = Q2; o[3 * ms] = Q3;
-#pragma unroll
-        for (int b = 0; b < 2; ++b)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) mom[(b * 4 + i) * ms] = C.beam[b][i];
+    {
+        double* o = mo + (n + 1) * 4 * ms;                      // :278
+        o[0] = Q0; o[ms] = Q1; o[2 * ms] = Q2; o[3 * ms] = Q3;
     }
+    const double w = C.wconst * nis_div(num, den);
     // ---- cuts (:285-301); x1 = x2 = 1 so the lab frame is the CM frame -------------------------
     bool ok = true;
-    double ptmin = NIS_HUGE;
-#pragma unroll
-    for (int j = 0; j < N; ++j) ptmin = fmin(ptmin, sqrt(fx[j] * fx[j] + fy[j] * fy[j]));
-    if (ptmin < C.pT_min) ok = false;
+    const double* fin = mo + 8 * ms;                            // final-state particle j at fin + 4*j*ms
+    double* e2 = mo;                                            // exp(2 eta_j), j < n <= 8 (beam slots)
     const bool need_eta = C.rap_max > 0.0 || C.dR_min > 0.0;
-    if (need_eta) {
-        double eta[N], pt[N];
-        double etamax = -NIS_HUGE;
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            eta[j] = rambo_pseudorap(fx[j], fy[j], fz[j]);
-            pt[j] = sqrt(fx[j] * fx[j] + fy[j] * fy[j]);
-            etamax = fmax(etamax, eta[j]);
+    if (C.pT_min > 0.0 || need_eta) {
+        double pt2min = NIS_HUGE, e2max = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) {
+            const double px = fin[(4 * j + 1) * ms], py = fin[(4 * j + 2) * ms], pz = fin[(4 * j + 3) * ms];
+            const double pt2 = px * px + py * py;
+            pt2min = fmin(pt2min, pt2);
+            if (need_eta) {
+                double v;
+                if (pt2 < NIS_SQRT_EPS * NIS_SQRT_EPS && pz * pz < NIS_SQRT_EPS * NIS_SQRT_EPS) {
+                    v = NIS_HUGE;                               // utils.py:157 `huge`
+                } else {
+                    const double P = nis_sqrt(pt2 + pz * pz);
+                    const double a = P + fabs(pz);              // exp(|eta|) = a / pT
+                    const double t = nis_div(a * a, pt2);
+                    v = pz >= 0.0 ? t : nis_div(1.0, t);
+                }
+                e2[j * ms] = v;
+                e2max = fmax(e2max, v);
+            }
         }
-        if (C.rap_max > 0.0 && C.rap_max < fabs(etamax)) ok = false;          // |max eta|, not max |eta|
-        if (C.dR_min > 0.0) {
-#pragma unroll
-            for (int i = 1; i < N; ++i)
-#pragma unroll
-                for (int j = 0; j < i; ++j) {
-                    const double deta = eta[i] - eta[j];
+        if (C.pT_min > 0.0 && pt2min < C.pT_min * C.pT_min) ok = false;              // :285-288
+        // rap_max < |max_j eta_j|  (|max eta|, not max |eta|, :298-301)
+        if (C.rap_max > 0.0 && (e2max > C.e2_rap || e2max < C.e2_rap_inv)) ok = false;
+    }
+    if (C.dR_min > 0.0) {                                       // :290-296
+        const double cut2 = C.dR_min * C.dR_min;
+#pragma unroll 1
+        for (int i = 1; i < n; ++i) {
+            const double xi = fin[(4 * i + 1) * ms], yi = fin[(4 * i + 2) * ms], ei = e2[i * ms];
+            const double pti2 = xi * xi + yi * yi;
+#pragma unroll 1
+            for (int j = 0; j < i; ++j) {
+                const double ej = e2[j * ms];
+                // quick reject, exact: |d eta| >= cut  =>  dR >= cut
+                if (!(ei < C.e2_dR * ej && ej < C.e2_dR * ei)) continue;
+                const double xj = fin[(4 * j + 1) * ms], yj = fin[(4 * j + 2) * ms];
+                const double dot = xi * xj + yi * yj;
+                const double A = pti2 * (xj * xj + yj * yj);
+                bool exact = true;
+                if (A > 0.0 && !C.dR_ge_pi && C.cos_dR >= 0.0 && ei < NIS_HUGE && ej < NIS_HUGE) {
+                    // quick reject, exact: d phi >= cut
+                    if (!(dot > 0.0 && dot * dot > C.cos_dR * C.cos_dR * A)) continue;
+                    // series bounds: d eta = atanh(z), z = (rho-1)/(rho+1), rho = exp(2 d eta) >= 1;
+                    // d phi = asin(s), s = |cross| / (pT_i pT_j)   (0 <= d phi < cut <= pi/2 here)
+                    const double rho = ei > ej ? nis_div(ei, ej) : nis_div(ej, ei);
+                    const double z = nis_div(rho - 1.0, rho + 1.0), z2 = z * z;
+                    const double Le = z * (1.0 + z2 * (1.0 / 3.0 + z2 * (1.0 / 5.0 + z2 * (1.0 / 7.0))));
+                    const double Ue = Le + nis_div(z2 * z2 * z2 * z2 * z, 9.0 * (1.0 - z2));
+                    const double cr = xi * yj - yi * xj;
+                    const double s2 = nis_div(cr * cr, A), sn = nis_sqrt(s2);
+                    const double Lp = sn * (1.0 + s2 * (1.0 / 6.0 + s2 * (3.0 / 40.0 + s2 * (15.0 / 336.0))));
+                    const double Up = Lp + nis_div(s2 * s2 * s2 * s2 * sn * (35.0 / 1152.0), 1.0 - s2);
+                    const double m = 1e-12 * cut2;              // rounding guard of the bound arithmetic
+                    if (Le * Le + Lp * Lp >= cut2 + m) continue;
+                    if (Ue * Ue + Up * Up < cut2 - m) { ok = false; exact = false; }
+                }
+                if (exact) {
+                    // the reference's formula (utils.py:151-187)
+                    const double etai = ei >= NIS_HUGE ? NIS_HUGE : 0.5 * log(ei);
+                    const double etaj = ej >= NIS_HUGE ? NIS_HUGE : 0.5 * log(ej);
+                    const double deta = etai - etaj;
                     double dphi;
-                    if (pt[i] == 0.0 || pt[j] == 0.0) dphi = NIS_HUGE;      // utils.py:170-180
+                    if (A == 0.0) dphi = NIS_HUGE;
                     else {
-                        double t = (fx[i] * fx[j] + fy[i] * fy[j]) / (pt[i] * pt[j]);
+                        double t = dot / sqrt(A);
                         if (fabs(t) > 1.0) t = t / fabs(t);
                         dphi = acos(t);
                     }
                     const double dR = sqrt(deta * deta + dphi * dphi);
                     if (fabs(dR) < C.dR_min) ok = false;
                 }
+            }
         }
     }
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) mo[i * ms] = C.beam[i >> 2][i & 3];
     pass = ok ? 1 : 0;
     weight = ok ? w : 0.0;
 }

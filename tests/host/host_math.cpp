@@ -5,12 +5,6 @@
 #include "../../nf_b200/csrc/spline.cuh"
 #include "../../nf_b200/csrc/rambo_core.cuh"
 
-template <int N>
-static void rambo_n(const RamboConst& C, long long B, const double* r, double* mom, double* w, uint8_t* pass) {
-    const int nd = 3 * N - 4, nm = (N + 2) * 4;
-    for (long long i = 0; i < B; ++i) rambo_event<N>(C, r + i * nd, 1, mom ? mom + i * nm : nullptr, 1, w[i], pass[i]);
-}
-
 extern "C" {
 
 // z: [n][K] logits (K = nb), overwritten with dL/dz.  gy, gJJ per point.
@@ -40,16 +34,9 @@ int host_rambo(const NisRamboDesc* d, long long B, const double* r, double* mom,
     RamboConst C;
     int rc = rambo_fill_const(d, &C);
     if (rc) return rc;
-    switch (d->n_final) {
-        case 2: rambo_n<2>(C, B, r, mom, w, pass); break;
-        case 3: rambo_n<3>(C, B, r, mom, w, pass); break;
-        case 4: rambo_n<4>(C, B, r, mom, w, pass); break;
-        case 5: rambo_n<5>(C, B, r, mom, w, pass); break;
-        case 6: rambo_n<6>(C, B, r, mom, w, pass); break;
-        case 7: rambo_n<7>(C, B, r, mom, w, pass); break;
-        case 8: rambo_n<8>(C, B, r, mom, w, pass); break;
-        default: return -4;
-    }
+    const int n = d->n_final, nd = 3 * n - 4, nm = (n + 2) * 4;
+    double scratch[(NIS_MAX_FINAL + 2) * 4];
+    for (long long i = 0; i < B; ++i) rambo_event(C, r + i * nd, 1, mom ? mom + i * nm : scratch, 1, w[i], pass[i]);
     return 0;
 }
 

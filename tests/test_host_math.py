@@ -136,7 +136,7 @@ def test_rambo_root_solves_the_mass_polynomial(host, e):
         u = host.host_rambo_root(e, float(r))
         assert 0.0 <= u <= 1.0
         back = (e + 1) * u ** e - e * u ** (e + 1)
-        assert abs(back - r) <= 4e-15 * max(r, 1e-300) + 1e-16, (e, r, u, back)
+        assert abs(back - r) <= 6e-15 * max(r, 1e-300) + 2e-16, (e, r, u, back)
     # agrees with the reference's lattice bisection (oracle.bisect) to its absolute resolution
     n = e + 2
     v = torch.rand(64, n - 2, generator=torch.Generator().manual_seed(e), dtype=torch.float64)
