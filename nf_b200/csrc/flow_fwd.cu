@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(NT) flow_fwd_generic_kernel(const __grid_const
 // ---------------------------------------------------------------------------------------------------
 size_t nis_flow_bwd_scratch_floats(const DevFlow& F, int64_t B);
 bool nis_tiled_supported(const DevFlow& F, int64_t B);
+size_t nis_tiled_zbuf_floats(int64_t B);
 int nis_launch_tiled(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 
 static size_t fwd_smem_bytes(const DevFlow& F, int NT) {
@@ -240,7 +241,11 @@ extern "C" size_t nis_flow_workspace_bytes(const NisFlowDesc* desc, int64_t B) {
     if (nis_build_dev_flow(desc, &F) != NIS_OK || B < 0) return 0;
     FlowWorkspace ws;
     size_t fwd = nis_flow_carve(F, B, nullptr, &ws);
-    return fwd + sizeof(float) * nis_flow_bwd_scratch_floats(F, B) + 256;
+    // the backward scratch and the tiled train path's activation buffers are never live together
+    size_t tail = nis_flow_bwd_scratch_floats(F, B);
+    const size_t zfl = nis_tiled_supported(F, B) ? 2 * nis_tiled_zbuf_floats(B) : 0;
+    if (zfl > tail) tail = zfl;
+    return fwd + sizeof(float) * tail + 256;
 }
 
 template <int NT>
@@ -297,6 +302,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     A.saved = saved; A.bins = bins_out;
     A.params = params; A.wpack = ws.wpack; A.bn_running = bn_running; A.bn_saved = bn_saved;
     A.partials = ws.partials; A.counter = ws.counter; A.B = B;
+    A.zin = nullptr; A.zout = nullptr;
     const bool tiled = nis_tiled_supported(F, B);
     const long long rows = (long long)B * (F.d + 1);
     if (bn_mode == NIS_BN_EVAL && !tiled) {
@@ -311,14 +317,24 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
         A.from_state = c > 0;
         A.state_in = c > 0 ? (saved ? saved + (long long)c * rows : ws.state) : nullptr;
         A.state_out = nullptr; A.to_out = 0;
+        float* zb[2] = {ws.bwd, ws.bwd + nis_tiled_zbuf_floats(B)};
         if (bn_mode == NIS_BN_TRAIN) {
             for (int l = 0; l <= F.depth; ++l) {
                 A.stats_layer = l;
-                rc = (tiled && l >= 1) ? nis_launch_tiled(F, A, s) : launch_fwd_any(F, A, s);
+                if (tiled && l >= 1) {
+                    // layer pass: reads the pre-BN activations of layer l-1, writes those of layer l
+                    A.zin = l >= 2 ? zb[(l - 1) & 1] : nullptr;
+                    A.zout = zb[l & 1];
+                    rc = nis_launch_tiled(F, A, s);
+                } else {
+                    rc = launch_fwd_any(F, A, s);
+                }
                 if (rc) return rc;
             }
         }
         A.stats_layer = -1;
+        A.zin = (tiled && bn_mode == NIS_BN_TRAIN) ? zb[F.depth & 1] : nullptr;
+        A.zout = nullptr;
         const bool last = c == F.n_cells - 1;
         A.to_out = last;
         A.state_out = saved ? saved + (long long)(c + 1) * rows : (last ? nullptr : ws.state);

@@ -13,6 +13,8 @@ struct FwdArgs {
     const float* params; float* wpack; float* bn_running; float* bn_saved;
     double* partials; unsigned* counter;
     long long B; int c_begin, c_end, stats_layer;
+    const float* zin;                            // tiled train path: pre-BN activations of the layer below,
+    float* zout;                                 // tile-blocked [tile][64][M] (written by a statistics pass)
 };
 
 

@@ -23,22 +23,32 @@ struct TiledSmem {
     int wl[NIS_MAX_HIDDEN + 1];                  // per-layer weight offsets inside W (last = output layer)
 };
 
-__host__ __device__ static inline TiledSmem tiled_layout(const DevFlow& F, int c, int M) {
+// Shared-memory plan of one launch: hidden layers [first, last) are computed, plus the output layer
+// when with_out.  Layer passes of the train path need one activation buffer and one layer of weights
+// (~50 KB at M=128), which lets two CTAs share an SM and overlap one's global traffic with the other's FMAs.
+__host__ __device__ static inline TiledSmem tiled_layout(const DevFlow& F, int c, int M, int first, int last, bool with_out) {
     TiledSmem s;
     const DevCell& q = F.cells[c];
     int o = 0;
     s.st = o; o += (F.d + 1) * M;
     s.A0 = o; o += TH * M;
-    s.A1 = o; o += TH * M;
+    s.A1 = o;
+    if (with_out || last - first >= 2) o += TH * M;
     s.W = o;
     int w = 0, in = q.P;
-    for (int l = 0; l < F.depth; ++l) { s.wl[l] = w; w += in * TH; in = TH; }
+    for (int l = 0; l < F.depth; ++l) {
+        s.wl[l] = w;
+        if (l >= first && l < last) w += in * TH;
+        in = TH;
+    }
     const int nch = (q.T * F.K + TCH - 1) / TCH;
-    s.wl[F.depth] = w; w += nch * TH * TCH;
+    s.wl[F.depth] = w;
+    if (with_out) w += nch * TH * TCH;
     o += w;
     s.aff = o; o += (F.depth + 1) * 2 * TH;
     s.bias = o; o += nch * TCH;
     s.fbuf = o; o += (TCH / F.K) * M;
+    if (o < s.A0 + 2 * (M / 4) * TH * 2 + 4 * F.maxW + 2) o = s.A0 + 2 * (M / 4) * TH * 2 + 4 * F.maxW + 2;   // statistics fold scratch
     s.total = o;
     return s;
 }
@@ -49,7 +59,7 @@ template <int M>
 __device__ __forceinline__ int swz(int row, int pt) { return row * M + ((((pt >> 2) ^ ((row >> 2) & 7)) << 2) | (pt & 3)); }
 
 template <int M, int TM>
-__global__ void __launch_bounds__(M * 8 / TM, 1) flow_cell_tiled_kernel(const __grid_constant__ DevFlow F, const FwdArgs A) {
+__global__ void __launch_bounds__(M * 8 / TM, (M == 128 && TM == 4) ? 2 : 1) flow_cell_tiled_kernel(const __grid_constant__ DevFlow F, const FwdArgs A) {
     constexpr int NT = M * 8 / TM;
     constexpr int NV = TM / 4;            // float4 per thread row
     extern __shared__ __align__(16) float sm[];
@@ -57,24 +67,29 @@ __global__ void __launch_bounds__(M * 8 / TM, 1) flow_cell_tiled_kernel(const __
     const int c = A.c_begin;
     const DevCell& q = F.cells[c];
     const int d = F.d, depth = F.depth, K = F.K, nb = F.nb;
-    const TiledSmem L = tiled_layout(F, c, M);
-    float* st = sm + L.st;
-    float* Ws = sm + L.W;
-    float* affs = sm + L.aff;
-    float* biass = sm + L.bias;
-    float* fbuf = sm + L.fbuf;
     const float* pk = A.wpack + q.pk_off;
     const int tpc = TCH / K;                                  // transformed dims per chunk
     const int nch = (q.T * K + TCH - 1) / TCH;
     const bool stats = A.stats_layer >= 1;
     const int last_layer = stats ? A.stats_layer : depth;     // hidden layers to run (1-based count)
+    // Train-mode layer passes: with A.zin the activations below `first_layer` are not recomputed; the
+    // pre-BN output of hidden layer first_layer-1 is read back (tile-blocked [tile][64][M]) and BN+ReLU
+    // of that layer is applied while it is staged into shared memory.
+    const int first_layer = A.zin ? last_layer - (stats ? 1 : 0) : 0;
+    const TiledSmem L = tiled_layout(F, c, M, first_layer, last_layer, !stats);
+    float* st = sm + L.st;
+    float* Ws = sm + L.W;
+    float* affs = sm + L.aff;
+    float* biass = sm + L.bias;
+    float* fbuf = sm + L.fbuf;
 
     // ---- stage the cell's weights / BN scale+shift / bias once ---------------------------------------
     {
         int in = q.P;
         for (int l = 0; l < last_layer; ++l) {
             const float* src = pk + q.wt_off[l];               // [in][64]
-            for (int i = tid; i < in * TH; i += NT) Ws[L.wl[l] + i] = src[i];
+            if (l >= first_layer)
+                for (int i = tid; i < in * TH; i += NT) Ws[L.wl[l] + i] = src[i];
             in = TH;
         }
         for (int l = 0; l <= depth; ++l) {
@@ -126,17 +141,30 @@ __global__ void __launch_bounds__(M * 8 / TM, 1) flow_cell_tiled_kernel(const __
             float* sv = A.saved + ((long long)c * A.B + base) * rowlen;
             for (int i = tid; i < cnt * (d + 1); i += NT) { const int pt = i / (d + 1), col = i - pt * (d + 1); sv[i] = st[col * M + pt]; }
         }
-        // ---- BN0 of the pass-through columns -> a0 --------------------------------------------------
+        // ---- input activations: BN0 of the pass-through columns, or BN+ReLU of the stored layer ------
         float* cur = sm + L.A0;
         float* nxt = sm + L.A1;
-        for (int i = tid; i < q.P * M; i += NT) {
-            const int k = i / M, pt = i - k * M;
-            cur[swz<M>(k, pt)] = fmaf(st[q.feed[k] * M + pt], affs[k], affs[TH + k]);
+        if (first_layer == 0) {
+            for (int i = tid; i < q.P * M; i += NT) {
+                const int k = i / M, pt = i - k * M;
+                cur[swz<M>(k, pt)] = fmaf(st[q.feed[k] * M + pt], affs[k], affs[TH + k]);
+            }
+        } else {
+            const float4* src = reinterpret_cast<const float4*>(A.zin + (size_t)tile * TH * M);
+            const float* sc = affs + first_layer * 2 * TH;
+            const float* sh = sc + TH;
+            for (int i = tid; i < TH * M / 4; i += NT) {
+                const int k = i / (M / 4), pt = (i - k * (M / 4)) * 4;
+                float4 v = src[i];
+                v.x = fmaxf(fmaf(v.x, sc[k], sh[k]), 0.f); v.y = fmaxf(fmaf(v.y, sc[k], sh[k]), 0.f);
+                v.z = fmaxf(fmaf(v.z, sc[k], sh[k]), 0.f); v.w = fmaxf(fmaf(v.w, sc[k], sh[k]), 0.f);
+                *reinterpret_cast<float4*>(cur + swz<M>(k, pt)) = v;
+            }
         }
         __syncthreads();
         // ---- hidden layers ---------------------------------------------------------------------------
-        int in = q.P;
-        for (int l = 0; l < last_layer; ++l) {
+        int in = first_layer == 0 ? q.P : TH;
+        for (int l = first_layer; l < last_layer; ++l) {
             float acc[TM][8];
 #pragma unroll
             for (int i = 0; i < TM; ++i)
@@ -170,6 +198,17 @@ __global__ void __launch_bounds__(M * 8 / TM, 1) flow_cell_tiled_kernel(const __
                         s += v; s2 = fmaf(v, v, s2);
                     }
                     dsum[j] += (double)s; dsq[j] += (double)s2;
+                }
+                if (A.zout) {      // leave the pre-BN activations for the next layer pass (whole tile, valid or not)
+                    float* dst = A.zout + (size_t)tile * TH * M;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int o = (j < 4 ? 0 : 28) + tc * 4 + j;
+#pragma unroll
+                        for (int v4 = 0; v4 < NV; ++v4)
+                            *reinterpret_cast<float4*>(dst + o * M + tr * TM + 4 * v4) =
+                                make_float4(acc[4 * v4][j], acc[4 * v4 + 1][j], acc[4 * v4 + 2][j], acc[4 * v4 + 3][j]);
+                    }
                 }
                 break;
             }
@@ -292,6 +331,8 @@ __global__ void __launch_bounds__(M * 8 / TM, 1) flow_cell_tiled_kernel(const __
 }
 
 // ---------------------------------------------------------------------------------------------------
+size_t nis_tiled_zbuf_floats(int64_t B) { return (size_t)((B + 255) / 256) * 256 * TH; }
+
 bool nis_tiled_supported(const DevFlow& F, int64_t B) {
     const char* off = getenv("NIS_DISABLE_TILED");        // test knob: force the shape-generic kernel
     if (off && off[0] == '1') return false;
@@ -300,21 +341,23 @@ bool nis_tiled_supported(const DevFlow& F, int64_t B) {
     if (F.K != 8 && F.K != 16 && F.K != 32 && F.K != 64) return false;
     if (F.maxW != TH) return false;
     for (int c = 0; c < F.n_cells; ++c) {
-        TiledSmem s = tiled_layout(F, c, 128);
-        size_t bytes = (size_t)s.total * 4;
-        size_t red = (size_t)(2 * 32 * TH + 2 * F.maxW) * 8;
-        if (bytes > 220 * 1024 || red > (size_t)2 * TH * 128 * 4) return false;
+        TiledSmem s = tiled_layout(F, c, 128, 0, F.depth, true);
+        if ((size_t)s.total * 4 > 220 * 1024) return false;
     }
     return true;
 }
 
 template <int M, int TM>
 static int launch_tiled_m(const DevFlow& F, const FwdArgs& A, int sms, cudaStream_t s) {
-    TiledSmem L = tiled_layout(F, A.c_begin, M);
+    const bool stats = A.stats_layer >= 1;
+    const int last = stats ? A.stats_layer : F.depth;
+    const int first = A.zin ? last - (stats ? 1 : 0) : 0;
+    TiledSmem L = tiled_layout(F, A.c_begin, M, first, last, !stats);
     const size_t smem = (size_t)L.total * sizeof(float);
     cudaFuncSetAttribute(flow_cell_tiled_kernel<M, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long long ntiles = (A.B + M - 1) / M;
-    int grid = (int)(ntiles < sms ? ntiles : sms);
+    const int per_sm = (M == 128 && TM == 4 && smem <= 110 * 1024) ? 2 : 1;
+    int grid = (int)(ntiles < (long long)sms * per_sm ? ntiles : (long long)sms * per_sm);
     flow_cell_tiled_kernel<M, TM><<<grid, M * 8 / TM, smem, s>>>(F, A);
     NIS_CUDA_CHECK_LAUNCH();
     return NIS_OK;
@@ -325,12 +368,15 @@ int nis_launch_tiled(const DevFlow& F, const FwdArgs& A, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    TiledSmem L256 = tiled_layout(F, A.c_begin, 256);
+    // train-mode layer passes exchange tile-blocked activations: every launch of a forward must use the
+    // same M; they run at M=128 with two CTAs per SM.  The fused eval cell runs at M=256.
+    const bool layer_pass = A.zin || A.zout;
+    TiledSmem L256 = tiled_layout(F, A.c_begin, 256, 0, F.depth, true);
     // 4x8 register tiles (16 warps/SM) measured faster than 8x8 (8 warps/SM) on B200: 26.0 vs 29.0 ms for
     // cfg2 eval at 2^22 points; NIS_TILED_VARIANT=8 selects the 8x8 variant for experiments.
     const char* v = getenv("NIS_TILED_VARIANT");
     const bool tm4 = !(v && v[0] == '8');
-    if ((size_t)L256.total * 4 <= 225 * 1024 && A.B >= (long long)sms * 256)
+    if (!layer_pass && (size_t)L256.total * 4 <= 225 * 1024 && A.B >= (long long)sms * 256)
         return tm4 ? launch_tiled_m<256, 4>(F, A, sms, s) : launch_tiled_m<256, 8>(F, A, sms, s);
     return tm4 ? launch_tiled_m<128, 4>(F, A, sms, s) : launch_tiled_m<128, 8>(F, A, sms, s);
 }
