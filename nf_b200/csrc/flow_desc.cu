@@ -90,10 +90,13 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // partials [NIS_BWD_GRID][max cell params], BN backward sums [n_cells][depth+1][2][maxW].
 size_t nis_flow_bwd_scratch_floats(const DevFlow& F, const NisFlowDesc* d, int64_t B);
 
+size_t nis_tc_pack_floats(const DevFlow& F);
+
 size_t nis_flow_carve(const DevFlow& F, int64_t B, void* base, FlowWorkspace* ws) {
     size_t off = 0;
     char* b = (char*)base;
     ws->wpack = (float*)(b + off); off = align256(off + sizeof(float) * (size_t)F.pack_total);
+    ws->tcpack = (float*)(b + off); off = align256(off + sizeof(float) * nis_tc_pack_floats(F));
     ws->state = (float*)(b + off); off = align256(off + sizeof(float) * (size_t)B * (F.d + 1));
     ws->partials = (double*)(b + off); off = align256(off + sizeof(double) * (size_t)NIS_MAX_GRID * 2 * F.maxW);
     ws->counter = (unsigned*)(b + off); off = align256(off + 256);

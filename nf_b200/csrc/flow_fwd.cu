@@ -227,6 +227,9 @@ __global__ void __launch_bounds__(NT) flow_fwd_generic_kernel(const __grid_const
 size_t nis_flow_bwd_scratch_floats(const DevFlow& F, int64_t B);
 bool nis_tiled_supported(const DevFlow& F, int64_t B);
 size_t nis_tiled_zbuf_floats(int64_t B);
+bool nis_tc_supported(const DevFlow& F, int64_t B, int bn_mode);
+int nis_tc_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream_t s);
+int nis_launch_tc(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaStream_t s);
 int nis_launch_tiled(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 
 static size_t fwd_smem_bytes(const DevFlow& F, int NT) {
@@ -304,6 +307,8 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     A.partials = ws.partials; A.counter = ws.counter; A.B = B;
     A.zin = nullptr; A.zout = nullptr;
     const bool tiled = nis_tiled_supported(F, B);
+    const bool tc = tiled && nis_tc_supported(F, B, bn_mode);
+    if (tc) { rc = nis_tc_pack(F, params, ws.tcpack, s); if (rc) return rc; }
     const long long rows = (long long)B * (F.d + 1);
     if (bn_mode == NIS_BN_EVAL && !tiled) {
         A.state_in = nullptr; A.state_out = nullptr; A.from_state = 0; A.to_out = 1;
@@ -325,7 +330,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
                     // layer pass: reads the pre-BN activations of layer l-1, writes those of layer l
                     A.zin = l >= 2 ? zb[(l - 1) & 1] : nullptr;
                     A.zout = zb[l & 1];
-                    rc = nis_launch_tiled(F, A, s);
+                    rc = tc ? nis_launch_tc(F, A, ws.tcpack, s) : nis_launch_tiled(F, A, s);
                 } else {
                     rc = launch_fwd_any(F, A, s);
                 }
@@ -338,7 +343,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
         const bool last = c == F.n_cells - 1;
         A.to_out = last;
         A.state_out = saved ? saved + (long long)(c + 1) * rows : (last ? nullptr : ws.state);
-        rc = tiled ? nis_launch_tiled(F, A, s) : launch_fwd_any(F, A, s);
+        rc = tc ? nis_launch_tc(F, A, ws.tcpack, s) : (tiled ? nis_launch_tiled(F, A, s) : launch_fwd_any(F, A, s));
         if (rc) return rc;
     }
     return NIS_OK;

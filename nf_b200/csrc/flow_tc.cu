@@ -1,0 +1,508 @@
+// Fused coupling-cell forward on the 5th-generation tensor cores (tcgen05 + TMEM), width-64 PWLin cells.
+//
+// The FP32-pipe kernel (flow_tiled.cu) is bound by shared-memory -> register fill (ncu: 83 % of the
+// shared pipe, FMA pipe 46 %).  tcgen05.mma reads its operands straight from shared memory and
+// accumulates in tensor memory, so that bound disappears.  To keep the float32 contract (1e-5 on points
+// and log-Jacobians) every conditioner product runs as a 3xTF32 split: a = a_hi + a_lo with a_hi the
+// value truncated to TF32's 10-bit mantissa (exact) and a_lo = a - a_hi (exact in float32), likewise w;
+// D += a_hi*w_hi + a_hi*w_lo + a_lo*w_hi drops only a_lo*w_lo (~2^-22 relative), the same order as the
+// rounding of a float32 FMA chain of length 64.
+//
+// Warp-specialised CTA of 9 warps: two groups of 4 warps each own a tile of 128 points (thread m of a
+// group owns TMEM lane m) and one warp issues the MMAs for both, so one group's epilogue / spline work on
+// the FP32 pipe overlaps the other group's tensor-core work.  Layer 0 (K = P <= 16) runs on the FP32
+// pipe; every 64x64 hidden layer and the 64 -> T*K output layer are tcgen05.mma.kind::tf32 with M=128,
+// K=8 per instruction, the A operand (activations) read from TENSOR MEMORY, where the epilogue
+// (tcgen05.ld of the accumulator row, BN scale/shift, ReLU, hi/lo split) writes it back with tcgen05.st,
+// and the B operand (weights, split once per forward) from shared memory in the K-major 128-byte-swizzled
+// canonical layout.  The spline (softmax, CDF, bin, Jacobian) runs on the thread's 32 logits in
+// registers.  Groups and the MMA warp hand tiles to each other through mbarriers (128 arrivals when a
+// group's A operand is in TMEM; tcgen05.commit when its accumulator is complete).
+//
+// The same kernel serves the train-mode layer passes of flow_tiled.cu's scheme (statistics pass L: read
+// the stored pre-BN activations of layer L-1, one MMA layer, per-feature sums by recursive-halving warp
+// shuffles, store layer L), whose tile-blocked [tile][64][128] buffers it shares.
+#include <stdlib.h>
+#include "common.cuh"
+#include "flow_fwd_common.cuh"
+
+#define TCM 128              // points per CTA tile (= MMA M)
+#define TCH 64               // hidden width
+#define TC_KT 32             // tf32 elements per 128-byte swizzle row
+#define TC_NOUT 128          // output-layer width handled (T*K <= 128)
+
+// ---- tiny PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+// bounded wait: a broken pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (int it = 0; it < (1 << 22); ++it) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]^T, kind::tf32, cta_group::1 (A from tensor memory)
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in
+// bits [0,14), leading byte offset >> 4 in [16,30) (unused for swizzled K-major: 1), stride byte offset
+// >> 4 in [32,46) (= 1024 B between 8-row groups), version 1 in [46,48), layout type 2 (128B swizzle) in [61,64).
+__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format TF32 (2) at
+// [7,10)/[10,13), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// byte offset of element (row, k) of a [rows x 64] tf32 operand stored as two K-tiles of [rows x 32]
+// (128 B per row, 8-row groups of 1024 B, 16-byte chunks XOR-swizzled with row % 8)
+__host__ __device__ static inline int tc_off(int rows, int row, int k) {
+    const int kt = k >> 5, kk = k & 31;
+    return kt * rows * 128 + (row >> 3) * 1024 + (row & 7) * 128 + ((((kk >> 2) ^ (row & 7)) << 4) | ((kk & 3) << 2));
+}
+
+// floats in one cell's tensor-core weight pack: hidden layers 1..depth-1 (hi, lo) then output (hi, lo)
+__host__ __device__ static inline int tc_cell_floats(const DevFlow& F) { return (F.depth - 1) * 2 * TCH * TCH + 2 * TC_NOUT * TCH; }
+
+__global__ void flow_tc_pack_kernel(DevFlow F, const float* __restrict__ params, float* __restrict__ tcpack) {
+    const int c = blockIdx.y;
+    const DevCell& q = F.cells[c];
+    const float* p = params + q.param_off;
+    char* dst = reinterpret_cast<char*>(tcpack + (size_t)c * tc_cell_floats(F));
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int l = 1; l <= F.depth; ++l) {
+        const bool outl = l == F.depth;
+        const int rows = outl ? TC_NOUT : TCH;
+        const int real_rows = outl ? q.T * F.K : TCH;
+        const float* w = p + F.p_lin(c, l);                     // [rows][64] torch layout (out, in)
+        char* hi = dst + (size_t)(l - 1) * 2 * TCH * TCH * 4;
+        char* lo = hi + (size_t)rows * TCH * 4;
+        for (int i = tid; i < rows * TCH; i += nth) {
+            const int n = i / TCH, k = i - n * TCH;
+            const float v = n < real_rows ? w[(size_t)n * TCH + k] : 0.f;
+            const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            const int o = tc_off(rows, n, k);
+            *reinterpret_cast<float*>(hi + o) = h;
+            *reinterpret_cast<float*>(lo + o) = v - h;
+        }
+    }
+}
+
+
+#define TC_THREADS 288       // 2 groups x 4 warps + 1 MMA warp
+#define TC_COLS_PER_GROUP 256
+#define TC_COL_AHI 128
+#define TC_COL_ALO 192
+
+struct TcSmem {      // byte offsets from the 1024-aligned base
+    int w, w0, aff, bias, st, red, total;
+    int wl[NIS_MAX_HIDDEN + 1];     // per MMA layer l (1..depth): offset of (hi, lo) inside w, or -1
+};
+// MMA layers [l_begin, l_end] are staged (hidden: 2 x 16 KB, output: 2 x 32 KB)
+__host__ __device__ static inline TcSmem tc_layout(const DevFlow& F, int P, int l_begin, int l_end) {
+    TcSmem s;
+    int o = 0;
+    s.w = o;
+    for (int l = 0; l <= F.depth; ++l) {
+        s.wl[l] = -1;
+        if (l >= 1 && l >= l_begin && l <= l_end) { s.wl[l] = o; o += 2 * (l == F.depth ? TC_NOUT : TCH) * TCH * 4; }
+    }
+    s.w0 = o; o += pad8(P) * TCH * 4;
+    s.aff = o; o += (F.depth + 1) * 2 * TCH * 4;
+    s.bias = o; o += TC_NOUT * 4;
+    s.st = o; o += 2 * (F.d + 1) * TCM * 4;
+    o = (o + 7) & ~7;
+    s.red = o; o += (8 * 2 * TCH + 2 * F.maxW) * 8;
+    s.total = o;
+    return s;
+}
+
+#define TC_R32(v, b) "=r"(v[b+0]), "=r"(v[b+1]), "=r"(v[b+2]), "=r"(v[b+3]), "=r"(v[b+4]), "=r"(v[b+5]), "=r"(v[b+6]), "=r"(v[b+7])
+#define TC_W32(v, b) "r"(v[b+0]), "r"(v[b+1]), "r"(v[b+2]), "r"(v[b+3]), "r"(v[b+4]), "r"(v[b+5]), "r"(v[b+6]), "r"(v[b+7])
+
+// 32 consecutive columns of this thread's TMEM lane <-> registers
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* vf) {
+    uint32_t* v = reinterpret_cast<uint32_t*>(vf);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : TC_R32(v, 0), TC_R32(v, 8), TC_R32(v, 16), TC_R32(v, 24)
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const float* vf) {
+    const uint32_t* v = reinterpret_cast<const uint32_t*>(vf);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
+        :: TC_W32(v, 0), TC_W32(v, 8), TC_W32(v, 16), TC_W32(v, 24), "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// BN scale/shift + ReLU of this thread's 64 pre-activations, split into TF32 hi / residual lo, written to
+// the group's A-operand columns of tensor memory
+__device__ __forceinline__ void tc_store_act(const float* v, const float* sc, const float* sh, uint32_t t_hi, uint32_t t_lo) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float a = fmaxf(fmaf(v[32 * h + j], sc[32 * h + j], sh[32 * h + j]), 0.f);
+            hi[j] = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+            lo[j] = a - hi[j];
+        }
+        tc_st32(t_hi + 32 * h, hi);
+        tc_st32(t_lo + 32 * h, lo);
+    }
+    tc_st_wait();
+}
+
+// 3xTF32 product of the group's [128 x 64] activations (TMEM) with a [N x 64] weight matrix (smem): 8 K-steps x 3
+__device__ __forceinline__ void tc_issue_layer(uint32_t tmem_d, uint32_t t_hi, uint32_t t_lo, uint32_t w_hi, uint32_t w_lo,
+                                               int n_rows, uint32_t idesc) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t wo = (ks >> 2) * n_rows * 128 + (ks & 3) * 32;
+        tc_mma_tf32_ts(tmem_d, t_hi + ks * 8, tc_desc(w_hi + wo), idesc, acc);
+        acc = 1;
+        tc_mma_tf32_ts(tmem_d, t_hi + ks * 8, tc_desc(w_lo + wo), idesc, 1);
+        tc_mma_tf32_ts(tmem_d, t_lo + ks * 8, tc_desc(w_hi + wo), idesc, 1);
+    }
+}
+
+// per-feature sums over the 32 lanes of a warp by recursive halving: afterwards lane i holds the sums of
+// features 2i and 2i+1.  62 shuffles instead of 64 x 5.
+__device__ __forceinline__ void tc_warp_feature_sums(const float* v, int lane, float& s0, float& s1) {
+    float a[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const bool up = lane & 16;
+        const float keep = up ? v[i + 32] : v[i], send = up ? v[i] : v[i + 32];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const bool up = lane & 8;
+        const float keep = up ? a[i + 16] : a[i], send = up ? a[i] : a[i + 16];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool up = lane & 4;
+        const float keep = up ? a[i + 8] : a[i], send = up ? a[i] : a[i + 8];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool up = lane & 2;
+        const float keep = up ? a[i + 4] : a[i], send = up ? a[i] : a[i + 4];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool up = lane & 1;
+        const float keep = up ? a[i + 2] : a[i], send = up ? a[i] : a[i + 2];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    s0 = a[0]; s1 = a[1];
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __grid_constant__ DevFlow F, const FwdArgs A,
+                                                                      const float* __restrict__ tcpack) {
+    extern __shared__ char smraw[];
+    __shared__ uint64_t a_ready[2], d_ready[2];
+    __shared__ uint32_t tmem_base_s;
+    char* sm = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = A.c_begin;
+    const DevCell& q = F.cells[c];
+    const int d = F.d, depth = F.depth;
+    // which slice of the cell this launch computes (see the table in flow_tiled.cu / DESIGN.md)
+    const bool stats = A.stats_layer >= 1;
+    const bool from_z = A.zin != nullptr;
+    const int lz = from_z ? (stats ? A.stats_layer - 1 : depth) : 1;      // v starts as z_{lz}
+    const int l_end = stats ? A.stats_layer - 1 : depth;                   // MMA layers lz .. l_end
+    const TcSmem L = tc_layout(F, q.P, lz, l_end);
+    float* w0s = reinterpret_cast<float*>(sm + L.w0);
+    float* affs = reinterpret_cast<float*>(sm + L.aff);
+    float* biass = reinterpret_cast<float*>(sm + L.bias);
+    const float* pk = A.wpack + q.pk_off;
+
+    // ---- one-time setup: weights, barriers, tensor memory ---------------------------------------------
+    for (int l = lz; l <= l_end; ++l) {
+        if (L.wl[l] < 0) continue;
+        const int fl = 2 * (l == depth ? TC_NOUT : TCH) * TCH;
+        const float4* src = reinterpret_cast<const float4*>(tcpack + (size_t)c * tc_cell_floats(F) + (size_t)(l - 1) * 2 * TCH * TCH);
+        float4* dst = reinterpret_cast<float4*>(sm + L.wl[l]);
+        for (int i = tid; i < fl / 4; i += TC_THREADS) dst[i] = src[i];
+    }
+    if (!from_z) {
+        const float* s0 = pk + q.wt_off[0];                       // layer 0, [P][64] k-major
+        for (int i = tid; i < q.P * TCH; i += TC_THREADS) w0s[i] = s0[i];
+    }
+    for (int l = 0; l <= depth; ++l) {
+        const int W = l == 0 ? q.P : TCH, Wp = pad8(W);
+        const float* s = pk + q.aff_off[l];
+        for (int i = tid; i < W; i += TC_THREADS) { affs[l * 2 * TCH + i] = s[i]; affs[l * 2 * TCH + TCH + i] = s[Wp + i]; }
+    }
+    for (int i = tid; i < TC_NOUT; i += TC_THREADS) {
+        const int t = i / F.K, jj = i % F.K;
+        biass[i] = t < q.T ? pk[q.bo_off + t * F.Kpad + jj] : 0.f;
+    }
+    if (tid == 0) {
+        mbar_init(&a_ready[0], TCM); mbar_init(&a_ready[1], TCM);
+        mbar_init(&d_ready[0], 1); mbar_init(&d_ready[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const long long ntiles = (A.B + TCM - 1) / TCM;
+    const long long rowlen = d + 1;
+    double dsum[2] = {0.0, 0.0}, dsq[2] = {0.0, 0.0};
+
+    if (warp == 8) {
+        // ===================== MMA issuer ======================================================
+        if (lane == 0 && lz <= l_end) {
+            uint32_t pa[2] = {0, 0};
+            const uint32_t idesc64 = tc_idesc(TCM, TCH), idesc128 = tc_idesc(TCM, TC_NOUT);
+            for (long long it = 0;; ++it) {
+                const long long t0 = ((long long)blockIdx.x + it * gridDim.x) * 2;
+                if (t0 >= ntiles) break;
+                for (int l = lz; l <= l_end; ++l) {
+                    const bool outl = l == depth;
+                    const int rows = outl ? TC_NOUT : TCH;
+                    const uint32_t whi = smem_u32(sm + L.wl[l]);
+                    for (int g = 0; g < 2; ++g) {
+                        if (t0 + g >= ntiles) continue;
+                        mbar_wait(&a_ready[g], pa[g]);
+                        pa[g] ^= 1;
+                        tc_fence_after();
+                        const uint32_t tb = tmem_base + g * TC_COLS_PER_GROUP;
+                        tc_issue_layer(tb, tb + TC_COL_AHI, tb + TC_COL_ALO, whi, whi + rows * TCH * 4, rows,
+                                       outl ? idesc128 : idesc64);
+                        tc_commit(&d_ready[g]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== point groups ====================================================
+        const int g = warp >> 2, gt = tid & (TCM - 1);
+        float* st = reinterpret_cast<float*>(sm + L.st) + g * (d + 1) * TCM + gt;   // this thread's state row
+        const uint32_t tg = tmem_base + g * TC_COLS_PER_GROUP + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t pd = 0;
+        for (long long it = 0;; ++it) {
+            const long long tile = ((long long)blockIdx.x + it * gridDim.x) * 2 + g;
+            if (tile >= ntiles) break;
+            const long long pt = tile * TCM + gt;
+            const bool valid = pt < A.B;
+            // ---- this thread's point --------------------------------------------------------------
+            if (valid) {
+                if (A.from_state) {
+                    for (int i = 0; i <= d; ++i) st[i * TCM] = A.state_in[pt * rowlen + i];
+                } else {
+                    for (int i = 0; i < d; ++i) st[i * TCM] = load_io(A.in, A.in_dtype, pt * A.in_cols + i);
+                    st[d * TCM] = A.in_cols > d ? load_io(A.in, A.in_dtype, pt * A.in_cols + d) : 1.f;
+                }
+                if (!stats && A.saved && !A.from_state) {
+                    float* sv = A.saved + ((long long)c * A.B + pt) * rowlen;
+                    for (int i = 0; i <= d; ++i) sv[i] = st[i * TCM];
+                }
+            } else {
+                for (int i = 0; i < d; ++i) st[i * TCM] = 0.5f;
+                st[d * TCM] = 1.f;
+            }
+            // ---- v = z_{lz}: stored activations, or layer 0 on the FP32 pipe ---------------------------
+            float v[TCH];
+            if (from_z) {
+                const float* zr = A.zin + (size_t)tile * TCH * TCM + gt;
+#pragma unroll
+                for (int j = 0; j < TCH; ++j) v[j] = zr[(size_t)j * TCM];
+            } else {
+#pragma unroll
+                for (int j = 0; j < TCH; ++j) v[j] = 0.f;
+                for (int k = 0; k < q.P; ++k) {
+                    const float a = fmaf(st[q.feed[k] * TCM], affs[k], affs[TCH + k]);
+                    const float4* wr = reinterpret_cast<const float4*>(w0s + k * TCH);
+#pragma unroll
+                    for (int j4 = 0; j4 < TCH / 4; ++j4) {
+                        const float4 w = wr[j4];
+                        v[4 * j4] = fmaf(a, w.x, v[4 * j4]); v[4 * j4 + 1] = fmaf(a, w.y, v[4 * j4 + 1]);
+                        v[4 * j4 + 2] = fmaf(a, w.z, v[4 * j4 + 2]); v[4 * j4 + 3] = fmaf(a, w.w, v[4 * j4 + 3]);
+                    }
+                }
+            }
+            // ---- MMA layers -------------------------------------------------------------------------------
+            for (int l = lz; l <= l_end; ++l) {
+                tc_store_act(v, affs + l * 2 * TCH, affs + l * 2 * TCH + TCH, tg + TC_COL_AHI, tg + TC_COL_ALO);
+                tc_fence_before();
+                mbar_arrive(&a_ready[g]);
+                mbar_wait(&d_ready[g], pd);
+                pd ^= 1;
+                tc_fence_after();
+                if (l < depth) {
+                    tc_ld32(tg, v);
+                    tc_ld32(tg + 32, v + 32);
+                    tc_ld_wait();
+                }
+            }
+            if (stats) {
+                // ---- statistics pass: sums of z_L over the batch, and z_L itself for the next pass --------
+                if (A.zout) {
+                    float* zr = A.zout + (size_t)tile * TCH * TCM + gt;
+#pragma unroll
+                    for (int j = 0; j < TCH; ++j) zr[(size_t)j * TCM] = v[j];
+                }
+                float sq[TCH];
+#pragma unroll
+                for (int j = 0; j < TCH; ++j) { v[j] = valid ? v[j] : 0.f; sq[j] = v[j] * v[j]; }
+                float s0, s1, q0, q1;
+                tc_warp_feature_sums(v, lane, s0, s1);
+                tc_warp_feature_sums(sq, lane, q0, q1);
+                dsum[0] += (double)s0; dsum[1] += (double)s1; dsq[0] += (double)q0; dsq[1] += (double)q1;
+                continue;
+            }
+            // ---- splines on this thread's logits (PWLin, 32 bins; coupling_cells.py:114-141) ---------------
+            float jfac = 1.f;
+            for (int t = 0; t < q.T; ++t) {
+                float z[32];
+                tc_ld32(tg + t * 32, z);
+                tc_ld_wait();
+                const float xv = st[q.trafo[t] * TCM];
+                const float a = xv * 32.f;
+                int kb = (int)floorf(a);
+                kb = kb < 0 ? 0 : (kb > 31 ? 31 : kb);
+                const float alpha = a - (float)kb;
+                float m = -3.0e38f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { z[j] += biass[t * 32 + j]; m = fmaxf(m, z[j]); }
+                float S = 0.f, C = 0.f, ek = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float e = expf(z[j] - m);
+                    S += e;
+                    C += j < kb ? e : 0.f;
+                    ek = j == kb ? e : ek;
+                }
+                const float inv = 1.f / S;
+                st[q.trafo[t] * TCM] = (ek * alpha + C) * inv;
+                jfac *= ek * inv * 32.f;
+                if (A.bins && valid) A.bins[((long long)c * A.B + pt) * d + t] = kb;
+            }
+            st[d * TCM] *= jfac;
+            // ---- store ----------------------------------------------------------------------------------
+            if (valid) {
+                if (A.state_out) {
+                    float* so = A.state_out + pt * rowlen;
+                    for (int i = 0; i <= d; ++i) so[i] = st[i * TCM];
+                }
+                if (A.to_out) {
+                    for (int i = 0; i < d; ++i) store_io(A.out, A.out_dtype, pt * rowlen + i, st[F.out_perm[i] * TCM]);
+                    store_io(A.out, A.out_dtype, pt * rowlen + d, st[d * TCM]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (!stats) return;
+    // ---- fold the per-warp feature sums (lane i of each warp: features 2i, 2i+1), then the shared finalisation
+    double* red = reinterpret_cast<double*>(sm + L.red);          // [8 warps][2][64]
+    double* sacc = red + 8 * 2 * TCH;                              // [2 * maxW]
+    if (warp < 8) {
+        red[(warp * 2 + 0) * TCH + 2 * lane] = dsum[0]; red[(warp * 2 + 0) * TCH + 2 * lane + 1] = dsum[1];
+        red[(warp * 2 + 1) * TCH + 2 * lane] = dsq[0];  red[(warp * 2 + 1) * TCH + 2 * lane + 1] = dsq[1];
+    }
+    for (int i = tid; i < 2 * F.maxW; i += TC_THREADS) sacc[i] = 0.0;
+    __syncthreads();
+    if (tid < TCH) {
+        double s = 0.0, s2 = 0.0;
+        for (int w = 0; w < 8; ++w) { s += red[(w * 2 + 0) * TCH + tid]; s2 += red[(w * 2 + 1) * TCH + tid]; }
+        sacc[tid] = s; sacc[F.maxW + tid] = s2;
+    }
+    bn_stats_finalize(F, A, sacc, TC_THREADS);
+}
+
+// ---------------------------------------------------------------------------------------------------
+size_t nis_tc_pack_floats(const DevFlow& F) {
+    if (F.depth < 1) return 0;
+    return (size_t)F.n_cells * tc_cell_floats(F);
+}
+
+bool nis_tc_supported(const DevFlow& F, int64_t B, int bn_mode) {
+    (void)bn_mode;
+    const char* off = getenv("NIS_TC");                   // NIS_TC=0 forces the FP32-pipe kernels (test knob)
+    if (off && off[0] == '0') return false;
+    if (F.kind != NIS_KIND_PWLIN || F.depth < 1 || B < 2048 || F.maxW != TCH) return false;
+    for (int l = 0; l < F.depth; ++l) if (F.widths[l] != TCH) return false;
+    if (F.K != 32 || F.nb != 32) return false;
+    for (int c = 0; c < F.n_cells; ++c) {
+        if (F.cells[c].T * F.K > TC_NOUT || F.cells[c].P > 16) return false;
+        if ((size_t)tc_layout(F, F.cells[c].P, 1, F.depth).total + 1024 > 225 * 1024) return false;
+    }
+    return true;
+}
+
+int nis_tc_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream_t s) {
+    flow_tc_pack_kernel<<<dim3(16, F.n_cells), 256, 0, s>>>(F, params, tcpack);
+    NIS_CUDA_CHECK_LAUNCH();
+    return NIS_OK;
+}
+
+int nis_launch_tc(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaStream_t s) {
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    const bool stats = A.stats_layer >= 1;
+    const int lz = A.zin ? (stats ? A.stats_layer - 1 : F.depth) : 1;
+    const int l_end = stats ? A.stats_layer - 1 : F.depth;
+    const size_t smem = (size_t)tc_layout(F, F.cells[A.c_begin].P, lz, l_end).total + 1024;
+    cudaFuncSetAttribute(flow_cell_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long long npairs = ((A.B + TCM - 1) / TCM + 1) / 2;
+    int grid = (int)(npairs < sms ? npairs : sms);
+    flow_cell_tc_kernel<<<grid, TC_THREADS, smem, s>>>(F, A, tcpack);
+    NIS_CUDA_CHECK_LAUNCH();
+    return NIS_OK;
+}
