@@ -87,6 +87,23 @@ def test_forward_matches_oracle_at_size(cfg, mode):
                  fp32_yardstick=ref32)
 
 
+@pytest.mark.parametrize("backend", ["tcgen05", "fp32_tiled_4x8", "fp32_tiled_8x8", "generic"])
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_every_kernel_family_agrees_with_the_oracle_on_cfg2(monkeypatch, backend, mode):
+    """cfg2 is served by the tcgen05 kernel by default; the FP32-pipe register-tiled kernels and the
+    shape-generic kernel stay selectable (library test knobs) and must meet the same parity bar."""
+    env = {"tcgen05": {}, "fp32_tiled_4x8": {"NIS_TC": "0"}, "fp32_tiled_8x8": {"NIS_TC": "0", "NIS_TILED_VARIANT": "8"},
+           "generic": {"NIS_TC": "0", "NIS_DISABLE_TILED": "1"}}[backend]
+    for k in ("NIS_TC", "NIS_TILED_VARIANT", "NIS_DISABLE_TILED"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    test_forward_matches_oracle_at_size(BIG[0], mode)
+    # ragged batch (not a multiple of any tile size) through the same kernels
+    cfg = dict(BIG[0], B=(1 << 13) + 77)
+    test_forward_matches_oracle_at_size(cfg, mode)
+
+
 def test_flow_is_a_bijection_of_the_unit_cube_at_full_size():
     """Size-independent properties at cfg2's full batch (2^22 points): <J> = 1 within Monte Carlo error,
     outputs stay in [0,1], pass-through columns of the last cell are bit-identical to its input."""
