@@ -231,6 +231,7 @@ bool nis_tc_supported(const DevFlow& F, int64_t B, int bn_mode);
 int nis_tc_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream_t s);
 int nis_launch_tc(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaStream_t s);
 int nis_launch_tiled(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
+int nis_launch_col_stats(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 
 static size_t fwd_smem_bytes(const DevFlow& F, int NT) {
     const int bw = F.maxW > F.Kpad ? F.maxW : F.Kpad;
@@ -331,6 +332,8 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
                     A.zin = l >= 2 ? zb[(l - 1) & 1] : nullptr;
                     A.zout = zb[l & 1];
                     rc = tc ? nis_launch_tc(F, A, ws.tcpack, s) : nis_launch_tiled(F, A, s);
+                } else if (tiled && l == 0) {
+                    rc = nis_launch_col_stats(F, A, s);
                 } else {
                     rc = launch_fwd_any(F, A, s);
                 }

@@ -62,6 +62,12 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a,
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -125,11 +131,11 @@ __global__ void flow_tc_pack_kernel(DevFlow F, const float* __restrict__ params,
 #define TC_COL_ALO 192
 
 struct TcSmem {      // byte offsets from the 1024-aligned base
-    int w, w0, aff, bias, st, red, total;
+    int w, w0, aff, bias, st, red, zb, total;
     int wl[NIS_MAX_HIDDEN + 1];     // per MMA layer l (1..depth): offset of (hi, lo) inside w, or -1
 };
 // MMA layers [l_begin, l_end] are staged (hidden: 2 x 16 KB, output: 2 x 32 KB)
-__host__ __device__ static inline TcSmem tc_layout(const DevFlow& F, int P, int l_begin, int l_end) {
+__host__ __device__ static inline TcSmem tc_layout(const DevFlow& F, int P, int l_begin, int l_end, bool from_z = false) {
     TcSmem s;
     int o = 0;
     s.w = o;
@@ -143,6 +149,9 @@ __host__ __device__ static inline TcSmem tc_layout(const DevFlow& F, int P, int 
     s.st = o; o += 2 * (F.d + 1) * TCM * 4;
     o = (o + 7) & ~7;
     s.red = o; o += (8 * 2 * TCH + 2 * F.maxW) * 8;
+    o = (o + 127) & ~127;
+    s.zb = o;                                  // [2 groups][2 buffers][64][128] floats, bulk-copy landing zone
+    if (from_z) o += 2 * 2 * TCH * TCM * 4;
     s.total = o;
     return s;
 }
@@ -243,7 +252,7 @@ __device__ __forceinline__ void tc_warp_feature_sums(const float* v, int lane, f
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __grid_constant__ DevFlow F, const FwdArgs A,
                                                                       const float* __restrict__ tcpack) {
     extern __shared__ char smraw[];
-    __shared__ uint64_t a_ready[2], d_ready[2];
+    __shared__ uint64_t a_ready[2], d_ready[2], z_full[2][2];
     __shared__ uint32_t tmem_base_s;
     char* sm = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -255,7 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
     const bool from_z = A.zin != nullptr;
     const int lz = from_z ? (stats ? A.stats_layer - 1 : depth) : 1;      // v starts as z_{lz}
     const int l_end = stats ? A.stats_layer - 1 : depth;                   // MMA layers lz .. l_end
-    const TcSmem L = tc_layout(F, q.P, lz, l_end);
+    const TcSmem L = tc_layout(F, q.P, lz, l_end, from_z);
     float* w0s = reinterpret_cast<float*>(sm + L.w0);
     float* affs = reinterpret_cast<float*>(sm + L.aff);
     float* biass = reinterpret_cast<float*>(sm + L.bias);
@@ -285,6 +294,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
     if (tid == 0) {
         mbar_init(&a_ready[0], TCM); mbar_init(&a_ready[1], TCM);
         mbar_init(&d_ready[0], 1); mbar_init(&d_ready[1], 1);
+        mbar_init(&z_full[0][0], 1); mbar_init(&z_full[0][1], 1); mbar_init(&z_full[1][0], 1); mbar_init(&z_full[1][1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
@@ -331,9 +341,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
         float* st = reinterpret_cast<float*>(sm + L.st) + g * (d + 1) * TCM + gt;   // this thread's state row
         const uint32_t tg = tmem_base + g * TC_COLS_PER_GROUP + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t pd = 0;
+        // stored activations arrive by bulk copy, one tile ahead: the copy of tile it+1 is issued when tile
+        // it starts (its buffer was last read during tile it-1, which every thread of the group left
+        // before the MMA of that tile could complete)
+        float* zs = reinterpret_cast<float*>(sm + L.zb) + g * 2 * TCH * TCM;
+        constexpr uint32_t ZBYTES = TCH * TCM * 4;
+        if (from_z && gt == 0) {
+            const long long t0 = (long long)blockIdx.x * 2 + g;
+            if (t0 < ntiles) bulk_load(zs, A.zin + (size_t)t0 * TCH * TCM, ZBYTES, &z_full[g][0]);
+        }
         for (long long it = 0;; ++it) {
             const long long tile = ((long long)blockIdx.x + it * gridDim.x) * 2 + g;
             if (tile >= ntiles) break;
+            if (from_z && gt == 0) {
+                const long long tn = ((long long)blockIdx.x + (it + 1) * gridDim.x) * 2 + g;
+                if (tn < ntiles) bulk_load(zs + ((it + 1) & 1) * TCH * TCM, A.zin + (size_t)tn * TCH * TCM, ZBYTES, &z_full[g][(it + 1) & 1]);
+            }
             const long long pt = tile * TCM + gt;
             const bool valid = pt < A.B;
             // ---- this thread's point --------------------------------------------------------------
@@ -355,9 +378,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
             // ---- v = z_{lz}: stored activations, or layer 0 on the FP32 pipe ---------------------------
             float v[TCH];
             if (from_z) {
-                const float* zr = A.zin + (size_t)tile * TCH * TCM + gt;
+                mbar_wait(&z_full[g][it & 1], (uint32_t)((it >> 1) & 1));
+                const float* zr = zs + (it & 1) * TCH * TCM + gt;
 #pragma unroll
-                for (int j = 0; j < TCH; ++j) v[j] = zr[(size_t)j * TCM];
+                for (int j = 0; j < TCH; ++j) v[j] = zr[j * TCM];
             } else {
 #pragma unroll
                 for (int j = 0; j < TCH; ++j) v[j] = 0.f;
@@ -480,6 +504,7 @@ bool nis_tc_supported(const DevFlow& F, int64_t B, int bn_mode) {
     for (int c = 0; c < F.n_cells; ++c) {
         if (F.cells[c].T * F.K > TC_NOUT || F.cells[c].P > 16) return false;
         if ((size_t)tc_layout(F, F.cells[c].P, 1, F.depth).total + 1024 > 225 * 1024) return false;
+        if ((size_t)tc_layout(F, F.cells[c].P, F.depth, F.depth, true).total + 1024 > 226 * 1024) return false;
     }
     return true;
 }
@@ -498,7 +523,7 @@ int nis_launch_tc(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaS
     const bool stats = A.stats_layer >= 1;
     const int lz = A.zin ? (stats ? A.stats_layer - 1 : F.depth) : 1;
     const int l_end = stats ? A.stats_layer - 1 : F.depth;
-    const size_t smem = (size_t)tc_layout(F, F.cells[A.c_begin].P, lz, l_end).total + 1024;
+    const size_t smem = (size_t)tc_layout(F, F.cells[A.c_begin].P, lz, l_end, A.zin != nullptr).total + 1024;
     cudaFuncSetAttribute(flow_cell_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long long npairs = ((A.B + TCM - 1) / TCM + 1) / 2;
     int grid = (int)(npairs < sms ? npairs : sms);

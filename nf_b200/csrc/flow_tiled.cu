@@ -331,6 +331,54 @@ __global__ void __launch_bounds__(M * 8 / TM, (M == 128 && TM == 4) ? 2 : 1) flo
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Batch statistics of the pass-through columns (BN layer 0 of a cell) straight from the state rows: a
+// streaming reduction (the shape-generic statistics pass stages whole tiles through shared memory and
+// costs 10x the HBM time of this read).
+__global__ void __launch_bounds__(256) flow_col_stats_kernel(const __grid_constant__ DevFlow F, const FwdArgs A) {
+    __shared__ double red[8][2][NIS_MAX_DIM];
+    __shared__ double sacc_s[2 * NIS_MAX_WIDTH];
+    const int c = A.c_begin;
+    const DevCell& q = F.cells[c];
+    const int d = F.d, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double s[NIS_MAX_DIM], s2[NIS_MAX_DIM];
+#pragma unroll
+    for (int k = 0; k < NIS_MAX_DIM; ++k) { s[k] = 0.0; s2[k] = 0.0; }
+    for (long long pt = (long long)blockIdx.x * 256 + tid; pt < A.B; pt += (long long)gridDim.x * 256) {
+#pragma unroll
+        for (int k = 0; k < NIS_MAX_DIM; ++k) {
+            if (k < q.P) {
+                const int col = q.feed[k];
+                const float x = A.from_state ? A.state_in[pt * (d + 1) + col] : load_io(A.in, A.in_dtype, pt * A.in_cols + col);
+                s[k] += (double)x; s2[k] += (double)x * (double)x;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NIS_MAX_DIM; ++k) {
+        if (k < q.P) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { s[k] += __shfl_xor_sync(0xffffffffu, s[k], o); s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o); }
+            if (lane == 0) { red[warp][0][k] = s[k]; red[warp][1][k] = s2[k]; }
+        }
+    }
+    for (int i = tid; i < 2 * F.maxW; i += 256) sacc_s[i] = 0.0;
+    __syncthreads();
+    if (tid < q.P) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) { a += red[w][0][tid]; b += red[w][1][tid]; }
+        sacc_s[tid] = a; sacc_s[F.maxW + tid] = b;
+    }
+    bn_stats_finalize(F, A, sacc_s, 256);
+}
+
+int nis_launch_col_stats(const DevFlow& F, const FwdArgs& A, cudaStream_t s) {
+    long long blocks = (A.B + 255) / 256;
+    int grid = (int)(blocks < 592 ? blocks : 592);
+    flow_col_stats_kernel<<<grid, 256, 0, s>>>(F, A);
+    NIS_CUDA_CHECK_LAUNCH();
+    return NIS_OK;
+}
+
 size_t nis_tiled_zbuf_floats(int64_t B) { return (size_t)((B + 255) / 256) * 256 * TH; }
 
 bool nis_tiled_supported(const DevFlow& F, int64_t B) {
