@@ -4,9 +4,9 @@
 // shared pipe, FMA pipe 46 %).  tcgen05.mma reads its operands straight from shared memory and
 // accumulates in tensor memory, so that bound disappears.  To keep the float32 contract (1e-5 on points
 // and log-Jacobians) every conditioner product runs as a 3xTF32 split: a = a_hi + a_lo with a_hi the
-// value truncated to TF32's 10-bit mantissa (exact) and a_lo = a - a_hi (exact in float32), likewise w;
+// value rounded to TF32's 10-bit mantissa and a_lo = a - a_hi (exact in float32, then rounded), likewise w;
 // D += a_hi*w_hi + a_hi*w_lo + a_lo*w_hi drops only a_lo*w_lo (~2^-22 relative), the same order as the
-// rounding of a float32 FMA chain of length 64.
+// rounding of a float32 FMA chain of length 64.  (hi/lo are formed with round-to-nearest, see tf32_rn.)
 //
 // Warp-specialised CTA of 9 warps: two groups of 4 warps each own a tile of 128 points (thread m of a
 // group owns TMEM lane m) and one warp issues the MMAs for both, so one group's epilogue / spline work on
@@ -32,6 +32,13 @@
 #define TC_NOUT 128          // output-layer width handled (T*K <= 128)
 
 // ---- tiny PTX wrappers ------------------------------------------------------------------------------
+// TF32 split with round-to-nearest on both parts: hi = rn_tf32(a), lo = rn_tf32(a - hi).  (Masking the
+// low mantissa bits instead — truncation — leaves a one-sided 2^-20 relative bias in every product,
+// measured as a 5x loss of accuracy on log J; rounding makes the residual ~2^-22 and unbiased.)
+// (integer add + mask on the ALU pipe = cvt.rna.tf32.f32, which would run on the quarter-rate XU pipe)
+__device__ __forceinline__ float tf32_rn(float a) {
+    return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xFFFFE000u);
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -68,6 +75,13 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// 1-D bulk copy shared -> global; the shared source may be reused once wait_group.read has returned
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(TCM) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -116,10 +130,10 @@ __global__ void flow_tc_pack_kernel(DevFlow F, const float* __restrict__ params,
         for (int i = tid; i < rows * TCH; i += nth) {
             const int n = i / TCH, k = i - n * TCH;
             const float v = n < real_rows ? w[(size_t)n * TCH + k] : 0.f;
-            const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            const float h = tf32_rn(v);
             const int o = tc_off(rows, n, k);
             *reinterpret_cast<float*>(hi + o) = h;
-            *reinterpret_cast<float*>(lo + o) = v - h;
+            *reinterpret_cast<float*>(lo + o) = tf32_rn(v - h);
         }
     }
 }
@@ -135,7 +149,7 @@ struct TcSmem {      // byte offsets from the 1024-aligned base
     int wl[NIS_MAX_HIDDEN + 1];     // per MMA layer l (1..depth): offset of (hi, lo) inside w, or -1
 };
 // MMA layers [l_begin, l_end] are staged (hidden: 2 x 16 KB, output: 2 x 32 KB)
-__host__ __device__ static inline TcSmem tc_layout(const DevFlow& F, int P, int l_begin, int l_end, bool from_z = false) {
+__host__ __device__ static inline TcSmem tc_layout(const DevFlow& F, int P, int l_begin, int l_end, bool zstage = false) {
     TcSmem s;
     int o = 0;
     s.w = o;
@@ -151,7 +165,7 @@ __host__ __device__ static inline TcSmem tc_layout(const DevFlow& F, int P, int 
     s.red = o; o += (8 * 2 * TCH + 2 * F.maxW) * 8;
     o = (o + 127) & ~127;
     s.zb = o;                                  // [2 groups][2 buffers][64][128] floats, bulk-copy landing zone
-    if (from_z) o += 2 * 2 * TCH * TCM * 4;
+    if (zstage) o += 2 * 2 * TCH * TCM * 4;
     s.total = o;
     return s;
 }
@@ -189,8 +203,8 @@ __device__ __forceinline__ void tc_store_act(const float* v, const float* sc, co
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const float a = fmaxf(fmaf(v[32 * h + j], sc[32 * h + j], sh[32 * h + j]), 0.f);
-            hi[j] = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
-            lo[j] = a - hi[j];
+            hi[j] = tf32_rn(a);
+            lo[j] = tf32_rn(a - hi[j]);
         }
         tc_st32(t_hi + 32 * h, hi);
         tc_st32(t_lo + 32 * h, lo);
@@ -264,7 +278,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
     const bool from_z = A.zin != nullptr;
     const int lz = from_z ? (stats ? A.stats_layer - 1 : depth) : 1;      // v starts as z_{lz}
     const int l_end = stats ? A.stats_layer - 1 : depth;                   // MMA layers lz .. l_end
-    const TcSmem L = tc_layout(F, q.P, lz, l_end, from_z);
+    const TcSmem L = tc_layout(F, q.P, lz, l_end, from_z || A.zout != nullptr);
     float* w0s = reinterpret_cast<float*>(sm + L.w0);
     float* affs = reinterpret_cast<float*>(sm + L.aff);
     float* biass = reinterpret_cast<float*>(sm + L.bias);
@@ -355,6 +369,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
             if (tile >= ntiles) break;
             if (from_z && gt == 0) {
                 const long long tn = ((long long)blockIdx.x + (it + 1) * gridDim.x) * 2 + g;
+                if (A.zout) bulk_store_wait_read();       // tile it-1's output has left that buffer
                 if (tn < ntiles) bulk_load(zs + ((it + 1) & 1) * TCH * TCM, A.zin + (size_t)tn * TCH * TCM, ZBYTES, &z_full[g][(it + 1) & 1]);
             }
             const long long pt = tile * TCM + gt;
@@ -411,19 +426,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
                 }
             }
             if (stats) {
-                // ---- statistics pass: sums of z_L over the batch, and z_L itself for the next pass --------
-                if (A.zout) {
-                    float* zr = A.zout + (size_t)tile * TCH * TCM + gt;
+                // ---- statistics pass: z_L goes to the staging tile [64][128] (in place over the input tile),
+                //      from there to HBM by ONE bulk store, and its per-feature sums are row sums of the tile
+                float* zo = zs + (it & 1) * TCH * TCM;
+                if (!from_z && gt == 0) bulk_store_wait_read();          // (no prefetch in this pass: guard reuse here)
+                if (!from_z) group_sync(g);
 #pragma unroll
-                    for (int j = 0; j < TCH; ++j) zr[(size_t)j * TCM] = v[j];
+                for (int j = 0; j < TCH; ++j) zo[j * TCM + gt] = valid ? v[j] : 0.f;
+                proxy_fence();
+                group_sync(g);
+                if (gt == 0 && A.zout) bulk_store(A.zout + (size_t)tile * TCH * TCM, zo, ZBYTES);
+                {
+                    const float* row = zo + (gt & 63) * TCM + (gt >> 6) * 64;
+                    float s_ = 0.f, q_ = 0.f;
+#pragma unroll 8
+                    for (int i = 0; i < 64; ++i) {
+                        const float x = row[(i + lane) & 63];
+                        s_ += x; q_ = fmaf(x, x, q_);
+                    }
+                    dsum[0] += (double)s_; dsq[0] += (double)q_;
                 }
-                float sq[TCH];
-#pragma unroll
-                for (int j = 0; j < TCH; ++j) { v[j] = valid ? v[j] : 0.f; sq[j] = v[j] * v[j]; }
-                float s0, s1, q0, q1;
-                tc_warp_feature_sums(v, lane, s0, s1);
-                tc_warp_feature_sums(sq, lane, q0, q1);
-                dsum[0] += (double)s0; dsum[1] += (double)s1; dsq[0] += (double)q0; dsq[1] += (double)q1;
+                group_sync(g);
                 continue;
             }
             // ---- splines on this thread's logits (PWLin, 32 bins; coupling_cells.py:114-141) ---------------
@@ -467,22 +490,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
             }
         }
     }
+    bulk_store_wait_read();
     tc_fence_before();
     __syncthreads();
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     if (!stats) return;
-    // ---- fold the per-warp feature sums (lane i of each warp: features 2i, 2i+1), then the shared finalisation
-    double* red = reinterpret_cast<double*>(sm + L.red);          // [8 warps][2][64]
+    // ---- fold: thread gt of a group holds the sums of feature gt & 63 over half of each of its tiles -----------
+    double* red = reinterpret_cast<double*>(sm + L.red);          // [2][256]: sum / sum of squares per group thread
     double* sacc = red + 8 * 2 * TCH;                              // [2 * maxW]
-    if (warp < 8) {
-        red[(warp * 2 + 0) * TCH + 2 * lane] = dsum[0]; red[(warp * 2 + 0) * TCH + 2 * lane + 1] = dsum[1];
-        red[(warp * 2 + 1) * TCH + 2 * lane] = dsq[0];  red[(warp * 2 + 1) * TCH + 2 * lane + 1] = dsq[1];
-    }
+    if (warp < 8) { red[tid] = dsum[0]; red[256 + tid] = dsq[0]; }
     for (int i = tid; i < 2 * F.maxW; i += TC_THREADS) sacc[i] = 0.0;
     __syncthreads();
     if (tid < TCH) {
         double s = 0.0, s2 = 0.0;
-        for (int w = 0; w < 8; ++w) { s += red[(w * 2 + 0) * TCH + tid]; s2 += red[(w * 2 + 1) * TCH + tid]; }
+        for (int k = 0; k < 4; ++k) { s += red[tid + 64 * k]; s2 += red[256 + tid + 64 * k]; }
         sacc[tid] = s; sacc[F.maxW + tid] = s2;
     }
     bn_stats_finalize(F, A, sacc, TC_THREADS);
@@ -505,6 +526,7 @@ bool nis_tc_supported(const DevFlow& F, int64_t B, int bn_mode) {
         if (F.cells[c].T * F.K > TC_NOUT || F.cells[c].P > 16) return false;
         if ((size_t)tc_layout(F, F.cells[c].P, 1, F.depth).total + 1024 > 225 * 1024) return false;
         if ((size_t)tc_layout(F, F.cells[c].P, F.depth, F.depth, true).total + 1024 > 226 * 1024) return false;
+        if ((size_t)tc_layout(F, F.cells[c].P, 1, 1, true).total + 1024 > 226 * 1024) return false;
     }
     return true;
 }
@@ -523,7 +545,7 @@ int nis_launch_tc(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaS
     const bool stats = A.stats_layer >= 1;
     const int lz = A.zin ? (stats ? A.stats_layer - 1 : F.depth) : 1;
     const int l_end = stats ? A.stats_layer - 1 : F.depth;
-    const size_t smem = (size_t)tc_layout(F, F.cells[A.c_begin].P, lz, l_end, A.zin != nullptr).total + 1024;
+    const size_t smem = (size_t)tc_layout(F, F.cells[A.c_begin].P, lz, l_end, A.zin != nullptr || A.zout != nullptr).total + 1024;
     cudaFuncSetAttribute(flow_cell_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long long npairs = ((A.B + TCM - 1) / TCM + 1) / 2;
     int grid = (int)(npairs < sms ? npairs : sms);
