@@ -1,0 +1,104 @@
+"""Two-GPU checks (NCCL): data-parallel training gradient == single-GPU gradient over the same
+minibatches (one rank = one minibatch, per-rank BN statistics, sum-allreduce), and sharded
+integrate().  Skipped unless two CUDA devices are visible (run with `gpurun --gpus 2`)."""
+import math
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def camel(x):
+    return torch.exp(-((x[:, 0] - 0.75) ** 2 + (x[:, 1] - 0.75) ** 2) / (0.2 ** 2)) + \
+        torch.exp(-((x[:, 0] - 0.25) ** 2 + (x[:, 1] - 0.25) ** 2) / (0.2 ** 2))
+
+
+def _build(dev):
+    from nf_b200.normalizing_flows.manager import PWLinManager
+    torch.manual_seed(5)
+    NF = PWLinManager(n_flow=8)
+    NF.create_model(4, 3, 32, [64, 64], 4)
+    NF._model.to(dev)
+    return NF
+
+
+def _minibatches():
+    g = torch.Generator().manual_seed(99)
+    return [torch.rand(4096, 8, generator=g, dtype=torch.float32).double() for _ in range(2)]
+
+
+def _fun(x):
+    return torch.exp(-((x - 0.5) ** 2).sum(-1) / 0.3)
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from nf_b200.normalizing_flows.manager import BasicManager, PWQuadManager
+        NF = _build(dev)
+        NF._sync_model()
+        model = NF._model.train()
+        mb = _minibatches()[rank].to(dev)
+        XJ = model(NF.format_input(mb, dev))
+        loss = torch.var(_fun(XJ[:, :-1].detach()) * XJ[:, -1]) / world
+        loss.backward()
+        params = [p for p in model.parameters()]
+        BasicManager._allreduce_grads(params)
+        flat = torch.cat([p.grad.reshape(-1) for p in params]).cpu()
+        # sharded integrate of the camel function with an untrained 2-D flow
+        torch.manual_seed(7)
+        Q = PWQuadManager(n_flow=2)
+        Q.create_model(2, 4, [3] * 3, dev=rank)
+        Q._sync_model() if False else None
+        sig, err = Q.integrate(camel, 10, 20000, rank)
+        out.put((rank, flat, float(sig), float(err)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_gradient_equals_single_gpu_and_integrate_shards():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([out.get(timeout=300) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    # single GPU: both minibatches accumulated before one backward (manager.py:219-278)
+    dev = torch.device("cuda", 0)
+    NF = _build(dev)
+    model = NF._model.train()
+    loss = 0
+    for mb in _minibatches():
+        XJ = model(NF.format_input(mb.to(dev), dev))
+        loss = loss + torch.var(_fun(XJ[:, :-1].detach()) * XJ[:, -1])
+    (loss / 2).backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).cpu()
+    scale = float(ref.abs().max())
+    for rank, flat, sig, err in res:
+        assert float((flat - ref).abs().max()) <= 2e-4 * scale, "rank %d gradient differs" % rank
+    assert torch.equal(res[0][1], res[1][1])                     # every rank holds the same reduced gradient
+    analytic = 2 * (0.5 * math.sqrt(0.04 * math.pi) * (math.erf(3.75) + math.erf(1.25))) ** 2
+    assert res[0][2] == res[1][2]                                # identical estimate on every rank
+    assert abs(res[0][2] - analytic) < 5 * math.sqrt(10) * res[0][3]
