@@ -232,6 +232,8 @@ int nis_tc_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream
 int nis_launch_tc(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaStream_t s);
 int nis_launch_tiled(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 int nis_launch_col_stats(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
+bool nis_moments_supported(const DevFlow& F, int c);
+int nis_launch_col_moments(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 
 static size_t fwd_smem_bytes(const DevFlow& F, int NT) {
     const int bw = F.maxW > F.Kpad ? F.maxW : F.Kpad;
@@ -324,12 +326,22 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
         A.state_in = c > 0 ? (saved ? saved + (long long)c * rows : ws.state) : nullptr;
         A.state_out = nullptr; A.to_out = 0;
         float* zb[2] = {ws.bwd, ws.bwd + nis_tiled_zbuf_floats(B)};
+        // BN0 + BN1 from one streaming pass over the pass-through columns (flow_col_moments_kernel), then
+        // the layer passes start at layer 2 (recomputing the K=P layer 0 on the way)
+        const bool moments = tiled && bn_mode == NIS_BN_TRAIN && nis_moments_supported(F, c);
         if (bn_mode == NIS_BN_TRAIN) {
-            for (int l = 0; l <= F.depth; ++l) {
+            int l0 = 0;
+            if (moments) {
+                A.stats_layer = 0;
+                rc = nis_launch_col_moments(F, A, s);
+                if (rc) return rc;
+                l0 = 2;
+            }
+            for (int l = l0; l <= F.depth; ++l) {
                 A.stats_layer = l;
                 if (tiled && l >= 1) {
                     // layer pass: reads the pre-BN activations of layer l-1, writes those of layer l
-                    A.zin = l >= 2 ? zb[(l - 1) & 1] : nullptr;
+                    A.zin = (l >= 2 && !(moments && l == 2)) ? zb[(l - 1) & 1] : nullptr;
                     A.zout = zb[l & 1];
                     rc = tc ? nis_launch_tc(F, A, ws.tcpack, s) : nis_launch_tiled(F, A, s);
                 } else if (tiled && l == 0) {
@@ -341,7 +353,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
             }
         }
         A.stats_layer = -1;
-        A.zin = (tiled && bn_mode == NIS_BN_TRAIN) ? zb[F.depth & 1] : nullptr;
+        A.zin = (tiled && bn_mode == NIS_BN_TRAIN && !(moments && F.depth == 1)) ? zb[F.depth & 1] : nullptr;
         A.zout = nullptr;
         const bool last = c == F.n_cells - 1;
         A.to_out = last;

@@ -371,6 +371,142 @@ __global__ void __launch_bounds__(256) flow_col_stats_kernel(const __grid_consta
     bn_stats_finalize(F, A, sacc_s, 256);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// BN layers 0 AND 1 of a cell from the first and second moments of its pass-through columns.
+// z1 = W0 * a0 with a0 = BN0(x) is linear in x, so its batch mean and variance follow from mean(x) and
+// Cov(x):  mean(z1_j) = sum_k W0[j][k] beta0_k ,  var(z1_j) = w~_j^T Cov(x) w~_j  with
+// w~_jk = W0[j][k] gamma0_k / sqrt(var_k + eps)  — evaluated in float64.  This replaces two passes over
+// the batch (the BN0 statistics pass and the layer-1 statistics pass with its 256 B/point store) by one
+// streaming read of P columns.  Used when P <= 8.
+// ---------------------------------------------------------------------------------------------------
+#define MOM_P 8
+#define MOM_N (MOM_P + MOM_P * (MOM_P + 1) / 2)      // 44 sums
+__global__ void __launch_bounds__(256) flow_col_moments_kernel(const __grid_constant__ DevFlow F, const FwdArgs A) {
+    __shared__ double red[8][MOM_N];
+    __shared__ double tot[MOM_N];
+    __shared__ double sc0s[MOM_P];
+    __shared__ bool s_last;
+    const int c = A.c_begin;
+    const DevCell& q = F.cells[c];
+    const int d = F.d, P = q.P, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc[MOM_N];
+#pragma unroll
+    for (int i = 0; i < MOM_N; ++i) acc[i] = 0.0;
+    for (long long pt = (long long)blockIdx.x * 256 + tid; pt < A.B; pt += (long long)gridDim.x * 256) {
+        float x[MOM_P];
+#pragma unroll
+        for (int k = 0; k < MOM_P; ++k)
+            x[k] = k < P ? (A.from_state ? A.state_in[pt * (d + 1) + q.feed[k]]
+                                         : load_io(A.in, A.in_dtype, pt * A.in_cols + q.feed[k])) : 0.f;
+        int o = MOM_P;
+#pragma unroll
+        for (int k = 0; k < MOM_P; ++k) {
+            acc[k] += (double)x[k];
+#pragma unroll
+            for (int k2 = k; k2 < MOM_P; ++k2) acc[o++] += (double)x[k] * (double)x[k2];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MOM_N; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        if (lane == 0) red[warp][i] = acc[i];
+    }
+    __syncthreads();
+    double* mine = A.partials + (size_t)blockIdx.x * MOM_N;
+    if (tid < MOM_N) {
+        double s_ = 0.0;
+        for (int w = 0; w < 8; ++w) s_ += red[w][tid];
+        mine[tid] = s_;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(A.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < MOM_N) {
+        double s_ = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) s_ += __ldcg(A.partials + (size_t)b * MOM_N + tid);
+        tot[tid] = s_;
+    }
+    __syncthreads();
+    const double n = (double)A.B, mom = (double)F.momentum, unb = A.B > 1 ? n / (n - 1.0) : 1.0;
+    const float* prm = A.params + q.param_off;
+    float* pk = A.wpack + q.pk_off;
+    const int maxW = F.maxW;
+    // index of S2[k][k2], k <= k2, in the packed upper triangle
+    auto s2i = [](int k, int k2) { return MOM_P + k * MOM_P - k * (k - 1) / 2 + (k2 - k); };
+    // ---- BN0 -------------------------------------------------------------------------------------------
+    if (tid < pad8(P)) {
+        float sc = 0.f, sh = 0.f;
+        if (tid < P) {
+            const double mean = tot[tid] / n;
+            double var = tot[s2i(tid, tid)] / n - mean * mean;
+            var = var > 0.0 ? var : 0.0;
+            const double invstd = 1.0 / sqrt(var + (double)F.eps);
+            const double g = (double)prm[tid], b = (double)prm[P + tid];
+            sc = (float)(g * invstd);
+            sh = (float)(b - mean * g * invstd);
+            sc0s[tid] = g * invstd;
+            if (A.bn_saved) { A.bn_saved[q.sv_off + tid] = (float)mean; A.bn_saved[q.sv_off + maxW + tid] = (float)invstd; }
+            if (A.bn_running) {
+                float* rs = A.bn_running + q.bn_off + F.r_mean(c, 0);
+                rs[tid] = (float)((1.0 - mom) * (double)rs[tid] + mom * mean);
+                rs[P + tid] = (float)((1.0 - mom) * (double)rs[P + tid] + mom * var * unb);
+            }
+        }
+        pk[q.aff_off[0] + tid] = sc;
+        pk[q.aff_off[0] + pad8(P) + tid] = sh;
+    }
+    __syncthreads();
+    // ---- BN1 from the moments ------------------------------------------------------------------------------
+    const int H = F.widths[0], Hp = pad8(H);
+    const float* W0 = prm + F.p_lin(c, 0);                 // [H][P]
+    const float* g1 = prm + F.p_bn_gamma(c, 1);
+    for (int j = tid; j < Hp; j += 256) {
+        float sc = 0.f, sh = 0.f;
+        if (j < H) {
+            double mean1 = 0.0, var1 = 0.0;
+            for (int k = 0; k < P; ++k) {
+                const double wk = (double)W0[j * P + k];
+                mean1 += wk * (double)prm[P + k];
+                const double mk = tot[k] / n;
+                for (int k2 = 0; k2 < P; ++k2) {
+                    const double cov = tot[k <= k2 ? s2i(k, k2) : s2i(k2, k)] / n - mk * (tot[k2] / n);
+                    var1 += wk * sc0s[k] * (double)W0[j * P + k2] * sc0s[k2] * cov;
+                }
+            }
+            var1 = var1 > 0.0 ? var1 : 0.0;
+            const double invstd = 1.0 / sqrt(var1 + (double)F.eps);
+            sc = (float)((double)g1[j] * invstd);
+            sh = (float)((double)g1[H + j] - mean1 * (double)g1[j] * invstd);
+            if (A.bn_saved) {
+                A.bn_saved[q.sv_off + 2 * maxW + j] = (float)mean1;
+                A.bn_saved[q.sv_off + 2 * maxW + maxW + j] = (float)invstd;
+            }
+            if (A.bn_running) {
+                float* rs = A.bn_running + q.bn_off + F.r_mean(c, 1);
+                rs[j] = (float)((1.0 - mom) * (double)rs[j] + mom * mean1);
+                rs[H + j] = (float)((1.0 - mom) * (double)rs[H + j] + mom * var1 * unb);
+            }
+        }
+        pk[q.aff_off[1] + j] = sc;
+        pk[q.aff_off[1] + Hp + j] = sh;
+    }
+    if (tid == 0) *A.counter = 0u;
+}
+
+bool nis_moments_supported(const DevFlow& F, int c) { return F.depth >= 1 && F.cells[c].P <= MOM_P; }
+
+int nis_launch_col_moments(const DevFlow& F, const FwdArgs& A, cudaStream_t s) {
+    long long blocks = (A.B + 255) / 256;
+    int grid = (int)(blocks < 592 ? blocks : 592);
+    flow_col_moments_kernel<<<grid, 256, 0, s>>>(F, A);
+    NIS_CUDA_CHECK_LAUNCH();
+    return NIS_OK;
+}
+
 int nis_launch_col_stats(const DevFlow& F, const FwdArgs& A, cudaStream_t s) {
     long long blocks = (A.B + 255) / 256;
     int grid = (int)(blocks < 592 ? blocks : 592);
