@@ -302,8 +302,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = world * N_POINTS / (ms * 1e-3)
     n_cells, depth = 6, 3
-    # pack + tensor-core weight pack + per cell (column statistics, `depth` layer passes, final pass)
-    launches_per_step = 2 + n_cells * (depth + 2) + (1 if world > 1 else 0)
+    # pack + tensor-core weight pack + per cell (column moments -> BN0/BN1, depth-1 layer passes, final pass)
+    launches_per_step = 2 + n_cells * (depth + 1) + (1 if world > 1 else 0)
 
     # ---- end to end through the public API from pinned host buffers ---------------------------------
     # Every step copies its 2^22 points host->device and its [2^22, 9] result device->host inside the timed
@@ -368,7 +368,8 @@ def main():
         tfl_exec = N_POINTS * tensor_flop_pt / (ms * 1e-3) / 1e12
         tf32_peak = pk["bf16_tflops"] / 2.0
         tfl = N_POINTS * FLOP_PER_POINT / (ms * 1e-3) / 1e12
-        train_bytes_pt = n_cells * (36 + (36 + 256) + 2 * (depth - 1) * 256 + (256 + 36 + 36))    # layer-pass design
+        # moments pass reads the rows; first layer pass reads rows, writes z2; later passes read+write 256 B; final
+        train_bytes_pt = n_cells * (36 + (36 + 256) + 2 * (depth - 2) * 256 + (256 + 36 + 36))
         gbs_design = N_POINTS * train_bytes_pt / (ms * 1e-3) / 1e9
         gbs = N_POINTS * IO_BYTES_PER_POINT / (ms * 1e-3) / 1e9
         line["roofline"] = {
@@ -376,7 +377,7 @@ def main():
             "traffic": None,
             "peak_kind": "%s bf16 cuBLAS peak / 2 (kind::tf32 runs at half the bf16 rate)" % peak_kind,
             "kernel": "flow_cell_tc_kernel: %d launches per step (per cell %d train-mode layer passes + 1 final pass) "
-                      "+ %d flow_col_stats_kernel" % (n_cells * (depth + 1), depth, n_cells),
+                      "+ %d flow_col_moments_kernel" % (n_cells * depth, depth - 1, n_cells),
             "tensor_flop_per_point": tensor_flop_pt,
             "note": "executed TF32 flops (3xTF32 split: 3 tensor MACs per conditioner MAC); the step is not "
                     "tensor-bound: see hbm_design and fp32_equivalent",
