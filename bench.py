@@ -221,6 +221,59 @@ def workload_config(points):
             "l2": "inputs larger than L2 (134 MB fp32 points per step > 126 MB)"}
 
 
+def bench_train_step(steps, warmup, world, dev):
+    """variance-loss training step of the cfg2 flow — forward + fused backward on a
+    per-rank minibatch of 2^16 fresh points, gradient sum-allreduce (NCCL) when N > 1."""
+    from nf_b200.normalizing_flows.manager import BasicManager
+    NF = build_flow()
+    model = NF._model.train()
+    params = list(model.parameters())
+    n = 1 << 16
+    x = torch.rand(n, 8, device=dev, dtype=torch.float32)
+    f = torch.exp(-((x - 0.5) ** 2).sum(-1) / 0.2)
+
+    def step():
+        model.zero_grad(set_to_none=False)
+        XJ = model(x)
+        torch.var(f * XJ[:, -1]).backward()
+        if world > 1:
+            BasicManager._allreduce_grads(params)
+
+    ms = time_steps(step, steps, warmup, world)
+    return {"metric": "nis_train_step_points_per_sec", "value": world * n / (ms * 1e-3), "unit": "points/s",
+            "ms_per_step": ms, "config": {"workload": "cfg2 flow, variance loss, forward + fused backward "
+                                          "(+ gradient all-reduce), 2^16 points per rank per step"}}
+
+
+def bench_integrate(world, dev):
+    """SURVEY.md 8(d)(iv) / BASELINE configs[3]: end-to-end NIS integrate — 8D PWQuad flow (6 mask cells, 32
+    bins, [64]*3) -> RAMBO 2->4 massless at E_cm = 1000 -> |M|^2 = 1, through the public API
+    (PWQuadManager.integrate + FlatInvertiblePhasespace); the estimate has the known answer
+    0.0664828... (flat weight / 2s), since the flow is a bijection of the unit cube."""
+    from nf_b200.normalizing_flows.manager import PWQuadManager
+    from nf_b200.PhaseSpace.flat_phase_space_generator import FlatInvertiblePhasespace
+    torch.manual_seed(1234)
+    NF = PWQuadManager(n_flow=8)
+    NF.create_model(6, 32, [64] * 3, dev=dev.index)
+    ps = FlatInvertiblePhasespace([0.0] * 2, [0.0] * 4)
+    ps.check_nan = False
+
+    def f(X):
+        return ps.generateKinematics_batch(1000.0, X, momenta=False)[1]
+
+    nitn, neval = 4, (1 << 20) * world
+    NF.integrate(f, 1, neval, dev.index)                      # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sig, err = NF.integrate(f, nitn, neval, dev.index)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"metric": "nis_integrate_points_per_sec", "value": nitn * neval / dt, "unit": "points/s",
+            "estimate": float(sig), "reported_error": float(err), "known_answer": 0.06648282151394422,
+            "config": {"workload": "configs[3]: 8D PWQuad flow -> RAMBO 2->4 massless -> |M|^2=1, nitn=%d x neval=%d "
+                                   "sharded over the ranks, sum-allreduce of the moments" % (nitn, neval)}}
+
+
 def bench_rambo(steps, warmup, world, hbm_peak, peak_kind):
     from nf_b200.PhaseSpace.flat_phase_space_generator import FlatInvertiblePhasespace
     ps = FlatInvertiblePhasespace([100.0] * 2, [100.0] * 4, pdf=None, pdf_active=False)
@@ -407,6 +460,8 @@ def main():
         del x
         torch.cuda.empty_cache()
         line["rambo"] = bench_rambo(max(3, args.steps // 2), args.warmup, world, pk["hbm_gbs"], peak_kind)
+        line["train_step"] = bench_train_step(max(3, args.steps // 2), args.warmup, world, dev)
+        line["integrate"] = bench_integrate(world, dev)
         if rank == 0 and world == 1:
             threads = os.cpu_count() or 1
             sample = 1 << 17
