@@ -230,6 +230,7 @@ size_t nis_tiled_zbuf_floats(int64_t B);
 bool nis_tc_supported(const DevFlow& F, int64_t B, int bn_mode);
 int nis_tc_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream_t s);
 int nis_launch_tc(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaStream_t s);
+bool nis_tc_split_eval(const DevFlow& F);
 int nis_launch_tiled(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 int nis_launch_col_stats(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 bool nis_moments_supported(const DevFlow& F, int c);
@@ -249,7 +250,7 @@ extern "C" size_t nis_flow_workspace_bytes(const NisFlowDesc* desc, int64_t B) {
     size_t fwd = nis_flow_carve(F, B, nullptr, &ws);
     // the backward scratch and the tiled train path's activation buffers are never live together
     size_t tail = nis_flow_bwd_scratch_floats(F, B);
-    const size_t zfl = nis_tiled_supported(F, B) ? 2 * nis_tiled_zbuf_floats(B) : 0;
+    const size_t zfl = (nis_tiled_supported(F, B) || nis_tc_supported(F, B, NIS_BN_TRAIN)) ? 2 * nis_tiled_zbuf_floats(B) : 0;
     if (zfl > tail) tail = zfl;
     return fwd + sizeof(float) * tail + 256;
 }
@@ -308,9 +309,10 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     A.saved = saved; A.bins = bins_out;
     A.params = params; A.wpack = ws.wpack; A.bn_running = bn_running; A.bn_saved = bn_saved;
     A.partials = ws.partials; A.counter = ws.counter; A.B = B;
-    A.zin = nullptr; A.zout = nullptr;
-    const bool tiled = nis_tiled_supported(F, B);
-    const bool tc = tiled && nis_tc_supported(F, B, bn_mode);
+    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0;
+    // per-cell launch sequences: tcgen05 kernel where it applies, else the FP32 register-tiled kernel
+    const bool tc = nis_tc_supported(F, B, bn_mode);
+    const bool tiled = tc || nis_tiled_supported(F, B);
     if (tc) { rc = nis_tc_pack(F, params, ws.tcpack, s); if (rc) return rc; }
     const long long rows = (long long)B * (F.d + 1);
     if (bn_mode == NIS_BN_EVAL && !tiled) {
@@ -355,6 +357,13 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
         A.stats_layer = -1;
         A.zin = (tiled && bn_mode == NIS_BN_TRAIN && !(moments && F.depth == 1)) ? zb[F.depth & 1] : nullptr;
         A.zout = nullptr;
+        if (tc && bn_mode == NIS_BN_EVAL && nis_tc_split_eval(F)) {
+            // eval, PWQuad: hidden layers in one launch (activations of the last hidden layer to HBM), then the final pass
+            A.stats_layer = F.depth; A.no_stats = 1; A.zin = nullptr; A.zout = zb[F.depth & 1];
+            rc = nis_launch_tc(F, A, ws.tcpack, s);
+            if (rc) return rc;
+            A.stats_layer = -1; A.no_stats = 0; A.zin = zb[F.depth & 1]; A.zout = nullptr;
+        }
         const bool last = c == F.n_cells - 1;
         A.to_out = last;
         A.state_out = saved ? saved + (long long)(c + 1) * rows : (last ? nullptr : ws.state);

@@ -15,6 +15,7 @@ struct FwdArgs {
     long long B; int c_begin, c_end, stats_layer;
     const float* zin;                            // tiled train path: pre-BN activations of the layer below,
     float* zout;                                 // tile-blocked [tile][64][M] (written by a statistics pass)
+    int no_stats;                                // layer pass that only stores its activations (eval-mode split cell)
 };
 
 

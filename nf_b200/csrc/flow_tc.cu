@@ -24,12 +24,13 @@
 // shuffles, store layer L), whose tile-blocked [tile][64][128] buffers it shares.
 #include <stdlib.h>
 #include "common.cuh"
+#include "spline.cuh"
 #include "flow_fwd_common.cuh"
 
 #define TCM 128              // points per CTA tile (= MMA M)
 #define TCH 64               // hidden width
 #define TC_KT 32             // tf32 elements per 128-byte swizzle row
-#define TC_NOUT 128          // output-layer width handled (T*K <= 128)
+#define TC_NOUT 128          // widest output-layer MMA block
 
 // ---- tiny PTX wrappers ------------------------------------------------------------------------------
 // TF32 split with round-to-nearest on both parts: hi = rn_tf32(a), lo = rn_tf32(a - hi).  (Masking the
@@ -111,8 +112,22 @@ __host__ __device__ static inline int tc_off(int rows, int row, int k) {
     return kt * rows * 128 + (row >> 3) * 1024 + (row & 7) * 128 + ((((kk >> 2) ^ (row & 7)) << 4) | ((kk & 3) << 2));
 }
 
-// floats in one cell's tensor-core weight pack: hidden layers 1..depth-1 (hi, lo) then output (hi, lo)
-__host__ __device__ static inline int tc_cell_floats(const DevFlow& F) { return (F.depth - 1) * 2 * TCH * TCH + 2 * TC_NOUT * TCH; }
+// Output layer as a sequence of MMA blocks: PWLin with 32 bins -> ONE block of N=128 covering four
+// transformed dimensions; otherwise (PWQuad with 32 bins: 65 logits per dimension) one block of N=80 per
+// transformed dimension, issued one after the other into the same accumulator columns.
+__host__ __device__ static inline int tc_out_n(const DevFlow& F) { return F.K == 32 ? 128 : 80; }
+__host__ __device__ static inline int tc_out_tper(const DevFlow& F) { return F.K == 32 ? 4 : 1; }
+__host__ __device__ static inline int tc_out_slot(const DevFlow& F) { return F.K == 32 ? 32 : 80; }
+__host__ __device__ static inline int tc_out_blocks(const DevFlow& F, int T) { return (T + tc_out_tper(F) - 1) / tc_out_tper(F); }
+__host__ __device__ static inline int tc_max_blocks(const DevFlow& F) {
+    int m = 1;
+    for (int c = 0; c < F.n_cells; ++c) { const int b = tc_out_blocks(F, F.cells[c].T); m = b > m ? b : m; }
+    return m;
+}
+// floats in one cell's tensor-core weight pack: hidden layers 1..depth-1 (hi, lo), then the output blocks (hi, lo)
+__host__ __device__ static inline int tc_cell_floats(const DevFlow& F) {
+    return (F.depth - 1) * 2 * TCH * TCH + tc_max_blocks(F) * 2 * tc_out_n(F) * TCH;
+}
 
 __global__ void flow_tc_pack_kernel(DevFlow F, const float* __restrict__ params, float* __restrict__ tcpack) {
     const int c = blockIdx.y;
@@ -120,18 +135,30 @@ __global__ void flow_tc_pack_kernel(DevFlow F, const float* __restrict__ params,
     const float* p = params + q.param_off;
     char* dst = reinterpret_cast<char*>(tcpack + (size_t)c * tc_cell_floats(F));
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (int l = 1; l <= F.depth; ++l) {
-        const bool outl = l == F.depth;
-        const int rows = outl ? TC_NOUT : TCH;
-        const int real_rows = outl ? q.T * F.K : TCH;
-        const float* w = p + F.p_lin(c, l);                     // [rows][64] torch layout (out, in)
+    for (int l = 1; l < F.depth; ++l) {
+        const float* w = p + F.p_lin(c, l);                     // [64][64] torch layout (out, in)
         char* hi = dst + (size_t)(l - 1) * 2 * TCH * TCH * 4;
-        char* lo = hi + (size_t)rows * TCH * 4;
-        for (int i = tid; i < rows * TCH; i += nth) {
+        char* lo = hi + (size_t)TCH * TCH * 4;
+        for (int i = tid; i < TCH * TCH; i += nth) {
             const int n = i / TCH, k = i - n * TCH;
-            const float v = n < real_rows ? w[(size_t)n * TCH + k] : 0.f;
+            const float v = w[(size_t)n * TCH + k];
             const float h = tf32_rn(v);
-            const int o = tc_off(rows, n, k);
+            const int o = tc_off(TCH, n, k);
+            *reinterpret_cast<float*>(hi + o) = h;
+            *reinterpret_cast<float*>(lo + o) = tf32_rn(v - h);
+        }
+    }
+    const float* wo = p + F.p_lin(c, F.depth);                  // [T*K][64]
+    const int Nb = tc_out_n(F), tper = tc_out_tper(F), slot = tc_out_slot(F);
+    for (int b = 0; b < tc_out_blocks(F, q.T); ++b) {
+        char* hi = dst + (size_t)(F.depth - 1) * 2 * TCH * TCH * 4 + (size_t)b * 2 * Nb * TCH * 4;
+        char* lo = hi + (size_t)Nb * TCH * 4;
+        for (int i = tid; i < Nb * TCH; i += nth) {
+            const int n = i / TCH, k = i - n * TCH;
+            const int t = b * tper + n / slot, jj = n % slot;
+            const float v = (t < q.T && jj < F.K) ? wo[((size_t)t * F.K + jj) * TCH + k] : 0.f;
+            const float h = tf32_rn(v);
+            const int o = tc_off(Nb, n, k);
             *reinterpret_cast<float*>(hi + o) = h;
             *reinterpret_cast<float*>(lo + o) = tf32_rn(v - h);
         }
@@ -155,11 +182,14 @@ __host__ __device__ static inline TcSmem tc_layout(const DevFlow& F, int P, int 
     s.w = o;
     for (int l = 0; l <= F.depth; ++l) {
         s.wl[l] = -1;
-        if (l >= 1 && l >= l_begin && l <= l_end) { s.wl[l] = o; o += 2 * (l == F.depth ? TC_NOUT : TCH) * TCH * 4; }
+        if (l >= 1 && l >= l_begin && l <= l_end) {
+            s.wl[l] = o;
+            o += l == F.depth ? tc_max_blocks(F) * 2 * tc_out_n(F) * TCH * 4 : 2 * TCH * TCH * 4;
+        }
     }
     s.w0 = o; o += pad8(P) * TCH * 4;
     s.aff = o; o += (F.depth + 1) * 2 * TCH * 4;
-    s.bias = o; o += TC_NOUT * 4;
+    s.bias = o; o += tc_max_blocks(F) * tc_out_n(F) * 4;
     s.st = o; o += 2 * (F.d + 1) * TCM * 4;
     o = (o + 7) & ~7;
     s.red = o; o += (8 * 2 * TCH + 2 * F.maxW) * 8;
@@ -181,6 +211,14 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* vf) {
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
         : TC_R32(v, 0), TC_R32(v, 8), TC_R32(v, 16), TC_R32(v, 24)
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* vf) {
+    uint32_t* v = reinterpret_cast<uint32_t*>(vf);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : TC_R32(v, 0), TC_R32(v, 8)
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -263,6 +301,51 @@ __device__ __forceinline__ void tc_warp_feature_sums(const float* v, int lane, f
     s0 = a[0]; s1 = a[1];
 }
 
+// PWQuad with 32 bins on a register-resident logit vector z[0..64] (33 vertex heights, 32 widths): the
+// reference's map (coupling_cells.py:167-225, see spline.cuh::pwquad_fwd) with static indexing only — the bin
+// is found by counting edges, the per-bin quantities by predicated accumulation.
+__device__ __forceinline__ void pwquad32_regs(const float* z, float x, float& y, float& f, int& kbin) {
+    float mv = z[0], mw = z[33];
+#pragma unroll
+    for (int j = 1; j <= 32; ++j) mv = fmaxf(mv, z[j]);
+#pragma unroll
+    for (int j = 1; j < 32; ++j) mw = fmaxf(mw, z[33 + j]);
+    float w[32], v[33];
+    double Sw = 0.0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { w[j] = expf(z[33 + j] - mw); Sw += (double)w[j]; }
+#pragma unroll
+    for (int j = 0; j <= 32; ++j) v[j] = expf(z[j] - mv);
+    double Araw = 0.0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) Araw += 0.5 * ((double)v[j] + (double)v[j + 1]) * (double)w[j];
+    const float xb = x > NIS_QUAD_CLAMP ? NIS_QUAD_CLAMP : x;
+    const double target = (double)xb * Sw;
+    int k = 0;
+    double cum = 0.0;
+#pragma unroll
+    for (int j = 0; j < 31; ++j) { cum += (double)w[j]; k += cum <= target ? 1 : 0; }
+    double cw = 0.0, ca = 0.0;
+    float wk = 0.f, vk = 0.f, vk1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const bool below = j < k;
+        cw += below ? (double)w[j] : 0.0;
+        ca += below ? 0.5 * ((double)v[j] + (double)v[j + 1]) * (double)w[j] : 0.0;
+        wk = j == k ? w[j] : wk;
+        vk = j == k ? v[j] : vk;
+        vk1 = j == k ? v[j + 1] : vk1;
+    }
+    const float invA = (float)(Sw / Araw);
+    const float alpha = (float)((target - cw) / (double)wk);
+    const float Vk = vk * invA, Vk1 = vk1 * invA;
+    const float Wk = (float)((double)wk / Sw);
+    y = alpha * alpha * 0.5f * (Vk1 - Vk) * Wk + alpha * Vk * Wk + (float)(ca / Araw);
+    f = Vk + alpha * (Vk1 - Vk);
+    kbin = k;
+}
+
+template <int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __grid_constant__ DevFlow F, const FwdArgs A,
                                                                       const float* __restrict__ tcpack) {
     extern __shared__ char smraw[];
@@ -278,7 +361,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
     const bool from_z = A.zin != nullptr;
     const int lz = from_z ? (stats ? A.stats_layer - 1 : depth) : 1;      // v starts as z_{lz}
     const int l_end = stats ? A.stats_layer - 1 : depth;                   // MMA layers lz .. l_end
-    const TcSmem L = tc_layout(F, q.P, lz, l_end, from_z || A.zout != nullptr);
+    // stored activations are staged through shared memory (bulk copies) unless the out-layer weights of a
+    // PWQuad final pass leave no room: then the rows are read straight from global memory
+    const bool zst = (from_z || A.zout != nullptr) && (stats || F.K == 32);
+    const TcSmem L = tc_layout(F, q.P, lz, l_end, zst);
     float* w0s = reinterpret_cast<float*>(sm + L.w0);
     float* affs = reinterpret_cast<float*>(sm + L.aff);
     float* biass = reinterpret_cast<float*>(sm + L.bias);
@@ -287,7 +373,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
     // ---- one-time setup: weights, barriers, tensor memory ---------------------------------------------
     for (int l = lz; l <= l_end; ++l) {
         if (L.wl[l] < 0) continue;
-        const int fl = 2 * (l == depth ? TC_NOUT : TCH) * TCH;
+        const int fl = l == depth ? tc_out_blocks(F, q.T) * 2 * tc_out_n(F) * TCH : 2 * TCH * TCH;
         const float4* src = reinterpret_cast<const float4*>(tcpack + (size_t)c * tc_cell_floats(F) + (size_t)(l - 1) * 2 * TCH * TCH);
         float4* dst = reinterpret_cast<float4*>(sm + L.wl[l]);
         for (int i = tid; i < fl / 4; i += TC_THREADS) dst[i] = src[i];
@@ -301,9 +387,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
         const float* s = pk + q.aff_off[l];
         for (int i = tid; i < W; i += TC_THREADS) { affs[l * 2 * TCH + i] = s[i]; affs[l * 2 * TCH + TCH + i] = s[Wp + i]; }
     }
-    for (int i = tid; i < TC_NOUT; i += TC_THREADS) {
-        const int t = i / F.K, jj = i % F.K;
-        biass[i] = t < q.T ? pk[q.bo_off + t * F.Kpad + jj] : 0.f;
+    {
+        const int Nb = tc_out_n(F), tper = tc_out_tper(F), slot = tc_out_slot(F);
+        for (int i = tid; i < tc_out_blocks(F, q.T) * Nb; i += TC_THREADS) {
+            const int b = i / Nb, n = i - b * Nb, t = b * tper + n / slot, jj = n % slot;
+            biass[i] = (t < q.T && jj < F.K) ? pk[q.bo_off + t * F.Kpad + jj] : 0.f;
+        }
     }
     if (tid == 0) {
         mbar_init(&a_ready[0], TCM); mbar_init(&a_ready[1], TCM);
@@ -328,23 +417,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
         // ===================== MMA issuer ======================================================
         if (lane == 0 && lz <= l_end) {
             uint32_t pa[2] = {0, 0};
-            const uint32_t idesc64 = tc_idesc(TCM, TCH), idesc128 = tc_idesc(TCM, TC_NOUT);
+            const int Nb = tc_out_n(F), nblk = tc_out_blocks(F, q.T);
+            const uint32_t idesc64 = tc_idesc(TCM, TCH), idescO = tc_idesc(TCM, Nb);
             for (long long it = 0;; ++it) {
                 const long long t0 = ((long long)blockIdx.x + it * gridDim.x) * 2;
                 if (t0 >= ntiles) break;
                 for (int l = lz; l <= l_end; ++l) {
                     const bool outl = l == depth;
-                    const int rows = outl ? TC_NOUT : TCH;
-                    const uint32_t whi = smem_u32(sm + L.wl[l]);
-                    for (int g = 0; g < 2; ++g) {
-                        if (t0 + g >= ntiles) continue;
-                        mbar_wait(&a_ready[g], pa[g]);
-                        pa[g] ^= 1;
-                        tc_fence_after();
-                        const uint32_t tb = tmem_base + g * TC_COLS_PER_GROUP;
-                        tc_issue_layer(tb, tb + TC_COL_AHI, tb + TC_COL_ALO, whi, whi + rows * TCH * 4, rows,
-                                       outl ? idesc128 : idesc64);
-                        tc_commit(&d_ready[g]);
+                    const int nb_ = outl ? nblk : 1;
+                    for (int b = 0; b < nb_; ++b) {
+                        const int rows = outl ? Nb : TCH;
+                        const uint32_t whi = smem_u32(sm + L.wl[l]) + (outl ? (uint32_t)b * 2 * Nb * TCH * 4 : 0u);
+                        for (int g = 0; g < 2; ++g) {
+                            if (t0 + g >= ntiles) continue;
+                            mbar_wait(&a_ready[g], pa[g]);
+                            pa[g] ^= 1;
+                            tc_fence_after();
+                            const uint32_t tb = tmem_base + g * TC_COLS_PER_GROUP;
+                            tc_issue_layer(tb, tb + TC_COL_AHI, tb + TC_COL_ALO, whi, whi + rows * TCH * 4, rows,
+                                           outl ? idescO : idesc64);
+                            tc_commit(&d_ready[g]);
+                        }
                     }
                 }
             }
@@ -360,14 +453,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
         // before the MMA of that tile could complete)
         float* zs = reinterpret_cast<float*>(sm + L.zb) + g * 2 * TCH * TCM;
         constexpr uint32_t ZBYTES = TCH * TCM * 4;
-        if (from_z && gt == 0) {
+        if (from_z && zst && gt == 0) {
             const long long t0 = (long long)blockIdx.x * 2 + g;
             if (t0 < ntiles) bulk_load(zs, A.zin + (size_t)t0 * TCH * TCM, ZBYTES, &z_full[g][0]);
         }
         for (long long it = 0;; ++it) {
             const long long tile = ((long long)blockIdx.x + it * gridDim.x) * 2 + g;
             if (tile >= ntiles) break;
-            if (from_z && gt == 0) {
+            if (from_z && zst && gt == 0) {
                 const long long tn = ((long long)blockIdx.x + (it + 1) * gridDim.x) * 2 + g;
                 if (A.zout) bulk_store_wait_read();       // tile it-1's output has left that buffer
                 if (tn < ntiles) bulk_load(zs + ((it + 1) & 1) * TCH * TCM, A.zin + (size_t)tn * TCH * TCM, ZBYTES, &z_full[g][(it + 1) & 1]);
@@ -392,11 +485,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
             }
             // ---- v = z_{lz}: stored activations, or layer 0 on the FP32 pipe ---------------------------
             float v[TCH];
-            if (from_z) {
+            if (from_z && zst) {
                 mbar_wait(&z_full[g][it & 1], (uint32_t)((it >> 1) & 1));
                 const float* zr = zs + (it & 1) * TCH * TCM + gt;
 #pragma unroll
                 for (int j = 0; j < TCH; ++j) v[j] = zr[j * TCM];
+            } else if (from_z) {
+                const float* zr = A.zin + (size_t)tile * TCH * TCM + gt;
+#pragma unroll
+                for (int j = 0; j < TCH; ++j) v[j] = zr[(size_t)j * TCM];
             } else {
 #pragma unroll
                 for (int j = 0; j < TCH; ++j) v[j] = 0.f;
@@ -411,19 +508,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
                     }
                 }
             }
-            // ---- MMA layers -------------------------------------------------------------------------------
-            for (int l = lz; l <= l_end; ++l) {
+            // ---- hidden MMA layers ------------------------------------------------------------------------
+            const int l_hid = l_end < depth ? l_end : depth - 1;
+            for (int l = lz; l <= l_hid; ++l) {
                 tc_store_act(v, affs + l * 2 * TCH, affs + l * 2 * TCH + TCH, tg + TC_COL_AHI, tg + TC_COL_ALO);
                 tc_fence_before();
                 mbar_arrive(&a_ready[g]);
                 mbar_wait(&d_ready[g], pd);
                 pd ^= 1;
                 tc_fence_after();
-                if (l < depth) {
-                    tc_ld32(tg, v);
-                    tc_ld32(tg + 32, v + 32);
-                    tc_ld_wait();
-                }
+                tc_ld32(tg, v);
+                tc_ld32(tg + 32, v + 32);
+                tc_ld_wait();
             }
             if (stats) {
                 // ---- statistics pass: z_L goes to the staging tile [64][128] (in place over the input tile),
@@ -436,7 +532,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
                 proxy_fence();
                 group_sync(g);
                 if (gt == 0 && A.zout) bulk_store(A.zout + (size_t)tile * TCH * TCM, zo, ZBYTES);
-                {
+                if (!A.no_stats) {
                     const float* row = zo + (gt & 63) * TCM + (gt >> 6) * 64;
                     float s_ = 0.f, q_ = 0.f;
 #pragma unroll 8
@@ -449,32 +545,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
                 group_sync(g);
                 continue;
             }
-            // ---- splines on this thread's logits (PWLin, 32 bins; coupling_cells.py:114-141) ---------------
+            // ---- output layer, one MMA block at a time, and the splines on this thread's logits ----------------
+            tc_store_act(v, affs + depth * 2 * TCH, affs + depth * 2 * TCH + TCH, tg + TC_COL_AHI, tg + TC_COL_ALO);
             float jfac = 1.f;
-            for (int t = 0; t < q.T; ++t) {
-                float z[32];
-                tc_ld32(tg + t * 32, z);
-                tc_ld_wait();
-                const float xv = st[q.trafo[t] * TCM];
-                const float a = xv * 32.f;
-                int kb = (int)floorf(a);
-                kb = kb < 0 ? 0 : (kb > 31 ? 31 : kb);
-                const float alpha = a - (float)kb;
-                float m = -3.0e38f;
+            const int nblk = tc_out_blocks(F, q.T), tper = tc_out_tper(F), Nb = tc_out_n(F);
+            tc_fence_before();
+            mbar_arrive(&a_ready[g]);
+            for (int b = 0; b < nblk; ++b) {
+                mbar_wait(&d_ready[g], pd);
+                pd ^= 1;
+                tc_fence_after();
+                for (int tt = 0; tt < tper; ++tt) {
+                    const int t = b * tper + tt;
+                    if (t >= q.T) break;
+                    const float xv = st[q.trafo[t] * TCM];
+                    float y, f;
+                    int kb;
+                    if (KIND == NIS_KIND_PWLIN) {
+                        // PWLin, 32 bins (coupling_cells.py:114-141), registers only
+                        float z[32];
+                        tc_ld32(tg + tt * 32, z);
+                        tc_ld_wait();
+                        const float a = xv * 32.f;
+                        kb = (int)floorf(a);
+                        kb = kb < 0 ? 0 : (kb > 31 ? 31 : kb);
+                        const float alpha = a - (float)kb;
+                        float m = -3.0e38f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { z[j] += biass[t * 32 + j]; m = fmaxf(m, z[j]); }
-                float S = 0.f, C = 0.f, ek = 0.f;
+                        for (int j = 0; j < 32; ++j) { z[j] += biass[b * Nb + tt * 32 + j]; m = fmaxf(m, z[j]); }
+                        float S = 0.f, C = 0.f, ek = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float e = expf(z[j] - m);
-                    S += e;
-                    C += j < kb ? e : 0.f;
-                    ek = j == kb ? e : ek;
+                        for (int j = 0; j < 32; ++j) {
+                            const float e = expf(z[j] - m);
+                            S += e;
+                            C += j < kb ? e : 0.f;
+                            ek = j == kb ? e : ek;
+                        }
+                        const float inv = 1.f / S;
+                        y = (ek * alpha + C) * inv;
+                        f = ek * inv * 32.f;
+                    } else {
+                        float z[80];
+                        tc_ld32(tg, z);
+                        tc_ld32(tg + 32, z + 32);
+                        tc_ld16(tg + 64, z + 64);
+                        tc_ld_wait();
+                        if (b + 1 < nblk) {                 // accumulator consumed: the next block's MMA may overwrite it
+                            tc_fence_before();
+                            mbar_arrive(&a_ready[g]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 65; ++j) z[j] += biass[b * Nb + j];
+                        pwquad32_regs(z, xv, y, f, kb);
+                    }
+                    st[q.trafo[t] * TCM] = y;
+                    jfac *= f;
+                    if (A.bins && valid) A.bins[((long long)c * A.B + pt) * d + t] = kb;
                 }
-                const float inv = 1.f / S;
-                st[q.trafo[t] * TCM] = (ek * alpha + C) * inv;
-                jfac *= ek * inv * 32.f;
-                if (A.bins && valid) A.bins[((long long)c * A.B + pt) * d + t] = kb;
             }
             st[d * TCM] *= jfac;
             // ---- store ----------------------------------------------------------------------------------
@@ -494,7 +621,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
     tc_fence_before();
     __syncthreads();
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-    if (!stats) return;
+    if (!stats || A.no_stats) return;
     // ---- fold: thread gt of a group holds the sums of feature gt & 63 over half of each of its tiles -----------
     double* red = reinterpret_cast<double*>(sm + L.red);          // [2][256]: sum / sum of squares per group thread
     double* sacc = red + 8 * 2 * TCH;                              // [2 * maxW]
@@ -519,17 +646,24 @@ bool nis_tc_supported(const DevFlow& F, int64_t B, int bn_mode) {
     (void)bn_mode;
     const char* off = getenv("NIS_TC");                   // NIS_TC=0 forces the FP32-pipe kernels (test knob)
     if (off && off[0] == '0') return false;
-    if (F.kind != NIS_KIND_PWLIN || F.depth < 1 || B < 2048 || F.maxW != TCH) return false;
+    if (F.depth < 1 || B < 2048 || F.maxW != TCH || F.nb != 32) return false;
     for (int l = 0; l < F.depth; ++l) if (F.widths[l] != TCH) return false;
-    if (F.K != 32 || F.nb != 32) return false;
+    if (F.kind == NIS_KIND_PWLIN ? F.K != 32 : F.K != 65) return false;
     for (int c = 0; c < F.n_cells; ++c) {
-        if (F.cells[c].T * F.K > TC_NOUT || F.cells[c].P > 16) return false;
-        if ((size_t)tc_layout(F, F.cells[c].P, 1, F.depth).total + 1024 > 225 * 1024) return false;
-        if ((size_t)tc_layout(F, F.cells[c].P, F.depth, F.depth, true).total + 1024 > 226 * 1024) return false;
-        if ((size_t)tc_layout(F, F.cells[c].P, 1, 1, true).total + 1024 > 226 * 1024) return false;
+        const int P = F.cells[c].P, T = F.cells[c].T;
+        if (P > 16) return false;
+        if (F.K == 32 && T * 32 > TC_NOUT) return false;
+        const size_t lim = 226 * 1024;
+        if ((size_t)tc_layout(F, P, 1, F.depth, false).total + 1024 > lim && F.K == 32) return false;      // fused eval cell
+        if ((size_t)tc_layout(F, P, 1, F.depth - 1, true).total + 1024 > lim) return false;               // hidden pass(es)
+        if ((size_t)tc_layout(F, P, F.depth, F.depth, F.K == 32).total + 1024 > lim) return false;        // final pass
     }
     return true;
 }
+
+// PWQuad cells keep 160 KB of output-layer weights resident, so their eval-mode cell is split in two
+// launches (hidden layers -> stored activations -> output layer + spline) like the train-mode passes.
+bool nis_tc_split_eval(const DevFlow& F) { return F.K != 32; }
 
 int nis_tc_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream_t s) {
     flow_tc_pack_kernel<<<dim3(16, F.n_cells), 256, 0, s>>>(F, params, tcpack);
@@ -545,11 +679,13 @@ int nis_launch_tc(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaS
     const bool stats = A.stats_layer >= 1;
     const int lz = A.zin ? (stats ? A.stats_layer - 1 : F.depth) : 1;
     const int l_end = stats ? A.stats_layer - 1 : F.depth;
-    const size_t smem = (size_t)tc_layout(F, F.cells[A.c_begin].P, lz, l_end, A.zin != nullptr || A.zout != nullptr).total + 1024;
-    cudaFuncSetAttribute(flow_cell_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool zst = (A.zin != nullptr || A.zout != nullptr) && (stats || F.K == 32);
+    const size_t smem = (size_t)tc_layout(F, F.cells[A.c_begin].P, lz, l_end, zst).total + 1024;
+    auto kern = F.kind == NIS_KIND_PWLIN ? flow_cell_tc_kernel<NIS_KIND_PWLIN> : flow_cell_tc_kernel<NIS_KIND_PWQUAD>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long long npairs = ((A.B + TCM - 1) / TCM + 1) / 2;
     int grid = (int)(npairs < sms ? npairs : sms);
-    flow_cell_tc_kernel<<<grid, TC_THREADS, smem, s>>>(F, A, tcpack);
+    kern<<<grid, TC_THREADS, smem, s>>>(F, A, tcpack);
     NIS_CUDA_CHECK_LAUNCH();
     return NIS_OK;
 }

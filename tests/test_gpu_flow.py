@@ -89,18 +89,19 @@ def test_forward_matches_oracle_at_size(cfg, mode):
 
 @pytest.mark.parametrize("backend", ["tcgen05", "fp32_tiled_4x8", "fp32_tiled_8x8", "generic"])
 @pytest.mark.parametrize("mode", ["eval", "train"])
-def test_every_kernel_family_agrees_with_the_oracle_on_cfg2(monkeypatch, backend, mode):
-    """cfg2 is served by the tcgen05 kernel by default; the FP32-pipe register-tiled kernels and the
-    shape-generic kernel stay selectable (library test knobs) and must meet the same parity bar."""
+@pytest.mark.parametrize("which", [0, 1], ids=["cfg2", "cfg4"])
+def test_every_kernel_family_agrees_with_the_oracle(monkeypatch, backend, mode, which):
+    """cfg2 (PWLin) and cfg4 (PWQuad) are served by the tcgen05 kernel by default; the FP32-pipe register-tiled
+    kernels and the shape-generic kernel stay selectable (library test knobs) and must meet the same parity bar."""
     env = {"tcgen05": {}, "fp32_tiled_4x8": {"NIS_TC": "0"}, "fp32_tiled_8x8": {"NIS_TC": "0", "NIS_TILED_VARIANT": "8"},
            "generic": {"NIS_TC": "0", "NIS_DISABLE_TILED": "1"}}[backend]
     for k in ("NIS_TC", "NIS_TILED_VARIANT", "NIS_DISABLE_TILED"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    test_forward_matches_oracle_at_size(BIG[0], mode)
+    test_forward_matches_oracle_at_size(BIG[which], mode)
     # ragged batch (not a multiple of any tile size) through the same kernels
-    cfg = dict(BIG[0], B=(1 << 13) + 77)
+    cfg = dict(BIG[which], B=(1 << 13) + 77)
     test_forward_matches_oracle_at_size(cfg, mode)
 
 
