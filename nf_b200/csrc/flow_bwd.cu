@@ -475,6 +475,12 @@ static int launch_bwd(const DevFlow& F, const BwdArgs& A, int grid, cudaStream_t
 __global__ void flow_pack_kernel(DevFlow F, const float* __restrict__ params, const float* __restrict__ bn_running,
                                  float* __restrict__ wpack, int bn_mode);
 
+// tensor-core train-mode backward (flow_bwd_tc.cu)
+bool nis_bwd_tc_supported(const DevFlow& F, int64_t B, int bn_mode);
+int nis_flow_backward_tc(const DevFlow& F, const FlowWorkspace& ws, const float* params, const float* bn_running,
+                         const float* saved, const float* bn_saved, const void* grad_out, int grad_dtype,
+                         float* grad_params, void* grad_in, int64_t B, cudaStream_t s);
+
 static int launch_bwd_any(const DevFlow& F, const BwdArgs& A, int NT, int grid, cudaStream_t s) {
     switch (NT) {
         case 128: return launch_bwd<128>(F, A, grid, s);
@@ -498,11 +504,13 @@ extern "C" int nis_flow_backward(const NisFlowDesc* desc, const float* params, c
     if (!train && !bn_running) return NIS_EINVAL;
     if (workspace_bytes < nis_flow_workspace_bytes(desc, B)) return NIS_EWORKSPACE;
     if (B == 0) return NIS_OK;
-    const int NT = bwd_pick_nt(F);
-    if (!NT) return NIS_EUNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     FlowWorkspace ws;
     nis_flow_carve(F, B, workspace, &ws);
+    if (nis_bwd_tc_supported(F, B, bn_mode))
+        return nis_flow_backward_tc(F, ws, params, bn_running, saved, bn_saved, grad_out, grad_dtype, grad_params, grad_in, B, s);
+    const int NT = bwd_pick_nt(F);
+    if (!NT) return NIS_EUNSUPPORTED;
     BwdScratch sc;
     bwd_carve(F, B, ws.bwd, &sc);
     const int grid = bwd_grid(F, B, NT);

@@ -1,0 +1,801 @@
+// Train-mode backward of width-64 PWLin cells (32 bins) on the 5th-generation tensor cores.
+//
+// What torch.autograd does for the reference's loss.backward() (manager.py:278) through one coupling cell
+// (coupling_cells.py:107-142, 230-254) is, per cell and in reverse order, a chain of small GEMMs with a
+// batch-wide BatchNorm reduction between every two of them.  The chain is cut at those reductions:
+//
+//   head   : recompute the conditioner (same 3xTF32 tcgen05 pipeline as the forward), store the pre-BN
+//            activations z_1..z_depth, run the spline forward + hand-derived spline backward on the logits
+//            in registers -> dL/dlogits (stored), dL/dx of the transformed columns, dL/dJ
+//   layer  : one launch per linear layer lam = depth (output layer) .. 0.  Upstream gradient dz (logits
+//            gradient, or BN backward of the stored dL/dh with the batch means the previous launch left)
+//              dgrad  dL/dh_lam = dz W_lam        A = dz in TENSOR MEMORY (lane = point), B = W_lam^T in smem
+//              wgrad  dL/dW_lam += dz^T h_lam     both operands in shared memory, K = the 128 points of the
+//                                                 tile, accumulated in tensor memory over ALL tiles of the
+//                                                 CTA and read out once (per-CTA slices, no atomics)
+//            then ReLU mask, store dL/dh_lam, per-feature sums of dL/dh and dL/dh * xhat (recursive-halving
+//            warp shuffles, float64 across tiles, last CTA finalises = dL/dbeta, dL/dgamma and the means the
+//            next launch needs)
+//   tail   : BatchNorm backward of the input normalisation -> dL/dx of the pass-through columns
+//
+// 3xTF32 everywhere (hi/lo round-to-nearest splits).  For the wgrad the hi and lo parts of dz are STACKED
+// along M ([dz_hi ; dz_lo], 128 rows) so that two M=128 MMAs (against h_hi and h_lo) give all four partial
+// products; rows o and 64+o of the accumulator are added on read-out.
+//
+// Same CTA shape as the forward (two point groups of 128 threads + one MMA-issuing warp).  The wgrad operand
+// slab (128 KB) is shared by the two groups: a group fills it while the other one runs its epilogue.
+#include <stdlib.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+#define BT_GROUP_COLS 192     // per point group: dz hi [0,64), dz lo [64,128), dgrad accumulator [128,192)
+#define BT_COL_LO 64
+#define BT_COL_D 128
+#define BT_COL_ACC 384        // weight-gradient accumulators [384,448) and (output layer) [448,512)
+#define BT_TILE (TCH * TCM)   // floats in one stored [64][128] activation tile
+
+struct BtArgs {
+    const float* saved;                    // [C+1][B][d+1]
+    const void* grad_out; int grad_dtype;
+    void* grad_in;
+    float* gstate;                         // [B][d+1]
+    const float* params; const float* wpack; const float* bn_saved;
+    const float* tcpack;                   // forward operands (flow_tc.cu pack)
+    const float* bdpack;                   // dgrad operands (W^T hi/lo)
+    float* zbuf;                           // [depth][tiles][64][128] pre-BN activations z_1..z_depth
+    float* dl;                             // [tiles][128][128] dL/dlogits
+    const float* dh_in; float* dh_out;     // [tiles][64][128] dL/dh between the layer launches
+    float* bnb;                            // [depth+1][2][maxW] batch means of dL/dh and dL/dh*xhat
+    float* slices;                         // [depth+1][grid][2][128][64] per-CTA wgrad accumulators
+    float* grad_params;
+    double* partials; unsigned* counter;
+    long long B, ntiles;
+    int c, lam, first, grid;
+};
+
+__host__ __device__ static inline int bd_layer_off(const DevFlow& F, int lam) {      // floats, inside a cell's block
+    return lam == 0 ? 0 : 2 * 16 * TCH + (lam - 1) * 2 * TCH * TCH;
+}
+__host__ __device__ static inline int bd_cell_floats(const DevFlow& F) { return bd_layer_off(F, F.depth) + 2 * 2 * TCH * TCH; }
+
+// dgrad operands + this batch's BN scale/shift.  B operand of "dL/dh = dz W": rows n = input feature i,
+// K = output feature o, i.e. W^T, K-major swizzled; the output layer has K = 128 as two blocks of 64.
+__global__ void flow_bwd_tc_pack_kernel(DevFlow F, const float* __restrict__ params, const float* __restrict__ bn_saved,
+                                        float* __restrict__ wpack, float* __restrict__ bdpack) {
+    const int c = blockIdx.y;
+    const DevCell& q = F.cells[c];
+    const float* p = params + q.param_off;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    char* dst = reinterpret_cast<char*>(bdpack + (size_t)c * bd_cell_floats(F));
+    for (int lam = 0; lam <= F.depth; ++lam) {
+        const int rows = lam == 0 ? 16 : TCH, in = lam == 0 ? q.P : TCH;
+        const int nblk = lam == F.depth ? 2 : 1;
+        const int nout = lam == F.depth ? q.T * F.K : TCH;
+        const float* w = p + F.p_lin(c, lam);                      // [nout][in]
+        for (int b = 0; b < nblk; ++b) {
+            char* hi = dst + (size_t)bd_layer_off(F, lam) * 4 + (size_t)b * 2 * rows * TCH * 4;
+            char* lo = hi + (size_t)rows * TCH * 4;
+            for (int i = tid; i < rows * TCH; i += nth) {
+                const int n = i / TCH, k = i - n * TCH, o = b * TCH + k;
+                const float v = (n < in && o < nout) ? w[(size_t)o * in + n] : 0.f;
+                const float h = tf32_rn(v);
+                const int off = tc_off(rows, n, k);
+                *reinterpret_cast<float*>(hi + off) = h;
+                *reinterpret_cast<float*>(lo + off) = tf32_rn(v - h);
+            }
+        }
+    }
+    for (int l = 0; l <= F.depth; ++l) {
+        const int W = F.W(c, l), Wp = F.Wp(c, l);
+        const long long g = F.p_bn_gamma(c, l);
+        const float* sv = bn_saved + q.sv_off + l * 2 * F.maxW;
+        float* aff = wpack + q.pk_off + q.aff_off[l];
+        for (int j = tid; j < Wp; j += nth) {
+            float sc = 0.f, sh = 0.f;
+            if (j < W) { sc = p[g + j] * sv[F.maxW + j]; sh = p[g + W + j] - sv[j] * sc; }
+            aff[j] = sc; aff[Wp + j] = sh;
+        }
+    }
+}
+
+__device__ __forceinline__ float bt_load_g(const void* p, int dtype, long long idx) {
+    return dtype == NIS_F64 ? (float)reinterpret_cast<const double*>(p)[idx] : reinterpret_cast<const float*>(p)[idx];
+}
+
+// ===================================================================================================
+// head: conditioner recompute + spline backward
+// ===================================================================================================
+__global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_head_kernel(const __grid_constant__ DevFlow F, const BtArgs A) {
+    extern __shared__ char smraw[];
+    __shared__ uint64_t a_ready[2], d_ready[2];
+    __shared__ uint32_t tmem_base_s;
+    char* sm = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = A.c;
+    const DevCell& q = F.cells[c];
+    const int d = F.d, depth = F.depth;
+    const TcSmem L = tc_layout(F, q.P, 1, depth, false);
+    float* w0s = reinterpret_cast<float*>(sm + L.w0);
+    float* affs = reinterpret_cast<float*>(sm + L.aff);
+    float* biass = reinterpret_cast<float*>(sm + L.bias);
+    float* gsm = reinterpret_cast<float*>(sm + L.total);            // gradient rows [2][(d+1)][128]
+    const float* pk = A.wpack + q.pk_off;
+
+    for (int l = 1; l <= depth; ++l) {
+        const int fl = l == depth ? 2 * TC_NOUT * TCH : 2 * TCH * TCH;
+        const float4* src = reinterpret_cast<const float4*>(A.tcpack + (size_t)c * tc_cell_floats(F) + (size_t)(l - 1) * 2 * TCH * TCH);
+        float4* dst = reinterpret_cast<float4*>(sm + L.wl[l]);
+        for (int i = tid; i < fl / 4; i += TC_THREADS) dst[i] = src[i];
+    }
+    {
+        const float* s0 = pk + q.wt_off[0];
+        for (int i = tid; i < q.P * TCH; i += TC_THREADS) w0s[i] = s0[i];
+    }
+    for (int l = 0; l <= depth; ++l) {
+        const int W = l == 0 ? q.P : TCH, Wp = pad8(W);
+        const float* s = pk + q.aff_off[l];
+        for (int i = tid; i < W; i += TC_THREADS) { affs[l * 2 * TCH + i] = s[i]; affs[l * 2 * TCH + TCH + i] = s[Wp + i]; }
+    }
+    for (int i = tid; i < TC_NOUT; i += TC_THREADS) {
+        const int t = i >> 5, jj = i & 31;
+        biass[i] = t < q.T ? pk[q.bo_off + t * F.Kpad + jj] : 0.f;
+    }
+    if (tid == 0) {
+        mbar_init(&a_ready[0], TCM); mbar_init(&a_ready[1], TCM);
+        mbar_init(&d_ready[0], 1); mbar_init(&d_ready[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const long long ntiles = A.ntiles;
+    const long long rowlen = d + 1;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            uint32_t pa[2] = {0, 0};
+            const uint32_t idesc64 = tc_idesc(TCM, TCH), idescO = tc_idesc(TCM, TC_NOUT);
+            for (long long it = 0;; ++it) {
+                const long long t0 = ((long long)blockIdx.x + it * gridDim.x) * 2;
+                if (t0 >= ntiles) break;
+                for (int l = 1; l <= depth; ++l) {
+                    const bool outl = l == depth;
+                    const int rows = outl ? TC_NOUT : TCH;
+                    const uint32_t whi = smem_u32(sm + L.wl[l]);
+                    for (int g = 0; g < 2; ++g) {
+                        if (t0 + g >= ntiles) continue;
+                        mbar_wait(&a_ready[g], pa[g]);
+                        pa[g] ^= 1;
+                        tc_fence_after();
+                        const uint32_t tb = tmem_base + g * TC_COLS_PER_GROUP;
+                        tc_issue_layer(tb, tb + TC_COL_AHI, tb + TC_COL_ALO, whi, whi + rows * TCH * 4, rows, outl ? idescO : idesc64);
+                        tc_commit(&d_ready[g]);
+                    }
+                }
+            }
+        }
+    } else {
+        const int g = warp >> 2, gt = tid & (TCM - 1);
+        float* st = reinterpret_cast<float*>(sm + L.st) + g * (d + 1) * TCM + gt;
+        float* gr = gsm + g * (d + 1) * TCM + gt;
+        const uint32_t tg = tmem_base + g * TC_COLS_PER_GROUP + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t pd = 0;
+        for (long long it = 0;; ++it) {
+            const long long tile = ((long long)blockIdx.x + it * gridDim.x) * 2 + g;
+            if (tile >= ntiles) break;
+            const long long pt = tile * TCM + gt;
+            const bool valid = pt < A.B;
+            float Jout = 1.f;
+            if (valid) {
+                const float* sv = A.saved + ((long long)c * A.B + pt) * rowlen;
+                for (int i = 0; i <= d; ++i) st[i * TCM] = sv[i];
+                Jout = A.saved[((long long)(c + 1) * A.B + pt) * rowlen + d];
+                if (A.first) {
+                    for (int i = 0; i < d; ++i) gr[F.out_perm[i] * TCM] = bt_load_g(A.grad_out, A.grad_dtype, pt * rowlen + i);
+                    gr[d * TCM] = bt_load_g(A.grad_out, A.grad_dtype, pt * rowlen + d);
+                } else {
+                    for (int i = 0; i <= d; ++i) gr[i * TCM] = A.gstate[pt * rowlen + i];
+                }
+            } else {
+                for (int i = 0; i < d; ++i) { st[i * TCM] = 0.5f; gr[i * TCM] = 0.f; }
+                st[d * TCM] = 1.f; gr[d * TCM] = 0.f;
+            }
+            // layer 0 on the FP32 pipe -> z_1
+            float v[TCH];
+#pragma unroll
+            for (int j = 0; j < TCH; ++j) v[j] = 0.f;
+            for (int k = 0; k < q.P; ++k) {
+                const float a = fmaf(st[q.feed[k] * TCM], affs[k], affs[TCH + k]);
+                const float4* wr = reinterpret_cast<const float4*>(w0s + k * TCH);
+#pragma unroll
+                for (int j4 = 0; j4 < TCH / 4; ++j4) {
+                    const float4 w = wr[j4];
+                    v[4 * j4] = fmaf(a, w.x, v[4 * j4]); v[4 * j4 + 1] = fmaf(a, w.y, v[4 * j4 + 1]);
+                    v[4 * j4 + 2] = fmaf(a, w.z, v[4 * j4 + 2]); v[4 * j4 + 3] = fmaf(a, w.w, v[4 * j4 + 3]);
+                }
+            }
+            for (int l = 1; l <= depth; ++l) {
+                float* zo = A.zbuf + ((size_t)(l - 1) * ntiles + tile) * BT_TILE + gt;       // z_l, read back by the layer launches
+#pragma unroll
+                for (int j = 0; j < TCH; ++j) zo[(size_t)j * TCM] = v[j];
+                tc_store_act(v, affs + l * 2 * TCH, affs + l * 2 * TCH + TCH, tg + TC_COL_AHI, tg + TC_COL_ALO);
+                tc_fence_before();
+                mbar_arrive(&a_ready[g]);
+                mbar_wait(&d_ready[g], pd);
+                pd ^= 1;
+                tc_fence_after();
+                if (l < depth) {
+                    tc_ld32(tg, v);
+                    tc_ld32(tg + 32, v + 32);
+                    tc_ld_wait();
+                }
+            }
+            // splines: forward + backward on the 32 logits of each transformed dimension (coupling_cells.py:114-141)
+            const float gJ = gr[d * TCM];
+            const float gJJ = gJ * Jout;
+            float Fprod = 1.f;
+            float* dlo = A.dl + (size_t)tile * 2 * BT_TILE + gt;
+            for (int t = 0; t < 4; ++t) {
+                float z[32];
+                if (t < q.T) {
+                    tc_ld32(tg + t * 32, z);
+                    tc_ld_wait();
+                    const int col = q.trafo[t];
+                    const float xv = st[col * TCM], gy = gr[col * TCM];
+                    const float a = xv * 32.f;
+                    int kb = (int)floorf(a);
+                    kb = kb < 0 ? 0 : (kb > 31 ? 31 : kb);
+                    const float alpha = a - (float)kb;
+                    float m = -3.0e38f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { z[j] += biass[t * 32 + j]; m = fmaxf(m, z[j]); }
+                    float S = 0.f, C = 0.f, ek = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float e = expf(z[j] - m);
+                        z[j] = e;
+                        S += e;
+                        C += j < kb ? e : 0.f;
+                        ek = j == kb ? e : ek;
+                    }
+                    const float inv = 1.f / S;
+                    const float y = (ek * alpha + C) * inv;
+                    const float f = ek * inv * 32.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float p = z[j] * inv;
+                        const float ind = j < kb ? 1.f : (j == kb ? alpha : 0.f);
+                        z[j] = gy * p * (ind - y) + gJJ * ((j == kb ? 1.f : 0.f) - p);
+                    }
+                    gr[col * TCM] = gy * f;
+                    Fprod *= f;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) z[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dlo[(size_t)(t * 32 + j) * TCM] = z[j];
+            }
+            if (valid) {
+                float* so = A.gstate + pt * rowlen;
+                for (int i = 0; i < d; ++i) so[i] = gr[i * TCM];
+                so[d] = gJ * Fprod;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+// ===================================================================================================
+// layer: dgrad + wgrad of linear layer lam, ReLU/BN bookkeeping for BN layer lam
+// ===================================================================================================
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T
+__device__ __forceinline__ void bt_mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// byte offset of (row, point) in a [rows x 128 points] K-major operand: four K-tiles of 32 points
+__device__ __forceinline__ int bt_slab_off(int rows, int row, int p) {
+    return (p >> 5) * rows * 128 + (row >> 3) * 1024 + (row & 7) * 128 + (((((p & 31) >> 2) ^ (row & 7)) << 4) | ((p & 3) << 2));
+}
+
+struct BtSmem { int slabA, slabBh, slabBl, bd, coef, total; };
+__host__ __device__ static inline BtSmem bt_layout(int KW) {
+    BtSmem s;
+    s.slabA = 0;                         // [128 rows: dz hi (64) ; dz lo (64)][128 points]
+    s.slabBh = 65536;                    // [nin rows][128 points] h hi
+    s.slabBl = 98304;                    //                         h lo
+    s.bd = 131072;                       // dgrad operand: KW/64 blocks of (hi, lo) [nin][64]
+    s.coef = s.bd + (KW / 64) * 2 * TCH * TCH * 4;
+    s.total = s.coef + 8 * TCH * 4;
+    return s;
+}
+
+template <int KW>
+__global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const __grid_constant__ DevFlow F, const BtArgs A) {
+    constexpr int NH = KW / 64;
+    extern __shared__ char smraw[];
+    __shared__ uint64_t a_ready[2], done[2], slab_free;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ bool s_last;
+    char* sm = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = A.c, lam = A.lam;
+    const DevCell& q = F.cells[c];
+    const int d = F.d, maxW = F.maxW;
+    const int nin = lam == 0 ? 16 : TCH;          // N of both MMAs
+    const int win = lam == 0 ? q.P : TCH;         // real width of h_lam
+    const BtSmem L = bt_layout(KW);
+    char* slabA = sm + L.slabA;
+    char* slabBh = sm + L.slabBh;
+    char* slabBl = sm + L.slabBl;
+    float* coef = reinterpret_cast<float*>(sm + L.coef);
+    float* cA1 = coef, *cA2 = coef + TCH, *cA3 = coef + 2 * TCH;              // dz = cA1*dh + cA2*z + cA3
+    float* scp = coef + 3 * TCH, *shp = coef + 4 * TCH, *mup = coef + 5 * TCH, *rsp = coef + 6 * TCH;
+    const float* pk = A.wpack + q.pk_off;
+
+    {   // dgrad operand blocks
+        const int fl = NH * 2 * nin * TCH;
+        const float4* src = reinterpret_cast<const float4*>(A.bdpack + (size_t)c * bd_cell_floats(F) + bd_layer_off(F, lam));
+        float4* dst = reinterpret_cast<float4*>(sm + L.bd);
+        for (int i = tid; i < fl / 4; i += TC_THREADS) dst[i] = src[i];
+    }
+    for (int j = tid; j < TCH; j += TC_THREADS) {
+        if (KW == 64) {          // BN layer lam+1 sits between dL/dh_{lam+1} and dz_{lam+1}
+            const int lu = lam + 1;
+            const float* sv = A.bn_saved + q.sv_off + lu * 2 * maxW;
+            const float sc = pk[q.aff_off[lu] + j];
+            const float m1 = A.bnb[lu * 2 * maxW + j], m2 = A.bnb[lu * 2 * maxW + maxW + j];
+            const float mu = sv[j], rs = sv[maxW + j];
+            cA1[j] = sc;
+            cA2[j] = -sc * m2 * rs;
+            cA3[j] = -sc * m1 + sc * m2 * rs * mu;
+        }
+        if (j < win) {
+            const float* sv = A.bn_saved + q.sv_off + lam * 2 * maxW;
+            scp[j] = pk[q.aff_off[lam] + j];
+            shp[j] = pk[q.aff_off[lam] + pad8(win) + j];
+            mup[j] = sv[j];
+            rsp[j] = sv[maxW + j];
+        } else {
+            scp[j] = 0.f; shp[j] = 0.f; mup[j] = 0.f; rsp[j] = 0.f;
+        }
+    }
+    if (tid == 0) {
+        mbar_init(&a_ready[0], TCM); mbar_init(&a_ready[1], TCM);
+        mbar_init(&done[0], 1); mbar_init(&done[1], 1);
+        mbar_init(&slab_free, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const long long ntiles = A.ntiles;
+    const long long rowlen = d + 1;
+    double acc1[2] = {0.0, 0.0}, acc2[2] = {0.0, 0.0}, accb[NH][2];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) { accb[h][0] = 0.0; accb[h][1] = 0.0; }
+
+    if (warp == 8) {
+        // ===================== MMA issuer ======================================================
+        if (lane == 0) {
+            uint32_t pa[2] = {0, 0};
+            const uint32_t idesc = tc_idesc(TCM, nin);
+            const uint32_t sA = smem_u32(slabA), sBh = smem_u32(slabBh), sBl = smem_u32(slabBl), sBd = smem_u32(sm + L.bd);
+            for (long long it = 0;; ++it) {
+                const long long t0 = ((long long)blockIdx.x + it * gridDim.x) * 2;
+                if (t0 >= ntiles) break;
+                for (int g = 0; g < 2; ++g) {
+                    if (t0 + g >= ntiles) continue;
+                    const uint32_t tb = tmem_base + g * BT_GROUP_COLS;
+                    for (int h = 0; h < NH; ++h) {
+                        mbar_wait(&a_ready[g], pa[g]);
+                        pa[g] ^= 1;
+                        tc_fence_after();
+                        // dgrad: dL/dh (+)= dz[:, 64h..64h+63] W^T block h        (A from tensor memory)
+                        const uint32_t bh = sBd + h * 2 * nin * TCH * 4, bl = bh + nin * TCH * 4;
+                        uint32_t acc = h > 0;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+                            const uint32_t wo = (ks >> 2) * nin * 128 + (ks & 3) * 32;
+                            tc_mma_tf32_ts(tb + BT_COL_D, tb + ks * 8, tc_desc(bh + wo), idesc, acc);
+                            acc = 1;
+                            tc_mma_tf32_ts(tb + BT_COL_D, tb + ks * 8, tc_desc(bl + wo), idesc, 1);
+                            tc_mma_tf32_ts(tb + BT_COL_D, tb + BT_COL_LO + ks * 8, tc_desc(bh + wo), idesc, 1);
+                        }
+                        // wgrad: acc_h += [dz_hi ; dz_lo]^T-stacked (128 rows) x h_lam (hi, then lo), K = 128 points
+                        const uint32_t ta = tmem_base + BT_COL_ACC + h * TCH;
+                        uint32_t accw = !(it == 0 && g == 0);
+#pragma unroll
+                        for (int ks = 0; ks < 16; ++ks) {
+                            const uint32_t ao = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
+                            const uint32_t bo = (ks >> 2) * nin * 128 + (ks & 3) * 32;
+                            bt_mma_tf32_ss(ta, tc_desc(sA + ao), tc_desc(sBh + bo), idesc, accw);
+                            accw = 1;
+                            bt_mma_tf32_ss(ta, tc_desc(sA + ao), tc_desc(sBl + bo), idesc, 1);
+                        }
+                        tc_commit(&done[g]);
+                        if (h == NH - 1) tc_commit(&slab_free);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== point groups ====================================================
+        const int g = warp >> 2, gt = tid & (TCM - 1);
+        const uint32_t tg = tmem_base + g * BT_GROUP_COLS + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t pd = 0;
+        for (long long it = 0;; ++it) {
+            const long long tile = ((long long)blockIdx.x + it * gridDim.x) * 2 + g;
+            if (tile >= ntiles) break;
+            const long long pt = tile * TCM + gt;
+            const bool valid = pt < A.B;
+            const long long seq = 2 * it + g;
+            const float* zp = lam > 0 ? A.zbuf + ((size_t)(lam - 1) * ntiles + tile) * BT_TILE + gt : nullptr;
+            const float* xs = A.saved + ((long long)c * A.B + (valid ? pt : 0)) * rowlen;
+            // the slab is shared by the two groups, whose tiles alternate g0, g1, g0, ...: wait for the
+            // weight-gradient MMAs of the previous user
+            if (seq > 0) mbar_wait(&slab_free, (uint32_t)((seq - 1) & 1));
+            // ---- B operand of the wgrad: h_lam = ReLU(BN_lam(z_lam)) (lam = 0: the normalised input, no ReLU) ----
+            uint64_t mask = 0;
+            if (lam > 0) {
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb) {
+                    float zv[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) zv[j] = zp[(size_t)(32 * cb + j) * TCM];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int r = 32 * cb + j;
+                        const float a = fmaf(zv[j], scp[r], shp[r]);
+                        mask |= (uint64_t)(a > 0.f) << r;
+                        const float hv = fmaxf(a, 0.f);
+                        const float hi = tf32_rn(hv);
+                        const int off = bt_slab_off(TCH, r, gt);
+                        *reinterpret_cast<float*>(slabBh + off) = hi;
+                        *reinterpret_cast<float*>(slabBl + off) = tf32_rn(hv - hi);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float a = k < q.P ? fmaf(xs[q.feed[k]], scp[k], shp[k]) : 0.f;
+                    const float hi = tf32_rn(a);
+                    const int off = bt_slab_off(16, k, gt);
+                    *reinterpret_cast<float*>(slabBh + off) = hi;
+                    *reinterpret_cast<float*>(slabBl + off) = tf32_rn(a - hi);
+                }
+            }
+            // ---- upstream gradient dz, 64 features at a time: tensor memory (dgrad A) + slab (wgrad A) ----------
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                if (h > 0) {                   // the MMAs of the previous half have consumed both copies
+                    mbar_wait(&done[g], pd);
+                    pd ^= 1;
+                    tc_fence_after();
+                }
+                float dz[TCH];
+                if (KW == 128) {
+                    const float* up = A.dl + (size_t)tile * 2 * BT_TILE + (size_t)h * BT_TILE + gt;
+#pragma unroll
+                    for (int j = 0; j < TCH; ++j) dz[j] = up[(size_t)j * TCM];
+                } else {
+                    const float* up = A.dh_in + (size_t)tile * BT_TILE + gt;
+                    const float* zu = A.zbuf + ((size_t)lam * ntiles + tile) * BT_TILE + gt;       // z_{lam+1}
+#pragma unroll
+                    for (int j = 0; j < TCH; ++j) dz[j] = up[(size_t)j * TCM];
+#pragma unroll
+                    for (int j = 0; j < TCH; ++j) {
+                        const float zl = zu[(size_t)j * TCM];
+                        dz[j] = valid ? fmaf(cA1[j], dz[j], fmaf(cA2[j], zl, cA3[j])) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb) {
+                    float hi[32], lo[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int r = 32 * cb + j;
+                        hi[j] = tf32_rn(dz[r]);
+                        lo[j] = tf32_rn(dz[r] - hi[j]);
+                        *reinterpret_cast<float*>(slabA + bt_slab_off(128, r, gt)) = hi[j];
+                        *reinterpret_cast<float*>(slabA + bt_slab_off(128, TCH + r, gt)) = lo[j];
+                    }
+                    tc_st32(tg + 32 * cb, hi);
+                    tc_st32(tg + BT_COL_LO + 32 * cb, lo);
+                }
+                tc_st_wait();
+                proxy_fence();
+                tc_fence_before();
+                mbar_arrive(&a_ready[g]);
+                if (KW == 128) {               // output-layer bias gradient = column sums of dL/dlogits
+                    float s0, s1;
+                    tc_warp_feature_sums(dz, lane, s0, s1);
+                    accb[h][0] += (double)s0; accb[h][1] += (double)s1;
+                }
+            }
+            mbar_wait(&done[g], pd);
+            pd ^= 1;
+            tc_fence_after();
+            // ---- epilogue: dL/dh_lam = mask * (dz W_lam); store; sums for BN layer lam ---------------------------
+            float dv[TCH];
+            if (lam > 0) {
+                tc_ld32(tg + BT_COL_D, dv);
+                tc_ld32(tg + BT_COL_D + 32, dv + 32);
+            } else {
+                tc_ld16(tg + BT_COL_D, dv);
+#pragma unroll
+                for (int j = 16; j < TCH; ++j) dv[j] = 0.f;
+            }
+            tc_ld_wait();
+            float* out = A.dh_out + (size_t)tile * BT_TILE + gt;
+            float pr[TCH];
+            if (lam > 0) {
+#pragma unroll
+                for (int j = 0; j < TCH; ++j) {
+                    dv[j] = ((mask >> j) & 1) ? dv[j] : 0.f;
+                    out[(size_t)j * TCM] = dv[j];
+                    pr[j] = dv[j] * (zp[(size_t)j * TCM] - mup[j]) * rsp[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    dv[j] = j < q.P ? dv[j] : 0.f;
+                    out[(size_t)j * TCM] = dv[j];
+                    pr[j] = j < q.P ? dv[j] * (xs[q.feed[j]] - mup[j]) * rsp[j] : 0.f;
+                }
+#pragma unroll
+                for (int j = 16; j < TCH; ++j) pr[j] = 0.f;
+            }
+            float s0, s1;
+            tc_warp_feature_sums(dv, lane, s0, s1);
+            acc1[0] += (double)s0; acc1[1] += (double)s1;
+            tc_warp_feature_sums(pr, lane, s0, s1);
+            acc2[0] += (double)s0; acc2[1] += (double)s1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // ---- weight-gradient accumulators -> this CTA's slice ----------------------------------------------------------
+    if (warp < 4) {
+        const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16) + BT_COL_ACC;
+        float* sl = A.slices + (((size_t)lam * A.grid + blockIdx.x) * 2) * 128 * TCH + (size_t)tid * TCH;
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            float r[TCH];
+            if (lam > 0) {
+                tc_ld32(tl + h * TCH, r);
+                tc_ld32(tl + h * TCH + 32, r + 32);
+            } else {
+                tc_ld16(tl, r);
+            }
+            tc_ld_wait();
+            float4* o4 = reinterpret_cast<float4*>(sl + (size_t)h * 128 * TCH);
+#pragma unroll
+            for (int j = 0; j < TCH / 4; ++j)
+                if (4 * j < nin) o4[j] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    // ---- per-feature sums: warps -> CTA -> grid (last CTA finalises) ---------------------------------------------------
+    double* red = reinterpret_cast<double*>(sm);            // [8 warps][32 lanes][8]   (the slab is idle now)
+    if (warp < 8) {
+        double* r = red + ((size_t)warp * 32 + lane) * 8;
+        r[0] = acc1[0]; r[1] = acc1[1]; r[2] = acc2[0]; r[3] = acc2[1];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) { r[4 + 2 * h] = accb[h][0]; r[5 + 2 * h] = accb[h][1]; }
+        if (NH == 1) { r[6] = 0.0; r[7] = 0.0; }
+    }
+    __syncthreads();
+    // partials row of this CTA: [0,64) sum dh, [64,128) sum dh*xhat, [128,256) bias gradient
+    double* mine = A.partials + (size_t)blockIdx.x * 256;
+    for (int i = tid; i < 256; i += TC_THREADS) {
+        const int f = i & 63, kind = i >> 6;                // kind 0: s1, 1: s2, 2: bias half 0, 3: bias half 1
+        const int ln = f >> 1, ix = f & 1;
+        const int slot = kind == 0 ? ix : kind == 1 ? 2 + ix : kind == 2 ? 4 + ix : 6 + ix;
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[((size_t)w * 32 + ln) * 8 + slot];
+        mine[i] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(A.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float* gp = A.grad_params + q.param_off;
+    for (int i = tid; i < 256; i += TC_THREADS) {
+        const int f = i & 63, kind = i >> 6;
+        double s = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(A.partials + (size_t)b * 256 + i);
+        if (kind == 0 && f < win) {
+            A.bnb[lam * 2 * maxW + f] = (float)(s / (double)A.B);
+            gp[F.p_bn_gamma(c, lam) + win + f] += (float)s;                 // dL/dbeta
+        } else if (kind == 1 && f < win) {
+            A.bnb[lam * 2 * maxW + maxW + f] = (float)(s / (double)A.B);
+            gp[F.p_bn_gamma(c, lam) + f] += (float)s;                       // dL/dgamma
+        } else if (kind >= 2 && KW == 128) {
+            const int n = (kind - 2) * TCH + f;
+            if (n < q.T * F.K) gp[F.p_out_b(c) + n] += (float)s;
+        }
+    }
+    if (tid == 0) *A.counter = 0u;
+}
+
+// ===================================================================================================
+// tail: BatchNorm backward of the input normalisation, dL/dx of the pass-through columns
+// ===================================================================================================
+__global__ void __launch_bounds__(256) flow_bwd_tc_tail_kernel(const __grid_constant__ DevFlow F, const BtArgs A) {
+    const int c = A.c;
+    const DevCell& q = F.cells[c];
+    const int d = F.d, maxW = F.maxW;
+    const long long rowlen = d + 1;
+    const float* pk = A.wpack + q.pk_off;
+    const float* sv = A.bn_saved + q.sv_off;
+    for (long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x; pt < A.B; pt += (long long)gridDim.x * blockDim.x) {
+        const float* xs = A.saved + ((long long)c * A.B + pt) * rowlen;
+        float* gs = A.gstate + pt * rowlen;
+        const float* da = A.dh_in + (size_t)(pt >> 7) * BT_TILE + (pt & 127);
+        float g[NIS_MAX_DIM + 1];
+        for (int i = 0; i <= d; ++i) g[i] = gs[i];
+        for (int k = 0; k < q.P; ++k) {
+            const int col = q.feed[k];
+            const float xh = (xs[col] - sv[k]) * sv[maxW + k];
+            const float dz = pk[q.aff_off[0] + k] * (da[(size_t)k * TCM] - A.bnb[k] - xh * A.bnb[maxW + k]);
+            g[col] += dz;
+        }
+        for (int i = 0; i <= d; ++i) gs[i] = g[i];
+        if (A.grad_in) {
+            for (int i = 0; i <= d; ++i) {
+                if (A.grad_dtype == NIS_F64) reinterpret_cast<double*>(A.grad_in)[pt * rowlen + i] = (double)g[i];
+                else reinterpret_cast<float*>(A.grad_in)[pt * rowlen + i] = g[i];
+            }
+        }
+    }
+}
+
+// grad_params[cell] += per-CTA slices (fixed order).  blockIdx.y = linear layer.
+__global__ void flow_bwd_tc_reduce_kernel(DevFlow F, const float* __restrict__ slices, int grid, int c, float* __restrict__ grad_params) {
+    const int lam = blockIdx.y;
+    const DevCell& q = F.cells[c];
+    const int in = lam == 0 ? q.P : TCH;
+    const int nout = lam == F.depth ? q.T * F.K : TCH;
+    float* gw = grad_params + q.param_off + F.p_lin(c, lam);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nout * in; i += gridDim.x * blockDim.x) {
+        const int o = i / in, k = i - o * in;
+        const int h = o >> 6, r = o & 63;
+        float s = 0.f;
+        for (int b = 0; b < grid; ++b) {
+            const float* sl = slices + ((((size_t)lam * grid + b) * 2 + h) * 128) * TCH;
+            s += sl[(size_t)r * TCH + k] + sl[(size_t)(TCH + r) * TCH + k];
+        }
+        gw[i] += s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+bool nis_tc_supported(const DevFlow& F, int64_t B, int bn_mode);
+int nis_tc_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream_t s);
+__global__ void flow_pack_kernel(DevFlow F, const float* __restrict__ params, const float* __restrict__ bn_running,
+                                 float* __restrict__ wpack, int bn_mode);
+
+bool nis_bwd_tc_supported(const DevFlow& F, int64_t B, int bn_mode) {
+    const char* off = getenv("NIS_BWD_TC");               // NIS_BWD_TC=0 forces the shape-generic backward (test knob)
+    if (off && off[0] == '0') return false;
+    if (bn_mode != NIS_BN_TRAIN || F.kind != NIS_KIND_PWLIN || F.K != 32) return false;
+    if (!nis_tc_supported(F, B, bn_mode)) return false;
+    for (int c = 0; c < F.n_cells; ++c)
+        if (F.cells[c].P > 16 || F.cells[c].T * F.K > TC_NOUT) return false;
+    return true;
+}
+
+static int bt_grid(int64_t B) {
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    const long long npairs = ((B + TCM - 1) / TCM + 1) / 2;
+    return (int)(npairs < sms ? npairs : sms);
+}
+
+struct BtScratch { float *gstate, *zbuf, *dl, *dh[2], *bnb, *slices, *bdpack; size_t floats; };
+static void bt_carve(const DevFlow& F, int64_t B, float* base, BtScratch* s) {
+    auto up = [](size_t x) { return (x + 63) & ~(size_t)63; };
+    const size_t tiles = (size_t)((B + TCM - 1) / TCM);
+    size_t off = 0;
+    s->gstate = base + off; off = up(off + (size_t)B * (F.d + 1));
+    s->zbuf = base + off; off = up(off + (size_t)F.depth * tiles * BT_TILE);
+    s->dl = base + off; off = up(off + tiles * 2 * BT_TILE);
+    s->dh[0] = base + off; off = up(off + tiles * BT_TILE);
+    s->dh[1] = base + off; off = up(off + tiles * BT_TILE);
+    s->bnb = base + off; off = up(off + (size_t)(F.depth + 1) * 2 * F.maxW);
+    s->slices = base + off; off = up(off + (size_t)(F.depth + 1) * 148 * 2 * 128 * TCH);
+    s->bdpack = base + off; off = up(off + (size_t)F.n_cells * bd_cell_floats(F));
+    s->floats = off;
+}
+
+size_t nis_bwd_tc_scratch_floats(const DevFlow& F, int64_t B) {
+    BtScratch s;
+    bt_carve(F, B, nullptr, &s);
+    return s.floats;
+}
+
+int nis_flow_backward_tc(const DevFlow& F, const FlowWorkspace& ws, const float* params, const float* bn_running,
+                         const float* saved, const float* bn_saved, const void* grad_out, int grad_dtype,
+                         float* grad_params, void* grad_in, int64_t B, cudaStream_t s) {
+    BtScratch sc;
+    bt_carve(F, B, ws.bwd, &sc);
+    int grid = bt_grid(B);
+    if (grid > 148) grid = 148;
+    cudaMemsetAsync(ws.counter, 0, 256, s);
+    {
+        int mx = 0;
+        for (int c = 0; c < F.n_cells; ++c) {
+            int sz = (c + 1 < F.n_cells ? F.cells[c + 1].pk_off : F.pack_total) - F.cells[c].pk_off;
+            if (sz > mx) mx = sz;
+        }
+        int bx = (mx + 255) / 256;
+        if (bx > 64) bx = 64;
+        flow_pack_kernel<<<dim3(bx, F.n_cells), 256, 0, s>>>(F, params, bn_running, ws.wpack, NIS_BN_TRAIN);
+        NIS_CUDA_CHECK_LAUNCH();
+        flow_bwd_tc_pack_kernel<<<dim3(16, F.n_cells), 256, 0, s>>>(F, params, bn_saved, ws.wpack, sc.bdpack);
+        NIS_CUDA_CHECK_LAUNCH();
+        int rc = nis_tc_pack(F, params, ws.tcpack, s);
+        if (rc) return rc;
+    }
+    BtArgs A;
+    A.saved = saved; A.grad_out = grad_out; A.grad_dtype = grad_dtype; A.grad_in = nullptr;
+    A.gstate = sc.gstate; A.params = params; A.wpack = ws.wpack; A.bn_saved = bn_saved;
+    A.tcpack = ws.tcpack; A.bdpack = sc.bdpack; A.zbuf = sc.zbuf; A.dl = sc.dl;
+    A.bnb = sc.bnb; A.slices = sc.slices; A.grad_params = grad_params;
+    A.partials = ws.partials; A.counter = ws.counter; A.B = B; A.ntiles = (B + TCM - 1) / TCM; A.grid = grid;
+    A.dh_in = nullptr; A.dh_out = nullptr; A.lam = 0;
+    const size_t smem64 = (size_t)bt_layout(64).total + 1024, smem128 = (size_t)bt_layout(128).total + 1024;
+    cudaFuncSetAttribute(flow_bwd_tc_layer_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64);
+    cudaFuncSetAttribute(flow_bwd_tc_layer_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128);
+    for (int c = F.n_cells - 1; c >= 0; --c) {
+        A.c = c; A.first = c == F.n_cells - 1;
+        const size_t smem_head = (size_t)tc_layout(F, F.cells[c].P, 1, F.depth, false).total + 2 * (F.d + 1) * TCM * 4 + 1024;
+        cudaFuncSetAttribute(flow_bwd_tc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head);
+        flow_bwd_tc_head_kernel<<<grid, TC_THREADS, smem_head, s>>>(F, A);
+        NIS_CUDA_CHECK_LAUNCH();
+        int pp = 0;
+        for (int lam = F.depth; lam >= 0; --lam) {
+            A.lam = lam;
+            A.dh_in = sc.dh[pp]; A.dh_out = sc.dh[pp ^ 1];
+            if (lam == F.depth) flow_bwd_tc_layer_kernel<128><<<grid, TC_THREADS, smem128, s>>>(F, A);
+            else flow_bwd_tc_layer_kernel<64><<<grid, TC_THREADS, smem64, s>>>(F, A);
+            NIS_CUDA_CHECK_LAUNCH();
+            pp ^= 1;
+        }
+        A.dh_in = sc.dh[pp];
+        A.grad_in = c == 0 ? grad_in : nullptr;
+        long long blocks = (B + 255) / 256;
+        flow_bwd_tc_tail_kernel<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, s>>>(F, A);
+        NIS_CUDA_CHECK_LAUNCH();
+        A.grad_in = nullptr;
+        flow_bwd_tc_reduce_kernel<<<dim3(32, F.depth + 1), 256, 0, s>>>(F, sc.slices, grid, c, grad_params);
+        NIS_CUDA_CHECK_LAUNCH();
+    }
+    return NIS_OK;
+}

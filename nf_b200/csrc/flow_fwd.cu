@@ -231,6 +231,8 @@ bool nis_tc_supported(const DevFlow& F, int64_t B, int bn_mode);
 int nis_tc_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream_t s);
 int nis_launch_tc(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaStream_t s);
 bool nis_tc_split_eval(const DevFlow& F);
+bool nis_bwd_tc_supported(const DevFlow& F, int64_t B, int bn_mode);
+size_t nis_bwd_tc_scratch_floats(const DevFlow& F, int64_t B);
 int nis_launch_tiled(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 int nis_launch_col_stats(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 bool nis_moments_supported(const DevFlow& F, int c);
@@ -252,6 +254,8 @@ extern "C" size_t nis_flow_workspace_bytes(const NisFlowDesc* desc, int64_t B) {
     size_t tail = nis_flow_bwd_scratch_floats(F, B);
     const size_t zfl = (nis_tiled_supported(F, B) || nis_tc_supported(F, B, NIS_BN_TRAIN)) ? 2 * nis_tiled_zbuf_floats(B) : 0;
     if (zfl > tail) tail = zfl;
+    const size_t tcb = nis_bwd_tc_supported(F, B, NIS_BN_TRAIN) ? nis_bwd_tc_scratch_floats(F, B) : 0;
+    if (tcb > tail) tail = tcb;
     return fwd + sizeof(float) * tail + 256;
 }
 

@@ -118,3 +118,46 @@ def test_gradients_match_oracle_autograd_at_size(cfg, mode):
     gscale = max(float(sd64[k].grad.abs().max()) for k, _ in model.named_parameters())
     for k, p in model.named_parameters():
         close(p.grad, sd64[k].grad, k, gscale, flips=True)
+
+
+@pytest.mark.parametrize("B", [2048, (1 << 13) + 77])
+def test_tensor_core_backward_agrees_with_generic_backward_and_oracle(monkeypatch, B):
+    """Train-mode backward of cfg2 runs on the tcgen05 kernels (flow_bwd_tc.cu) by default; NIS_BWD_TC=0 selects
+    the shape-generic kernel.  Both must meet the parity bar against float64 autograd through the oracle, for the
+    parameter gradients and for the gradient with respect to the input points (ragged last tile included)."""
+    cfg = dict(BIG[0], B=B)
+    layers = oracle_layers(cfg)
+    cells, _ = oflow.compile_layers(layers, cfg["n_flow"])
+    sd = oflow.init_state_dict(cells, cfg["n_flow"], cfg["kind"], cfg["n_bins"], cfg["NN"], seed=21,
+                               dtype=torch.float32, bn_jitter=0.2)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.rand(B, cfg["n_flow"], generator=gen, dtype=torch.float32).double()
+    fres = torch.exp(-((x - 0.5) ** 2).sum(-1) / 0.2)
+    sd64 = {k: (v.double().requires_grad_(k.endswith("weight") or k.endswith("bias")) if v.dtype.is_floating_point else v)
+            for k, v in sd.items()}
+    xj64 = torch.cat((x, torch.ones(B, 1, dtype=torch.float64)), 1).requires_grad_(True)
+    XJr, _ = oflow.flow_forward(layers, sd64, xj64, cfg["kind"], cfg["n_bins"], train=True)
+    ref = onis.minibatch_loss(fres, XJr[:, -1], fres.max(), "var") + (XJr[:, :-1] ** 2).mean()
+    ref.backward()
+    gscale = max(float(v.grad.abs().max()) for v in sd64.values() if getattr(v, "grad", None) is not None)
+    grads = {}
+    for backend, env in (("tcgen05", None), ("generic", "0")):
+        monkeypatch.delenv("NIS_BWD_TC", raising=False)
+        if env is not None:
+            monkeypatch.setenv("NIS_BWD_TC", env)
+        torch.manual_seed(3)
+        NF = make_manager(cfg)
+        model = NF._model
+        model.load_state_dict(sd)
+        model.train()
+        xj = NF.format_input(x, torch.device("cuda")).requires_grad_(True)
+        XJ = model(xj)
+        loss = torch.var(fres.cuda() * XJ[:, -1] / fres.max()) + (XJ[:, :-1] ** 2).mean()
+        loss.backward()
+        assert abs(float(loss) - float(ref)) <= 2e-5 * abs(float(ref))
+        for k, p in model.named_parameters():
+            close(p.grad, sd64[k].grad, backend + ":" + k, gscale, flips=True)
+        close(xj.grad, xj64.grad, backend + ":dL/dx", float(xj64.grad.abs().max()), flips=True)
+        grads[backend] = {k: p.grad.detach().cpu().double() for k, p in model.named_parameters()}
+    for k in grads["tcgen05"]:
+        close(grads["tcgen05"][k], grads["generic"][k], "tc vs generic:" + k, gscale, flips=True)
