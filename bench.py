@@ -221,14 +221,15 @@ def workload_config(points):
             "l2": "inputs larger than L2 (134 MB fp32 points per step > 126 MB)"}
 
 
-def bench_train_step(steps, warmup, world, dev):
-    """variance-loss training step of the cfg2 flow — forward + fused backward on a
-    per-rank minibatch of 2^16 fresh points, gradient sum-allreduce (NCCL) when N > 1."""
+def bench_train_step(steps, warmup, world, dev, log2n=16):
+    """variance-loss training step of the cfg2 flow — forward + backward (tcgen05 kernels
+    of flow_tc.cu / flow_bwd_tc.cu) on a per-rank minibatch of 2^log2n points, gradient sum-allreduce (NCCL)
+    when N > 1."""
     from nf_b200.normalizing_flows.manager import BasicManager
     NF = build_flow()
     model = NF._model.train()
     params = list(model.parameters())
-    n = 1 << 16
+    n = 1 << log2n
     x = torch.rand(n, 8, device=dev, dtype=torch.float32)
     f = torch.exp(-((x - 0.5) ** 2).sum(-1) / 0.2)
 
@@ -241,8 +242,8 @@ def bench_train_step(steps, warmup, world, dev):
 
     ms = time_steps(step, steps, warmup, world)
     return {"metric": "nis_train_step_points_per_sec", "value": world * n / (ms * 1e-3), "unit": "points/s",
-            "ms_per_step": ms, "config": {"workload": "cfg2 flow, variance loss, forward + fused backward "
-                                          "(+ gradient all-reduce), 2^16 points per rank per step"}}
+            "ms_per_step": ms, "config": {"workload": "cfg2 flow, variance loss, forward + backward on the tcgen05 "
+                                          "kernels (+ gradient all-reduce), 2^%d points per rank per step" % log2n}}
 
 
 def bench_integrate(world, dev):
@@ -461,6 +462,7 @@ def main():
         torch.cuda.empty_cache()
         line["rambo"] = bench_rambo(max(3, args.steps // 2), args.warmup, world, pk["hbm_gbs"], peak_kind)
         line["train_step"] = bench_train_step(max(3, args.steps // 2), args.warmup, world, dev)
+        line["train_step_large"] = bench_train_step(max(3, args.steps // 2), args.warmup, world, dev, log2n=20)
         line["integrate"] = bench_integrate(world, dev)
         if rank == 0 and world == 1:
             threads = os.cpu_count() or 1

@@ -310,6 +310,44 @@ __device__ __forceinline__ int bt_slab_off(int rows, int row, int p) {
     return (p >> 5) * rows * 128 + (row >> 3) * 1024 + (row & 7) * 128 + (((((p & 31) >> 2) ^ (row & 7)) << 4) | ((p & 3) << 2));
 }
 
+__device__ __forceinline__ void bt_prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// per-feature sums of 32 values over the 32 lanes of a warp (recursive halving): lane i returns the sum of feature i
+__device__ __forceinline__ float bt_warp_feature_sums32(const float* v, int lane) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const bool up = lane & 16;
+        const float keep = up ? v[i + 16] : v[i], send = up ? v[i] : v[i + 16];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool up = lane & 8;
+        const float keep = up ? a[i + 8] : a[i], send = up ? a[i] : a[i + 8];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool up = lane & 4;
+        const float keep = up ? a[i + 4] : a[i], send = up ? a[i] : a[i + 4];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool up = lane & 2;
+        const float keep = up ? a[i + 2] : a[i], send = up ? a[i] : a[i + 2];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    {
+        const bool up = lane & 1;
+        const float keep = up ? a[1] : a[0], send = up ? a[0] : a[1];
+        a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    return a[0];
+}
+
 struct BtSmem { int slabA, slabBh, slabBl, bd, coef, total; };
 __host__ __device__ static inline BtSmem bt_layout(int KW) {
     BtSmem s;
@@ -450,63 +488,115 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
             const long long seq = 2 * it + g;
             const float* zp = lam > 0 ? A.zbuf + ((size_t)(lam - 1) * ntiles + tile) * BT_TILE + gt : nullptr;
             const float* xs = A.saved + ((long long)c * A.B + (valid ? pt : 0)) * rowlen;
-            // the slab is shared by the two groups, whose tiles alternate g0, g1, g0, ...: wait for the
-            // weight-gradient MMAs of the previous user
-            if (seq > 0) mbar_wait(&slab_free, (uint32_t)((seq - 1) & 1));
-            // ---- B operand of the wgrad: h_lam = ReLU(BN_lam(z_lam)) (lam = 0: the normalised input, no ReLU) ----
+            // next tile's inputs -> L2 while this one is processed
+            if (gt == 0) {
+                const long long tn = ((long long)blockIdx.x + (it + 1) * gridDim.x) * 2 + g;
+                if (tn < ntiles) {
+                    if (lam > 0) bt_prefetch_l2(A.zbuf + ((size_t)(lam - 1) * ntiles + tn) * BT_TILE, BT_TILE * 4);
+                    if (KW == 128) bt_prefetch_l2(A.dl + (size_t)tn * 2 * BT_TILE, 2 * BT_TILE * 4);
+                    else {
+                        bt_prefetch_l2(A.dh_in + (size_t)tn * BT_TILE, BT_TILE * 4);
+                        bt_prefetch_l2(A.zbuf + ((size_t)lam * ntiles + tn) * BT_TILE, BT_TILE * 4);
+                    }
+                }
+            }
+            // ---- upstream gradient dz (first 64 features), 32 at a time: split and parked in the group's own
+            //      tensor-memory A columns (dgrad operand); no shared resource is held while the loads are in flight
+#pragma unroll
+            for (int cb = 0; cb < 2; ++cb) {
+                float dz[32];
+                if (KW == 128) {
+                    const float* up = A.dl + (size_t)tile * 2 * BT_TILE + (size_t)(32 * cb) * TCM + gt;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dz[j] = up[(size_t)j * TCM];
+                } else {
+                    const float* up = A.dh_in + (size_t)tile * BT_TILE + (size_t)(32 * cb) * TCM + gt;
+                    const float* zu = A.zbuf + ((size_t)lam * ntiles + tile) * BT_TILE + (size_t)(32 * cb) * TCM + gt;   // z_{lam+1}
+                    float zl[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { dz[j] = up[(size_t)j * TCM]; zl[j] = zu[(size_t)j * TCM]; }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        dz[j] = valid ? fmaf(cA1[32 * cb + j], dz[j], fmaf(cA2[32 * cb + j], zl[j], cA3[32 * cb + j])) : 0.f;
+                }
+                float lo[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float hi = tf32_rn(dz[j]);
+                    lo[j] = tf32_rn(dz[j] - hi);
+                    dz[j] = hi;
+                }
+                tc_st32(tg + 32 * cb, dz);
+                tc_st32(tg + BT_COL_LO + 32 * cb, lo);
+                if (KW == 128) {               // output-layer bias gradient = column sums of dL/dlogits
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dz[j] += lo[j];
+                    accb[0][cb] += (double)bt_warp_feature_sums32(dz, lane);
+                }
+            }
+            tc_st_wait();
+            // ---- h_lam = ReLU(BN_lam(z_lam)) (lam = 0: the normalised input, no ReLU) in registers ------------------
             uint64_t mask = 0;
+            float hv[TCH];
             if (lam > 0) {
 #pragma unroll
-                for (int cb = 0; cb < 2; ++cb) {
-                    float zv[32];
+                for (int j = 0; j < TCH; ++j) hv[j] = zp[(size_t)j * TCM];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) zv[j] = zp[(size_t)(32 * cb + j) * TCM];
+                for (int j = 0; j < TCH; ++j) {
+                    const float a = fmaf(hv[j], scp[j], shp[j]);
+                    mask |= (uint64_t)(a > 0.f) << j;
+                    hv[j] = fmaxf(a, 0.f);
+                }
+            } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int r = 32 * cb + j;
-                        const float a = fmaf(zv[j], scp[r], shp[r]);
-                        mask |= (uint64_t)(a > 0.f) << r;
-                        const float hv = fmaxf(a, 0.f);
-                        const float hi = tf32_rn(hv);
-                        const int off = bt_slab_off(TCH, r, gt);
-                        *reinterpret_cast<float*>(slabBh + off) = hi;
-                        *reinterpret_cast<float*>(slabBl + off) = tf32_rn(hv - hi);
-                    }
+                for (int k = 0; k < 16; ++k) hv[k] = k < q.P ? fmaf(xs[q.feed[k]], scp[k], shp[k]) : 0.f;
+            }
+            // ---- the operand slab is shared by the two groups, whose tiles alternate g0, g1, g0, ...: wait for
+            //      the weight-gradient MMAs of the previous user, then fill it (stores only)
+            if (seq > 0) mbar_wait(&slab_free, (uint32_t)((seq - 1) & 1));
+            if (lam > 0) {
+#pragma unroll
+                for (int r = 0; r < TCH; ++r) {
+                    const float hi = tf32_rn(hv[r]);
+                    const int off = bt_slab_off(TCH, r, gt);
+                    *reinterpret_cast<float*>(slabBh + off) = hi;
+                    *reinterpret_cast<float*>(slabBl + off) = tf32_rn(hv[r] - hi);
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
-                    const float a = k < q.P ? fmaf(xs[q.feed[k]], scp[k], shp[k]) : 0.f;
-                    const float hi = tf32_rn(a);
+                    const float hi = tf32_rn(hv[k]);
                     const int off = bt_slab_off(16, k, gt);
                     *reinterpret_cast<float*>(slabBh + off) = hi;
-                    *reinterpret_cast<float*>(slabBl + off) = tf32_rn(a - hi);
+                    *reinterpret_cast<float*>(slabBl + off) = tf32_rn(hv[k] - hi);
                 }
             }
-            // ---- upstream gradient dz, 64 features at a time: tensor memory (dgrad A) + slab (wgrad A) ----------
 #pragma unroll
-            for (int h = 0; h < NH; ++h) {
-                if (h > 0) {                   // the MMAs of the previous half have consumed both copies
-                    mbar_wait(&done[g], pd);
-                    pd ^= 1;
-                    tc_fence_after();
+            for (int cb = 0; cb < 2; ++cb) {
+                float hi[32], lo[32];
+                tc_ld32(tg + 32 * cb, hi);
+                tc_ld32(tg + BT_COL_LO + 32 * cb, lo);
+                tc_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int r = 32 * cb + j;
+                    *reinterpret_cast<float*>(slabA + bt_slab_off(128, r, gt)) = hi[j];
+                    *reinterpret_cast<float*>(slabA + bt_slab_off(128, TCH + r, gt)) = lo[j];
                 }
+            }
+            proxy_fence();
+            tc_fence_before();
+            mbar_arrive(&a_ready[g]);
+            if (KW == 128) {
+                // second 64 logits: loaded while the MMAs of the first half run, written once those have
+                // consumed the tensor-memory columns and the slab rows
                 float dz[TCH];
-                if (KW == 128) {
-                    const float* up = A.dl + (size_t)tile * 2 * BT_TILE + (size_t)h * BT_TILE + gt;
+                const float* up = A.dl + (size_t)tile * 2 * BT_TILE + BT_TILE + gt;
 #pragma unroll
-                    for (int j = 0; j < TCH; ++j) dz[j] = up[(size_t)j * TCM];
-                } else {
-                    const float* up = A.dh_in + (size_t)tile * BT_TILE + gt;
-                    const float* zu = A.zbuf + ((size_t)lam * ntiles + tile) * BT_TILE + gt;       // z_{lam+1}
-#pragma unroll
-                    for (int j = 0; j < TCH; ++j) dz[j] = up[(size_t)j * TCM];
-#pragma unroll
-                    for (int j = 0; j < TCH; ++j) {
-                        const float zl = zu[(size_t)j * TCM];
-                        dz[j] = valid ? fmaf(cA1[j], dz[j], fmaf(cA2[j], zl, cA3[j])) : 0.f;
-                    }
-                }
+                for (int j = 0; j < TCH; ++j) dz[j] = up[(size_t)j * TCM];
+                mbar_wait(&done[g], pd);
+                pd ^= 1;
+                tc_fence_after();
 #pragma unroll
                 for (int cb = 0; cb < 2; ++cb) {
                     float hi[32], lo[32];
@@ -525,11 +615,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
                 proxy_fence();
                 tc_fence_before();
                 mbar_arrive(&a_ready[g]);
-                if (KW == 128) {               // output-layer bias gradient = column sums of dL/dlogits
-                    float s0, s1;
-                    tc_warp_feature_sums(dz, lane, s0, s1);
-                    accb[h][0] += (double)s0; accb[h][1] += (double)s1;
-                }
+                float s0, s1;
+                tc_warp_feature_sums(dz, lane, s0, s1);
+                accb[1][0] += (double)s0; accb[1][1] += (double)s1;
             }
             mbar_wait(&done[g], pd);
             pd ^= 1;
@@ -611,7 +699,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
     double* mine = A.partials + (size_t)blockIdx.x * 256;
     for (int i = tid; i < 256; i += TC_THREADS) {
         const int f = i & 63, kind = i >> 6;                // kind 0: s1, 1: s2, 2: bias half 0, 3: bias half 1
-        const int ln = f >> 1, ix = f & 1;
+        // 64-wide butterflies leave features (2 lane, 2 lane + 1) on a lane, the 32-wide ones of the first
+        // logit half feature 32 chunk + lane
+        const int ln = kind == 2 ? (f & 31) : (f >> 1), ix = kind == 2 ? (f >> 5) : (f & 1);
         const int slot = kind == 0 ? ix : kind == 1 ? 2 + ix : kind == 2 ? 4 + ix : 6 + ix;
         double s = 0.0;
         for (int w = 0; w < 8; ++w) s += red[((size_t)w * 32 + ln) * 8 + slot];
