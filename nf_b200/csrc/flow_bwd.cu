@@ -32,6 +32,7 @@ struct BwdArgs {
     float* grad_params;
     double* partials; unsigned* counter;
     long long B; int c, step_begin, step_end, train, first, cell_params;
+    int rotate;                            // activations in three rotating buffers (single-step launches of wide conditioners)
 };
 
 // backward weight pack: torch rows padded to 8 so that W^T dz is a dense8 sweep
@@ -168,8 +169,15 @@ __global__ void __launch_bounds__(NT) flow_bwd_generic_kernel(const __grid_const
     float* st0 = sm + rows * NT; rows += d + 1;
     float* g0 = sm + rows * NT; rows += d + 1;
     float* act0[NIS_MAX_HIDDEN + 1];
-    act0[0] = sm + rows * NT; rows += maxW;               // a_0 (BN0 output), P <= maxW rows used
-    for (int l = 1; l <= depth; ++l) { act0[l] = sm + rows * NT; rows += pad8(F.widths[l - 1]); }
+    if (A.rotate) {
+        // a launch that runs ONE step touches a_l and a_{l-1} only: layer l lives in buffer l % 3, so the
+        // recompute never overwrites the two it still needs
+        for (int l = 0; l <= depth; ++l) act0[l] = sm + (rows + (l % 3) * maxW) * NT;
+        rows += 3 * maxW;
+    } else {
+        act0[0] = sm + rows * NT; rows += maxW;           // a_0 (BN0 output), P <= maxW rows used
+        for (int l = 1; l <= depth; ++l) { act0[l] = sm + rows * NT; rows += pad8(F.widths[l - 1]); }
+    }
     float* lg0 = sm + rows * NT; rows += F.Kpad;
     float* GA0 = sm + rows * NT; rows += maxW;
     float* GB0 = sm + rows * NT; rows += maxW;
@@ -420,19 +428,27 @@ static int max_cell_params(const DevFlow& F) {
 }
 static int wb_total(const DevFlow& F) { return wb_cell_off(F, F.n_cells); }
 
-static size_t bwd_smem_bytes(const DevFlow& F, int NT) {
-    int rows = 2 * (F.d + 1) + F.maxW;
-    for (int l = 1; l <= F.depth; ++l) rows += pad8(F.widths[l - 1]);
+static size_t bwd_smem_bytes(const DevFlow& F, int NT, bool rotate = false) {
+    int rows = 2 * (F.d + 1);
+    if (rotate) rows += 3 * F.maxW;
+    else {
+        rows += F.maxW;
+        for (int l = 1; l <= F.depth; ++l) rows += pad8(F.widths[l - 1]);
+    }
     rows += F.Kpad + 2 * F.maxW;
     size_t fl = (size_t)rows * NT;
     fl += fl & 1;
     return fl * sizeof(float) + sizeof(double) * 2 * F.maxW;
 }
-static int bwd_pick_nt(const DevFlow& F) {
+// Points per CTA.  Train-mode launches run one step each and may keep the activations in three rotating
+// buffers (`rotate`), which is what lets deep/wide conditioners (cfg5: [256]*4, 64 bins) fit.
+static int bwd_pick_nt(const DevFlow& F, bool train = false, bool* rotate = nullptr) {
     const size_t lim = 227 * 1024 - 1024;
+    if (rotate) *rotate = false;
     if (bwd_smem_bytes(F, 128) <= lim / 2) return 128;
     if (bwd_smem_bytes(F, 64) <= lim) return 64;
     if (bwd_smem_bytes(F, 32) <= lim) return 32;
+    if (train && rotate && bwd_smem_bytes(F, 32, true) <= lim) { *rotate = true; return 32; }
     return 0;
 }
 static int bwd_grid(const DevFlow& F, int64_t B, int NT) {
@@ -452,7 +468,8 @@ static void bwd_carve(const DevFlow& F, int64_t B, float* base, BwdScratch* s) {
     s->dact = base + off; off = up(off + (size_t)((B + 127) / 128) * 128 * F.maxW);
     s->bnb = base + off; off = up(off + (size_t)(F.depth + 1) * 2 * F.maxW);
     s->gpart = base + off;
-    int NT = bwd_pick_nt(F);
+    bool rot = false;
+    int NT = bwd_pick_nt(F, true, &rot);
     off = up(off + (size_t)(NT ? bwd_grid(F, B, NT) : 0) * max_cell_params(F));
     s->floats = off;
 }
@@ -465,7 +482,7 @@ size_t nis_flow_bwd_scratch_floats(const DevFlow& F, int64_t B) {
 
 template <int NT>
 static int launch_bwd(const DevFlow& F, const BwdArgs& A, int grid, cudaStream_t s) {
-    const size_t smem = bwd_smem_bytes(F, NT);
+    const size_t smem = bwd_smem_bytes(F, NT, A.rotate != 0);
     cudaFuncSetAttribute(flow_bwd_generic_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     flow_bwd_generic_kernel<NT><<<grid, NT, smem, s>>>(F, A);
     NIS_CUDA_CHECK_LAUNCH();
@@ -509,7 +526,8 @@ extern "C" int nis_flow_backward(const NisFlowDesc* desc, const float* params, c
     nis_flow_carve(F, B, workspace, &ws);
     if (nis_bwd_tc_supported(F, B, bn_mode))
         return nis_flow_backward_tc(F, ws, params, bn_running, saved, bn_saved, grad_out, grad_dtype, grad_params, grad_in, B, s);
-    const int NT = bwd_pick_nt(F);
+    bool rotate = false;
+    const int NT = bwd_pick_nt(F, train != 0, &rotate);
     if (!NT) return NIS_EUNSUPPORTED;
     BwdScratch sc;
     bwd_carve(F, B, ws.bwd, &sc);
@@ -532,7 +550,7 @@ extern "C" int nis_flow_backward(const NisFlowDesc* desc, const float* params, c
     A.saved = saved; A.grad_out = grad_out; A.grad_dtype = grad_dtype;
     A.gstate = sc.gstate; A.dact = sc.dact; A.params = params; A.wpack = ws.wpack; A.wb = sc.wb;
     A.bnb = sc.bnb; A.gpart = sc.gpart; A.grad_params = grad_params;
-    A.partials = ws.partials; A.counter = ws.counter; A.B = B; A.train = train;
+    A.partials = ws.partials; A.counter = ws.counter; A.B = B; A.train = train; A.rotate = rotate;
     const int OUT = F.depth + 1;
     for (int c = F.n_cells - 1; c >= 0; --c) {
         const int np = (int)(F.p_out_b(c) + (long long)F.cells[c].T * F.K);
