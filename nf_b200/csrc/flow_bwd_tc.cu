@@ -51,6 +51,7 @@ struct BtArgs {
     double* partials; unsigned* counter;
     long long B, ntiles;
     int c, lam, first, grid;
+    int flush_every;                       // iterations between flushes of the wgrad accumulators (0: only at the end)
 };
 
 __host__ __device__ static inline int bd_layer_off(const DevFlow& F, int lam) {      // floats, inside a cell's block
@@ -348,6 +349,33 @@ __device__ __forceinline__ float bt_warp_feature_sums32(const float* v, int lane
     return a[0];
 }
 
+// tcgen05.mma adds each K=8 step into the fp32 accumulator with TRUNCATION (tools/tc_accum_probe.cu: about
+// one ulp lost per instruction, always toward zero), so an accumulator that lives across all tiles of a CTA
+// would drift by ~1e-4 relative after a few thousand instructions.  The wgrad accumulators are therefore
+// added to the CTA's slice in global memory (fp32, round-to-nearest) every BT_FLUSH iterations (16 tiles, 512 instructions) and restarted.
+#define BT_FLUSH 8
+__device__ __forceinline__ bool bt_flush_after(long long it, long long t_first, unsigned grid, long long ntiles, int every) {
+    const long long next0 = ((t_first >> 1) + grid) * 2;          // first tile of this CTA's next iteration
+    return every > 0 && ((it + 1) % every) == 0 && next0 < ntiles;
+}
+template <int NH>
+__device__ __noinline__ void bt_flush_acc(uint32_t tl, float* sl, int lam, int nin, bool add) {
+    for (int h = 0; h < NH; ++h) {
+        for (int j0 = 0; j0 < nin; j0 += 16) {
+            float r[16];
+            tc_ld16(tl + h * TCH + j0, r);
+            tc_ld_wait();
+            float4* o4 = reinterpret_cast<float4*>(sl + (size_t)h * 128 * TCH + j0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 v = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                if (add) { const float4 o = o4[j]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                o4[j] = v;
+            }
+        }
+    }
+}
+
 struct BtSmem { int slabA, slabBh, slabBl, bd, coef, total; };
 __host__ __device__ static inline BtSmem bt_layout(int KW) {
     BtSmem s;
@@ -364,7 +392,7 @@ template <int KW>
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const __grid_constant__ DevFlow F, const BtArgs A) {
     constexpr int NH = KW / 64;
     extern __shared__ char smraw[];
-    __shared__ uint64_t a_ready[2], done[2], slab_free;
+    __shared__ uint64_t a_ready[2], done[2], slab_free, acc_ready, acc_free;
     __shared__ uint32_t tmem_base_s;
     __shared__ bool s_last;
     char* sm = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
@@ -414,6 +442,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
         mbar_init(&a_ready[0], TCM); mbar_init(&a_ready[1], TCM);
         mbar_init(&done[0], 1); mbar_init(&done[1], 1);
         mbar_init(&slab_free, 1);
+        mbar_init(&acc_ready, 1); mbar_init(&acc_free, TCM);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
@@ -427,6 +456,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
     const uint32_t tmem_base = tmem_base_s;
     const long long ntiles = A.ntiles;
     const long long rowlen = d + 1;
+    int nflush = 0;                        // flushes of the wgrad accumulators done by this thread (group 0)
     double acc1[2] = {0.0, 0.0}, acc2[2] = {0.0, 0.0}, accb[NH][2];
 #pragma unroll
     for (int h = 0; h < NH; ++h) { accb[h][0] = 0.0; accb[h][1] = 0.0; }
@@ -434,12 +464,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
     if (warp == 8) {
         // ===================== MMA issuer ======================================================
         if (lane == 0) {
-            uint32_t pa[2] = {0, 0};
+            uint32_t pa[2] = {0, 0}, pf = 0;
+            bool fresh = true;                 // the next wgrad MMA starts a new accumulation
             const uint32_t idesc = tc_idesc(TCM, nin);
             const uint32_t sA = smem_u32(slabA), sBh = smem_u32(slabBh), sBl = smem_u32(slabBl), sBd = smem_u32(sm + L.bd);
             for (long long it = 0;; ++it) {
                 const long long t0 = ((long long)blockIdx.x + it * gridDim.x) * 2;
                 if (t0 >= ntiles) break;
+                const bool flush = bt_flush_after(it, t0, gridDim.x, ntiles, A.flush_every);
                 for (int g = 0; g < 2; ++g) {
                     if (t0 + g >= ntiles) continue;
                     const uint32_t tb = tmem_base + g * BT_GROUP_COLS;
@@ -460,7 +492,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
                         }
                         // wgrad: acc_h += [dz_hi ; dz_lo]^T-stacked (128 rows) x h_lam (hi, then lo), K = 128 points
                         const uint32_t ta = tmem_base + BT_COL_ACC + h * TCH;
-                        uint32_t accw = !(it == 0 && g == 0);
+                        uint32_t accw = !(fresh && g == 0);
 #pragma unroll
                         for (int ks = 0; ks < 16; ++ks) {
                             const uint32_t ao = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
@@ -473,13 +505,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
                         if (h == NH - 1) tc_commit(&slab_free);
                     }
                 }
+                fresh = false;
+                if (flush) {                   // group 0 adds the accumulators to the CTA's slice, then we start over
+                    tc_commit(&acc_ready);
+                    mbar_wait(&acc_free, pf);
+                    pf ^= 1;
+                    tc_fence_after();
+                    fresh = true;
+                }
             }
         }
     } else {
         // ===================== point groups ====================================================
         const int g = warp >> 2, gt = tid & (TCM - 1);
         const uint32_t tg = tmem_base + g * BT_GROUP_COLS + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t pd = 0;
+        uint32_t pd = 0, pfr = 0;
         for (long long it = 0;; ++it) {
             const long long tile = ((long long)blockIdx.x + it * gridDim.x) * 2 + g;
             if (tile >= ntiles) break;
@@ -657,31 +697,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
             acc1[0] += (double)s0; acc1[1] += (double)s1;
             tc_warp_feature_sums(pr, lane, s0, s1);
             acc2[0] += (double)s0; acc2[1] += (double)s1;
+            // ---- periodic flush of the weight-gradient accumulators (group 0 owns lanes 0..127 of them) -------------
+            if (g == 0 && bt_flush_after(it, tile, gridDim.x, ntiles, A.flush_every)) {
+                mbar_wait(&acc_ready, pfr);
+                pfr ^= 1;
+                tc_fence_after();
+                bt_flush_acc<NH>(tmem_base + ((uint32_t)(warp * 32) << 16) + BT_COL_ACC,
+                                 A.slices + (((size_t)lam * A.grid + blockIdx.x) * 2) * 128 * TCH + (size_t)tid * TCH, lam, nin, nflush > 0);
+                ++nflush;
+                tc_fence_before();
+                mbar_arrive(&acc_free);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     // ---- weight-gradient accumulators -> this CTA's slice ----------------------------------------------------------
-    if (warp < 4) {
-        const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16) + BT_COL_ACC;
-        float* sl = A.slices + (((size_t)lam * A.grid + blockIdx.x) * 2) * 128 * TCH + (size_t)tid * TCH;
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            float r[TCH];
-            if (lam > 0) {
-                tc_ld32(tl + h * TCH, r);
-                tc_ld32(tl + h * TCH + 32, r + 32);
-            } else {
-                tc_ld16(tl, r);
-            }
-            tc_ld_wait();
-            float4* o4 = reinterpret_cast<float4*>(sl + (size_t)h * 128 * TCH);
-#pragma unroll
-            for (int j = 0; j < TCH / 4; ++j)
-                if (4 * j < nin) o4[j] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        }
-    }
+    if (warp < 4)
+        bt_flush_acc<NH>(tmem_base + ((uint32_t)(warp * 32) << 16) + BT_COL_ACC,
+                         A.slices + (((size_t)lam * A.grid + blockIdx.x) * 2) * 128 * TCH + (size_t)tid * TCH, lam, nin, nflush > 0);
     tc_fence_before();
     __syncthreads();
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -860,6 +895,10 @@ int nis_flow_backward_tc(const DevFlow& F, const FlowWorkspace& ws, const float*
     A.bnb = sc.bnb; A.slices = sc.slices; A.grad_params = grad_params;
     A.partials = ws.partials; A.counter = ws.counter; A.B = B; A.ntiles = (B + TCM - 1) / TCM; A.grid = grid;
     A.dh_in = nullptr; A.dh_out = nullptr; A.lam = 0;
+    {
+        const char* fe = getenv("NIS_BWD_FLUSH");         // test knob: 0 = accumulate over the whole CTA without flushing
+        A.flush_every = fe ? atoi(fe) : BT_FLUSH;
+    }
     const size_t smem64 = (size_t)bt_layout(64).total + 1024, smem128 = (size_t)bt_layout(128).total + 1024;
     cudaFuncSetAttribute(flow_bwd_tc_layer_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64);
     cudaFuncSetAttribute(flow_bwd_tc_layer_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128);

@@ -91,12 +91,16 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t nis_flow_bwd_scratch_floats(const DevFlow& F, const NisFlowDesc* d, int64_t B);
 
 size_t nis_tc_pack_floats(const DevFlow& F);
+size_t nis_wide_pack_floats(const DevFlow& F);
 
 size_t nis_flow_carve(const DevFlow& F, int64_t B, void* base, FlowWorkspace* ws) {
     size_t off = 0;
     char* b = (char*)base;
     ws->wpack = (float*)(b + off); off = align256(off + sizeof(float) * (size_t)F.pack_total);
-    ws->tcpack = (float*)(b + off); off = align256(off + sizeof(float) * nis_tc_pack_floats(F));
+    {   // tensor-core operand pack: resident-weights layout (flow_tc.cu) or K-panels (flow_wide.cu)
+        size_t fl = nis_tc_pack_floats(F), wf = nis_wide_pack_floats(F);
+        ws->tcpack = (float*)(b + off); off = align256(off + sizeof(float) * (fl > wf ? fl : wf));
+    }
     ws->state = (float*)(b + off); off = align256(off + sizeof(float) * (size_t)B * (F.d + 1));
     ws->partials = (double*)(b + off); off = align256(off + sizeof(double) * (size_t)NIS_MAX_GRID * 2 * F.maxW);
     ws->counter = (unsigned*)(b + off); off = align256(off + 256);

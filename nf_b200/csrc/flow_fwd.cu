@@ -232,6 +232,11 @@ int nis_tc_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream
 int nis_launch_tc(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaStream_t s);
 bool nis_tc_split_eval(const DevFlow& F);
 bool nis_bwd_tc_supported(const DevFlow& F, int64_t B, int bn_mode);
+bool nis_wide_supported(const DevFlow& F, int64_t B, int bn_mode);
+int nis_wide_pack(const DevFlow& F, const float* params, float* widepack, cudaStream_t s);
+int nis_launch_wide(const DevFlow& F, const FwdArgs& A, const float* widepack, cudaStream_t s);
+// floats of one stored-activation buffer ([tile][width][128], tiles padded to pairs)
+static size_t zbuf_floats(const DevFlow& F, int64_t B) { return nis_tiled_zbuf_floats(B) / 64 * (size_t)(F.maxW > 64 ? F.maxW : 64); }
 size_t nis_bwd_tc_scratch_floats(const DevFlow& F, int64_t B);
 int nis_launch_tiled(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 int nis_launch_col_stats(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
@@ -252,7 +257,8 @@ extern "C" size_t nis_flow_workspace_bytes(const NisFlowDesc* desc, int64_t B) {
     size_t fwd = nis_flow_carve(F, B, nullptr, &ws);
     // the backward scratch and the tiled train path's activation buffers are never live together
     size_t tail = nis_flow_bwd_scratch_floats(F, B);
-    const size_t zfl = (nis_tiled_supported(F, B) || nis_tc_supported(F, B, NIS_BN_TRAIN)) ? 2 * nis_tiled_zbuf_floats(B) : 0;
+    const size_t zfl = (nis_tiled_supported(F, B) || nis_tc_supported(F, B, NIS_BN_TRAIN) || nis_wide_supported(F, B, NIS_BN_EVAL))
+                           ? 2 * zbuf_floats(F, B) : 0;
     if (zfl > tail) tail = zfl;
     const size_t tcb = nis_bwd_tc_supported(F, B, NIS_BN_TRAIN) ? nis_bwd_tc_scratch_floats(F, B) : 0;
     if (tcb > tail) tail = tcb;
@@ -316,8 +322,10 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     A.zin = nullptr; A.zout = nullptr; A.no_stats = 0;
     // per-cell launch sequences: tcgen05 kernel where it applies, else the FP32 register-tiled kernel
     const bool tc = nis_tc_supported(F, B, bn_mode);
-    const bool tiled = tc || nis_tiled_supported(F, B);
+    const bool wide = !tc && nis_wide_supported(F, B, bn_mode);       // streamed-weights tcgen05 kernel (flow_wide.cu)
+    const bool tiled = tc || wide || nis_tiled_supported(F, B);
     if (tc) { rc = nis_tc_pack(F, params, ws.tcpack, s); if (rc) return rc; }
+    if (wide) { rc = nis_wide_pack(F, params, ws.tcpack, s); if (rc) return rc; }
     const long long rows = (long long)B * (F.d + 1);
     if (bn_mode == NIS_BN_EVAL && !tiled) {
         A.state_in = nullptr; A.state_out = nullptr; A.from_state = 0; A.to_out = 1;
@@ -331,7 +339,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
         A.from_state = c > 0;
         A.state_in = c > 0 ? (saved ? saved + (long long)c * rows : ws.state) : nullptr;
         A.state_out = nullptr; A.to_out = 0;
-        float* zb[2] = {ws.bwd, ws.bwd + nis_tiled_zbuf_floats(B)};
+        float* zb[2] = {ws.bwd, ws.bwd + zbuf_floats(F, B)};
         // BN0 + BN1 from one streaming pass over the pass-through columns (flow_col_moments_kernel), then
         // the layer passes start at layer 2 (recomputing the K=P layer 0 on the way)
         const bool moments = tiled && bn_mode == NIS_BN_TRAIN && nis_moments_supported(F, c);
@@ -349,7 +357,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
                     // layer pass: reads the pre-BN activations of layer l-1, writes those of layer l
                     A.zin = (l >= 2 && !(moments && l == 2)) ? zb[(l - 1) & 1] : nullptr;
                     A.zout = zb[l & 1];
-                    rc = tc ? nis_launch_tc(F, A, ws.tcpack, s) : nis_launch_tiled(F, A, s);
+                    rc = tc ? nis_launch_tc(F, A, ws.tcpack, s) : wide ? nis_launch_wide(F, A, ws.tcpack, s) : nis_launch_tiled(F, A, s);
                 } else if (tiled && l == 0) {
                     rc = nis_launch_col_stats(F, A, s);
                 } else {
@@ -368,10 +376,23 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
             if (rc) return rc;
             A.stats_layer = -1; A.no_stats = 0; A.zin = zb[F.depth & 1]; A.zout = nullptr;
         }
+        if (wide && bn_mode == NIS_BN_EVAL) {
+            // eval, wide conditioner: one launch per hidden layer (no statistics), then the final pass
+            A.no_stats = 1;
+            for (int l = 2; l <= F.depth; ++l) {
+                A.stats_layer = l;
+                A.zin = l > 2 ? zb[(l - 1) & 1] : nullptr;
+                A.zout = zb[l & 1];
+                rc = nis_launch_wide(F, A, ws.tcpack, s);
+                if (rc) return rc;
+            }
+            A.stats_layer = -1; A.no_stats = 0; A.zin = F.depth >= 2 ? zb[F.depth & 1] : nullptr; A.zout = nullptr;
+        }
         const bool last = c == F.n_cells - 1;
         A.to_out = last;
         A.state_out = saved ? saved + (long long)(c + 1) * rows : (last ? nullptr : ws.state);
-        rc = tc ? nis_launch_tc(F, A, ws.tcpack, s) : (tiled ? nis_launch_tiled(F, A, s) : launch_fwd_any(F, A, s));
+        rc = tc ? nis_launch_tc(F, A, ws.tcpack, s) : wide ? nis_launch_wide(F, A, ws.tcpack, s)
+                : (tiled ? nis_launch_tiled(F, A, s) : launch_fwd_any(F, A, s));
         if (rc) return rc;
     }
     return NIS_OK;

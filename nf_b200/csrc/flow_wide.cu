@@ -1,0 +1,463 @@
+// Coupling-cell forward for WIDE conditioners (hidden width 128..256, any bin count) on tcgen05 / TMEM —
+// BASELINE configs[4]: 16-D PWQuad, 64 bins, MLP [256]*4, where the conditioner is a real dense contraction
+// (7.4 MFLOP per point).
+//
+// A 256-wide layer does not fit the resident-weights scheme of flow_tc.cu (one layer's hi/lo operand is
+// 512 KB), so the layer runs as a streamed GEMM per 128-point tile:
+//   * weights are packed once per forward as K-panels of 32 input features, [N rows][32] hi then lo in the
+//     K-major 128B-swizzled UMMA layout, and STREAMED from L2 through a ring of shared-memory slots by
+//     cp.async.bulk (TMA) from a dedicated producer warp (full/empty mbarriers per slot);
+//   * the activations enter as the A operand from TENSOR MEMORY, 64 input features at a time (two ping-pong
+//     chunks of 64 hi + 64 lo columns): the point threads load the stored pre-BN activations of the previous
+//     layer, apply BN scale/shift + ReLU, split hi/lo and tcgen05.st them while the MMAs of the previous
+//     chunk run; the accumulator D[128 x N <= 256] occupies the other 256 columns;
+//   * 3xTF32 as everywhere (hi*hi + hi*lo + lo*hi).
+// One launch = one layer of one cell (the train-mode layer-pass scheme of flow_tiled.cu / flow_tc.cu, which
+// also serves eval mode here: activations round-trip through HBM tile-blocked [tile][W][128], 1 KB/point/layer,
+// far below the tensor time).  The final pass runs the output layer one transformed dimension at a time
+// (N = K logits padded to 16), stages the logits in shared memory and runs the spline of spline.cuh on them.
+#include <stdlib.h>
+#include "common.cuh"
+#include "spline.cuh"
+#include "tc_common.cuh"
+#include "flow_fwd_common.cuh"
+
+#define WD_THREADS 192        // 4 point warps + MMA issuer + TMA producer
+#define WD_COL_A 256          // A chunks: [256,384) and [384,512): 64 hi + 64 lo columns each
+#define WD_MAX_SLOTS 4
+
+__host__ __device__ static inline int wd_kp16(const DevFlow& F) { return (F.K + 15) & ~15; }
+// floats of one cell's operand pack: hidden layers 1..depth-1 as W/32 panels of [W][32] (hi, lo), then per
+// transformed dimension the output layer as W/32 panels of [Kp16][32] (hi, lo)
+__host__ __device__ static inline size_t wd_cell_floats(const DevFlow& F) {
+    const int W = F.widths[0];
+    int T = 0;
+    for (int c = 0; c < F.n_cells; ++c) T = F.cells[c].T > T ? F.cells[c].T : T;
+    return (size_t)(F.depth - 1) * W * W * 2 + (size_t)T * wd_kp16(F) * W * 2;
+}
+
+__global__ void flow_wide_pack_kernel(DevFlow F, const float* __restrict__ params, float* __restrict__ widepack) {
+    const int c = blockIdx.y;
+    const DevCell& q = F.cells[c];
+    const float* p = params + q.param_off;
+    const int W = F.widths[0], Kp = wd_kp16(F);
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    char* dst = reinterpret_cast<char*>(widepack + (size_t)c * wd_cell_floats(F));
+    for (int l = 1; l < F.depth; ++l) {
+        const float* w = p + F.p_lin(c, l);                 // [W][W]
+        char* base = dst + (size_t)(l - 1) * W * W * 2 * 4;
+        for (long long i = tid; i < (long long)W * W; i += nth) {
+            const int n = (int)(i / W), k = (int)(i - (long long)n * W);
+            const int kt = k >> 5, kk = k & 31;
+            const float v = w[i];
+            const float h = tf32_rn(v);
+            char* panel = base + (size_t)kt * W * 64 * 4;
+            const int off = (n >> 3) * 1024 + (n & 7) * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2));
+            *reinterpret_cast<float*>(panel + off) = h;
+            *reinterpret_cast<float*>(panel + (size_t)W * 128 + off) = tf32_rn(v - h);
+        }
+    }
+    const float* wo = p + F.p_out_w(c);                     // [T*K][W]
+    char* obase = dst + (size_t)(F.depth - 1) * W * W * 2 * 4;
+    for (long long i = tid; i < (long long)q.T * Kp * W; i += nth) {
+        const int t = (int)(i / ((long long)Kp * W));
+        const int r = (int)(i - (long long)t * Kp * W);
+        const int n = r / W, k = r - n * W;
+        const int kt = k >> 5, kk = k & 31;
+        const float v = n < F.K ? wo[((size_t)t * F.K + n) * W + k] : 0.f;
+        const float h = tf32_rn(v);
+        char* panel = obase + ((size_t)t * Kp * W * 2 + (size_t)kt * Kp * 64) * 4;
+        const int off = (n >> 3) * 1024 + (n & 7) * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2));
+        *reinterpret_cast<float*>(panel + off) = h;
+        *reinterpret_cast<float*>(panel + (size_t)Kp * 128 + off) = tf32_rn(v - h);
+    }
+}
+
+// float64 variant of tc_warp_feature_sums: sums of a[i] and a[i]^2 over the warp's 32 points, features
+// (2 lane, 2 lane + 1) on each lane.  The pre-BN activations of a wide layer are sums of 256 products; their
+// batch variance is formed as E[z^2] - E[z]^2, and float32 partial sums cost a factor two in log J here.
+__device__ __forceinline__ void wd_warp_feature_sums64(const float* v, int lane, double* s, double* s2) {
+    double a[32], b[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const bool up = lane & 16;
+        const double x0 = (double)v[i], x1 = (double)v[i + 32];
+        const double keep = up ? x1 : x0, send = up ? x0 : x1;
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        b[i] = keep * keep + __shfl_xor_sync(0xffffffffu, send * send, 16);
+    }
+#pragma unroll
+    for (int w = 16; w >= 2; w >>= 1) {
+        const int m = w >> 1;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i < w) {
+                const bool up = lane & m;
+                const double ka = up ? a[i + w] : a[i], sa = up ? a[i] : a[i + w];
+                const double kb = up ? b[i + w] : b[i], sb = up ? b[i] : b[i + w];
+                a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, m);
+                b[i] = kb + __shfl_xor_sync(0xffffffffu, sb, m);
+            }
+        }
+    }
+    s[0] = a[0]; s[1] = a[1]; s2[0] = b[0]; s2[1] = b[1];
+}
+
+struct WdSmem { int ring, slots, slot_bytes, w0, aff, bias, st, stg, red, total; };
+__host__ __device__ static inline WdSmem wd_layout(const DevFlow& F, int P, bool final_pass, bool from_state) {
+    WdSmem s;
+    const int W = F.widths[0], Kp = wd_kp16(F);
+    int T = 0;
+    for (int c = 0; c < F.n_cells; ++c) T = F.cells[c].T > T ? F.cells[c].T : T;
+    const int npanel = final_pass ? Kp : W;
+    s.slot_bytes = npanel * 256;
+    int other = 0;
+    const int w0b = from_state ? pad8(P) * W * 4 : 0;
+    const int affb = (2 * 16 + 2 * W) * 4;
+    const int biasb = final_pass ? T * Kp * 4 : 0;
+    const int stb = (F.d + 1) * TCM * 4;
+    const int stgb = final_pass ? Kp * TCM * 4 : 0;
+    const int redb = 2 * W * 8;
+    other = w0b + affb + biasb + stb + stgb + redb + 256;
+    int slots = (226 * 1024 - other) / s.slot_bytes;
+    if (slots > WD_MAX_SLOTS) slots = WD_MAX_SLOTS;
+    s.slots = slots;
+    int o = 0;
+    s.ring = o; o += slots * s.slot_bytes;
+    s.w0 = o; o += w0b;
+    s.aff = o; o += affb;
+    s.bias = o; o += biasb;
+    s.st = o; o += stb;
+    s.stg = o; o += stgb;
+    o = (o + 7) & ~7;
+    s.red = o; o += redb;
+    s.total = o;
+    return s;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __grid_constant__ DevFlow F, const FwdArgs A,
+                                                                      const float* __restrict__ widepack) {
+    extern __shared__ char smraw[];
+    __shared__ uint64_t full[WD_MAX_SLOTS], empty[WD_MAX_SLOTS], a_ready[2], a_free[2], d_ready, d_free;
+    __shared__ uint32_t tmem_base_s;
+    char* sm = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = A.c_begin;
+    const DevCell& q = F.cells[c];
+    const int d = F.d, depth = F.depth, W = F.widths[0], kb = W >> 6, Kp = wd_kp16(F);
+    const bool stats = A.stats_layer >= 1;                 // hidden pass producing z_{stats_layer}
+    const bool final_pass = !stats;
+    const int lam = stats ? A.stats_layer - 1 : depth;     // the linear layer this launch multiplies by (1..depth)
+    const bool from_z = A.zin != nullptr;                  // else lam == 1 and z_1 is computed from the state
+    const WdSmem L = wd_layout(F, q.P, final_pass, !from_z);
+    const int RS = L.slots;
+    const int npanel = final_pass ? Kp : W;                // N of the MMAs
+    const int rounds = final_pass ? q.T : 1;
+    float* w0s = reinterpret_cast<float*>(sm + L.w0);
+    float* affs = reinterpret_cast<float*>(sm + L.aff);    // sc0[16] sh0[16] sc_lam[W] sh_lam[W]
+    float* biass = reinterpret_cast<float*>(sm + L.bias);
+    const float* pk = A.wpack + q.pk_off;
+    const float* cellpack = widepack + (size_t)c * wd_cell_floats(F);
+
+    if (!from_z) {
+        const float* s0 = pk + q.wt_off[0];                // layer 0, [P][W] k-major
+        for (int i = tid; i < q.P * W; i += WD_THREADS) w0s[i] = s0[i];
+    }
+    for (int i = tid; i < 16; i += WD_THREADS) {
+        affs[i] = i < q.P ? pk[q.aff_off[0] + i] : 0.f;
+        affs[16 + i] = i < q.P ? pk[q.aff_off[0] + pad8(q.P) + i] : 0.f;
+    }
+    for (int i = tid; i < W; i += WD_THREADS) {
+        affs[32 + i] = pk[q.aff_off[lam] + i];
+        affs[32 + W + i] = pk[q.aff_off[lam] + W + i];
+    }
+    if (final_pass)
+        for (int i = tid; i < q.T * Kp; i += WD_THREADS) {
+            const int t = i / Kp, n = i - t * Kp;
+            biass[i] = n < F.K ? pk[q.bo_off + t * F.Kpad + n] : 0.f;
+        }
+    if (tid == 0) {
+        for (int s = 0; s < WD_MAX_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&a_ready[0], TCM); mbar_init(&a_ready[1], TCM);
+        mbar_init(&a_free[0], 1); mbar_init(&a_free[1], 1);
+        mbar_init(&d_ready, 1); mbar_init(&d_free, TCM);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const long long ntiles = (A.B + TCM - 1) / TCM;
+    const long long rowlen = d + 1;
+    const int kpanels = W >> 5;                             // K-panels of 32 per round
+    const size_t panel_floats = (size_t)npanel * 64;
+    double dsum[4][2], dsq[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dsum[j][0] = dsum[j][1] = dsq[j][0] = dsq[j][1] = 0.0; }
+
+    if (warp == 5) {
+        // ===================== weight producer: panels in consumption order through the ring ===============
+        if (lane == 0) {
+            unsigned pc = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int r = 0; r < rounds; ++r) {
+                    const float* src = cellpack + (final_pass ? (size_t)(depth - 1) * W * W * 2 + (size_t)r * Kp * W * 2
+                                                              : (size_t)(lam - 1) * W * W * 2);
+                    for (int p = 0; p < kpanels; ++p, ++pc) {
+                        const unsigned slot = pc % RS;
+                        mbar_wait(&empty[slot], ((pc / RS) & 1) ^ 1);
+                        bulk_load(sm + L.ring + slot * L.slot_bytes, src + p * panel_floats, (uint32_t)L.slot_bytes, &full[slot]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ===================== MMA issuer ======================================================
+        if (lane == 0) {
+            unsigned pc = 0, cc = 0, rr = 0;
+            const uint32_t idesc = tc_idesc(TCM, npanel);
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int r = 0; r < rounds; ++r, ++rr) {
+                    mbar_wait(&d_free, (rr & 1) ^ 1);               // the previous accumulator has been read out
+                    tc_fence_after();
+                    uint32_t acc = 0;
+                    for (int i = 0; i < kb; ++i, ++cc) {
+                        const unsigned buf = cc & 1;
+                        mbar_wait(&a_ready[buf], (cc >> 1) & 1);
+                        tc_fence_after();
+                        const uint32_t ta = tmem_base + WD_COL_A + buf * 128;
+                        for (int kt = 0; kt < 2; ++kt, ++pc) {
+                            const unsigned slot = pc % RS;
+                            mbar_wait(&full[slot], (pc / RS) & 1);
+                            tc_fence_after();
+                            const uint32_t bh = smem_u32(sm + L.ring + slot * L.slot_bytes), bl = bh + npanel * 128;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint32_t ah = ta + kt * 32 + ks * 8;
+                                tc_mma_tf32_ts(tmem_base, ah, tc_desc(bh + ks * 32), idesc, acc);
+                                acc = 1;
+                                tc_mma_tf32_ts(tmem_base, ah, tc_desc(bl + ks * 32), idesc, 1);
+                                tc_mma_tf32_ts(tmem_base, ah + 64, tc_desc(bh + ks * 32), idesc, 1);
+                            }
+                            tc_commit(&empty[slot]);
+                        }
+                        tc_commit(&a_free[buf]);
+                    }
+                    tc_commit(&d_ready);
+                }
+            }
+        }
+    } else {
+        // ===================== point threads ====================================================
+        const int gt = tid;
+        float* st = reinterpret_cast<float*>(sm + L.st) + gt;
+        float* stg = reinterpret_cast<float*>(sm + L.stg) + gt;
+        const uint32_t tg = tmem_base + ((uint32_t)(warp * 32) << 16);
+        unsigned cc = 0, rr = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long pt = tile * TCM + gt;
+            const bool valid = pt < A.B;
+            if (valid) {
+                if (A.from_state) {
+                    for (int i = 0; i <= d; ++i) st[i * TCM] = A.state_in[pt * rowlen + i];
+                } else {
+                    for (int i = 0; i < d; ++i) st[i * TCM] = load_io(A.in, A.in_dtype, pt * A.in_cols + i);
+                    st[d * TCM] = A.in_cols > d ? load_io(A.in, A.in_dtype, pt * A.in_cols + d) : 1.f;
+                }
+                if (final_pass && A.saved && !A.from_state) {
+                    float* sv = A.saved + ((long long)c * A.B + pt) * rowlen;
+                    for (int i = 0; i <= d; ++i) sv[i] = st[i * TCM];
+                }
+            } else {
+                for (int i = 0; i < d; ++i) st[i * TCM] = 0.5f;
+                st[d * TCM] = 1.f;
+            }
+            float a0[16];
+            if (!from_z) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) a0[k] = k < q.P ? fmaf(st[q.feed[k] * TCM], affs[k], affs[16 + k]) : 0.f;
+            }
+            float jfac = 1.f;
+            for (int r = 0; r < rounds; ++r, ++rr) {
+                // ---- A operand: h_lam = ReLU(BN_lam(z_lam)), 64 features per chunk ---------------------------------
+                for (int i = 0; i < kb; ++i, ++cc) {
+                    const unsigned buf = cc & 1;
+                    float v[TCH];
+                    if (from_z) {
+                        const float* zr = A.zin + ((size_t)tile * W + 64 * i) * TCM + gt;
+#pragma unroll
+                        for (int j = 0; j < TCH; ++j) v[j] = zr[(size_t)j * TCM];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < TCH; ++j) v[j] = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            if (k < q.P) {
+                                const float4* wr = reinterpret_cast<const float4*>(w0s + k * W + 64 * i);
+#pragma unroll
+                                for (int j4 = 0; j4 < TCH / 4; ++j4) {
+                                    const float4 w = wr[j4];
+                                    v[4 * j4] = fmaf(a0[k], w.x, v[4 * j4]); v[4 * j4 + 1] = fmaf(a0[k], w.y, v[4 * j4 + 1]);
+                                    v[4 * j4 + 2] = fmaf(a0[k], w.z, v[4 * j4 + 2]); v[4 * j4 + 3] = fmaf(a0[k], w.w, v[4 * j4 + 3]);
+                                }
+                            }
+                        }
+                    }
+                    mbar_wait(&a_free[buf], ((cc >> 1) & 1) ^ 1);      // the MMAs that read this chunk buffer are done
+                    tc_fence_after();
+                    const uint32_t ta = tg + WD_COL_A + buf * 128;
+                    tc_store_act(v, affs + 32 + 64 * i, affs + 32 + W + 64 * i, ta, ta + 64);
+                    tc_fence_before();
+                    mbar_arrive(&a_ready[buf]);
+                }
+                mbar_wait(&d_ready, rr & 1);
+                tc_fence_after();
+                if (stats) {
+                    // ---- hidden pass: z_{lam+1} to HBM (tile-blocked) and its per-feature sums ----------------------
+                    float* zo = A.zout + (size_t)tile * W * TCM + gt;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j >= kb) break;
+                        float v[TCH];
+                        tc_ld32(tg + 64 * j, v);
+                        tc_ld32(tg + 64 * j + 32, v + 32);
+                        tc_ld_wait();
+#pragma unroll
+                        for (int x = 0; x < TCH; ++x) {
+                            v[x] = valid ? v[x] : 0.f;
+                            zo[(size_t)(64 * j + x) * TCM] = v[x];
+                        }
+                        if (!A.no_stats) {
+                            double s[2], s2[2];
+                            wd_warp_feature_sums64(v, lane, s, s2);
+                            dsum[j][0] += s[0]; dsum[j][1] += s[1];
+                            dsq[j][0] += s2[0]; dsq[j][1] += s2[1];
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&d_free);
+                } else {
+                    // ---- final pass, transformed dimension t = r: logits -> shared memory -> spline ----------------
+                    const int t = r;
+                    for (int j0 = 0; j0 < Kp; j0 += 16) {
+                        float v[16];
+                        tc_ld16(tg + j0, v);
+                        tc_ld_wait();
+#pragma unroll
+                        for (int x = 0; x < 16; ++x) stg[(j0 + x) * TCM] = v[x] + biass[t * Kp + j0 + x];
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&d_free);
+                    const int col = q.trafo[t];
+                    const float xv = st[col * TCM];
+                    float y, f;
+                    int kbin;
+                    if (KIND == NIS_KIND_PWLIN) {
+                        float S, al;
+                        y = pwlin_fwd(stg, TCM, F.nb, xv, f, kbin, S, al);
+                    } else {
+                        QuadCtx qc;
+                        pwquad_fwd(stg, TCM, F.nb, xv, qc);
+                        y = qc.y; f = qc.f; kbin = qc.k;
+                    }
+                    st[col * TCM] = y;
+                    jfac *= f;
+                    if (A.bins && valid) A.bins[((long long)c * A.B + pt) * d + t] = kbin;
+                }
+            }
+            if (final_pass) {
+                st[d * TCM] *= jfac;
+                if (valid) {
+                    if (A.state_out) {
+                        float* so = A.state_out + pt * rowlen;
+                        for (int i = 0; i <= d; ++i) so[i] = st[i * TCM];
+                    }
+                    if (A.to_out) {
+                        for (int i = 0; i < d; ++i) store_io(A.out, A.out_dtype, pt * rowlen + i, st[F.out_perm[i] * TCM]);
+                        store_io(A.out, A.out_dtype, pt * rowlen + d, st[d * TCM]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (!stats || A.no_stats) return;
+    // ---- fold the per-lane sums: lane i of a warp holds features 64 j + 2 i, 64 j + 2 i + 1 ---------------------
+    double* red = reinterpret_cast<double*>(sm + L.ring);            // [4 warps][32 lanes][16]   (the ring is idle now)
+    double* sacc = reinterpret_cast<double*>(sm + L.red);            // [2 * maxW]
+    if (warp < 4) {
+        double* r = red + ((size_t)warp * 32 + lane) * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { r[4 * j] = dsum[j][0]; r[4 * j + 1] = dsum[j][1]; r[4 * j + 2] = dsq[j][0]; r[4 * j + 3] = dsq[j][1]; }
+    }
+    __syncthreads();
+    for (int f = tid; f < F.maxW; f += WD_THREADS) {
+        double s = 0.0, s2 = 0.0;
+        if (f < W) {
+            const int j = f >> 6, ln = (f & 63) >> 1, ix = f & 1;
+            for (int w = 0; w < 4; ++w) {
+                s += red[((size_t)w * 32 + ln) * 16 + 4 * j + ix];
+                s2 += red[((size_t)w * 32 + ln) * 16 + 4 * j + 2 + ix];
+            }
+        }
+        sacc[f] = s; sacc[F.maxW + f] = s2;
+    }
+    bn_stats_finalize(F, A, sacc, WD_THREADS);
+}
+
+// ---------------------------------------------------------------------------------------------------
+bool nis_moments_supported(const DevFlow& F, int c);
+
+bool nis_wide_supported(const DevFlow& F, int64_t B, int bn_mode) {
+    const char* off = getenv("NIS_TC");                   // NIS_TC=0 forces the FP32-pipe kernels (test knob)
+    if (off && off[0] == '0') return false;
+    if (F.depth < 1 || B < 1024) return false;
+    const int W = F.widths[0];
+    if (W < 128 || W > 256 || (W & 63)) return false;
+    for (int l = 0; l < F.depth; ++l) if (F.widths[l] != W) return false;
+    if (F.maxW != W) return false;
+    if (wd_kp16(F) > 256) return false;
+    for (int c = 0; c < F.n_cells; ++c) {
+        if (F.cells[c].P > 16) return false;
+        if (bn_mode == NIS_BN_TRAIN && !nis_moments_supported(F, c)) return false;
+        if (wd_layout(F, F.cells[c].P, true, F.depth == 1).slots < 2) return false;
+        if (wd_layout(F, F.cells[c].P, false, true).slots < 2) return false;
+    }
+    return true;
+}
+
+size_t nis_wide_pack_floats(const DevFlow& F) {
+    if (F.depth < 1 || F.widths[0] < 128) return 0;
+    return (size_t)F.n_cells * wd_cell_floats(F);
+}
+
+int nis_wide_pack(const DevFlow& F, const float* params, float* widepack, cudaStream_t s) {
+    flow_wide_pack_kernel<<<dim3(128, F.n_cells), 256, 0, s>>>(F, params, widepack);
+    NIS_CUDA_CHECK_LAUNCH();
+    return NIS_OK;
+}
+
+int nis_launch_wide(const DevFlow& F, const FwdArgs& A, const float* widepack, cudaStream_t s) {
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    const bool final_pass = A.stats_layer < 1;
+    const WdSmem L = wd_layout(F, F.cells[A.c_begin].P, final_pass, A.zin == nullptr);
+    const size_t smem = (size_t)L.total + 1024;
+    auto kern = F.kind == NIS_KIND_PWLIN ? flow_wide_tc_kernel<NIS_KIND_PWLIN> : flow_wide_tc_kernel<NIS_KIND_PWQUAD>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long long ntiles = (A.B + TCM - 1) / TCM;
+    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    kern<<<grid, WD_THREADS, smem, s>>>(F, A, widepack);
+    NIS_CUDA_CHECK_LAUNCH();
+    return NIS_OK;
+}

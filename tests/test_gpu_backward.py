@@ -169,3 +169,35 @@ def test_full_size_cfg5_trains_through_the_generic_backward():
     makes this width fit.  Gradients against float64 autograd through the oracle."""
     cfg = dict(name="cfg5", kind="quad", n_flow=16, n_cells=8, n_bins=64, NN=[256] * 4, B=640)
     test_gradients_match_oracle_autograd_at_size(cfg, "train")
+
+
+def test_tensor_core_backward_at_large_batch_matches_generic(monkeypatch):
+    """Many tiles per CTA (2^18 points): the weight-gradient accumulators in tensor memory are flushed to the CTA's
+    slice every few tiles because tcgen05 accumulation truncates; the result must agree with the FP32 generic
+    kernel (itself pinned against the oracle above)."""
+    cfg = dict(BIG[0], B=1 << 18)
+    layers = oracle_layers(cfg)
+    cells, _ = oflow.compile_layers(layers, cfg["n_flow"])
+    sd = oflow.init_state_dict(cells, cfg["n_flow"], cfg["kind"], cfg["n_bins"], cfg["NN"], seed=33,
+                               dtype=torch.float32, bn_jitter=0.2)
+    gen = torch.Generator().manual_seed(6)
+    x = torch.rand(cfg["B"], cfg["n_flow"], generator=gen, dtype=torch.float32)
+    fres = torch.exp(-((x - 0.5) ** 2).sum(-1) / 0.2).cuda()
+    grads = {}
+    for backend, env in (("tcgen05", None), ("generic", "0")):
+        monkeypatch.delenv("NIS_BWD_TC", raising=False)
+        if env is not None:
+            monkeypatch.setenv("NIS_BWD_TC", env)
+        NF = make_manager(cfg)
+        model = NF._model
+        model.load_state_dict(sd)
+        model.train()
+        XJ = model(x.cuda())
+        torch.var(fres * XJ[:, -1]).backward()
+        grads[backend] = {k: p.grad.detach().cpu().double() for k, p in model.named_parameters()}
+    gscale = max(float(v.abs().max()) for v in grads["generic"].values())
+    worst = 0.0
+    for k in grads["generic"]:
+        close(grads["tcgen05"][k], grads["generic"][k], k, gscale, flips=True)
+        worst = max(worst, float((grads["tcgen05"][k] - grads["generic"][k]).abs().max()) / gscale)
+    print("tc vs generic backward at 2^18 points: worst |diff| / model gradient scale = %.2e" % worst)
