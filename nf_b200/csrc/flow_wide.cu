@@ -7,11 +7,16 @@
 //   * weights are packed once per forward as K-panels of 32 input features, [N rows][32] hi then lo in the
 //     K-major 128B-swizzled UMMA layout, and STREAMED from L2 through a ring of shared-memory slots by
 //     cp.async.bulk (TMA) from a dedicated producer warp (full/empty mbarriers per slot);
-//   * the activations enter as the A operand from TENSOR MEMORY, 64 input features at a time (two ping-pong
-//     chunks of 64 hi + 64 lo columns): the point threads load the stored pre-BN activations of the previous
+//   * the activations enter as the A operand from TENSOR MEMORY, 32 input features at a time (two ping-pong
+//     chunks of 32 hi + 32 lo columns): the point threads load the stored pre-BN activations of the previous
 //     layer, apply BN scale/shift + ReLU, split hi/lo and tcgen05.st them while the MMAs of the previous
-//     chunk run; the accumulator D[128 x N <= 256] occupies the other 256 columns;
-//   * 3xTF32 as everywhere (hi*hi + hi*lo + lo*hi).
+//     chunk run;
+//   * 3xTF32 as everywhere (hi*hi + hi*lo + lo*hi), but into TWO accumulators: tcgen05.mma truncates when it
+//     adds a K=8 step into the fp32 accumulator (tools/tc_accum_probe.cu: ~1 ulp per instruction, toward
+//     zero), and with K = 256 one accumulator would take 96 such steps (measured: log J twice as far from
+//     the float64 oracle as torch-fp32).  The hi*hi products (32 steps) go to D_hi, the two cross products
+//     (2^-11 smaller, so their truncation does not matter) to D_x, and the epilogue adds the two in fp32.
+//     N <= 192 per round (2 x 192 accumulator columns); a 256-wide layer is two rounds of 128 outputs.
 // One launch = one layer of one cell (the train-mode layer-pass scheme of flow_tiled.cu / flow_tc.cu, which
 // also serves eval mode here: activations round-trip through HBM tile-blocked [tile][W][128], 1 KB/point/layer,
 // far below the tensor time).  The final pass runs the output layer one transformed dimension at a time
@@ -23,7 +28,9 @@
 #include "flow_fwd_common.cuh"
 
 #define WD_THREADS 192        // 4 point warps + MMA issuer + TMA producer
-#define WD_COL_A 256          // A chunks: [256,384) and [384,512): 64 hi + 64 lo columns each
+#define WD_COL_X 192          // cross-term accumulator D_x [192,384); D_hi is [0,192)
+#define WD_COL_A 384          // A chunks: [384,448) and [448,512): 32 hi + 32 lo columns each
+#define WD_NMAX 192
 #define WD_MAX_SLOTS 4
 
 __host__ __device__ static inline int wd_kp16(const DevFlow& F) { return (F.K + 15) & ~15; }
@@ -36,6 +43,10 @@ __host__ __device__ static inline size_t wd_cell_floats(const DevFlow& F) {
     return (size_t)(F.depth - 1) * W * W * 2 + (size_t)T * wd_kp16(F) * W * 2;
 }
 
+// hidden layers: outputs per round (N of the MMAs) and rounds per tile
+__host__ __device__ static inline int wd_hid_n(int W) { return W <= WD_NMAX ? W : W / 2; }
+__host__ __device__ static inline int wd_hid_rounds(int W) { return W <= WD_NMAX ? 1 : 2; }
+
 __global__ void flow_wide_pack_kernel(DevFlow F, const float* __restrict__ params, float* __restrict__ widepack) {
     const int c = blockIdx.y;
     const DevCell& q = F.cells[c];
@@ -47,14 +58,15 @@ __global__ void flow_wide_pack_kernel(DevFlow F, const float* __restrict__ param
         const float* w = p + F.p_lin(c, l);                 // [W][W]
         char* base = dst + (size_t)(l - 1) * W * W * 2 * 4;
         for (long long i = tid; i < (long long)W * W; i += nth) {
-            const int n = (int)(i / W), k = (int)(i - (long long)n * W);
+            const int no = (int)(i / W), k = (int)(i - (long long)no * W);
+            const int Nr = wd_hid_n(W), r = no / Nr, n = no - r * Nr;      // round r holds outputs [r Nr, r Nr + Nr)
             const int kt = k >> 5, kk = k & 31;
             const float v = w[i];
             const float h = tf32_rn(v);
-            char* panel = base + (size_t)kt * W * 64 * 4;
+            char* panel = base + ((size_t)r * Nr * W * 2 + (size_t)kt * Nr * 64) * 4;
             const int off = (n >> 3) * 1024 + (n & 7) * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2));
             *reinterpret_cast<float*>(panel + off) = h;
-            *reinterpret_cast<float*>(panel + (size_t)W * 128 + off) = tf32_rn(v - h);
+            *reinterpret_cast<float*>(panel + (size_t)Nr * 128 + off) = tf32_rn(v - h);
         }
     }
     const float* wo = p + F.p_out_w(c);                     // [T*K][W]
@@ -109,7 +121,7 @@ __host__ __device__ static inline WdSmem wd_layout(const DevFlow& F, int P, bool
     const int W = F.widths[0], Kp = wd_kp16(F);
     int T = 0;
     for (int c = 0; c < F.n_cells; ++c) T = F.cells[c].T > T ? F.cells[c].T : T;
-    const int npanel = final_pass ? Kp : W;
+    const int npanel = final_pass ? Kp : wd_hid_n(W);
     s.slot_bytes = npanel * 256;
     int other = 0;
     const int w0b = from_state ? pad8(P) * W * 4 : 0;
@@ -145,15 +157,15 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c = A.c_begin;
     const DevCell& q = F.cells[c];
-    const int d = F.d, depth = F.depth, W = F.widths[0], kb = W >> 6, Kp = wd_kp16(F);
+    const int d = F.d, depth = F.depth, W = F.widths[0], kc = W >> 5, Kp = wd_kp16(F);     // kc: chunks of 32 features
     const bool stats = A.stats_layer >= 1;                 // hidden pass producing z_{stats_layer}
     const bool final_pass = !stats;
     const int lam = stats ? A.stats_layer - 1 : depth;     // the linear layer this launch multiplies by (1..depth)
     const bool from_z = A.zin != nullptr;                  // else lam == 1 and z_1 is computed from the state
     const WdSmem L = wd_layout(F, q.P, final_pass, !from_z);
     const int RS = L.slots;
-    const int npanel = final_pass ? Kp : W;                // N of the MMAs
-    const int rounds = final_pass ? q.T : 1;
+    const int npanel = final_pass ? Kp : wd_hid_n(W);      // N of the MMAs
+    const int rounds = final_pass ? q.T : wd_hid_rounds(W);
     float* w0s = reinterpret_cast<float*>(sm + L.w0);
     float* affs = reinterpret_cast<float*>(sm + L.aff);    // sc0[16] sh0[16] sc_lam[W] sh_lam[W]
     float* biass = reinterpret_cast<float*>(sm + L.bias);
@@ -195,7 +207,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
     const uint32_t tmem_base = tmem_base_s;
     const long long ntiles = (A.B + TCM - 1) / TCM;
     const long long rowlen = d + 1;
-    const int kpanels = W >> 5;                             // K-panels of 32 per round
+    const int kpanels = kc;                                 // K-panels of 32 per round (one per A chunk)
     const size_t panel_floats = (size_t)npanel * 64;
     double dsum[4][2], dsq[4][2];
 #pragma unroll
@@ -208,7 +220,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int r = 0; r < rounds; ++r) {
                     const float* src = cellpack + (final_pass ? (size_t)(depth - 1) * W * W * 2 + (size_t)r * Kp * W * 2
-                                                              : (size_t)(lam - 1) * W * W * 2);
+                                                              : (size_t)(lam - 1) * W * W * 2 + (size_t)r * npanel * W * 2);
                     for (int p = 0; p < kpanels; ++p, ++pc) {
                         const unsigned slot = pc % RS;
                         mbar_wait(&empty[slot], ((pc / RS) & 1) ^ 1);
@@ -227,26 +239,23 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
                     mbar_wait(&d_free, (rr & 1) ^ 1);               // the previous accumulator has been read out
                     tc_fence_after();
                     uint32_t acc = 0;
-                    for (int i = 0; i < kb; ++i, ++cc) {
+                    for (int i = 0; i < kc; ++i, ++cc, ++pc) {
                         const unsigned buf = cc & 1;
                         mbar_wait(&a_ready[buf], (cc >> 1) & 1);
+                        const unsigned slot = pc % RS;
+                        mbar_wait(&full[slot], (pc / RS) & 1);
                         tc_fence_after();
-                        const uint32_t ta = tmem_base + WD_COL_A + buf * 128;
-                        for (int kt = 0; kt < 2; ++kt, ++pc) {
-                            const unsigned slot = pc % RS;
-                            mbar_wait(&full[slot], (pc / RS) & 1);
-                            tc_fence_after();
-                            const uint32_t bh = smem_u32(sm + L.ring + slot * L.slot_bytes), bl = bh + npanel * 128;
+                        const uint32_t ta = tmem_base + WD_COL_A + buf * 64;
+                        const uint32_t bh = smem_u32(sm + L.ring + slot * L.slot_bytes), bl = bh + npanel * 128;
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint32_t ah = ta + kt * 32 + ks * 8;
-                                tc_mma_tf32_ts(tmem_base, ah, tc_desc(bh + ks * 32), idesc, acc);
-                                acc = 1;
-                                tc_mma_tf32_ts(tmem_base, ah, tc_desc(bl + ks * 32), idesc, 1);
-                                tc_mma_tf32_ts(tmem_base, ah + 64, tc_desc(bh + ks * 32), idesc, 1);
-                            }
-                            tc_commit(&empty[slot]);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t ah = ta + ks * 8;
+                            tc_mma_tf32_ts(tmem_base, ah, tc_desc(bh + ks * 32), idesc, acc);                 // D_hi += a_hi w_hi
+                            tc_mma_tf32_ts(tmem_base + WD_COL_X, ah, tc_desc(bl + ks * 32), idesc, acc);      // D_x  += a_hi w_lo
+                            acc = 1;
+                            tc_mma_tf32_ts(tmem_base + WD_COL_X, ah + 32, tc_desc(bh + ks * 32), idesc, 1);   // D_x  += a_lo w_hi
                         }
+                        tc_commit(&empty[slot]);
                         tc_commit(&a_free[buf]);
                     }
                     tc_commit(&d_ready);
@@ -286,22 +295,22 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
             float jfac = 1.f;
             for (int r = 0; r < rounds; ++r, ++rr) {
                 // ---- A operand: h_lam = ReLU(BN_lam(z_lam)), 64 features per chunk ---------------------------------
-                for (int i = 0; i < kb; ++i, ++cc) {
+                for (int i = 0; i < kc; ++i, ++cc) {
                     const unsigned buf = cc & 1;
-                    float v[TCH];
+                    float v[32];
                     if (from_z) {
-                        const float* zr = A.zin + ((size_t)tile * W + 64 * i) * TCM + gt;
+                        const float* zr = A.zin + ((size_t)tile * W + 32 * i) * TCM + gt;
 #pragma unroll
-                        for (int j = 0; j < TCH; ++j) v[j] = zr[(size_t)j * TCM];
+                        for (int j = 0; j < 32; ++j) v[j] = zr[(size_t)j * TCM];
                     } else {
 #pragma unroll
-                        for (int j = 0; j < TCH; ++j) v[j] = 0.f;
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
                             if (k < q.P) {
-                                const float4* wr = reinterpret_cast<const float4*>(w0s + k * W + 64 * i);
+                                const float4* wr = reinterpret_cast<const float4*>(w0s + k * W + 32 * i);
 #pragma unroll
-                                for (int j4 = 0; j4 < TCH / 4; ++j4) {
+                                for (int j4 = 0; j4 < 8; ++j4) {
                                     const float4 w = wr[j4];
                                     v[4 * j4] = fmaf(a0[k], w.x, v[4 * j4]); v[4 * j4 + 1] = fmaf(a0[k], w.y, v[4 * j4 + 1]);
                                     v[4 * j4 + 2] = fmaf(a0[k], w.z, v[4 * j4 + 2]); v[4 * j4 + 3] = fmaf(a0[k], w.w, v[4 * j4 + 3]);
@@ -309,10 +318,20 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
                             }
                         }
                     }
+                    float lo[32];
+                    const float* sc = affs + 32 + 32 * i, *sh = affs + 32 + W + 32 * i;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float a = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+                        v[j] = tf32_rn(a);
+                        lo[j] = tf32_rn(a - v[j]);
+                    }
                     mbar_wait(&a_free[buf], ((cc >> 1) & 1) ^ 1);      // the MMAs that read this chunk buffer are done
                     tc_fence_after();
-                    const uint32_t ta = tg + WD_COL_A + buf * 128;
-                    tc_store_act(v, affs + 32 + 64 * i, affs + 32 + W + 64 * i, ta, ta + 64);
+                    const uint32_t ta = tg + WD_COL_A + buf * 64;
+                    tc_st32(ta, v);
+                    tc_st32(ta + 32, lo);
+                    tc_st_wait();
                     tc_fence_before();
                     mbar_arrive(&a_ready[buf]);
                 }
@@ -320,24 +339,28 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
                 tc_fence_after();
                 if (stats) {
                     // ---- hidden pass: z_{lam+1} to HBM (tile-blocked) and its per-feature sums ----------------------
-                    float* zo = A.zout + (size_t)tile * W * TCM + gt;
+                    float* zo = A.zout + ((size_t)tile * W + (size_t)r * npanel) * TCM + gt;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (j >= kb) break;
-                        float v[TCH];
+                    for (int j = 0; j < 3; ++j) {
+                        if (64 * j >= npanel) break;
+                        float v[TCH], xx[TCH];
                         tc_ld32(tg + 64 * j, v);
                         tc_ld32(tg + 64 * j + 32, v + 32);
+                        tc_ld32(tg + WD_COL_X + 64 * j, xx);
+                        tc_ld32(tg + WD_COL_X + 64 * j + 32, xx + 32);
                         tc_ld_wait();
 #pragma unroll
                         for (int x = 0; x < TCH; ++x) {
-                            v[x] = valid ? v[x] : 0.f;
+                            v[x] = valid ? v[x] + xx[x] : 0.f;
                             zo[(size_t)(64 * j + x) * TCM] = v[x];
                         }
                         if (!A.no_stats) {
                             double s[2], s2[2];
                             wd_warp_feature_sums64(v, lane, s, s2);
-                            dsum[j][0] += s[0]; dsum[j][1] += s[1];
-                            dsq[j][0] += s2[0]; dsq[j][1] += s2[1];
+                            const int fb = (r * npanel >> 6) + j;          // 64-feature block of the layer
+#pragma unroll
+                            for (int y = 0; y < 4; ++y)
+                                if (y == fb) { dsum[y][0] += s[0]; dsum[y][1] += s[1]; dsq[y][0] += s2[0]; dsq[y][1] += s2[1]; }
                         }
                     }
                     tc_fence_before();
@@ -346,11 +369,12 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
                     // ---- final pass, transformed dimension t = r: logits -> shared memory -> spline ----------------
                     const int t = r;
                     for (int j0 = 0; j0 < Kp; j0 += 16) {
-                        float v[16];
+                        float v[16], xx[16];
                         tc_ld16(tg + j0, v);
+                        tc_ld16(tg + WD_COL_X + j0, xx);
                         tc_ld_wait();
 #pragma unroll
-                        for (int x = 0; x < 16; ++x) stg[(j0 + x) * TCM] = v[x] + biass[t * Kp + j0 + x];
+                        for (int x = 0; x < 16; ++x) stg[(j0 + x) * TCM] = (v[x] + xx[x]) + biass[t * Kp + j0 + x];
                     }
                     tc_fence_before();
                     mbar_arrive(&d_free);
@@ -424,7 +448,7 @@ bool nis_wide_supported(const DevFlow& F, int64_t B, int bn_mode) {
     if (W < 128 || W > 256 || (W & 63)) return false;
     for (int l = 0; l < F.depth; ++l) if (F.widths[l] != W) return false;
     if (F.maxW != W) return false;
-    if (wd_kp16(F) > 256) return false;
+    if (wd_kp16(F) > WD_NMAX) return false;
     for (int c = 0; c < F.n_cells; ++c) {
         if (F.cells[c].P > 16) return false;
         if (bn_mode == NIS_BN_TRAIN && !nis_moments_supported(F, c)) return false;

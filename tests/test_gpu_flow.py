@@ -89,10 +89,13 @@ def test_forward_matches_oracle_at_size(cfg, mode):
 
 @pytest.mark.parametrize("backend", ["tcgen05", "fp32_tiled_4x8", "fp32_tiled_8x8", "generic"])
 @pytest.mark.parametrize("mode", ["eval", "train"])
-@pytest.mark.parametrize("which", [0, 1], ids=["cfg2", "cfg4"])
+@pytest.mark.parametrize("which", [0, 1, 3], ids=["cfg2", "cfg4", "cfg5_small"])
 def test_every_kernel_family_agrees_with_the_oracle(monkeypatch, backend, mode, which):
-    """cfg2 (PWLin) and cfg4 (PWQuad) are served by the tcgen05 kernel by default; the FP32-pipe register-tiled
-    kernels and the shape-generic kernel stay selectable (library test knobs) and must meet the same parity bar."""
+    """cfg2 (PWLin) and cfg4 (PWQuad) are served by the resident-weights tcgen05 kernel by default, the 256-wide
+    cfg5 by the streamed-weights one (flow_wide.cu); the FP32-pipe register-tiled kernels and the shape-generic
+    kernel stay selectable (library test knobs) and must meet the same parity bar."""
+    if which == 3 and backend.startswith("fp32_tiled"):
+        pytest.skip("the register-tiled FP32 kernels are width-64 only")
     env = {"tcgen05": {}, "fp32_tiled_4x8": {"NIS_TC": "0"}, "fp32_tiled_8x8": {"NIS_TC": "0", "NIS_TILED_VARIANT": "8"},
            "generic": {"NIS_TC": "0", "NIS_DISABLE_TILED": "1"}}[backend]
     for k in ("NIS_TC", "NIS_TILED_VARIANT", "NIS_DISABLE_TILED"):
@@ -120,3 +123,18 @@ def test_flow_is_a_bijection_of_the_unit_cube_at_full_size():
     assert float(XJ[:, :-1].min()) >= 0.0 and float(XJ[:, :-1].max()) <= 1.0 + 1e-6
     # determinism: same input, same bits
     assert torch.equal(model(x), XJ)
+
+
+WIDE = [
+    dict(name="wide_lin128", kind="lin", n_flow=8, n_pass_through=4, n_cells=4, n_bins=48, NN=[128] * 3, roll_step=4, B=3000),
+    dict(name="wide_quad192", kind="quad", n_flow=6, n_cells=6, n_bins=20, NN=[192] * 2, B=2500),
+    dict(name="wide_quad256_deep", kind="quad", n_flow=16, n_cells=8, n_bins=64, NN=[256] * 4, B=1400),
+]
+
+
+@pytest.mark.parametrize("cfg", WIDE, ids=[c["name"] for c in WIDE])
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_streamed_weight_kernel_shapes(cfg, mode):
+    """flow_wide.cu beyond cfg5_small: width 128 (one round), 192 (one round of N = 192), 256 x 4 layers (two rounds
+    per hidden layer), PWLin and PWQuad, bin counts that are not multiples of 16, ragged last tile."""
+    test_forward_matches_oracle_at_size(cfg, mode)
