@@ -94,6 +94,8 @@ def build_flow(seed=1234):
     torch.manual_seed(seed)
     NF = PWLinManager(n_flow=CFG2["n_flow"])
     NF.create_model(CFG2["n_pass_through"], CFG2["n_cells"], CFG2["n_bins"], CFG2["NN"], CFG2["roll_step"])
+    if torch.cuda.is_available():
+        NF._model.to(torch.device("cuda", torch.cuda.current_device()))     # this rank's GPU (create_model uses cuda:0)
     return NF
 
 

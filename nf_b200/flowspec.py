@@ -270,6 +270,11 @@ class _FlowFn(torch.autograd.Function):
 
 def flow_apply(spec, xj, train):
     """Differentiable fused flow: [B, d(+1)] -> [B, d+1]."""
+    if xj.is_cuda:
+        # The parameters follow the input's device (they are re-homed as views of one arena there).  Do it
+        # before autograd records them as inputs, or the first backward after a device change sees gradients
+        # on another device than the one it noted for the parameters.
+        spec.param_arena.get(xj.device)
     return _FlowFn.apply(xj, spec, bool(train), *spec.params)
 
 
