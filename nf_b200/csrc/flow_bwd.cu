@@ -498,6 +498,12 @@ int nis_flow_backward_tc(const DevFlow& F, const FlowWorkspace& ws, const float*
                          const float* saved, const float* bn_saved, const void* grad_out, int grad_dtype,
                          float* grad_params, void* grad_in, int64_t B, cudaStream_t s);
 
+// wide-conditioner train-mode backward (flow_bwd_wide.cu)
+bool nis_bwd_wide_supported(const DevFlow& F, int64_t B, int bn_mode);
+int nis_flow_backward_wide(const DevFlow& F, const FlowWorkspace& ws, const float* params, const float* bn_running,
+                           const float* saved, const float* bn_saved, const void* grad_out, int grad_dtype,
+                           float* grad_params, void* grad_in, int64_t B, cudaStream_t s);
+
 static int launch_bwd_any(const DevFlow& F, const BwdArgs& A, int NT, int grid, cudaStream_t s) {
     switch (NT) {
         case 128: return launch_bwd<128>(F, A, grid, s);
@@ -526,6 +532,8 @@ extern "C" int nis_flow_backward(const NisFlowDesc* desc, const float* params, c
     nis_flow_carve(F, B, workspace, &ws);
     if (nis_bwd_tc_supported(F, B, bn_mode))
         return nis_flow_backward_tc(F, ws, params, bn_running, saved, bn_saved, grad_out, grad_dtype, grad_params, grad_in, B, s);
+    if (nis_bwd_wide_supported(F, B, bn_mode))
+        return nis_flow_backward_wide(F, ws, params, bn_running, saved, bn_saved, grad_out, grad_dtype, grad_params, grad_in, B, s);
     bool rotate = false;
     const int NT = bwd_pick_nt(F, train != 0, &rotate);
     if (!NT) return NIS_EUNSUPPORTED;

@@ -238,6 +238,8 @@ int nis_launch_wide(const DevFlow& F, const FwdArgs& A, const float* widepack, c
 // floats of one stored-activation buffer ([tile][width][128], tiles padded to pairs)
 static size_t zbuf_floats(const DevFlow& F, int64_t B) { return nis_tiled_zbuf_floats(B) / 64 * (size_t)(F.maxW > 64 ? F.maxW : 64); }
 size_t nis_bwd_tc_scratch_floats(const DevFlow& F, int64_t B);
+bool nis_bwd_wide_supported(const DevFlow& F, int64_t B, int bn_mode);
+size_t nis_bwd_wide_scratch_floats(const DevFlow& F, int64_t B);
 int nis_launch_tiled(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 int nis_launch_col_stats(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 bool nis_moments_supported(const DevFlow& F, int c);
@@ -262,6 +264,8 @@ extern "C" size_t nis_flow_workspace_bytes(const NisFlowDesc* desc, int64_t B) {
     if (zfl > tail) tail = zfl;
     const size_t tcb = nis_bwd_tc_supported(F, B, NIS_BN_TRAIN) ? nis_bwd_tc_scratch_floats(F, B) : 0;
     if (tcb > tail) tail = tcb;
+    const size_t wdb = nis_bwd_wide_supported(F, B, NIS_BN_TRAIN) ? nis_bwd_wide_scratch_floats(F, B) : 0;
+    if (wdb > tail) tail = wdb;
     return fwd + sizeof(float) * tail + 256;
 }
 
@@ -319,7 +323,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     A.saved = saved; A.bins = bins_out;
     A.params = params; A.wpack = ws.wpack; A.bn_running = bn_running; A.bn_saved = bn_saved;
     A.partials = ws.partials; A.counter = ws.counter; A.B = B;
-    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0;
+    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr;
     // per-cell launch sequences: tcgen05 kernel where it applies, else the FP32 register-tiled kernel
     const bool tc = nis_tc_supported(F, B, bn_mode);
     const bool wide = !tc && nis_wide_supported(F, B, bn_mode);       // streamed-weights tcgen05 kernel (flow_wide.cu)

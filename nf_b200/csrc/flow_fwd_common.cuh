@@ -16,6 +16,7 @@ struct FwdArgs {
     const float* zin;                            // tiled train path: pre-BN activations of the layer below,
     float* zout;                                 // tile-blocked [tile][64][M] (written by a statistics pass)
     int no_stats;                                // layer pass that only stores its activations (eval-mode split cell)
+    float* z1out;                          // wide kernel, pass from the state: also store z_1 (backward recompute) or null
 };
 
 

@@ -163,11 +163,16 @@ def test_tensor_core_backward_agrees_with_generic_backward_and_oracle(monkeypatc
         close(grads["tcgen05"][k], grads["generic"][k], "tc vs generic:" + k, gscale, flips=True)
 
 
-def test_full_size_cfg5_trains_through_the_generic_backward():
-    """BASELINE configs[4] at its full shape (16-D PWQuad, 8 cells, 64 bins, MLP [256]*4): the train-mode
-    backward keeps the activations of a launch's one step in three rotating shared-memory buffers, which is what
-    makes this width fit.  Gradients against float64 autograd through the oracle."""
-    cfg = dict(name="cfg5", kind="quad", n_flow=16, n_cells=8, n_bins=64, NN=[256] * 4, B=640)
+@pytest.mark.parametrize("backend", ["tcgen05", "generic"])
+def test_full_size_cfg5_gradients(monkeypatch, backend):
+    """BASELINE configs[4] at its full shape (16-D PWQuad, 8 cells, 64 bins, MLP [256]*4), gradients against
+    float64 autograd through the oracle: by default the streamed-weights tcgen05 backward (flow_bwd_wide.cu);
+    with NIS_BWD_TC=0 the shape-generic kernel, whose train-mode launches keep the activations of their one
+    step in three rotating shared-memory buffers (which is what makes this width fit)."""
+    monkeypatch.delenv("NIS_BWD_TC", raising=False)
+    if backend == "generic":
+        monkeypatch.setenv("NIS_BWD_TC", "0")
+    cfg = dict(name="cfg5", kind="quad", n_flow=16, n_cells=8, n_bins=64, NN=[256] * 4, B=2600)
     test_gradients_match_oracle_autograd_at_size(cfg, "train")
 
 
