@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
     const int c = A.c, lam = A.lam;
     const DevCell& q = F.cells[c];
     const int d = F.d, W = F.widths[0], Kp = wd_kp16(F);
-    const int N = lam == 0 ? 16 : 128;                      // columns of this CTA's block
+    const int N = lam == 0 ? 16 : (W < 128 ? W : 128);      // columns of this CTA's block
     const int nlog = q.T * Kp;
     const int nrows = OUTL ? nlog : W;                      // real upstream features
     const int rb = blockIdx.x, nh = blockIdx.y, part = blockIdx.z;
@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
     const float* pk = A.wpack + q.pk_off;
     for (int j = tid; j < 128; j += BWW_THREADS) {
         const int f = 128 * nh + j;
-        const bool ok = lam == 0 ? j < q.P : f < W;
+        const bool ok = lam == 0 ? j < q.P : (f < W && j < N);
         coef[j] = ok ? pk[q.aff_off[lam] + f] : 0.f;
         coef[128 + j] = ok ? pk[q.aff_off[lam] + pad8(lam == 0 ? q.P : W) + f] : 0.f;
     }
@@ -787,6 +787,7 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
                 const float* zp = A.zbuf + (((size_t)(lam - 1) * ntiles + tile) * W + 128 * nh) * TCM + gt;
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) {
+                    if (32 * cb >= N) break;
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = zp[(size_t)(32 * cb + j) * TCM];
@@ -795,8 +796,8 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
                         const int r = 32 * cb + j;
                         const float h = fmaxf(fmaf(v[j], coef[r], coef[128 + r]), 0.f);
                         const float hi = tf32_rn(h);
-                        *reinterpret_cast<float*>(slabBh + bww_slab_off(128, r, gt)) = hi;
-                        *reinterpret_cast<float*>(slabBl + bww_slab_off(128, r, gt)) = tf32_rn(h - hi);
+                        *reinterpret_cast<float*>(slabBh + bww_slab_off(N, r, gt)) = hi;
+                        *reinterpret_cast<float*>(slabBl + bww_slab_off(N, r, gt)) = tf32_rn(h - hi);
                     }
                 }
             } else {
@@ -909,7 +910,7 @@ bool nis_bwd_wide_supported(const DevFlow& F, int64_t B, int bn_mode) {
     if (off && off[0] == '0') return false;
     if (bn_mode != NIS_BN_TRAIN || !nis_wide_supported(F, B, bn_mode)) return false;
     const int W = F.widths[0];
-    if (W != 128 && W != 256) return false;                 // wgrad column blocks of 128
+    if (W != 64 && W != 128 && W != 256) return false;      // wgrad column blocks of min(W, 128)
     for (int c = 0; c < F.n_cells; ++c) {
         if (bw_head_layout(F, F.cells[c].P, F.depth == 1).slots < 2) return false;
         if (bw_kout(F, F.cells[c].T) > 4096) return false;
@@ -1024,7 +1025,7 @@ int nis_flow_backward_wide(const DevFlow& F, const FlowWorkspace& ws, const floa
             NIS_CUDA_CHECK_LAUNCH();
             pp ^= 1;
             const int nrows = lam == depth ? q.T * Kp : W;
-            const int nrb = (nrows + 63) / 64, nnh = lam == 0 ? 1 : W / 128;
+            const int nrb = (nrows + 63) / 64, nnh = lam == 0 ? 1 : (W + 127) / 128;
             int nparts = (2 * sms) / (nrb * nnh);
             if (nparts < 1) nparts = 1;
             if (nparts > 320 / (nrb * nnh)) nparts = 320 / (nrb * nnh);

@@ -370,7 +370,7 @@ bool nis_wide_supported(const DevFlow& F, int64_t B, int bn_mode) {
     if (off && off[0] == '0') return false;
     if (F.depth < 1 || B < 1024) return false;
     const int W = F.widths[0];
-    if (W < 128 || W > 256 || (W & 63)) return false;
+    if (W < 64 || W > 256 || (W & 63)) return false;          // (width 64 with 32 bins is taken by flow_tc.cu first)
     for (int l = 0; l < F.depth; ++l) if (F.widths[l] != W) return false;
     if (F.maxW != W) return false;
     if (wd_kp16(F) > WD_NMAX) return false;
@@ -384,7 +384,7 @@ bool nis_wide_supported(const DevFlow& F, int64_t B, int bn_mode) {
 }
 
 size_t nis_wide_pack_floats(const DevFlow& F) {
-    if (F.depth < 1 || F.widths[0] < 128) return 0;
+    if (F.depth < 1 || F.widths[0] < 64 || (F.widths[0] & 63) || F.widths[0] > 256) return 0;
     return (size_t)F.n_cells * wd_cell_floats(F);
 }
 

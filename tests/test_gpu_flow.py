@@ -128,6 +128,7 @@ def test_flow_is_a_bijection_of_the_unit_cube_at_full_size():
 WIDE = [
     dict(name="wide_lin128", kind="lin", n_flow=8, n_pass_through=4, n_cells=4, n_bins=48, NN=[128] * 3, roll_step=4, B=3000),
     dict(name="wide_quad192", kind="quad", n_flow=6, n_cells=6, n_bins=20, NN=[192] * 2, B=2500),
+    dict(name="quad64_20bins", kind="quad", n_flow=8, n_cells=6, n_bins=20, NN=[64] * 3, B=3000),
     dict(name="wide_quad256_deep", kind="quad", n_flow=16, n_cells=8, n_bins=64, NN=[256] * 4, B=1400),
 ]
 
