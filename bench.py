@@ -248,6 +248,46 @@ def bench_train_step(steps, warmup, world, dev, log2n=16):
                                           "kernels (+ gradient all-reduce), 2^%d points per rank per step" % log2n}}
 
 
+def bench_wide(steps, warmup, world, dev):
+    """BASELINE configs[4]: 16-D PWQuad flow, 8 mask cells, 64 bins, MLP [256]*4 (the tensor-core conditioner path:
+    flow_wide.cu / flow_bwd_wide.cu) — forward + log-det with train-mode BN, and one variance-loss training step
+    (forward + backward + gradient all-reduce), 2^16 points per rank per step."""
+    from nf_b200.normalizing_flows.manager import BasicManager, PWQuadManager
+    torch.manual_seed(1234)
+    NF = PWQuadManager(n_flow=16)
+    NF.create_model(8, 64, [256] * 4, dev=dev.index or 0)
+    model = NF._model.train()
+    params = list(model.parameters())
+    n = 1 << 16
+    flop = 8 * 2 * 462848                                    # SURVEY.md 8(d): 7.41 MFLOP per point forward
+    x = torch.rand(n, 16, device=dev, dtype=torch.float32)
+    f = torch.exp(-((x - 0.5) ** 2).sum(-1) / 0.4)
+
+    def fwd():
+        with torch.no_grad():
+            model(x)
+
+    def step():
+        model.zero_grad(set_to_none=False)
+        XJ = model(x)
+        torch.var(f * XJ[:, -1]).backward()
+        if world > 1:
+            BasicManager._allreduce_grads(params)
+
+    ms_f = time_steps(fwd, steps, warmup, world)
+    ms_s = time_steps(step, steps, warmup, world)
+    pk, _ = peaks()
+    tf32_peak = pk.get("bf16_tflops", 1590.0) / 2
+    ach = world * n * flop * 3 / (ms_f * 1e-3) / 1e12         # executed TF32 flops (3xTF32 split)
+    return {"metric": "nis_flow_fwd_logdet_points_per_sec", "value": world * n / (ms_f * 1e-3), "unit": "points/s",
+            "ms_per_step": ms_f,
+            "config": {"workload": "configs[4]: 16-D PWQuad flow, 8 cells, 64 bins, MLP [256]*4, train-mode BN, 2^16 points per rank"},
+            "roofline": {"bound": "tensor", "achieved": ach / world, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / world / tf32_peak,
+                         "algorithmic_tflops": ach / 3 / world, "note": "3xTF32: three tensor MACs per conditioner MAC"},
+            "train_step": {"metric": "nis_train_step_points_per_sec", "value": world * n / (ms_s * 1e-3), "unit": "points/s",
+                           "ms_per_step": ms_s}}
+
+
 def bench_integrate(world, dev):
     """SURVEY.md 8(d)(iv) / BASELINE configs[3]: end-to-end NIS integrate — 8D PWQuad flow (6 mask cells, 32
     bins, [64]*3) -> RAMBO 2->4 massless at E_cm = 1000 -> |M|^2 = 1, through the public API
@@ -430,7 +470,9 @@ def main():
         gbs = N_POINTS * IO_BYTES_PER_POINT / (ms * 1e-3) / 1e9
         line["roofline"] = {
             "bound": "tensor", "achieved": tfl_exec, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tfl_exec / tf32_peak,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE train-mode layer-pass launch of flow_cell_tc_kernel at
+            # 2^22 points, from the committed ncu --set full capture (profiles/r01_ncu_tc.md); not re-measured per run
+            "traffic": 2250729000 if N_POINTS == 1 << 22 else None,
             "peak_kind": "%s bf16 cuBLAS peak / 2 (kind::tf32 runs at half the bf16 rate)" % peak_kind,
             "kernel": "flow_cell_tc_kernel: %d launches per step (per cell %d train-mode layer passes + 1 final pass) "
                       "+ %d flow_col_moments_kernel" % (n_cells * depth, depth - 1, n_cells),
@@ -466,6 +508,7 @@ def main():
         line["train_step"] = bench_train_step(max(3, args.steps // 2), args.warmup, world, dev)
         line["train_step_large"] = bench_train_step(max(3, args.steps // 2), args.warmup, world, dev, log2n=20)
         line["integrate"] = bench_integrate(world, dev)
+        line["wide_flow"] = bench_wide(max(3, args.steps // 2), args.warmup, world, dev)
         if rank == 0 and world == 1:
             threads = os.cpu_count() or 1
             sample = 1 << 17
