@@ -21,13 +21,15 @@ __global__ void __launch_bounds__(RAMBO_NT) rambo_kernel(const __grid_constant__
     double* rs = smd;                       // [NT][NDP]
     double* mo = smd + RAMBO_NT * NDP;      // [NT][NMP]  (scratch even when momenta are not requested)
     const int tid = threadIdx.x;
+    // i / ND and i / NM by multiplication (exact for i < 2^14, divisor <= 128: i * (M d - 2^24) < 2^24)
+    const unsigned long long magD = (1u << 24) / ND + 1, magM = (1u << 24) / NM + 1;
     const long long ntiles = (B + RAMBO_NT - 1) / RAMBO_NT;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long base = tile * RAMBO_NT;
         const int cnt = (int)((B - base) < RAMBO_NT ? (B - base) : RAMBO_NT);
         const RT* src = r + base * ND;
         for (int i = tid; i < cnt * ND; i += RAMBO_NT) {
-            const int ev = i / ND, c = i - ev * ND;
+            const int ev = (int)(((unsigned long long)i * magD) >> 24), c = i - ev * ND;
             rs[ev * NDP + c] = (double)src[i];
         }
         __syncthreads();
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(RAMBO_NT) rambo_kernel(const __grid_constant__
         if (momenta) {
             double* dst = momenta + base * NM;
             for (int i = tid; i < cnt * NM; i += RAMBO_NT) {
-                const int ev = i / NM, c = i - ev * NM;
+                const int ev = (int)(((unsigned long long)i * magM) >> 24), c = i - ev * NM;
                 dst[i] = mo[ev * NMP + c];
             }
         }

@@ -113,9 +113,38 @@ static inline int rambo_fill_const(const NisRamboDesc* d, RamboConst* C) {
 
 // Root in [0,1] of  r = (e+1) u^e - e u^(e+1)  (flat_phase_space_generator.py:101-103,313-359; the
 // reference bisects 120-180 levels to float64 resolution).  Here: float32 start from the small-r /
-// large-r asymptote, five float32 Newton steps (FP32 pipe, no float64 division), then float64 Newton
-// until the step is below 1e-15 relative — three iterations for essentially every lane, so warps do not
-// diverge.  The bracket [lo,hi] always contains the root; a step leaving it is replaced by bisection.
+// large-r asymptote, four float32 Newton steps (FP32 pipe, no float64 division), then two
+// straight-line float64 Newton steps (see below).
+NIS_DEV double rambo_pow_em1(double X, int e) {           // X^(e-1), e >= 2
+    if (e == 2) return X;
+    if (e == 3) return X * X;
+    double p = X * X * X;
+    for (int i = 4; i < e; ++i) p *= X;
+    return p;
+}
+// bracketed Newton until the step is below float64 resolution (the rare lanes rambo_root hands over)
+#ifdef __CUDACC__
+__device__ __noinline__
+#else
+static
+#endif
+double rambo_root_slow(int e, double r, double X) {
+    const double ed = (double)e;
+    double LO = 0.0, HI = 1.0;
+    for (int it = 0; it < 80; ++it) {
+        const double xe1 = rambo_pow_em1(X, e);
+        const double g = xe1 * X * ((ed + 1.0) - ed * X) - r;
+        const double dg = ed * (ed + 1.0) * xe1 * (1.0 - X);
+        if (g > 0.0) HI = X; else LO = X;
+        double xn = X - nis_div(g, dg);
+        if (!(xn > LO && xn < HI)) xn = 0.5 * (LO + HI);
+        const double dx = fabs(xn - X);
+        X = xn;
+        if (dx <= 4.5e-16 * X) break;
+    }
+    return X;
+}
+
 NIS_DEV double rambo_root(int e, double r) {
     if (e == 1) return nis_div(r, 1.0 + nis_sqrt(1.0 - r));             // u = 1 - sqrt(1-r), stable form
     if (r <= 0.0) return 0.0;
@@ -126,34 +155,38 @@ NIS_DEV double rambo_root(int e, double r) {
     for (int i = 0; i < e; ++i) us *= ustar;
     const float rstar = us * ((ef + 1.f) - ef * ustar);
     const float rf = (float)r;
-    float lo, hi, x;
-    if (rf < rstar) { lo = 0.f; hi = ustar; x = exp2f(log2f(fmaxf(rf, 1e-37f) / (ef + 1.f)) / ef); }
-    else { lo = ustar; hi = 1.f; x = 1.f - sqrtf(2.f * fmaxf(1.f - rf, 0.f) / (ef * (ef + 1.f))); }
-    x = fminf(fmaxf(x, lo), hi);
-    for (int it = 0; it < 5; ++it) {
-        float xe1 = 1.f;
-        for (int i = 0; i < e - 1; ++i) xe1 *= x;
+    // start on the asymptote of the side the root is on, then four plain float32 Newton steps (a step that
+    // leaves (0,1) is dropped).  No bracket: a bracket narrowed with float32 function values ends up one ulp
+    // wide, and the bisection fallback then throws a converged iterate far away.
+    float x;
+    if (rf < rstar) x = exp2f(log2f(fmaxf(rf, 1e-37f) / (ef + 1.f)) / ef);
+    else x = 1.f - sqrtf(2.f * fmaxf(1.f - rf, 0.f) / (ef * (ef + 1.f)));
+    x = fminf(fmaxf(x, 0.f), 1.f);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        float xe1 = x;
+        for (int i = 2; i < e; ++i) xe1 *= x;
         const float g = xe1 * x * ((ef + 1.f) - ef * x) - rf;
         const float dg = ef * (ef + 1.f) * xe1 * (1.f - x);
-        float xn = x - g / dg;
-        if (!(xn > lo && xn < hi)) xn = 0.5f * (lo + hi);
-        if (g > 0.f) hi = fminf(hi, x); else lo = fmaxf(lo, x);
-        x = xn;
+        const float xn = x - g / dg;
+        if (xn > 0.f && xn < 1.f) x = xn;
     }
+    // float64 polish.  The float32 iterate is within ~1e-7 of the root, so two Newton steps reach float64
+    // resolution (quadratic convergence); they are straight-line code.  Only where the map is flat (r within
+    // ~1e-12 of 0 or 1: a handful of events per 10^7) the second step is still large, and those lanes finish in
+    // the bracketed loop of rambo_root_slow.
     const double ed = (double)e;
-    double X = (double)x, LO = 0.0, HI = 1.0;
-    for (int it = 0; it < 60; ++it) {
-        double xe1 = 1.0;
-        for (int i = 0; i < e - 1; ++i) xe1 *= X;
+    double X = (double)x, dx = 0.0;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double xe1 = rambo_pow_em1(X, e);
         const double g = xe1 * X * ((ed + 1.0) - ed * X) - r;
         const double dg = ed * (ed + 1.0) * xe1 * (1.0 - X);
-        if (g > 0.0) HI = X; else LO = X;
-        double xn = X - nis_div(g, dg);
-        if (!(xn > LO && xn < HI)) xn = 0.5 * (LO + HI);
-        const double dx = fabs(xn - X);
-        X = xn;
-        if (dx <= 4.5e-16 * X) break;
+        const double xn = X - nis_div(g, dg);
+        if (xn > 0.0 && xn < 1.0) { dx = fabs(xn - X); X = xn; }
+        else dx = 1.0;                                   // flat region (dg = 0): leave it to the slow path
     }
+    if (!(dx <= 1e-11 * X)) X = rambo_root_slow(e, r, X);
     return X;
 }
 
