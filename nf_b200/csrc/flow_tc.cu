@@ -114,7 +114,7 @@ template <int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __grid_constant__ DevFlow F, const FwdArgs A,
                                                                       const float* __restrict__ tcpack) {
     extern __shared__ char smraw[];
-    __shared__ uint64_t a_ready[2], d_ready[2], z_full[2][2];
+    __shared__ uint64_t a_ready[2], d_ready[2], z_full[2][2], s_full[2];
     __shared__ uint32_t tmem_base_s;
     char* sm = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
         mbar_init(&a_ready[0], TCM); mbar_init(&a_ready[1], TCM);
         mbar_init(&d_ready[0], 1); mbar_init(&d_ready[1], 1);
         mbar_init(&z_full[0][0], 1); mbar_init(&z_full[0][1], 1); mbar_init(&z_full[1][0], 1); mbar_init(&z_full[1][1], 1);
+        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
@@ -222,6 +223,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
             const long long t0 = (long long)blockIdx.x * 2 + g;
             if (t0 < ntiles) bulk_load(zs, A.zin + (size_t)t0 * TCH * TCM, ZBYTES, &z_full[g][0]);
         }
+        // the state rows of a full tile are one contiguous block: they arrive by bulk copy too, issued one tile
+        // ahead (the landing zone is free as soon as every thread has moved its row into its state column)
+        float* sst = reinterpret_cast<float*>(sm + L.sst) + g * (d + 1) * TCM;
+        const uint32_t SBYTES = (uint32_t)((d + 1) * TCM * 4);
+        const bool st_bulk = A.from_state && (reinterpret_cast<uintptr_t>(A.state_in) & 15) == 0;
+        uint32_t sph = 0;
+        if (st_bulk && gt == 0) {
+            const long long t0 = (long long)blockIdx.x * 2 + g;
+            if ((t0 + 1) * TCM <= A.B) bulk_load(sst, A.state_in + t0 * TCM * rowlen, SBYTES, &s_full[g]);
+        }
         for (long long it = 0;; ++it) {
             const long long tile = ((long long)blockIdx.x + it * gridDim.x) * 2 + g;
             if (tile >= ntiles) break;
@@ -233,7 +244,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
             const long long pt = tile * TCM + gt;
             const bool valid = pt < A.B;
             // ---- this thread's point --------------------------------------------------------------
-            if (valid) {
+            if (st_bulk && (tile + 1) * TCM <= A.B) {
+                mbar_wait(&s_full[g], sph);
+                sph ^= 1;
+                for (int i = 0; i <= d; ++i) st[i * TCM] = sst[gt * rowlen + i];
+                proxy_fence();                       // our reads of the landing zone precede the next bulk write into it
+                group_sync(g);
+                if (gt == 0) {
+                    const long long tn = ((long long)blockIdx.x + (it + 1) * gridDim.x) * 2 + g;
+                    if ((tn + 1) * TCM <= A.B) bulk_load(sst, A.state_in + tn * TCM * rowlen, SBYTES, &s_full[g]);
+                }
+            } else if (valid) {
                 if (A.from_state) {
                     for (int i = 0; i <= d; ++i) st[i * TCM] = A.state_in[pt * rowlen + i];
                 } else {
@@ -298,12 +319,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
                 group_sync(g);
                 if (gt == 0 && A.zout) bulk_store(A.zout + (size_t)tile * TCH * TCM, zo, ZBYTES);
                 if (!A.no_stats) {
-                    const float* row = zo + (gt & 63) * TCM + (gt >> 6) * 64;
+                    // thread gt sums half a row (64 points) of feature gt & 63, 16 bytes at a time; the start is
+                    // rotated by the lane so that a warp's 32 rows do not hit the same banks
+                    const float4* row = reinterpret_cast<const float4*>(zo + (gt & 63) * TCM + (gt >> 6) * 64);
                     float s_ = 0.f, q_ = 0.f;
-#pragma unroll 8
-                    for (int i = 0; i < 64; ++i) {
-                        const float x = row[(i + lane) & 63];
-                        s_ += x; q_ = fmaf(x, x, q_);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float4 x = row[(i + lane) & 15];
+                        s_ += (x.x + x.y) + (x.z + x.w);
+                        q_ = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, q_))));
                     }
                     dsum[0] += (double)s_; dsq[0] += (double)q_;
                 }

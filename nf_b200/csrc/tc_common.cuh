@@ -114,7 +114,7 @@ __host__ __device__ static inline int tc_cell_floats(const DevFlow& F) {
 #define TC_COL_ALO 192
 
 struct TcSmem {      // byte offsets from the 1024-aligned base
-    int w, w0, aff, bias, st, red, zb, total;
+    int w, w0, aff, bias, st, sst, red, zb, total;
     int wl[NIS_MAX_HIDDEN + 1];     // per MMA layer l (1..depth): offset of (hi, lo) inside w, or -1
 };
 // MMA layers [l_begin, l_end] are staged (hidden: 2 x 16 KB, output: 2 x 32 KB)
@@ -133,6 +133,8 @@ __host__ __device__ static inline TcSmem tc_layout(const DevFlow& F, int P, int 
     s.aff = o; o += (F.depth + 1) * 2 * TCH * 4;
     s.bias = o; o += tc_max_blocks(F) * tc_out_n(F) * 4;
     s.st = o; o += 2 * (F.d + 1) * TCM * 4;
+    o = (o + 15) & ~15;
+    s.sst = o; o += 2 * (F.d + 1) * TCM * 4;     // landing zone of the next tile's state rows (bulk copy), per group
     o = (o + 7) & ~7;
     s.red = o; o += (8 * 2 * TCH + 2 * F.maxW) * 8;
     o = (o + 127) & ~127;
