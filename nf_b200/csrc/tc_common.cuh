@@ -186,7 +186,7 @@ __device__ __forceinline__ void tc_store_act(const float* v, const float* sc, co
         for (int j = 0; j < 32; ++j) {
             const float a = fmaxf(fmaf(v[32 * h + j], sc[32 * h + j], sh[32 * h + j]), 0.f);
             hi[j] = tf32_rn(a);
-            lo[j] = tf32_rn(a - hi[j]);
+            lo[j] = a - hi[j];            // exact; the MMA reads its top 19 bits (truncation of a value of random sign: unbiased)
         }
         tc_st32(t_hi + 32 * h, hi);
         tc_st32(t_lo + 32 * h, lo);
