@@ -248,6 +248,34 @@ def bench_train_step(steps, warmup, world, dev, log2n=16):
                                           "kernels (+ gradient all-reduce), 2^%d points per rank per step" % log2n}}
 
 
+def bench_readme(dev):
+    """BASELINE configs[0], the reference's README example: 2-D camel, PWQuadManager, 4 bins, MLP [3]*3, 10000
+    points per batch, 300 epochs of Adamax variance training through _train_variance_forward_seq, then integrate.
+    Latency-bound (shape-generic kernels, ~50 launches per epoch); wall seconds on rank 0."""
+    import tempfile
+    from nf_b200.normalizing_flows.manager import PWQuadManager
+
+    def camel(x):
+        return torch.exp(-((x[:, 0] - 0.75) ** 2 + (x[:, 1] - 0.75) ** 2) / (0.2 ** 2)) + \
+            torch.exp(-((x[:, 0] - 0.25) ** 2 + (x[:, 1] - 0.25) ** 2) / (0.2 ** 2))
+
+    torch.manual_seed(0)
+    NF = PWQuadManager(n_flow=2)
+    NF.create_model(2, 4, [3] * 3, dev=dev.index or 0)
+    optim = torch.optim.Adamax(NF._model.parameters(), lr=2e-3, weight_decay=1e-04)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    NF._train_variance_forward_seq(camel, optim, True, tempfile.mkdtemp(), 10000, 300, dev.index or 0, False, True, preburn_time=50)
+    torch.cuda.synchronize()
+    t1 = time.time()
+    sig, err = NF.integrate(camel, 10, 10000, dev.index or 0)
+    torch.cuda.synchronize()
+    return {"metric": "readme_example_wall_seconds", "value": t1 - t0, "unit": "s", "higher_is_better": False,
+            "integrate_seconds": time.time() - t1, "estimate": float(sig), "reported_error": float(err),
+            "analytic": 0.232322, "best_loss": float(NF.best_loss), "int_loss": float(NF.int_loss),
+            "reference": "368 s on 8 CPU cores, best_loss 0.024 from int_loss 0.071 (BASELINE.md)"}
+
+
 def bench_wide(steps, warmup, world, dev):
     """BASELINE configs[4]: 16-D PWQuad flow, 8 mask cells, 64 bins, MLP [256]*4 (the tensor-core conditioner path:
     flow_wide.cu / flow_bwd_wide.cu) — forward + log-det with train-mode BN, and one variance-loss training step
@@ -509,6 +537,8 @@ def main():
         line["train_step_large"] = bench_train_step(max(3, args.steps // 2), args.warmup, world, dev, log2n=20)
         line["integrate"] = bench_integrate(world, dev)
         line["wide_flow"] = bench_wide(max(3, args.steps // 2), args.warmup, world, dev)
+        if world == 1:
+            line["readme_example"] = bench_readme(dev)
         if rank == 0 and world == 1:
             threads = os.cpu_count() or 1
             sample = 1 << 17
