@@ -298,19 +298,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_head_kernel(const _
 // ===================================================================================================
 // layer: dgrad + wgrad of linear layer lam, ReLU/BN bookkeeping for BN layer lam
 // ===================================================================================================
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T
-__device__ __forceinline__ void bt_mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-// byte offset of (row, point) in a [rows x 128 points] K-major operand: four K-tiles of 32 points
-__device__ __forceinline__ int bt_slab_off(int rows, int row, int p) {
-    return (p >> 5) * rows * 128 + (row >> 3) * 1024 + (row & 7) * 128 + (((((p & 31) >> 2) ^ (row & 7)) << 4) | ((p & 3) << 2));
-}
-
 __device__ __forceinline__ void bt_prefetch_l2(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
@@ -497,9 +484,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
                         for (int ks = 0; ks < 16; ++ks) {
                             const uint32_t ao = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
                             const uint32_t bo = (ks >> 2) * nin * 128 + (ks & 3) * 32;
-                            bt_mma_tf32_ss(ta, tc_desc(sA + ao), tc_desc(sBh + bo), idesc, accw);
+                            tc_mma_tf32_ss(ta, tc_desc(sA + ao), tc_desc(sBh + bo), idesc, accw);
                             accw = 1;
-                            bt_mma_tf32_ss(ta, tc_desc(sA + ao), tc_desc(sBl + bo), idesc, 1);
+                            tc_mma_tf32_ss(ta, tc_desc(sA + ao), tc_desc(sBl + bo), idesc, 1);
                         }
                         tc_commit(&done[g]);
                         if (h == NH - 1) tc_commit(&slab_free);
@@ -598,7 +585,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
 #pragma unroll
                 for (int r = 0; r < TCH; ++r) {
                     const float hi = tf32_rn(hv[r]);
-                    const int off = bt_slab_off(TCH, r, gt);
+                    const int off = tc_slab_off(TCH, r, gt);
                     *reinterpret_cast<float*>(slabBh + off) = hi;
                     *reinterpret_cast<float*>(slabBl + off) = tf32_rn(hv[r] - hi);
                 }
@@ -606,7 +593,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const float hi = tf32_rn(hv[k]);
-                    const int off = bt_slab_off(16, k, gt);
+                    const int off = tc_slab_off(16, k, gt);
                     *reinterpret_cast<float*>(slabBh + off) = hi;
                     *reinterpret_cast<float*>(slabBl + off) = tf32_rn(hv[k] - hi);
                 }
@@ -620,8 +607,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int r = 32 * cb + j;
-                    *reinterpret_cast<float*>(slabA + bt_slab_off(128, r, gt)) = hi[j];
-                    *reinterpret_cast<float*>(slabA + bt_slab_off(128, TCH + r, gt)) = lo[j];
+                    *reinterpret_cast<float*>(slabA + tc_slab_off(128, r, gt)) = hi[j];
+                    *reinterpret_cast<float*>(slabA + tc_slab_off(128, TCH + r, gt)) = lo[j];
                 }
             }
             proxy_fence();
@@ -645,8 +632,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
                         const int r = 32 * cb + j;
                         hi[j] = tf32_rn(dz[r]);
                         lo[j] = tf32_rn(dz[r] - hi[j]);
-                        *reinterpret_cast<float*>(slabA + bt_slab_off(128, r, gt)) = hi[j];
-                        *reinterpret_cast<float*>(slabA + bt_slab_off(128, TCH + r, gt)) = lo[j];
+                        *reinterpret_cast<float*>(slabA + tc_slab_off(128, r, gt)) = hi[j];
+                        *reinterpret_cast<float*>(slabA + tc_slab_off(128, TCH + r, gt)) = lo[j];
                     }
                     tc_st32(tg + 32 * cb, hi);
                     tc_st32(tg + BT_COL_LO + 32 * cb, lo);

@@ -685,15 +685,6 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_bwd_wide_dgrad_kernel(cons
 // ===================================================================================================
 #define BWW_THREADS 160       // 4 point warps + MMA issuer
 #define BWW_FLUSH 8
-__device__ __forceinline__ void bww_mma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ int bww_slab_off(int rows, int row, int p) {
-    return (p >> 5) * rows * 128 + (row >> 3) * 1024 + (row & 7) * 128 + (((((p & 31) >> 2) ^ (row & 7)) << 4) | ((p & 3) << 2));
-}
 
 // grid = (row blocks of 64 upstream features) x (column blocks of 128 features of h_lam) x nparts
 template <bool OUTL>
@@ -750,9 +741,9 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
                 for (int ks = 0; ks < 16; ++ks) {
                     const uint32_t ao = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
                     const uint32_t bo = (ks >> 2) * N * 128 + (ks & 3) * 32;
-                    bww_mma_ss(tmem_base, tc_desc(sA + ao), tc_desc(sBh + bo), idesc, acc);
+                    tc_mma_tf32_ss(tmem_base, tc_desc(sA + ao), tc_desc(sBh + bo), idesc, acc);
                     acc = 1;
-                    bww_mma_ss(tmem_base, tc_desc(sA + ao), tc_desc(sBl + bo), idesc, 1);
+                    tc_mma_tf32_ss(tmem_base, tc_desc(sA + ao), tc_desc(sBl + bo), idesc, 1);
                 }
                 tc_commit(&done);
             }
@@ -777,8 +768,8 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
                     for (int j = 0; j < 32; ++j) {
                         const int r = 32 * cb + j;
                         const float hi = tf32_rn(v[j]);
-                        *reinterpret_cast<float*>(slabA + bww_slab_off(128, r, gt)) = hi;
-                        *reinterpret_cast<float*>(slabA + bww_slab_off(128, 64 + r, gt)) = tf32_rn(v[j] - hi);
+                        *reinterpret_cast<float*>(slabA + tc_slab_off(128, r, gt)) = hi;
+                        *reinterpret_cast<float*>(slabA + tc_slab_off(128, 64 + r, gt)) = tf32_rn(v[j] - hi);
                     }
                 }
             }
@@ -796,8 +787,8 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
                         const int r = 32 * cb + j;
                         const float h = fmaxf(fmaf(v[j], coef[r], coef[128 + r]), 0.f);
                         const float hi = tf32_rn(h);
-                        *reinterpret_cast<float*>(slabBh + bww_slab_off(N, r, gt)) = hi;
-                        *reinterpret_cast<float*>(slabBl + bww_slab_off(N, r, gt)) = tf32_rn(h - hi);
+                        *reinterpret_cast<float*>(slabBh + tc_slab_off(N, r, gt)) = hi;
+                        *reinterpret_cast<float*>(slabBl + tc_slab_off(N, r, gt)) = tf32_rn(h - hi);
                     }
                 }
             } else {
@@ -806,8 +797,8 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
                 for (int k = 0; k < 16; ++k) {
                     const float a = k < q.P ? fmaf(xs[q.feed[k]], coef[k], coef[128 + k]) : 0.f;
                     const float hi = tf32_rn(a);
-                    *reinterpret_cast<float*>(slabBh + bww_slab_off(16, k, gt)) = hi;
-                    *reinterpret_cast<float*>(slabBl + bww_slab_off(16, k, gt)) = tf32_rn(a - hi);
+                    *reinterpret_cast<float*>(slabBh + tc_slab_off(16, k, gt)) = hi;
+                    *reinterpret_cast<float*>(slabBl + tc_slab_off(16, k, gt)) = tf32_rn(a - hi);
                 }
             }
             proxy_fence();

@@ -49,6 +49,13 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a,
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::tf32, cta_group::1 (both operands from shared memory)
+__device__ __forceinline__ void tc_mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
 // 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -89,6 +96,12 @@ __host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
 __host__ __device__ static inline int tc_off(int rows, int row, int k) {
     const int kt = k >> 5, kk = k & 31;
     return kt * rows * 128 + (row >> 3) * 1024 + (row & 7) * 128 + ((((kk >> 2) ^ (row & 7)) << 4) | ((kk & 3) << 2));
+}
+
+// byte offset of (row, point) in a [rows x 128 points] K-major operand whose K dimension is the tile's points
+// (weight-gradient MMAs): four K-tiles of 32 points, same 128-byte swizzle
+__host__ __device__ static inline int tc_slab_off(int rows, int row, int p) {
+    return (p >> 5) * rows * 128 + (row >> 3) * 1024 + (row & 7) * 128 + (((((p & 31) >> 2) ^ (row & 7)) << 4) | ((p & 3) << 2));
 }
 
 // Output layer as a sequence of MMA blocks: PWLin with 32 bins -> ONE block of N=128 covering four
