@@ -206,3 +206,17 @@ def test_tensor_core_backward_at_large_batch_matches_generic(monkeypatch):
         close(grads["tcgen05"][k], grads["generic"][k], k, gscale, flips=True)
         worst = max(worst, float((grads["tcgen05"][k] - grads["generic"][k]).abs().max()) / gscale)
     print("tc vs generic backward at 2^18 points: worst |diff| / model gradient scale = %.2e" % worst)
+
+
+WIDE_BWD = [
+    dict(name="wide_lin128", kind="lin", n_flow=8, n_pass_through=4, n_cells=4, n_bins=48, NN=[128] * 3, roll_step=4, B=2400),
+    dict(name="quad64_20bins", kind="quad", n_flow=8, n_cells=6, n_bins=20, NN=[64] * 2, B=2600),
+    dict(name="wide_quad128_1layer", kind="quad", n_flow=6, n_cells=6, n_bins=12, NN=[128], B=2300),
+]
+
+
+@pytest.mark.parametrize("cfg", WIDE_BWD, ids=[c["name"] for c in WIDE_BWD])
+def test_streamed_weight_backward_shapes(cfg):
+    """flow_bwd_wide.cu beyond cfg4 / cfg5: PWLin cells, width 64 with a bin count the resident-weights kernel
+    does not take, a single hidden layer (z_1 stored by the head itself), ragged last tile."""
+    test_gradients_match_oracle_autograd_at_size(cfg, "train")
