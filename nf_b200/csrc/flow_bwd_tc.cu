@@ -22,8 +22,8 @@
 // along M ([dz_hi ; dz_lo], 128 rows) so that two M=128 MMAs (against h_hi and h_lo) give all four partial
 // products; rows o and 64+o of the accumulator are added on read-out.
 //
-// Same CTA shape as the forward (two point groups of 128 threads + one MMA-issuing warp).  The wgrad operand
-// slab (128 KB) is shared by the two groups: a group fills it while the other one runs its epilogue.
+// Same CTA shape as the forward (8 point warps + one MMA-issuing warp); in the layer launches the 8 warps work
+// on ONE tile, two threads per point (see flow_bwd_tc_layer_kernel).
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -339,12 +339,8 @@ __device__ __forceinline__ float bt_warp_feature_sums32(const float* v, int lane
 // tcgen05.mma adds each K=8 step into the fp32 accumulator with TRUNCATION (tools/tc_accum_probe.cu: about
 // one ulp lost per instruction, always toward zero), so an accumulator that lives across all tiles of a CTA
 // would drift by ~1e-4 relative after a few thousand instructions.  The wgrad accumulators are therefore
-// added to the CTA's slice in global memory (fp32, round-to-nearest) every BT_FLUSH iterations (16 tiles, 512 instructions) and restarted.
+// added to the CTA's slice in global memory (fp32, round-to-nearest) every 2 BT_FLUSH tiles (512 instructions) and restarted.
 #define BT_FLUSH 8
-__device__ __forceinline__ bool bt_flush_after(long long it, long long t_first, unsigned grid, long long ntiles, int every) {
-    const long long next0 = ((t_first >> 1) + grid) * 2;          // first tile of this CTA's next iteration
-    return every > 0 && ((it + 1) % every) == 0 && next0 < ntiles;
-}
 template <int NH>
 __device__ __noinline__ void bt_flush_acc(uint32_t tl, float* sl, int lam, int nin, bool add) {
     for (int h = 0; h < NH; ++h) {
@@ -375,11 +371,23 @@ __host__ __device__ static inline BtSmem bt_layout(int KW) {
     return s;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// ONE tile in flight per CTA, TWO threads per point.  (The first version gave each of two point groups its own
+// tile and made them take turns on the operand slab; with a thread carrying all 64 features the loads of a
+// tile could not be issued together and half of the stall samples sat on the slab hand-over: 22.8 ms per
+// 2^20-point training step against 18.9 ms now.)
+// Warps 0-3 own features 0..31 of a point's 64-feature blocks and warps 4-7 features 32..63 (a warp may touch
+// the 32 TMEM lanes 32 (warp % 4).., any column), so a thread carries half the loads and half the operand
+// preparation and nobody queues for the operand slab.  The tensor-memory columns of the A operand and of the
+// dgrad accumulator are double-buffered by tile parity: while the MMAs of tile i run, every thread already
+// loads and prepares tile i+1 (its dz goes to the other A buffer, its h_lam waits in registers), then runs
+// the epilogue of tile i and only then fills the slab for tile i+1 (the wgrad MMAs of tile i are done by then).
+// ---------------------------------------------------------------------------------------------------
 template <int KW>
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const __grid_constant__ DevFlow F, const BtArgs A) {
     constexpr int NH = KW / 64;
     extern __shared__ char smraw[];
-    __shared__ uint64_t a_ready[2], done[2], slab_free, acc_ready, acc_free;
+    __shared__ uint64_t a_ready, done[2], hdone, acc_ready, acc_free;
     __shared__ uint32_t tmem_base_s;
     __shared__ bool s_last;
     char* sm = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
@@ -387,48 +395,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
     const int c = A.c, lam = A.lam;
     const DevCell& q = F.cells[c];
     const int d = F.d, maxW = F.maxW;
-    const int nin = lam == 0 ? 16 : TCH;          // N of both MMAs
-    const int win = lam == 0 ? q.P : TCH;         // real width of h_lam
+    const int nin = lam == 0 ? 16 : TCH;
+    const int win = lam == 0 ? q.P : TCH;
     const BtSmem L = bt_layout(KW);
     char* slabA = sm + L.slabA;
     char* slabBh = sm + L.slabBh;
     char* slabBl = sm + L.slabBl;
     float* coef = reinterpret_cast<float*>(sm + L.coef);
-    float* cA1 = coef, *cA2 = coef + TCH, *cA3 = coef + 2 * TCH;              // dz = cA1*dh + cA2*z + cA3
+    float* cA1 = coef, *cA2 = coef + TCH, *cA3 = coef + 2 * TCH;
     float* scp = coef + 3 * TCH, *shp = coef + 4 * TCH, *mup = coef + 5 * TCH, *rsp = coef + 6 * TCH;
     const float* pk = A.wpack + q.pk_off;
-
-    {   // dgrad operand blocks
+    {
         const int fl = NH * 2 * nin * TCH;
         const float4* src = reinterpret_cast<const float4*>(A.bdpack + (size_t)c * bd_cell_floats(F) + bd_layer_off(F, lam));
         float4* dst = reinterpret_cast<float4*>(sm + L.bd);
         for (int i = tid; i < fl / 4; i += TC_THREADS) dst[i] = src[i];
     }
     for (int j = tid; j < TCH; j += TC_THREADS) {
-        if (KW == 64) {          // BN layer lam+1 sits between dL/dh_{lam+1} and dz_{lam+1}
+        if (KW == 64) {
             const int lu = lam + 1;
             const float* sv = A.bn_saved + q.sv_off + lu * 2 * maxW;
             const float sc = pk[q.aff_off[lu] + j];
             const float m1 = A.bnb[lu * 2 * maxW + j], m2 = A.bnb[lu * 2 * maxW + maxW + j];
             const float mu = sv[j], rs = sv[maxW + j];
-            cA1[j] = sc;
-            cA2[j] = -sc * m2 * rs;
-            cA3[j] = -sc * m1 + sc * m2 * rs * mu;
+            cA1[j] = sc; cA2[j] = -sc * m2 * rs; cA3[j] = -sc * m1 + sc * m2 * rs * mu;
         }
         if (j < win) {
             const float* sv = A.bn_saved + q.sv_off + lam * 2 * maxW;
             scp[j] = pk[q.aff_off[lam] + j];
             shp[j] = pk[q.aff_off[lam] + pad8(win) + j];
-            mup[j] = sv[j];
-            rsp[j] = sv[maxW + j];
-        } else {
-            scp[j] = 0.f; shp[j] = 0.f; mup[j] = 0.f; rsp[j] = 0.f;
-        }
+            mup[j] = sv[j]; rsp[j] = sv[maxW + j];
+        } else { scp[j] = 0.f; shp[j] = 0.f; mup[j] = 0.f; rsp[j] = 0.f; }
     }
     if (tid == 0) {
-        mbar_init(&a_ready[0], TCM); mbar_init(&a_ready[1], TCM);
-        mbar_init(&done[0], 1); mbar_init(&done[1], 1);
-        mbar_init(&slab_free, 1);
+        mbar_init(&a_ready, 2 * TCM);
+        mbar_init(&done[0], 1); mbar_init(&done[1], 1); mbar_init(&hdone, 1);
         mbar_init(&acc_ready, 1); mbar_init(&acc_free, TCM);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -441,59 +442,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    const long long ntiles = A.ntiles;
-    const long long rowlen = d + 1;
-    int nflush = 0;                        // flushes of the wgrad accumulators done by this thread (group 0)
-    double acc1[2] = {0.0, 0.0}, acc2[2] = {0.0, 0.0}, accb[NH][2];
+    const long long ntiles = A.ntiles, rowlen = d + 1;
+    const int fevery = A.flush_every * 2;                  // in tiles
+    int nflush = 0;
+    double acc1 = 0.0, acc2 = 0.0, accb[NH];
 #pragma unroll
-    for (int h = 0; h < NH; ++h) { accb[h][0] = 0.0; accb[h][1] = 0.0; }
+    for (int h = 0; h < NH; ++h) accb[h] = 0.0;
 
     if (warp == 8) {
         // ===================== MMA issuer ======================================================
         if (lane == 0) {
-            uint32_t pa[2] = {0, 0}, pf = 0;
-            bool fresh = true;                 // the next wgrad MMA starts a new accumulation
+            uint32_t pa = 0, pf = 0;
+            bool fresh = true;
             const uint32_t idesc = tc_idesc(TCM, nin);
             const uint32_t sA = smem_u32(slabA), sBh = smem_u32(slabBh), sBl = smem_u32(slabBl), sBd = smem_u32(sm + L.bd);
-            for (long long it = 0;; ++it) {
-                const long long t0 = ((long long)blockIdx.x + it * gridDim.x) * 2;
-                if (t0 >= ntiles) break;
-                const bool flush = bt_flush_after(it, t0, gridDim.x, ntiles, A.flush_every);
-                for (int g = 0; g < 2; ++g) {
-                    if (t0 + g >= ntiles) continue;
-                    const uint32_t tb = tmem_base + g * BT_GROUP_COLS;
-                    for (int h = 0; h < NH; ++h) {
-                        mbar_wait(&a_ready[g], pa[g]);
-                        pa[g] ^= 1;
-                        tc_fence_after();
-                        // dgrad: dL/dh (+)= dz[:, 64h..64h+63] W^T block h        (A from tensor memory)
-                        const uint32_t bh = sBd + h * 2 * nin * TCH * 4, bl = bh + nin * TCH * 4;
-                        uint32_t acc = h > 0;
+            long long it = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int b = (int)(it & 1);
+                const uint32_t tb = tmem_base + b * BT_GROUP_COLS;
+                for (int h = 0; h < NH; ++h) {
+                    mbar_wait(&a_ready, pa);
+                    pa ^= 1;
+                    tc_fence_after();
+                    const uint32_t bh = sBd + h * 2 * nin * TCH * 4, bl = bh + nin * TCH * 4;
+                    uint32_t acc = h > 0;
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {
-                            const uint32_t wo = (ks >> 2) * nin * 128 + (ks & 3) * 32;
-                            tc_mma_tf32_ts(tb + BT_COL_D, tb + ks * 8, tc_desc(bh + wo), idesc, acc);
-                            acc = 1;
-                            tc_mma_tf32_ts(tb + BT_COL_D, tb + ks * 8, tc_desc(bl + wo), idesc, 1);
-                            tc_mma_tf32_ts(tb + BT_COL_D, tb + BT_COL_LO + ks * 8, tc_desc(bh + wo), idesc, 1);
-                        }
-                        // wgrad: acc_h += [dz_hi ; dz_lo]^T-stacked (128 rows) x h_lam (hi, then lo), K = 128 points
-                        const uint32_t ta = tmem_base + BT_COL_ACC + h * TCH;
-                        uint32_t accw = !(fresh && g == 0);
-#pragma unroll
-                        for (int ks = 0; ks < 16; ++ks) {
-                            const uint32_t ao = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
-                            const uint32_t bo = (ks >> 2) * nin * 128 + (ks & 3) * 32;
-                            tc_mma_tf32_ss(ta, tc_desc(sA + ao), tc_desc(sBh + bo), idesc, accw);
-                            accw = 1;
-                            tc_mma_tf32_ss(ta, tc_desc(sA + ao), tc_desc(sBl + bo), idesc, 1);
-                        }
-                        tc_commit(&done[g]);
-                        if (h == NH - 1) tc_commit(&slab_free);
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t wo = (ks >> 2) * nin * 128 + (ks & 3) * 32;
+                        tc_mma_tf32_ts(tb + BT_COL_D, tb + ks * 8, tc_desc(bh + wo), idesc, acc);
+                        acc = 1;
+                        tc_mma_tf32_ts(tb + BT_COL_D, tb + ks * 8, tc_desc(bl + wo), idesc, 1);
+                        tc_mma_tf32_ts(tb + BT_COL_D, tb + BT_COL_LO + ks * 8, tc_desc(bh + wo), idesc, 1);
                     }
+                    const uint32_t ta = tmem_base + BT_COL_ACC + h * TCH;
+                    uint32_t accw = !fresh;
+#pragma unroll
+                    for (int ks = 0; ks < 16; ++ks) {
+                        const uint32_t ao = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
+                        const uint32_t bo = (ks >> 2) * nin * 128 + (ks & 3) * 32;
+                        tc_mma_tf32_ss(ta, tc_desc(sA + ao), tc_desc(sBh + bo), idesc, accw);
+                        accw = 1;
+                        tc_mma_tf32_ss(ta, tc_desc(sA + ao), tc_desc(sBl + bo), idesc, 1);
+                    }
+                    if (h < NH - 1) tc_commit(&hdone); else tc_commit(&done[b]);
                 }
                 fresh = false;
-                if (flush) {                   // group 0 adds the accumulators to the CTA's slice, then we start over
+                if (fevery > 0 && ((it + 1) % fevery) == 0 && tile + gridDim.x < ntiles) {
                     tc_commit(&acc_ready);
                     mbar_wait(&acc_free, pf);
                     pf ^= 1;
@@ -503,230 +497,217 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
             }
         }
     } else {
-        // ===================== point groups ====================================================
-        const int g = warp >> 2, gt = tid & (TCM - 1);
-        const uint32_t tg = tmem_base + g * BT_GROUP_COLS + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t pd = 0, pfr = 0;
-        for (long long it = 0;; ++it) {
-            const long long tile = ((long long)blockIdx.x + it * gridDim.x) * 2 + g;
-            if (tile >= ntiles) break;
-            const long long pt = tile * TCM + gt;
-            const bool valid = pt < A.B;
-            const long long seq = 2 * it + g;
-            const float* zp = lam > 0 ? A.zbuf + ((size_t)(lam - 1) * ntiles + tile) * BT_TILE + gt : nullptr;
-            const float* xs = A.saved + ((long long)c * A.B + (valid ? pt : 0)) * rowlen;
-            // next tile's inputs -> L2 while this one is processed
-            if (gt == 0) {
-                const long long tn = ((long long)blockIdx.x + (it + 1) * gridDim.x) * 2 + g;
-                if (tn < ntiles) {
-                    if (lam > 0) bt_prefetch_l2(A.zbuf + ((size_t)(lam - 1) * ntiles + tn) * BT_TILE, BT_TILE * 4);
-                    if (KW == 128) bt_prefetch_l2(A.dl + (size_t)tn * 2 * BT_TILE, 2 * BT_TILE * 4);
-                    else {
-                        bt_prefetch_l2(A.dh_in + (size_t)tn * BT_TILE, BT_TILE * 4);
-                        bt_prefetch_l2(A.zbuf + ((size_t)lam * ntiles + tn) * BT_TILE, BT_TILE * 4);
+        // ===================== point threads: (point gt, feature half sub) ===================================
+        const int sub = warp >> 2, gt = tid & (TCM - 1), f0 = 32 * sub;
+        const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t pdn[2] = {0, 0}, phd = 0, pfr = 0;
+        uint32_t mask = 0, maskn = 0;
+        float hv[32];
+        for (long long it = -1;; ++it) {
+            const long long tile = (long long)blockIdx.x + it * (long long)gridDim.x;            // current (epilogue)
+            const long long tn = tile + gridDim.x;                                               // next (operands)
+            const bool have_n = tn < ntiles;
+            const int bn = (int)((it + 1) & 1);
+            const uint32_t tgn = tl + bn * BT_GROUP_COLS;
+            const long long ptn = tn * TCM + gt;
+            const bool validn = have_n && ptn < A.B;
+            if (have_n) {
+                if (gt == 0 && sub == 0) {                       // the tile after the next one -> L2
+                    const long long t2 = tn + gridDim.x;
+                    if (t2 < ntiles) {
+                        if (lam > 0) bt_prefetch_l2(A.zbuf + ((size_t)(lam - 1) * ntiles + t2) * BT_TILE, BT_TILE * 4);
+                        if (KW == 128) bt_prefetch_l2(A.dl + (size_t)t2 * 2 * BT_TILE, 2 * BT_TILE * 4);
+                        else {
+                            bt_prefetch_l2(A.dh_in + (size_t)t2 * BT_TILE, BT_TILE * 4);
+                            bt_prefetch_l2(A.zbuf + ((size_t)lam * ntiles + t2) * BT_TILE, BT_TILE * 4);
+                        }
                     }
                 }
-            }
-            // ---- upstream gradient dz (first 64 features), 32 at a time: split and parked in the group's own
-            //      tensor-memory A columns (dgrad operand); no shared resource is held while the loads are in flight
+                // ---- stage 1: this thread's 32 features of dz (first 64-block) -> the other A buffer of tensor memory
+                {
+                    float dz[32], lo[32];
+                    if (KW == 128) {
+                        const float* up = A.dl + (size_t)tn * 2 * BT_TILE + (size_t)f0 * TCM + gt;
 #pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-                float dz[32];
-                if (KW == 128) {
-                    const float* up = A.dl + (size_t)tile * 2 * BT_TILE + (size_t)(32 * cb) * TCM + gt;
+                        for (int j = 0; j < 32; ++j) dz[j] = up[(size_t)j * TCM];
+                    } else {
+                        const float* up = A.dh_in + (size_t)tn * BT_TILE + (size_t)f0 * TCM + gt;
+                        const float* zu = A.zbuf + ((size_t)lam * ntiles + tn) * BT_TILE + (size_t)f0 * TCM + gt;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) dz[j] = up[(size_t)j * TCM];
-                } else {
-                    const float* up = A.dh_in + (size_t)tile * BT_TILE + (size_t)(32 * cb) * TCM + gt;
-                    const float* zu = A.zbuf + ((size_t)lam * ntiles + tile) * BT_TILE + (size_t)(32 * cb) * TCM + gt;   // z_{lam+1}
-                    float zl[32];
+                        for (int j = 0; j < 32; ++j) { dz[j] = up[(size_t)j * TCM]; lo[j] = zu[(size_t)j * TCM]; }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { dz[j] = up[(size_t)j * TCM]; zl[j] = zu[(size_t)j * TCM]; }
+                        for (int j = 0; j < 32; ++j)
+                            dz[j] = validn ? fmaf(cA1[f0 + j], dz[j], fmaf(cA2[f0 + j], lo[j], cA3[f0 + j])) : 0.f;
+                    }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        dz[j] = valid ? fmaf(cA1[32 * cb + j], dz[j], fmaf(cA2[32 * cb + j], zl[j], cA3[32 * cb + j])) : 0.f;
+                    for (int j = 0; j < 32; ++j) {
+                        const float a = dz[j];
+                        dz[j] = tf32_rn(a);
+                        lo[j] = a - dz[j];
+                    }
+                    tc_st32(tgn + f0, dz);
+                    tc_st32(tgn + BT_COL_LO + f0, lo);
+                    if (KW == 128) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) dz[j] += lo[j];
+                        accb[0] += (double)bt_warp_feature_sums32(dz, lane);
+                    }
+                    tc_st_wait();
                 }
-                float lo[32];
+                // ---- h_lam of the next tile, in registers until the slab is free
+                maskn = 0;
+                if (lam > 0) {
+                    const float* zpn = A.zbuf + ((size_t)(lam - 1) * ntiles + tn) * BT_TILE + (size_t)f0 * TCM + gt;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) hv[j] = zpn[(size_t)j * TCM];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float a = fmaf(hv[j], scp[f0 + j], shp[f0 + j]);
+                        maskn |= (uint32_t)(a > 0.f) << j;
+                        hv[j] = fmaxf(a, 0.f);
+                    }
+                } else if (sub == 0) {
+                    const float* xs = A.saved + ((long long)c * A.B + (validn ? ptn : 0)) * rowlen;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) hv[k] = k < q.P ? fmaf(xs[q.feed[k]], scp[k], shp[k]) : 0.f;
+                }
+            }
+            // ---- stage 2: epilogue of the current tile --------------------------------------------------------------
+            if (it >= 0) {
+                const int b = (int)(it & 1);
+                const uint32_t tg = tl + b * BT_GROUP_COLS;
+                const long long pt = tile * TCM + gt;
+                const bool valid = pt < A.B;
+                mbar_wait(&done[b], pdn[b]);
+                pdn[b] ^= 1;
+                tc_fence_after();
+                float* out = A.dh_out + (size_t)tile * BT_TILE + gt;
+                if (lam > 0) {
+                    const float* zp = A.zbuf + ((size_t)(lam - 1) * ntiles + tile) * BT_TILE + (size_t)f0 * TCM + gt;
+                    float dv[32], pr[32];
+                    tc_ld32(tg + BT_COL_D + f0, dv);
+                    tc_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        dv[j] = ((mask >> j) & 1u) ? dv[j] : 0.f;
+                        out[(size_t)(f0 + j) * TCM] = dv[j];
+                        pr[j] = dv[j] * (zp[(size_t)j * TCM] - mup[f0 + j]) * rsp[f0 + j];
+                    }
+                    acc1 += (double)bt_warp_feature_sums32(dv, lane);
+                    acc2 += (double)bt_warp_feature_sums32(pr, lane);
+                } else if (sub == 0) {
+                    const float* xs = A.saved + ((long long)c * A.B + (valid ? pt : 0)) * rowlen;
+                    float dv[32], pr[32];
+                    tc_ld16(tg + BT_COL_D, dv);
+                    tc_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        dv[j] = j < q.P ? dv[j] : 0.f;
+                        out[(size_t)j * TCM] = dv[j];
+                        pr[j] = j < q.P ? dv[j] * (xs[q.feed[j]] - mup[j]) * rsp[j] : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 16; j < 32; ++j) { dv[j] = 0.f; pr[j] = 0.f; }
+                    acc1 += (double)bt_warp_feature_sums32(dv, lane);
+                    acc2 += (double)bt_warp_feature_sums32(pr, lane);
+                }
+                if (sub == 0 && fevery > 0 && ((it + 1) % fevery) == 0 && have_n) {
+                    mbar_wait(&acc_ready, pfr);
+                    pfr ^= 1;
+                    tc_fence_after();
+                    bt_flush_acc<NH>(tl + BT_COL_ACC, A.slices + (((size_t)lam * A.grid + blockIdx.x) * 2) * 128 * TCH + (size_t)gt * TCH,
+                                     lam, nin, nflush > 0);
+                    ++nflush;
+                    tc_fence_before();
+                    mbar_arrive(&acc_free);
+                }
+            }
+            if (!have_n) break;
+            // ---- stage 3: the slab is free (the MMAs of the current tile are complete): operands of the next tile ----
+            mask = maskn;
+            if (lam > 0) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float hi = tf32_rn(dz[j]);
-                    lo[j] = tf32_rn(dz[j] - hi);
-                    dz[j] = hi;
-                }
-                tc_st32(tg + 32 * cb, dz);
-                tc_st32(tg + BT_COL_LO + 32 * cb, lo);
-                if (KW == 128) {               // output-layer bias gradient = column sums of dL/dlogits
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) dz[j] += lo[j];
-                    accb[0][cb] += (double)bt_warp_feature_sums32(dz, lane);
-                }
-            }
-            tc_st_wait();
-            // ---- h_lam = ReLU(BN_lam(z_lam)) (lam = 0: the normalised input, no ReLU) in registers ------------------
-            uint64_t mask = 0;
-            float hv[TCH];
-            if (lam > 0) {
-#pragma unroll
-                for (int j = 0; j < TCH; ++j) hv[j] = zp[(size_t)j * TCM];
-#pragma unroll
-                for (int j = 0; j < TCH; ++j) {
-                    const float a = fmaf(hv[j], scp[j], shp[j]);
-                    mask |= (uint64_t)(a > 0.f) << j;
-                    hv[j] = fmaxf(a, 0.f);
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) hv[k] = k < q.P ? fmaf(xs[q.feed[k]], scp[k], shp[k]) : 0.f;
-            }
-            // ---- the operand slab is shared by the two groups, whose tiles alternate g0, g1, g0, ...: wait for
-            //      the weight-gradient MMAs of the previous user, then fill it (stores only)
-            if (seq > 0) mbar_wait(&slab_free, (uint32_t)((seq - 1) & 1));
-            if (lam > 0) {
-#pragma unroll
-                for (int r = 0; r < TCH; ++r) {
-                    const float hi = tf32_rn(hv[r]);
-                    const int off = tc_slab_off(TCH, r, gt);
+                    const float hi = tf32_rn(hv[j]);
+                    const int off = tc_slab_off(TCH, f0 + j, gt);
                     *reinterpret_cast<float*>(slabBh + off) = hi;
-                    *reinterpret_cast<float*>(slabBl + off) = tf32_rn(hv[r] - hi);
+                    *reinterpret_cast<float*>(slabBl + off) = hv[j] - hi;
                 }
-            } else {
+            } else if (sub == 0) {
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const float hi = tf32_rn(hv[k]);
                     const int off = tc_slab_off(16, k, gt);
                     *reinterpret_cast<float*>(slabBh + off) = hi;
-                    *reinterpret_cast<float*>(slabBl + off) = tf32_rn(hv[k] - hi);
+                    *reinterpret_cast<float*>(slabBl + off) = hv[k] - hi;
                 }
             }
-#pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
+            {
                 float hi[32], lo[32];
-                tc_ld32(tg + 32 * cb, hi);
-                tc_ld32(tg + BT_COL_LO + 32 * cb, lo);
+                tc_ld32(tgn + f0, hi);
+                tc_ld32(tgn + BT_COL_LO + f0, lo);
                 tc_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int r = 32 * cb + j;
-                    *reinterpret_cast<float*>(slabA + tc_slab_off(128, r, gt)) = hi[j];
-                    *reinterpret_cast<float*>(slabA + tc_slab_off(128, TCH + r, gt)) = lo[j];
+                    *reinterpret_cast<float*>(slabA + tc_slab_off(128, f0 + j, gt)) = hi[j];
+                    *reinterpret_cast<float*>(slabA + tc_slab_off(128, TCH + f0 + j, gt)) = lo[j];
                 }
             }
             proxy_fence();
             tc_fence_before();
-            mbar_arrive(&a_ready[g]);
+            mbar_arrive(&a_ready);
             if (KW == 128) {
-                // second 64 logits: loaded while the MMAs of the first half run, written once those have
-                // consumed the tensor-memory columns and the slab rows
-                float dz[TCH];
-                const float* up = A.dl + (size_t)tile * 2 * BT_TILE + BT_TILE + gt;
+                // second 64 logits: loaded while the MMAs of the first block run
+                float dz[32], lo[32];
+                const float* up = A.dl + (size_t)tn * 2 * BT_TILE + BT_TILE + (size_t)f0 * TCM + gt;
 #pragma unroll
-                for (int j = 0; j < TCH; ++j) dz[j] = up[(size_t)j * TCM];
-                mbar_wait(&done[g], pd);
-                pd ^= 1;
+                for (int j = 0; j < 32; ++j) dz[j] = up[(size_t)j * TCM];
+                mbar_wait(&hdone, phd);
+                phd ^= 1;
                 tc_fence_after();
 #pragma unroll
-                for (int cb = 0; cb < 2; ++cb) {
-                    float hi[32], lo[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int r = 32 * cb + j;
-                        hi[j] = tf32_rn(dz[r]);
-                        lo[j] = tf32_rn(dz[r] - hi[j]);
-                        *reinterpret_cast<float*>(slabA + tc_slab_off(128, r, gt)) = hi[j];
-                        *reinterpret_cast<float*>(slabA + tc_slab_off(128, TCH + r, gt)) = lo[j];
-                    }
-                    tc_st32(tg + 32 * cb, hi);
-                    tc_st32(tg + BT_COL_LO + 32 * cb, lo);
+                for (int j = 0; j < 32; ++j) {
+                    const float a = dz[j];
+                    const float hi = tf32_rn(a);
+                    lo[j] = a - hi;
+                    *reinterpret_cast<float*>(slabA + tc_slab_off(128, f0 + j, gt)) = hi;
+                    *reinterpret_cast<float*>(slabA + tc_slab_off(128, TCH + f0 + j, gt)) = lo[j];
+                    dz[j] = hi;
                 }
+                tc_st32(tgn + f0, dz);
+                tc_st32(tgn + BT_COL_LO + f0, lo);
                 tc_st_wait();
                 proxy_fence();
                 tc_fence_before();
-                mbar_arrive(&a_ready[g]);
-                float s0, s1;
-                tc_warp_feature_sums(dz, lane, s0, s1);
-                accb[1][0] += (double)s0; accb[1][1] += (double)s1;
-            }
-            mbar_wait(&done[g], pd);
-            pd ^= 1;
-            tc_fence_after();
-            // ---- epilogue: dL/dh_lam = mask * (dz W_lam); store; sums for BN layer lam ---------------------------
-            float dv[TCH];
-            if (lam > 0) {
-                tc_ld32(tg + BT_COL_D, dv);
-                tc_ld32(tg + BT_COL_D + 32, dv + 32);
-            } else {
-                tc_ld16(tg + BT_COL_D, dv);
+                mbar_arrive(&a_ready);
 #pragma unroll
-                for (int j = 16; j < TCH; ++j) dv[j] = 0.f;
-            }
-            tc_ld_wait();
-            float* out = A.dh_out + (size_t)tile * BT_TILE + gt;
-            float pr[TCH];
-            if (lam > 0) {
-#pragma unroll
-                for (int j = 0; j < TCH; ++j) {
-                    dv[j] = ((mask >> j) & 1) ? dv[j] : 0.f;
-                    out[(size_t)j * TCM] = dv[j];
-                    pr[j] = dv[j] * (zp[(size_t)j * TCM] - mup[j]) * rsp[j];
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    dv[j] = j < q.P ? dv[j] : 0.f;
-                    out[(size_t)j * TCM] = dv[j];
-                    pr[j] = j < q.P ? dv[j] * (xs[q.feed[j]] - mup[j]) * rsp[j] : 0.f;
-                }
-#pragma unroll
-                for (int j = 16; j < TCH; ++j) pr[j] = 0.f;
-            }
-            float s0, s1;
-            tc_warp_feature_sums(dv, lane, s0, s1);
-            acc1[0] += (double)s0; acc1[1] += (double)s1;
-            tc_warp_feature_sums(pr, lane, s0, s1);
-            acc2[0] += (double)s0; acc2[1] += (double)s1;
-            // ---- periodic flush of the weight-gradient accumulators (group 0 owns lanes 0..127 of them) -------------
-            if (g == 0 && bt_flush_after(it, tile, gridDim.x, ntiles, A.flush_every)) {
-                mbar_wait(&acc_ready, pfr);
-                pfr ^= 1;
-                tc_fence_after();
-                bt_flush_acc<NH>(tmem_base + ((uint32_t)(warp * 32) << 16) + BT_COL_ACC,
-                                 A.slices + (((size_t)lam * A.grid + blockIdx.x) * 2) * 128 * TCH + (size_t)tid * TCH, lam, nin, nflush > 0);
-                ++nflush;
-                tc_fence_before();
-                mbar_arrive(&acc_free);
+                for (int j = 0; j < 32; ++j) dz[j] += lo[j];
+                accb[NH - 1] += (double)bt_warp_feature_sums32(dz, lane);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    // ---- weight-gradient accumulators -> this CTA's slice ----------------------------------------------------------
     if (warp < 4)
         bt_flush_acc<NH>(tmem_base + ((uint32_t)(warp * 32) << 16) + BT_COL_ACC,
                          A.slices + (((size_t)lam * A.grid + blockIdx.x) * 2) * 128 * TCH + (size_t)tid * TCH, lam, nin, nflush > 0);
     tc_fence_before();
     __syncthreads();
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-    // ---- per-feature sums: warps -> CTA -> grid (last CTA finalises) ---------------------------------------------------
-    double* red = reinterpret_cast<double*>(sm);            // [8 warps][32 lanes][8]   (the slab is idle now)
+    // ---- per-feature sums: lane l of a warp holds feature 32 sub + l ----------------------------------------------------
+    double* red = reinterpret_cast<double*>(sm);            // [8 warps][32 lanes][4]
     if (warp < 8) {
-        double* r = red + ((size_t)warp * 32 + lane) * 8;
-        r[0] = acc1[0]; r[1] = acc1[1]; r[2] = acc2[0]; r[3] = acc2[1];
-#pragma unroll
-        for (int h = 0; h < NH; ++h) { r[4 + 2 * h] = accb[h][0]; r[5 + 2 * h] = accb[h][1]; }
-        if (NH == 1) { r[6] = 0.0; r[7] = 0.0; }
+        double* r = red + ((size_t)warp * 32 + lane) * 4;
+        r[0] = acc1; r[1] = acc2; r[2] = accb[0]; r[3] = NH > 1 ? accb[NH - 1] : 0.0;
     }
     __syncthreads();
-    // partials row of this CTA: [0,64) sum dh, [64,128) sum dh*xhat, [128,256) bias gradient
     double* mine = A.partials + (size_t)blockIdx.x * 256;
     for (int i = tid; i < 256; i += TC_THREADS) {
-        const int f = i & 63, kind = i >> 6;                // kind 0: s1, 1: s2, 2: bias half 0, 3: bias half 1
-        // 64-wide butterflies leave features (2 lane, 2 lane + 1) on a lane, the 32-wide ones of the first
-        // logit half feature 32 chunk + lane
-        const int ln = kind == 2 ? (f & 31) : (f >> 1), ix = kind == 2 ? (f >> 5) : (f & 1);
-        const int slot = kind == 0 ? ix : kind == 1 ? 2 + ix : kind == 2 ? 4 + ix : 6 + ix;
+        const int f = i & 63, kind = i >> 6;                // kind 0: s1, 1: s2, 2: bias block 0, 3: bias block 1
+        const int sb = f >> 5, ln = f & 31;
         double s = 0.0;
-        for (int w = 0; w < 8; ++w) s += red[((size_t)w * 32 + ln) * 8 + slot];
+        for (int w = 0; w < 4; ++w) s += red[((size_t)(sb * 4 + w) * 32 + ln) * 4 + kind];
         mine[i] = s;
     }
     __threadfence();
@@ -739,13 +720,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
     for (int i = tid; i < 256; i += TC_THREADS) {
         const int f = i & 63, kind = i >> 6;
         double s = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(A.partials + (size_t)b * 256 + i);
+        for (unsigned bb = 0; bb < gridDim.x; ++bb) s += __ldcg(A.partials + (size_t)bb * 256 + i);
         if (kind == 0 && f < win) {
             A.bnb[lam * 2 * maxW + f] = (float)(s / (double)A.B);
-            gp[F.p_bn_gamma(c, lam) + win + f] += (float)s;                 // dL/dbeta
+            gp[F.p_bn_gamma(c, lam) + win + f] += (float)s;
         } else if (kind == 1 && f < win) {
             A.bnb[lam * 2 * maxW + maxW + f] = (float)(s / (double)A.B);
-            gp[F.p_bn_gamma(c, lam) + f] += (float)s;                       // dL/dgamma
+            gp[F.p_bn_gamma(c, lam) + f] += (float)s;
         } else if (kind >= 2 && KW == 128) {
             const int n = (kind - 2) * TCH + f;
             if (n < q.T * F.K) gp[F.p_out_b(c) + n] += (float)s;
@@ -889,6 +870,14 @@ int nis_flow_backward_tc(const DevFlow& F, const FlowWorkspace& ws, const float*
     const size_t smem64 = (size_t)bt_layout(64).total + 1024, smem128 = (size_t)bt_layout(128).total + 1024;
     cudaFuncSetAttribute(flow_bwd_tc_layer_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64);
     cudaFuncSetAttribute(flow_bwd_tc_layer_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128);
+    int sms1 = 0, dev1 = 0;
+    cudaGetDevice(&dev1);
+    cudaDeviceGetAttribute(&sms1, cudaDevAttrMultiProcessorCount, dev1);
+    if (sms1 <= 0) sms1 = 148;
+    const long long nt1 = (B + TCM - 1) / TCM;
+    const int grid1 = (int)(nt1 < sms1 ? nt1 : sms1);
+    const int lgrid = grid1;                               // CTAs of the layer launches (one tile at a time each) = slices per layer
+    A.grid = lgrid;
     for (int c = F.n_cells - 1; c >= 0; --c) {
         A.c = c; A.first = c == F.n_cells - 1;
         const size_t smem_head = (size_t)tc_layout(F, F.cells[c].P, 1, F.depth, false).total + 2 * (F.d + 1) * TCM * 4 + 1024;
@@ -899,8 +888,8 @@ int nis_flow_backward_tc(const DevFlow& F, const FlowWorkspace& ws, const float*
         for (int lam = F.depth; lam >= 0; --lam) {
             A.lam = lam;
             A.dh_in = sc.dh[pp]; A.dh_out = sc.dh[pp ^ 1];
-            if (lam == F.depth) flow_bwd_tc_layer_kernel<128><<<grid, TC_THREADS, smem128, s>>>(F, A);
-            else flow_bwd_tc_layer_kernel<64><<<grid, TC_THREADS, smem64, s>>>(F, A);
+            if (lam == F.depth) flow_bwd_tc_layer_kernel<128><<<lgrid, TC_THREADS, smem128, s>>>(F, A);
+            else flow_bwd_tc_layer_kernel<64><<<lgrid, TC_THREADS, smem64, s>>>(F, A);
             NIS_CUDA_CHECK_LAUNCH();
             pp ^= 1;
         }
@@ -910,7 +899,7 @@ int nis_flow_backward_tc(const DevFlow& F, const FlowWorkspace& ws, const float*
         flow_bwd_tc_tail_kernel<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, s>>>(F, A);
         NIS_CUDA_CHECK_LAUNCH();
         A.grad_in = nullptr;
-        flow_bwd_tc_reduce_kernel<<<dim3(32, F.depth + 1), 256, 0, s>>>(F, sc.slices, grid, c, grad_params);
+        flow_bwd_tc_reduce_kernel<<<dim3(32, F.depth + 1), 256, 0, s>>>(F, sc.slices, lgrid, c, grad_params);
         NIS_CUDA_CHECK_LAUNCH();
     }
     return NIS_OK;
