@@ -572,15 +572,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
                     for (int k = 0; k < 16; ++k) hv[k] = k < q.P ? fmaf(xs[q.feed[k]], scp[k], shp[k]) : 0.f;
                 }
             }
-            // ---- stage 2: epilogue of the current tile --------------------------------------------------------------
+            // ---- wait for the current tile --------------------------------------------------------------------------
+            const int b = (int)(it & 1);
+            if (it >= 0) {                                     // the MMAs of the current tile are complete: its dgrad
+                mbar_wait(&done[b], pdn[b]);                   // accumulator is valid and the operand slab is free
+                pdn[b] ^= 1;
+                tc_fence_after();
+            }
+            if (have_n) {
+                // ---- stage 2: operands of the next tile into the slab; its MMAs then overlap the epilogue below ----------
+                if (lam > 0) {
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float hi = tf32_rn(hv[j]);
+                        const int off = tc_slab_off(TCH, f0 + j, gt);
+                        *reinterpret_cast<float*>(slabBh + off) = hi;
+                        *reinterpret_cast<float*>(slabBl + off) = hv[j] - hi;
+                    }
+                } else if (sub == 0) {
+    #pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float hi = tf32_rn(hv[k]);
+                        const int off = tc_slab_off(16, k, gt);
+                        *reinterpret_cast<float*>(slabBh + off) = hi;
+                        *reinterpret_cast<float*>(slabBl + off) = hv[k] - hi;
+                    }
+                }
+                {
+                    float hi[32], lo[32];
+                    tc_ld32(tgn + f0, hi);
+                    tc_ld32(tgn + BT_COL_LO + f0, lo);
+                    tc_ld_wait();
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        *reinterpret_cast<float*>(slabA + tc_slab_off(128, f0 + j, gt)) = hi[j];
+                        *reinterpret_cast<float*>(slabA + tc_slab_off(128, TCH + f0 + j, gt)) = lo[j];
+                    }
+                }
+                proxy_fence();
+                tc_fence_before();
+                mbar_arrive(&a_ready);
+            }
+            // ---- stage 3: epilogue of the current tile ---------------------------------------------------------------
             if (it >= 0) {
-                const int b = (int)(it & 1);
                 const uint32_t tg = tl + b * BT_GROUP_COLS;
                 const long long pt = tile * TCM + gt;
                 const bool valid = pt < A.B;
-                mbar_wait(&done[b], pdn[b]);
-                pdn[b] ^= 1;
-                tc_fence_after();
                 float* out = A.dh_out + (size_t)tile * BT_TILE + gt;
                 if (lam > 0) {
                     const float* zp = A.zbuf + ((size_t)(lam - 1) * ntiles + tile) * BT_TILE + (size_t)f0 * TCM + gt;
@@ -623,39 +660,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
                 }
             }
             if (!have_n) break;
-            // ---- stage 3: the slab is free (the MMAs of the current tile are complete): operands of the next tile ----
-            mask = maskn;
-            if (lam > 0) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float hi = tf32_rn(hv[j]);
-                    const int off = tc_slab_off(TCH, f0 + j, gt);
-                    *reinterpret_cast<float*>(slabBh + off) = hi;
-                    *reinterpret_cast<float*>(slabBl + off) = hv[j] - hi;
-                }
-            } else if (sub == 0) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const float hi = tf32_rn(hv[k]);
-                    const int off = tc_slab_off(16, k, gt);
-                    *reinterpret_cast<float*>(slabBh + off) = hi;
-                    *reinterpret_cast<float*>(slabBl + off) = hv[k] - hi;
-                }
-            }
-            {
-                float hi[32], lo[32];
-                tc_ld32(tgn + f0, hi);
-                tc_ld32(tgn + BT_COL_LO + f0, lo);
-                tc_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    *reinterpret_cast<float*>(slabA + tc_slab_off(128, f0 + j, gt)) = hi[j];
-                    *reinterpret_cast<float*>(slabA + tc_slab_off(128, TCH + f0 + j, gt)) = lo[j];
-                }
-            }
-            proxy_fence();
-            tc_fence_before();
-            mbar_arrive(&a_ready);
             if (KW == 128) {
                 // second 64 logits: loaded while the MMAs of the first block run
                 float dz[32], lo[32];
@@ -684,6 +688,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
                 for (int j = 0; j < 32; ++j) dz[j] += lo[j];
                 accb[NH - 1] += (double)bt_warp_feature_sums32(dz, lane);
             }
+            mask = maskn;
         }
     }
     tc_fence_before();
