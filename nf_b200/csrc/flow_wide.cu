@@ -213,8 +213,8 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
                 for (int k = 0; k < 16; ++k) a0[k] = k < q.P ? fmaf(st[q.feed[k] * TCM], affs[k], affs[16 + k]) : 0.f;
             }
             float jfac = 1.f;
-            for (int r = 0; r < rounds; ++r, ++rr) {
-                // ---- A operand: h_lam = ReLU(BN_lam(z_lam)), 64 features per chunk ---------------------------------
+            // A operand of round r: h_lam = ReLU(BN_lam(z_lam)), 32 features per chunk, handed to the MMA warp chunk by chunk
+            auto feed = [&](int r) {
                 for (int i = 0; i < kc; ++i, ++cc) {
                     const unsigned buf = cc & 1;
                     float v[32];
@@ -260,6 +260,9 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
                     tc_fence_before();
                     mbar_arrive(&a_ready[buf]);
                 }
+            };
+            feed(0);
+            for (int r = 0; r < rounds; ++r, ++rr) {
                 mbar_wait(&d_ready, rr & 1);
                 tc_fence_after();
                 if (stats) {
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
                     }
                     tc_fence_before();
                     mbar_arrive(&d_free);
+                    if (r + 1 < rounds) feed(r + 1);
                 } else {
                     // ---- final pass, transformed dimension t = r: logits -> shared memory -> spline ----------------
                     const int t = r;
@@ -303,6 +307,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
                     }
                     tc_fence_before();
                     mbar_arrive(&d_free);
+                    if (r + 1 < rounds) feed(r + 1);           // the next dimension's MMAs run while this one's spline does
                     const int col = q.trafo[t];
                     const float xv = st[col * TCM];
                     float y, f;
