@@ -176,11 +176,13 @@ def test_full_size_cfg5_gradients(monkeypatch, backend):
     test_gradients_match_oracle_autograd_at_size(cfg, "train")
 
 
-def test_tensor_core_backward_at_large_batch_matches_generic(monkeypatch):
-    """Many tiles per CTA (2^18 points): the weight-gradient accumulators in tensor memory are flushed to the CTA's
-    slice every few tiles because tcgen05 accumulation truncates; the result must agree with the FP32 generic
-    kernel (itself pinned against the oracle above)."""
-    cfg = dict(BIG[0], B=1 << 18)
+@pytest.mark.parametrize("which,log2b", [(0, 19), (3, 15)], ids=["cfg2_2p19", "cfg5_small_2p15"])
+def test_tensor_core_backward_at_large_batch_matches_generic(monkeypatch, which, log2b):
+    """Many tiles per CTA (cfg2: 2^19 points = 28 tiles per CTA; the 128-wide cfg5_small: 2^15 points): the
+    weight-gradient accumulators in tensor memory are flushed to the CTA's slice every 16 (8) tiles because
+    tcgen05 accumulation truncates; the result must agree with the FP32 generic kernel (itself pinned against the
+    oracle above)."""
+    cfg = dict(BIG[which], B=1 << log2b)
     layers = oracle_layers(cfg)
     cells, _ = oflow.compile_layers(layers, cfg["n_flow"])
     sd = oflow.init_state_dict(cells, cfg["n_flow"], cfg["kind"], cfg["n_bins"], cfg["NN"], seed=33,
@@ -205,7 +207,7 @@ def test_tensor_core_backward_at_large_batch_matches_generic(monkeypatch):
     for k in grads["generic"]:
         close(grads["tcgen05"][k], grads["generic"][k], k, gscale, flips=True)
         worst = max(worst, float((grads["tcgen05"][k] - grads["generic"][k]).abs().max()) / gscale)
-    print("tc vs generic backward at 2^18 points: worst |diff| / model gradient scale = %.2e" % worst)
+    print("tc vs generic backward at 2^%d points: worst |diff| / model gradient scale = %.2e" % (log2b, worst))
 
 
 WIDE_BWD = [
