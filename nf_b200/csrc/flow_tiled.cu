@@ -392,18 +392,29 @@ __global__ void __launch_bounds__(256) flow_col_moments_kernel(const __grid_cons
     double acc[MOM_N];
 #pragma unroll
     for (int i = 0; i < MOM_N; ++i) acc[i] = 0.0;
-    for (long long pt = (long long)blockIdx.x * 256 + tid; pt < A.B; pt += (long long)gridDim.x * 256) {
-        float x[MOM_P];
+    // four points per thread and iteration: their loads are issued together (the kernel is latency-bound: 88
+    // accumulator registers leave two blocks per SM)
+    constexpr int MOM_U = 4;
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long pt0 = (long long)blockIdx.x * 256 + tid; pt0 < A.B; pt0 += MOM_U * stride) {
+        float x[MOM_U][MOM_P];
 #pragma unroll
-        for (int k = 0; k < MOM_P; ++k)
-            x[k] = k < P ? (A.from_state ? A.state_in[pt * (d + 1) + q.feed[k]]
-                                         : load_io(A.in, A.in_dtype, pt * A.in_cols + q.feed[k])) : 0.f;
-        int o = MOM_P;
+        for (int u = 0; u < MOM_U; ++u) {
+            const long long pt = pt0 + u * stride;
 #pragma unroll
-        for (int k = 0; k < MOM_P; ++k) {
-            acc[k] += (double)x[k];
+            for (int k = 0; k < MOM_P; ++k)
+                x[u][k] = (k < P && pt < A.B) ? (A.from_state ? A.state_in[pt * (d + 1) + q.feed[k]]
+                                                              : load_io(A.in, A.in_dtype, pt * A.in_cols + q.feed[k])) : 0.f;
+        }
 #pragma unroll
-            for (int k2 = k; k2 < MOM_P; ++k2) acc[o++] += (double)x[k] * (double)x[k2];
+        for (int u = 0; u < MOM_U; ++u) {
+            int o = MOM_P;
+#pragma unroll
+            for (int k = 0; k < MOM_P; ++k) {
+                acc[k] += (double)x[u][k];
+#pragma unroll
+                for (int k2 = k; k2 < MOM_P; ++k2) acc[o++] += (double)x[u][k] * (double)x[u][k2];
+            }
         }
     }
 #pragma unroll
