@@ -541,7 +541,7 @@ def main():
             line["readme_example"] = bench_readme(dev)
         if rank == 0 and world == 1:
             threads = os.cpu_count() or 1
-            sample = 1 << 17
+            sample = 1 << 20                                # ~5 s per pass on 16 host threads: ~15 s of CPU work
             v, dt, kind = cpu_reference_flow(sample, 2, threads)
             line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": threads, "kind": kind,
                                     "sample": "%d points (of 2^22), best of 2 after 1 warm-up, float64, train-mode BN, "
