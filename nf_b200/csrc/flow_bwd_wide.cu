@@ -107,30 +107,6 @@ __device__ __forceinline__ float bw_load_g(const void* p, int dtype, long long i
     return dtype == NIS_F64 ? (float)reinterpret_cast<const double*>(p)[idx] : reinterpret_cast<const float*>(p)[idx];
 }
 
-// per-feature sums of v[i] over the warp's 32 points in float64: features (2 lane, 2 lane + 1)
-__device__ __forceinline__ void bw_warp_sums64(const float* v, int lane, double* s) {
-    double a[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const bool up = lane & 16;
-        const double a0 = (double)v[i], a1 = (double)v[i + 32];
-        a[i] = (up ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up ? a0 : a1, 16);
-    }
-#pragma unroll
-    for (int w = 16; w >= 2; w >>= 1) {
-        const int m = w >> 1;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if (i < w) {
-                const bool up = lane & m;
-                const double ka = up ? a[i + w] : a[i], xa = up ? a[i] : a[i + w];
-                a[i] = ka + __shfl_xor_sync(0xffffffffu, xa, m);
-            }
-        }
-    }
-    s[0] = a[0]; s[1] = a[1];
-}
-
 // ===================================================================================================
 // head: output layer + spline backward
 // ===================================================================================================
@@ -601,17 +577,18 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_bwd_wide_dgrad_kernel(cons
                         dv[x] = on ? dv[x] : 0.f;
                         out[(size_t)r * TCM] = dv[x];
                     }
-                    double a[2], b[2];
-                    bw_warp_sums64(dv, lane, a);
+                    // per-warp sums in float32 (32 addends), float64 across tiles: ample for gradients
+                    float a[2], b[2];
+                    tc_warp_feature_sums(dv, lane, a[0], a[1]);
 #pragma unroll
                     for (int x = 0; x < TCH; ++x) {
                         const int r = 64 * jb + x;
                         dv[x] *= (zp[(size_t)r * TCM] - mup[r]) * rsp[r];
                     }
-                    bw_warp_sums64(dv, lane, b);
+                    tc_warp_feature_sums(dv, lane, b[0], b[1]);
 #pragma unroll
                     for (int y = 0; y < 4; ++y)
-                        if (y == jb) { s1[y][0] += a[0]; s1[y][1] += a[1]; s2[y][0] += b[0]; s2[y][1] += b[1]; }
+                        if (y == jb) { s1[y][0] += (double)a[0]; s1[y][1] += (double)a[1]; s2[y][0] += (double)b[0]; s2[y][1] += (double)b[1]; }
                 }
             } else {
                 const float* xs = A.saved + ((long long)c * A.B + (valid ? pt : 0)) * rowlen;
@@ -625,12 +602,12 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_bwd_wide_dgrad_kernel(cons
                 }
 #pragma unroll
                 for (int x = 16; x < TCH; ++x) dv[x] = 0.f;
-                double a[2], b[2];
-                bw_warp_sums64(dv, lane, a);
+                float a[2], b[2];
+                tc_warp_feature_sums(dv, lane, a[0], a[1]);
 #pragma unroll
                 for (int x = 0; x < 16; ++x) dv[x] = x < q.P ? dv[x] * (xs[q.feed[x]] - mup[x]) * rsp[x] : 0.f;
-                bw_warp_sums64(dv, lane, b);
-                s1[0][0] += a[0]; s1[0][1] += a[1]; s2[0][0] += b[0]; s2[0][1] += b[1];
+                tc_warp_feature_sums(dv, lane, b[0], b[1]);
+                s1[0][0] += (double)a[0]; s1[0][1] += (double)a[1]; s2[0][0] += (double)b[0]; s2[0][1] += (double)b[1];
             }
             tc_fence_before();
             mbar_arrive(&d_free);
