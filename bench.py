@@ -193,7 +193,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 1 << 17
+    sample = 1 << 19                     # ~2.4 s per step on 16 host threads: a 10+3-step run stays near half a minute
     fn, kind = reference_flow(threads)
     x = torch.rand(sample, CFG2["n_flow"], dtype=torch.float64)
     xj = torch.cat((x, torch.ones(sample, 1, dtype=torch.float64)), 1)
