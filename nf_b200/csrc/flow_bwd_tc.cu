@@ -466,13 +466,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
                     tc_fence_after();
                     const uint32_t bh = sBd + h * 2 * nin * TCH * 4, bl = bh + nin * TCH * 4;
                     uint32_t acc = h > 0;
+                    // cross terms first, hi*hi last (the accumulate truncation is relative to the accumulator, tc_common.cuh)
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint32_t wo = (ks >> 2) * nin * 128 + (ks & 3) * 32;
-                        tc_mma_tf32_ts(tb + BT_COL_D, tb + ks * 8, tc_desc(bh + wo), idesc, acc);
+                        tc_mma_tf32_ts(tb + BT_COL_D, tb + ks * 8, tc_desc(bl + wo), idesc, acc);
                         acc = 1;
-                        tc_mma_tf32_ts(tb + BT_COL_D, tb + ks * 8, tc_desc(bl + wo), idesc, 1);
                         tc_mma_tf32_ts(tb + BT_COL_D, tb + BT_COL_LO + ks * 8, tc_desc(bh + wo), idesc, 1);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t wo = (ks >> 2) * nin * 128 + (ks & 3) * 32;
+                        tc_mma_tf32_ts(tb + BT_COL_D, tb + ks * 8, tc_desc(bh + wo), idesc, 1);
                     }
                     const uint32_t ta = tmem_base + BT_COL_ACC + h * TCH;
                     uint32_t accw = !fresh;

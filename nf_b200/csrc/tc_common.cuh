@@ -207,17 +207,25 @@ __device__ __forceinline__ void tc_store_act(const float* v, const float* sc, co
     tc_st_wait();
 }
 
-// 3xTF32 product of the group's [128 x 64] activations (TMEM) with a [N x 64] weight matrix (smem): 8 K-steps x 3
+// 3xTF32 product of the group's [128 x 64] activations (TMEM) with a [N x 64] weight matrix (smem): 8 K-steps x 3.
+// tcgen05.mma truncates when it adds a K=8 step into the fp32 accumulator (tools/tc_accum_probe.cu), losing about
+// one ulp OF THE ACCUMULATOR per instruction.  The sixteen cross-term steps (a_hi w_lo, a_lo w_hi: 2^-11 of the
+// result) are therefore issued first, while the accumulator is still tiny, and the eight a_hi w_hi steps last:
+// the truncation of 8 instead of 24 steps is felt.
 __device__ __forceinline__ void tc_issue_layer(uint32_t tmem_d, uint32_t t_hi, uint32_t t_lo, uint32_t w_hi, uint32_t w_lo,
                                                int n_rows, uint32_t idesc) {
     uint32_t acc = 0;
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
         const uint32_t wo = (ks >> 2) * n_rows * 128 + (ks & 3) * 32;
-        tc_mma_tf32_ts(tmem_d, t_hi + ks * 8, tc_desc(w_hi + wo), idesc, acc);
+        tc_mma_tf32_ts(tmem_d, t_hi + ks * 8, tc_desc(w_lo + wo), idesc, acc);
         acc = 1;
-        tc_mma_tf32_ts(tmem_d, t_hi + ks * 8, tc_desc(w_lo + wo), idesc, 1);
         tc_mma_tf32_ts(tmem_d, t_lo + ks * 8, tc_desc(w_hi + wo), idesc, 1);
+    }
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t wo = (ks >> 2) * n_rows * 128 + (ks & 3) * 32;
+        tc_mma_tf32_ts(tmem_d, t_hi + ks * 8, tc_desc(w_hi + wo), idesc, 1);
     }
 }
 
