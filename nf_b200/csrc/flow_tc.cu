@@ -431,11 +431,17 @@ size_t nis_tc_pack_floats(const DevFlow& F) {
     return (size_t)F.n_cells * tc_cell_floats(F);
 }
 
+// smallest batch the tensor-core kernels take (below it the shape-generic kernel runs); NIS_TC_MIN_B overrides (test knob)
+int64_t nis_tc_min_batch(int64_t dflt) {
+    const char* e = getenv("NIS_TC_MIN_B");
+    return e ? atoll(e) : dflt;
+}
+
 bool nis_tc_supported(const DevFlow& F, int64_t B, int bn_mode) {
     (void)bn_mode;
     const char* off = getenv("NIS_TC");                   // NIS_TC=0 forces the FP32-pipe kernels (test knob)
     if (off && off[0] == '0') return false;
-    if (F.depth < 1 || B < 2048 || F.maxW != TCH || F.nb != 32) return false;
+    if (F.depth < 1 || B < nis_tc_min_batch(2048) || F.maxW != TCH || F.nb != 32) return false;
     for (int l = 0; l < F.depth; ++l) if (F.widths[l] != TCH) return false;
     if (F.kind == NIS_KIND_PWLIN ? F.K != 32 : F.K != 65) return false;
     for (int c = 0; c < F.n_cells; ++c) {
