@@ -161,3 +161,27 @@ def test_cabi_library_exports_every_declared_symbol():
     bad = _cabi.NisFlowDesc()
     assert lib.nis_flow_workspace_bytes(ctypes.byref(bad), 10) == 0       # invalid descriptor rejected on the host
     assert lib.nis_flow_cell_param_count(ctypes.byref(bad), 0) == -1
+
+
+@pytest.mark.parametrize("kind,n_flow,args,scratch_per_point", [
+    ("lin", 8, (4, 6, 32, [64] * 3, 4), 7 * 64 * 4),          # cfg2: z_1..z_3, dL/dlogits (2 tiles), two dL/dh buffers
+    ("quad", 8, (6, 32, [64] * 3), 6 * 64 * 4),               # cfg4: streamed-weights backward, width 64
+    ("quad", 16, (8, 64, [256] * 4), 7 * 256 * 4),            # cfg5: z_1..z_4, two dL/dh, dz + the logits-gradient tile
+])
+def test_workspace_covers_the_tensor_core_scratch(kind, n_flow, args, scratch_per_point):
+    """nis_flow_workspace_bytes is host code: without a GPU it must still size the workspace for every kernel path
+    the shape can take (forward activation buffers, tensor-core backward scratch), growing linearly with the batch."""
+    from nf_b200.normalizing_flows.manager import PWLinManager, PWQuadManager
+    NF = (PWLinManager if kind == "lin" else PWQuadManager)(n_flow=n_flow)
+    NF.create_model(*args)
+    d = NF._model.spec().desc
+    lib = _cabi.load()
+    b1, b2 = 1 << 14, 1 << 16
+    w1 = lib.nis_flow_workspace_bytes(ctypes.byref(d), b1)
+    w2 = lib.nis_flow_workspace_bytes(ctypes.byref(d), b2)
+    assert w2 > w1 > 0
+    per_point = (w2 - w1) / (b2 - b1)
+    assert per_point >= scratch_per_point, per_point
+    assert per_point <= 3 * scratch_per_point + 4096, per_point
+    small = lib.nis_flow_workspace_bytes(ctypes.byref(d), 100)      # below the tensor-core threshold: generic kernels only
+    assert 0 < small < w1
