@@ -441,7 +441,7 @@ bool nis_tc_supported(const DevFlow& F, int64_t B, int bn_mode) {
     (void)bn_mode;
     const char* off = getenv("NIS_TC");                   // NIS_TC=0 forces the FP32-pipe kernels (test knob)
     if (off && off[0] == '0') return false;
-    if (F.depth < 1 || B < nis_tc_min_batch(2048) || F.maxW != TCH || F.nb != 32) return false;
+    if (F.depth < 1 || B < nis_tc_min_batch(256) || F.maxW != TCH || F.nb != 32) return false;
     for (int l = 0; l < F.depth; ++l) if (F.widths[l] != TCH) return false;
     if (F.kind == NIS_KIND_PWLIN ? F.K != 32 : F.K != 65) return false;
     for (int c = 0; c < F.n_cells; ++c) {

@@ -222,3 +222,9 @@ def test_streamed_weight_backward_shapes(cfg):
     """flow_bwd_wide.cu beyond cfg4 / cfg5: PWLin cells, width 64 with a bin count the resident-weights kernel
     does not take, a single hidden layer (z_1 stored by the head itself), ragged last tile."""
     test_gradients_match_oracle_autograd_at_size(cfg, "train")
+
+
+@pytest.mark.parametrize("which", [0, 1, 3], ids=["cfg2", "cfg4", "cfg5_small"])
+def test_tensor_core_backward_at_small_batches(which):
+    """600 points in two minibatches of 300: tensor-core forward and backward on three tiles each."""
+    test_gradients_match_oracle_autograd_at_size(dict(BIG[which], B=600), "train")

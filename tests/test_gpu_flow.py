@@ -139,3 +139,11 @@ def test_streamed_weight_kernel_shapes(cfg, mode):
     """flow_wide.cu beyond cfg5_small: width 128 (one round), 192 (one round of N = 192), 256 x 4 layers (two rounds
     per hidden layer), PWLin and PWQuad, bin counts that are not multiples of 16, ragged last tile."""
     test_forward_matches_oracle_at_size(cfg, mode)
+
+
+@pytest.mark.parametrize("which", [0, 1, 3], ids=["cfg2", "cfg4", "cfg5_small"])
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_tensor_core_kernels_at_small_batches(which, mode):
+    """The tensor-core kernels take over from 256 points (a training minibatch of a few hundred points is common in
+    the reference's examples): three tiles, the last one ragged, a grid of two or three CTAs."""
+    test_forward_matches_oracle_at_size(dict(BIG[which], B=300), mode)
