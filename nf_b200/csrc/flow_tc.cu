@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_cell_tc_kernel(const __gri
                         float S = 0.f, C = 0.f, ek = 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float e = expf(z[j] - m);
+                            const float e = __expf(z[j] - m);
                             S += e;
                             C += j < kb ? e : 0.f;
                             ek = j == kb ? e : ek;
