@@ -11,14 +11,15 @@
 //            gradient, or BN backward of the stored dL/dh with the batch means the previous launch left)
 //              dgrad  dL/dh_lam = dz W_lam        A = dz in TENSOR MEMORY (lane = point), B = W_lam^T in smem
 //              wgrad  dL/dW_lam += dz^T h_lam     both operands in shared memory, K = the 128 points of the
-//                                                 tile, accumulated in tensor memory over ALL tiles of the
-//                                                 CTA and read out once (per-CTA slices, no atomics)
+//                                                 tile, accumulated in tensor memory over the tiles of the
+//                                                 CTA and added to its slice every 16 tiles (tcgen05
+//                                                 accumulation truncates); fixed-order reduce, no atomics
 //            then ReLU mask, store dL/dh_lam, per-feature sums of dL/dh and dL/dh * xhat (recursive-halving
 //            warp shuffles, float64 across tiles, last CTA finalises = dL/dbeta, dL/dgamma and the means the
 //            next launch needs)
 //   tail   : BatchNorm backward of the input normalisation -> dL/dx of the pass-through columns
 //
-// 3xTF32 everywhere (hi/lo round-to-nearest splits).  For the wgrad the hi and lo parts of dz are STACKED
+// 3xTF32 everywhere (hi rounded to nearest, exact residual).  For the wgrad the hi and lo parts of dz are STACKED
 // along M ([dz_hi ; dz_lo], 128 rows) so that two M=128 MMAs (against h_hi and h_lo) give all four partial
 // products; rows o and 64+o of the accumulator are added on read-out.
 //
