@@ -73,7 +73,31 @@ struct RamboConst {
     double e2_dR;                 // exp(2 dR_min)
     double cos_dR;                // cos(min(dR_min, pi))
     int dR_ge_pi;                 // dR_min >= pi: the d-phi quick reject never fires
+    double u_one[NIS_MAX_FINAL];  // u_one[e]: what the reference's lattice bisection returns for r == 1
 };
+
+// The reference's root finder (flat_phase_space_generator.py:333-348) never returns u = 0 or u = 1:
+//   * r == 0 makes its batch-wide error infinite at the first check, so the search stops after 60 levels on
+//     the lowest lattice point u = 2^-60 (NIS_U_FLOOR; the same happens for any r whose root is below it);
+//   * r == 1: the map value rounds to 1.0 once 1 - u < ~4e-9 and `v <= map(u)` then sends the search left,
+//     so it settles on 1 - 2^-27/e.  Every operation of that search is an exact or correctly rounded
+//     float64 operation, so it is replayed here on the host (independent of the level count >= 60) and
+//     handed to the kernel as a per-exponent constant.
+// With these two values the weight stays finite wherever the reference's is (massless: the rho ratio is 1).
+#define NIS_U_FLOOR 8.673617379884035e-19   /* 2^-60 */
+static inline double rambo_lattice_at_one(int e) {
+    double left = 0.0, right = 1.0, u = 1.0, scale = 0.5;
+    for (int level = 0; level < 60; ++level, scale *= 0.5) {
+        u = (left + right) * scale;
+        double p = 1.0;
+        for (int i = 0; i < e; ++i) p *= u;
+        const double check = p * ((double)(e + 1) - (double)e * u);
+        left *= 2.0; right *= 2.0;
+        const double adder = (1.0 <= check) ? -0.5 : 0.5;
+        left += adder + 0.5; right += adder - 0.5;
+    }
+    return u;
+}
 
 // Host: fold the descriptor into per-launch constants.
 static inline int rambo_fill_const(const NisRamboDesc* d, RamboConst* C) {
@@ -107,6 +131,8 @@ static inline int rambo_fill_const(const NisRamboDesc* d, RamboConst* C) {
     C->e2_dR = exp(2.0 * d->delR_mincut);
     C->dR_ge_pi = d->delR_mincut >= NIS_PI;
     C->cos_dR = cos(d->delR_mincut < NIS_PI ? d->delR_mincut : NIS_PI);
+    C->u_one[0] = 1.0;
+    for (int e = 1; e < NIS_MAX_FINAL; ++e) C->u_one[e] = rambo_lattice_at_one(e);
     return NIS_OK;
 }
 
@@ -145,10 +171,10 @@ double rambo_root_slow(int e, double r, double X) {
     return X;
 }
 
-NIS_DEV double rambo_root(int e, double r) {
-    if (e == 1) return nis_div(r, 1.0 + nis_sqrt(1.0 - r));             // u = 1 - sqrt(1-r), stable form
-    if (r <= 0.0) return 0.0;
-    if (r >= 1.0) return 1.0;
+NIS_DEV double rambo_root(int e, double r, double u_one) {
+    if (r >= 1.0) return u_one;                                // see NIS_U_FLOOR above
+    if (e == 1) return fmax(nis_div(r, 1.0 + nis_sqrt(1.0 - r)), NIS_U_FLOOR);   // u = 1 - sqrt(1-r), stable form
+    if (r <= 0.0) return NIS_U_FLOOR;
     const float ef = (float)e;
     const float ustar = (ef - 1.f) / ef;                      // inflection point of the map
     float us = 1.f;
@@ -187,10 +213,10 @@ NIS_DEV double rambo_root(int e, double r) {
         else dx = 1.0;                                   // flat region (dg = 0): leave it to the slow path
     }
     if (!(dx <= 1e-11 * X)) X = rambo_root_slow(e, r, X);
-    return X;
+    return fmax(X, NIS_U_FLOOR);
 }
 
-NIS_DEV double rambo_root_dyn(int e, double r) { return rambo_root(e, r); }
+NIS_DEV double rambo_root_dyn(int e, double r) { return rambo_root(e, r, rambo_lattice_at_one(e)); }
 
 // One event, runtime multiplicity n = C.n.  r: 3n-4 uniforms at stride rs.  mo: scratch AND output row of
 // (n+2)*4 doubles at stride ms (beams, final-state momenta; the two beam slots double as scratch for
@@ -221,7 +247,7 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
         double Kn = 0.0, Mn = C.m[n - 1];
         const double mj = C.m[j];
         if (j < n - 2) {                                        // :363-370, :391-392
-            const double u = rambo_root(n - 2 - j, r[j * rs]);
+            const double u = rambo_root(n - 2 - j, r[j * rs], C.u_one[n - 2 - j]);
             Kn = nis_sqrt(u) * Kj;
             Mn = Kn + C.msum[j + 1];
         }

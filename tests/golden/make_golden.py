@@ -201,6 +201,34 @@ def rambo_case(name, initial, final, E_cm, B, seed, **cuts):
     print("rambo", name, "pass fraction", float((w != 0).double().mean()), "w[0]", float(w[0]))
 
 
+def rambo_edge_case(name, initial, final, E_cm, seed, with_zero, **cuts):
+    """Uniforms on the ends of [0,1]: every column in turn, and pairs of mass columns, set to
+    0, denormal, 2^-24 (the float32 grid next to 0), 1-2^-24 and 1.  ``with_zero=False`` leaves 0 and the denormal
+    out, so that the reference's batch-wide stopping rule (:333-348) runs its usual 120+ levels instead of 60."""
+    gen = FlatInvertiblePhasespace(initial, final, pdf=None, pdf_active=False)
+    n = len(final)
+    nd = gen.nDimPhaseSpace()
+    vals = ([0.0, 5e-324] if with_zero else []) + [2.0 ** -24, 1.0 - 2.0 ** -24, 1.0]
+    rows = [(c, v, None, None) for c in range(nd) for v in vals]
+    rows += [(a, va, b, vb) for a in range(n - 2) for b in range(n - 2) if a < b for va in vals for vb in vals]
+    g = torch.Generator().manual_seed(seed)
+    r = torch.rand(len(rows) + 8, nd, generator=g, dtype=torch.float64)
+    for i, (a, va, b, vb) in enumerate(rows):
+        r[i, a] = va
+        if b is not None:
+            r[i, b] = vb
+    mom, w = gen.generateKinematics_batch(E_cm, r.clone(), **cuts)
+    # the weight is finite on every row; the reference's *momenta* are not (its boost divides by sqrt(1-beta^2),
+    # which rounds to 0 for a parent of mass ~2^-30 K: rows with r = 0 / denormal) - stored as they come
+    assert bool(torch.isfinite(w).all()), name
+    meta = dict(name=name, initial=initial, final=final, E_cm=E_cm, B=r.shape[0], seed=seed, cuts=cuts)
+    np.savez_compressed(os.path.join(HERE, "rambo_%s.npz" % name), r=r.numpy(), momenta=mom.numpy(),
+                        weight=w.numpy(), meta=np.array(json.dumps(meta)))
+    print("rambo", name, "B", r.shape[0], "pass fraction", float((w != 0).double().mean()), "w range",
+          float(w.min()), float(w.max()), "rows with non-finite momenta",
+          int((~torch.isfinite(mom).all(-1).all(-1)).sum()))
+
+
 class FakeRun:
     """Stand-in for the Sacred run object the reference logs to (manager.py:89-93,197-198,286-288)."""
     _id = "run"
@@ -261,8 +289,8 @@ if __name__ == "__main__":
         flow_case("lin8d", "lin", 8, 128, 18, n_pass_through=4, n_cells=6, n_bins=32, NN=[64] * 3, roll_step=4)
         flow_case("lin4d", "lin", 4, 200, 19, grad=True, n_pass_through=2, n_cells=3, n_bins=10, NN=[8, 8], roll_step=1)
         flow_case("lin5d", "lin", 5, 96, 20, n_pass_through=1, n_cells=4, n_bins=7, NN=[12], roll_step=2)
+    cuts = dict(pT_mincut=20, delR_mincut=0.4, rap_maxcut=2.5)
     if "rambo" in what:
-        cuts = dict(pT_mincut=20, delR_mincut=0.4, rap_maxcut=2.5)
         rambo_case("m4_cuts", [100.0] * 2, [100.0] * 4, 1000.0, 512, 31, **cuts)
         rambo_case("m4_nocuts", [100.0] * 2, [100.0] * 4, 1000.0, 256, 32)
         rambo_case("m0_4", [0.0] * 2, [0.0] * 4, 1000.0, 256, 33, **cuts)
@@ -271,6 +299,15 @@ if __name__ == "__main__":
         rambo_case("m5_cuts", [50.0, 100.0], [10.0, 20.0, 30.0, 40.0, 50.0], 2000.0, 256, 36, **cuts)
         rambo_case("m0_6", [0.0] * 2, [0.0] * 6, 13000.0, 128, 37, pT_mincut=30, delR_mincut=0.4, rap_maxcut=4.0)
         rambo_case("readme", [100.0] * 2, [100.0] * 4, 1000.0, 128, 38, pT_mincut=0, delR_mincut=0, rap_maxcut=-1)
+    if "rambo_edges" in what or "rambo" in what:
+        for z in (True, False):
+            t = "edge0" if z else "edge1"
+            rambo_edge_case(t + "_m0_4", [0.0] * 2, [0.0] * 4, 1000.0, 61, z)
+            rambo_edge_case(t + "_m4", [100.0] * 2, [100.0] * 4, 1000.0, 62, z)
+            rambo_edge_case(t + "_m4_cuts", [100.0] * 2, [100.0] * 4, 1000.0, 63, z, **cuts)
+            rambo_edge_case(t + "_m0_4_cuts", [0.0] * 2, [0.0] * 4, 1000.0, 64, z, **cuts)
+            rambo_edge_case(t + "_m5", [50.0, 100.0], [10.0, 20.0, 30.0, 40.0, 50.0], 2000.0, 65, z)
+            rambo_edge_case(t + "_m0_3", [0.0] * 2, [0.0, 0.0, 0.0], 500.0, 66, z)
     if "train" in what:
         train_case("a", 41, 40, 2000, 1000, preburn_time=10, kill_counter=7)
         train_case("b", 42, 60, 2000, 1000, preburn_time=5, kill_counter=1)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import RAMBO_CASES
+from conftest import RAMBO_CASES, RAMBO_EDGE_CASES, rambo_edge_rows, rambo_edge_weight_rtol
 from oracle import rambo as orambo
 
 from nf_b200.PhaseSpace.flat_phase_space_generator import FlatInvertiblePhasespace
@@ -27,6 +27,32 @@ def test_matches_reference_golden(golden, case, where):
     assert np.array_equal((w.cpu() != 0).numpy(), (ref_w != 0).numpy())
     assert torch.allclose(w.cpu(), ref_w, rtol=1e-9, atol=0)
     assert torch.allclose(mom.cpu(), ref_mom, rtol=1e-9, atol=1e-9 * m["E_cm"])
+
+
+@pytest.mark.parametrize("case", RAMBO_EDGE_CASES)
+def test_ends_of_the_unit_interval_match_reference(golden, case):
+    """Uniforms of exactly 0 / denormal / 2^-24 / 1-2^-24 / 1 in every column (reference-dumped fixture): weights
+    finite and equal to the reference's; momenta and cut masks equal wherever the reference's own momenta are finite
+    (its boost overflows for a parent of mass ~2^-30 K; see conftest.rambo_edge_rows)."""
+    g = golden("rambo_" + case)
+    m = g.meta
+    ps = FlatInvertiblePhasespace(m["initial"], m["final"], pdf=None, pdf_active=False)
+    mom, w, mask = ps.generateKinematics_batch(m["E_cm"], g.t("r").cuda(), return_cutmask=True, **m["cuts"])
+    mom, w, mask = mom.cpu().numpy(), w.cpu().numpy(), mask.cpu().numpy().astype(bool)
+    ref_w, ref_mom = g["weight"], g["momenta"]
+    assert np.isfinite(w).all() and np.isfinite(mom).all()
+    rows = rambo_edge_rows(ref_mom, g["r"], len(g.meta["final"]))
+    assert np.array_equal(mask[rows], (ref_w != 0)[rows]), "cut mask must be bit-exact"
+    cmp = rows | (mask & (ref_w != 0))
+    rt = rambo_edge_weight_rtol(g["r"], len(g.meta["final"]))
+    assert (np.abs(w - ref_w)[cmp] <= (rt * np.abs(ref_w))[cmp]).all(), np.abs(w / ref_w - 1)[cmp & (ref_w != 0)].max()
+    np.testing.assert_allclose(mom[rows], ref_mom[rows], rtol=1e-9, atol=1e-9 * m["E_cm"])
+    # the float32 grid: the same uniforms as float32 input give the same events
+    mom32, w32 = ps.generateKinematics_batch(m["E_cm"], g.t("r").float().cuda(), **m["cuts"])
+    r32 = g.t("r").float().double()
+    same = (r32 == g.t("r")).all(1).numpy()
+    assert np.isfinite(w32.cpu().numpy()).all()
+    assert np.array_equal(w32.cpu().numpy()[same], w[same])
 
 
 def test_float32_uniforms_and_weight_only_mode():

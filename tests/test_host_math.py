@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import RAMBO_CASES, ROOT
+from conftest import RAMBO_CASES, RAMBO_EDGE_CASES, ROOT, rambo_edge_rows, rambo_edge_weight_rtol
 from oracle import rambo as orambo
 
 SRC = os.path.join(ROOT, "tests", "host", "host_math.cpp")
@@ -171,3 +171,39 @@ def test_rambo_event_matches_reference_golden(host, golden, case):
     assert np.array_equal(ok.astype(bool), ref_w != 0), "cut mask"
     np.testing.assert_allclose(w, ref_w, rtol=1e-9)
     np.testing.assert_allclose(mom, ref_mom, rtol=1e-9, atol=1e-9 * m["E_cm"])
+
+
+def _host_rambo_case(host, g):
+    m = g.meta
+    n = len(m["final"])
+    cuts = dict(pT_mincut=-1, delR_mincut=-1, rap_maxcut=-1)
+    cuts.update(m["cuts"])
+    d = RamboDesc(n, (ctypes.c_double * 2)(*m["initial"]), (ctypes.c_double * 8)(*(m["final"] + [0.0] * (8 - n))),
+                  m["E_cm"], cuts["pT_mincut"], cuts["delR_mincut"], cuts["rap_maxcut"])
+    r = np.ascontiguousarray(g["r"])
+    B = r.shape[0]
+    mom = np.zeros((B, n + 2, 4))
+    w = np.zeros(B)
+    ok = np.zeros(B, np.uint8)
+    assert host.host_rambo(ctypes.byref(d), ctypes.c_longlong(B), fp(r, D), fp(mom, D), fp(w, D),
+                           ok.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))) == 0
+    return mom, w, ok
+
+
+@pytest.mark.parametrize("case", RAMBO_EDGE_CASES)
+def test_rambo_event_on_the_ends_of_the_unit_interval(host, golden, case):
+    """mass-dimension uniforms of exactly 0 / 1 (float32 uniforms hit 0 with p = 2^-24) used to
+    give 0/0.  The reference's weight is finite there (u = 2^-60 resp. 1 - 2^-27/e); ours must be the same number."""
+    g = golden("rambo_" + case)
+    mom, w, ok = _host_rambo_case(host, g)
+    ref_w, ref_mom = g["weight"], g["momenta"]
+    assert np.isfinite(w).all() and np.isfinite(mom).all()
+    rows = rambo_edge_rows(ref_mom, g["r"], len(g.meta["final"]))
+    assert np.array_equal(ok.astype(bool)[rows], (ref_w != 0)[rows]), "cut mask"
+    # rows on which the reference's momenta overflowed: its cuts compared NaNs (all pass); only the pre-cut weight
+    # is comparable there, and only when we did not cut the event
+    cmp = rows | (ok.astype(bool) & (ref_w != 0))
+    rt = rambo_edge_weight_rtol(g["r"], len(g.meta["final"]))
+    assert (np.abs(w - ref_w)[cmp] <= (rt * np.abs(ref_w))[cmp]).all(), np.abs(w / ref_w - 1)[cmp & (ref_w != 0)].max()
+    np.testing.assert_allclose(mom[rows], ref_mom[rows], rtol=1e-9, atol=1e-9 * g.meta["E_cm"])
+    assert cmp.sum() >= 0.5 * len(w)

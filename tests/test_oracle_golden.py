@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import FLOW_CASES, GRAD_CASES, RAMBO_CASES
+from conftest import RAMBO_EDGE_CASES, FLOW_CASES, GRAD_CASES, RAMBO_CASES
 from oracle import flow as oflow
 from oracle import nis as onis
 from oracle import rambo as orambo
@@ -109,6 +109,20 @@ def test_rambo_matches_reference(golden, case):
     assert np.array_equal((w != 0).numpy(), (ref_w != 0).numpy()), "cut mask"
     assert torch.allclose(w, ref_w, rtol=1e-12, atol=0), float(((w - ref_w) / ref_w.abs().clamp_min(1e-300)).abs().max())
     assert torch.allclose(mom, ref_mom, rtol=1e-12, atol=1e-10 * m["E_cm"] * 1e-3)
+
+
+@pytest.mark.parametrize("case", RAMBO_EDGE_CASES)
+def test_rambo_edges_match_reference(golden, case):
+    """r on the ends of [0,1]: the oracle follows the reference bit for bit, including where the reference's momenta
+    overflow (compared with inf / NaN in the same places)."""
+    g = golden("rambo_" + case)
+    m = g.meta
+    mom, w = orambo.generate_kinematics(m["E_cm"], g.t("r"), m["initial"], m["final"], **m["cuts"])
+    ref_mom, ref_w = g.t("momenta"), g.t("weight")
+    assert bool(torch.isfinite(ref_w).all()) and bool(torch.isfinite(w).all())
+    assert np.array_equal((w != 0).numpy(), (ref_w != 0).numpy()), "cut mask"
+    assert torch.allclose(w, ref_w, rtol=1e-12, atol=0)
+    assert torch.allclose(mom, ref_mom, rtol=1e-12, atol=1e-13 * m["E_cm"], equal_nan=True)
 
 
 def test_rambo_known_answers():
