@@ -126,6 +126,13 @@ size_t nis_reduce_workspace_bytes(void);
 int nis_reduce_moments(const void* v, int32_t dtype, int64_t n, double* out, int32_t accumulate,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same plus what the unweighting step needs and a non-finite guard (experiment_mg.py:73-76,101 take
+ * torch.max / torch.mean / torch.var of f*J):  out[0..6) = { sum v, sum v^2, n, max v, min v, number of non-finite
+ * entries }.  Sums, max and min follow torch semantics (a NaN propagates); out[5] lets the caller say how many
+ * entries were inf / NaN instead of returning a silent NaN estimate. */
+int nis_reduce_stats(const void* v, int32_t dtype, int64_t n, double* out, int32_t accumulate,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* Phase-space generator descriptor (flat_phase_space_generator.py:25-39). */
 typedef struct NisRamboDesc {
     int32_t n_final;

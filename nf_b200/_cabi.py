@@ -64,6 +64,8 @@ _PROTOS = {
     "nis_reduce_workspace_bytes": (ctypes.c_size_t, []),
     "nis_reduce_moments": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int64, _P, ctypes.c_int32, _P,
                                           ctypes.c_size_t, _P]),
+    "nis_reduce_stats": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int64, _P, ctypes.c_int32, _P,
+                                        ctypes.c_size_t, _P]),
     "nis_rambo_generate": (ctypes.c_int, [ctypes.POINTER(NisRamboDesc), _P, ctypes.c_int32, _P, _P, _P,
                                           ctypes.c_int64, _P]),
     "nis_uniform_fill": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, _P]),

@@ -88,7 +88,6 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Backward scratch (floats), see flow_bwd.cu: gradient state [B][d+1], per-CTA parameter-gradient
 // partials [NIS_BWD_GRID][max cell params], BN backward sums [n_cells][depth+1][2][maxW].
-size_t nis_flow_bwd_scratch_floats(const DevFlow& F, const NisFlowDesc* d, int64_t B);
 
 size_t nis_tc_pack_floats(const DevFlow& F);
 size_t nis_wide_pack_floats(const DevFlow& F);

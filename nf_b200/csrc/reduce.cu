@@ -6,62 +6,98 @@
 #define RED_NT 256
 #define RED_GRID 592   // 148 SMs x 4
 
-// Two-stage deterministic reduction: every CTA writes (sum, sum of squares) of its grid-stride slice
-// in float64; the last CTA to finish adds the partials in index order.
-template <typename T>
+// Two-stage deterministic reduction: every CTA writes the statistics of its grid-stride slice in float64; the
+// last CTA to finish combines the partials in index order.  NS = 2: (sum, sum of squares); NS = 5: also max, min
+// (NaN-propagating like torch.max / torch.min) and the number of non-finite entries.
+__device__ __forceinline__ double nan_max(double a, double b) { return (a != a || b != b) ? a + b : fmax(a, b); }
+__device__ __forceinline__ double nan_min(double a, double b) { return (a != a || b != b) ? a + b : fmin(a, b); }
+
+template <typename T, int NS>
 __global__ void __launch_bounds__(RED_NT) moments_kernel(const T* __restrict__ v, long long n, double* __restrict__ out,
                                                          int accumulate, double* __restrict__ partials,
                                                          unsigned* __restrict__ counter) {
-    double s = 0.0, q = 0.0;
+    double s = 0.0, q = 0.0, mx = -INFINITY, mn = INFINITY, bad = 0.0;
     for (long long i = (long long)blockIdx.x * RED_NT + threadIdx.x; i < n; i += (long long)gridDim.x * RED_NT) {
         const double x = (double)v[i];
         s += x; q += x * x;
+        if (NS > 2) {
+            mx = nan_max(mx, x); mn = nan_min(mn, x);
+            bad += (x - x == 0.0) ? 0.0 : 1.0;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
         q += __shfl_xor_sync(0xffffffffu, q, o);
+        if (NS > 2) {
+            mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        }
     }
-    __shared__ double ws[RED_NT / 32], wq[RED_NT / 32];
+    __shared__ double wsm[5][RED_NT / 32];
     __shared__ bool last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { ws[warp] = s; wq[warp] = q; }
+    if (lane == 0) { wsm[0][warp] = s; wsm[1][warp] = q; wsm[2][warp] = mx; wsm[3][warp] = mn; wsm[4][warp] = bad; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        s = 0.0; q = 0.0;
-        for (int i = 0; i < RED_NT / 32; ++i) { s += ws[i]; q += wq[i]; }
-        partials[2 * blockIdx.x] = s;
-        partials[2 * blockIdx.x + 1] = q;
+        s = 0.0; q = 0.0; mx = -INFINITY; mn = INFINITY; bad = 0.0;
+        for (int i = 0; i < RED_NT / 32; ++i) {
+            s += wsm[0][i]; q += wsm[1][i];
+            if (NS > 2) { mx = nan_max(mx, wsm[2][i]); mn = nan_min(mn, wsm[3][i]); bad += wsm[4][i]; }
+        }
+        double* p = partials + NS * blockIdx.x;
+        p[0] = s; p[1] = q;
+        if (NS > 2) { p[2] = mx; p[3] = mn; p[4] = bad; }
         __threadfence();
         last = atomicAdd(counter, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (!last || threadIdx.x != 0) return;
     __threadfence();
-    s = 0.0; q = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) { s += __ldcg(partials + 2 * b); q += __ldcg(partials + 2 * b + 1); }
+    s = 0.0; q = 0.0; mx = -INFINITY; mn = INFINITY; bad = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) {
+        const double* p = partials + NS * b;
+        s += __ldcg(p); q += __ldcg(p + 1);
+        if (NS > 2) { mx = nan_max(mx, __ldcg(p + 2)); mn = nan_min(mn, __ldcg(p + 3)); bad += __ldcg(p + 4); }
+    }
     if (accumulate) { out[0] += s; out[1] += q; out[2] += (double)n; }
     else { out[0] = s; out[1] = q; out[2] = (double)n; }
+    if (NS > 2) {
+        if (accumulate) { out[3] = nan_max(out[3], mx); out[4] = nan_min(out[4], mn); out[5] += bad; }
+        else { out[3] = mx; out[4] = mn; out[5] = bad; }
+    }
     *counter = 0u;
 }
 
-extern "C" size_t nis_reduce_workspace_bytes(void) { return sizeof(double) * 2 * RED_GRID + 256; }
+extern "C" size_t nis_reduce_workspace_bytes(void) { return sizeof(double) * 5 * RED_GRID + 256; }
 
-extern "C" int nis_reduce_moments(const void* v, int32_t dtype, int64_t n, double* out, int32_t accumulate,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
+template <int NS>
+static int reduce_launch(const void* v, int32_t dtype, int64_t n, double* out, int32_t accumulate, void* workspace,
+                         size_t workspace_bytes, void* stream) {
     if ((!v && n > 0) || !out || !workspace || n < 0) return NIS_EINVAL;
     if (workspace_bytes < nis_reduce_workspace_bytes()) return NIS_EWORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
     double* partials = (double*)workspace;
-    unsigned* counter = (unsigned*)((char*)workspace + sizeof(double) * 2 * RED_GRID);
+    unsigned* counter = (unsigned*)((char*)workspace + sizeof(double) * 5 * RED_GRID);
     cudaMemsetAsync(counter, 0, 4, s);
     long long blocks = (n + RED_NT - 1) / RED_NT;
     int grid = (int)(blocks < 1 ? 1 : (blocks < RED_GRID ? blocks : RED_GRID));
-    if (dtype == NIS_F64) moments_kernel<double><<<grid, RED_NT, 0, s>>>((const double*)v, n, out, accumulate, partials, counter);
-    else if (dtype == NIS_F32) moments_kernel<float><<<grid, RED_NT, 0, s>>>((const float*)v, n, out, accumulate, partials, counter);
+    if (dtype == NIS_F64) moments_kernel<double, NS><<<grid, RED_NT, 0, s>>>((const double*)v, n, out, accumulate, partials, counter);
+    else if (dtype == NIS_F32) moments_kernel<float, NS><<<grid, RED_NT, 0, s>>>((const float*)v, n, out, accumulate, partials, counter);
     else return NIS_EINVAL;
     NIS_CUDA_CHECK_LAUNCH();
     return NIS_OK;
+}
+
+extern "C" int nis_reduce_moments(const void* v, int32_t dtype, int64_t n, double* out, int32_t accumulate,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    return reduce_launch<2>(v, dtype, n, out, accumulate, workspace, workspace_bytes, stream);
+}
+
+extern "C" int nis_reduce_stats(const void* v, int32_t dtype, int64_t n, double* out, int32_t accumulate,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    return reduce_launch<5>(v, dtype, n, out, accumulate, workspace, workspace_bytes, stream);
 }
 
 // ---- Philox4x32-10 ---------------------------------------------------------------------------------

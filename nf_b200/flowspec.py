@@ -197,6 +197,9 @@ class FlowSpec:
         if xj.dtype not in (torch.float32, torch.float64):
             xj = xj.double()
         B, d = xj.shape[0], self.n_flow
+        if train and B == 1:
+            # batch statistics of one point: torch (and so the reference) refuses, BatchNorm1d in train mode
+            raise ValueError("Expected more than 1 value per channel when training, got input size [1, %d]" % d)
         with torch.cuda.device(dev):
             params = self.param_arena.get(dev)
             bn = self.bn_arena.get(dev)
@@ -245,7 +248,7 @@ class FlowSpec:
 class _FlowFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xj, spec, train, *params):
-        need = any(ctx.needs_input_grad)
+        need = torch.is_grad_enabled() and any(ctx.needs_input_grad)
         out, saved, bn_saved, _ = spec.forward(xj, train, want_saved=need)
         ctx.spec, ctx.train = spec, train
         ctx.in_cols, ctx.in_dtype, ctx.in_device = xj.shape[1], xj.dtype, xj.device

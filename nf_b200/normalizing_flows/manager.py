@@ -20,6 +20,7 @@ import copy
 import datetime
 import math
 import os
+import warnings
 
 import numpy as np
 import torch
@@ -31,6 +32,10 @@ from ..flowspec import FlowSequential
 from .layers.coupling_cells import PWLin, PWQuad
 from .layers.layers import AddJacobian, DeMaskLayer, MaskLayer, RollLayer
 from .misc import tqdm_recycled
+
+
+class NonFiniteWeightWarning(RuntimeWarning):
+    """Some f(x)*J(x) handed to ``integrate`` / ``weight_statistics`` were inf or NaN."""
 
 
 def get_bin(x, n=0):
@@ -130,9 +135,24 @@ class BasicManager(ModelAPI):
         self.best_model = None
 
     # ------------------------------------------------------------------------------------------
-    def _uniform(self, n, dev, dtype=torch.double):
-        """Latent points: torch's device generator, so ``torch.manual_seed`` controls the stream."""
-        return torch.rand(n, self.n_flow, device=dev, dtype=dtype)
+    def _uniform(self, n, dev, dtype=torch.double, generator=None):
+        """Latent points: torch's device generator, so ``torch.manual_seed`` controls the stream; under
+        torch.distributed the per-rank generator of ``_rank_generator``."""
+        return torch.rand(n, self.n_flow, device=dev, dtype=dtype, generator=generator)
+
+    @staticmethod
+    def _rank_generator(dev, rank, world):
+        """Ranks seeded alike (the usual ``torch.manual_seed(s)`` on every rank) would all draw the same latent
+        points and the summed gradient would be one minibatch repeated ``world`` times.  So under
+        torch.distributed the latent points come from a per-rank device generator seeded with (a draw from rank
+        0's CPU generator) + rank: reproducible from the user's seed, different on every rank."""
+        if world == 1:
+            return None
+        base = torch.empty((), dtype=torch.int64).random_(0, 2 ** 62).to(dev)
+        dist.broadcast(base, 0)
+        g = torch.Generator(device=dev)
+        g.manual_seed(int(base.item()) + rank)
+        return g
 
     def _train_variance_forward_seq(self, f, optimizer_object, log=True, logdir=None, batch_size=10000, epochs=10,
                                     epoch_start=0, pretty_progressbar=True, save_best=True, run=None, dev=0,
@@ -180,8 +200,9 @@ class BasicManager(ModelAPI):
         self.best_var = 0
         maxf = torch.zeros((), device=dev, dtype=torch.double)
         w = None
+        gen = self._rank_generator(dev, rank, world)
         for _ in range(self.n_flow):
-            w = self._uniform(2 * mini_batch_size, dev)
+            w = self._uniform(2 * mini_batch_size, dev, generator=gen)
             fres = f(w)
             integ[0] += torch.sum(fres) / (self.n_flow * 2 * mini_batch_size)
             err[0] += torch.var(fres) / self.n_flow
@@ -223,7 +244,7 @@ class BasicManager(ModelAPI):
             var = 0
             optimizer_object.zero_grad()
             for j in minibatch_progress:
-                w = self._uniform(mini_batch_size, dev)
+                w = self._uniform(mini_batch_size, dev, generator=gen)
                 XJ = self.model(self.format_input(w, dev))
                 X = XJ[:, :-1].detach()                 # the sample is fixed, the Jacobian is optimised
                 if state.preburner:
@@ -284,7 +305,7 @@ class BasicManager(ModelAPI):
                 model = self.best_model.eval()
                 for s in range(endpoint, epochs):
                     for t in my_minibatches:
-                        w = self._uniform(mini_batch_size, dev)
+                        w = self._uniform(mini_batch_size, dev, generator=gen)
                         XJ = model(self.format_input(w, dev)).detach()
                         fres = torch.mul(f(XJ[:, :-1]), XJ[:, -1])
                         integ[s + 1] += torch.mean(fres) / (n_minibatches * math.sqrt(mini_batch_size))
@@ -314,17 +335,34 @@ class BasicManager(ModelAPI):
 
     @staticmethod
     def _allreduce_grads(params):
-        """One flat sum-allreduce of all gradients (NCCL over NVLink when launched one rank per GPU)."""
+        """One sum-allreduce of all gradients (NCCL over NVLink when launched one rank per GPU).
+
+        ``nis_flow_backward`` writes the whole parameter gradient into ONE flat float32 buffer and autograd hands
+        the parameters views of it, so after ``zero_grad()`` (set_to_none) + ``backward()`` every ``p.grad`` is a
+        slice of that buffer: it is all-reduced in place with a single collective and no host-side fan-out.  Any
+        other situation (gradients accumulated elsewhere, a user calling ``zero_grad(set_to_none=False)``) takes
+        the gather / scatter path."""
+        flat = getattr(params[0].grad, "_base", None) if params and params[0].grad is not None else None
+        if flat is not None and flat.dim() == 1 and flat.is_contiguous():
+            lo, hi, isz, covered = flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size(), \
+                flat.element_size(), 0
+            for p in params:
+                g = p.grad
+                if g is None or g.dtype != flat.dtype or not g.is_contiguous() or getattr(g, "_base", None) is not flat \
+                        or not (lo <= g.data_ptr() and g.data_ptr() + g.numel() * isz <= hi):
+                    flat = None
+                    break
+                covered += g.numel()
+            if flat is not None and covered == flat.numel():
+                dist.all_reduce(flat)
+                return
         for p in params:
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
-        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        grads = [p.grad for p in params]
+        flat = torch.cat([g.reshape(-1) for g in grads])
         dist.all_reduce(flat)
-        off = 0
-        for p in params:
-            n = p.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p))
-            off += n
+        torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)])
 
     def _sync_model(self):
         """Ranks must start from identical weights: broadcast parameters and BN buffers from rank 0."""
@@ -339,19 +377,15 @@ class BasicManager(ModelAPI):
                 off += n
 
     # ------------------------------------------------------------------------------------------
-    def integrate(self, f, nitn, neval, dev=None):
-        """nitn independent estimates of neval points through ``best_model``, combined by inverse
-        variance (manager.py:380-405, including its error formula).  With torch.distributed the neval
-        points of every iteration are split over the ranks and (sum, sum of squares, n) are allreduced."""
-        if self.best_model is None:
-            print("No model has been trained")
-            return (0, 0)
+    def _weight_moments(self, f, nitn, neval, dev):
+        """[nitn, 6] float64 on the host: (sum, sum of squares, n, max, min, number of non-finite) of f(x) J(x) over
+        neval points per iteration through ``best_model``.  The points of an iteration are split over the ranks
+        (disjoint slices of one Philox stream); one sum- and one max-allreduce combine them."""
         dev = _device(0 if dev is None else dev)
         rank, world = _world()
-        neval, nitn = int(neval), int(nitn)
         first, share = shard_bounds(neval, rank, world)
         lib = _cabi.lib()
-        moments = torch.zeros(nitn, 3, dtype=torch.double, device=dev)
+        moments = torch.zeros(nitn, 6, dtype=torch.double, device=dev)
         rws = torch.empty(lib.nis_reduce_workspace_bytes(), dtype=torch.uint8, device=dev)
         w = torch.empty(share, self.n_flow, device=dev)                     # float32 like manager.py:390
         seed = int(torch.empty((), dtype=torch.int64).random_().item())     # drawn from torch's CPU generator
@@ -366,12 +400,33 @@ class BasicManager(ModelAPI):
                             "nis_uniform_fill")
                 X = self.best_model(self.format_input(w, dev)).detach()
                 fres = (f(X[:, :-1]) * X[:, -1]).contiguous()
-                _cabi.check(lib.nis_reduce_moments(_cabi.ptr(fres), _cabi.dtype_code(fres), fres.numel(),
-                                                   _cabi.ptr(moments[i]), 0, _cabi.ptr(rws), rws.numel(),
-                                                   _cabi.stream_ptr(dev)), "nis_reduce_moments")
+                _cabi.check(lib.nis_reduce_stats(_cabi.ptr(fres), _cabi.dtype_code(fres), fres.numel(),
+                                                 _cabi.ptr(moments[i]), 0, _cabi.ptr(rws), rws.numel(),
+                                                 _cabi.stream_ptr(dev)), "nis_reduce_stats")
         if world > 1:
-            dist.all_reduce(moments)
+            sums = moments[:, [0, 1, 2, 5]].contiguous()
+            ext = torch.stack((moments[:, 3], -moments[:, 4]), 1)
+            dist.all_reduce(sums)
+            dist.all_reduce(ext, op=dist.ReduceOp.MAX)
+            moments = torch.stack((sums[:, 0], sums[:, 1], sums[:, 2], ext[:, 0], -ext[:, 1], sums[:, 3]), 1)
         moments = moments.cpu()
+        self.n_nonfinite = int(moments[:, 5].sum())
+        if self.n_nonfinite:
+            warnings.warn("%d of %d integrand weights f(x)*J(x) are inf / NaN: the estimate below is not finite "
+                          "(the reference returns the same NaN silently)" % (self.n_nonfinite, int(moments[:, 2].sum())),
+                          NonFiniteWeightWarning, stacklevel=3)
+        return moments
+
+    def integrate(self, f, nitn, neval, dev=None):
+        """nitn independent estimates of neval points through ``best_model``, combined by inverse
+        variance (manager.py:380-405, including its error formula).  With torch.distributed the neval
+        points of every iteration are split over the ranks and (sum, sum of squares, n) are allreduced.
+        Non-finite weights are counted (``self.n_nonfinite``) and reported by a ``NonFiniteWeightWarning``."""
+        if self.best_model is None:
+            print("No model has been trained")
+            return (0, 0)
+        neval, nitn = int(neval), int(nitn)
+        moments = self._weight_moments(f, nitn, neval, dev)
         n = moments[:, 2]
         mean = moments[:, 0] / n
         var = (moments[:, 1] - n * mean ** 2) / (n - 1)                      # unbiased, like torch.var
@@ -379,6 +434,22 @@ class BasicManager(ModelAPI):
         sig = torch.sum(mean / var) / torch.sum(1 / var)
         sig_err = torch.sqrt(1 / torch.sum(1 / var)) / np.sqrt(neval * nitn)
         return (sig, sig_err)
+
+    def weight_statistics(self, f, neval, dev=None):
+        """What the reference's experiment harness computes after training from one batch of ``neval`` points
+        through ``best_model`` (utils/experiment_mg.py:66-76,101): final variance ``v_var`` (unbiased), ``w_max``,
+        ``w_mean`` and the unweighting efficiency ``w_mean / w_max`` — as ONE fused reduction on the device
+        (``nis_reduce_stats``), sharded over the ranks like ``integrate``."""
+        if self.best_model is None:
+            print("No model has been trained")
+            return None
+        m = self._weight_moments(f, 1, int(neval), dev)[0]
+        n = float(m[2])
+        mean = float(m[0]) / n
+        var = (float(m[1]) - n * mean * mean) / (n - 1)
+        return {"v_var": var, "w_mean": mean, "w_max": float(m[3]), "w_min": float(m[4]),
+                "unweighting_efficiency": mean / float(m[3]) if float(m[3]) != 0 else float("nan"),
+                "n": int(n), "n_nonfinite": int(m[5])}
 
 
 def _finish_model(manager, model, dev):

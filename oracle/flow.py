@@ -167,8 +167,9 @@ def rectnn(sd, cell, xA, train, stats=None):
 # ----------------------------------------------------------------------------------------------
 # coupling cells
 # ----------------------------------------------------------------------------------------------
-def pwlin_cell(sd, cell, x, P, n_bins, train, stats=None):
-    """coupling_cells.py:107-142.  x: [B, d+1].  Returns (out [B, d+1], bins [B, T])."""
+def pwlin_cell(sd, cell, x, P, n_bins, train, stats=None, edges=None):
+    """coupling_cells.py:107-142.  x: [B, d+1].  Returns (out [B, d+1], bins [B, T]).
+    ``edges`` (list) receives the distance [B, T] of every transformed coordinate to its nearest bin edge."""
     d = x.shape[1] - 1
     T = d - P
     xA, xB, J = x[:, :P], x[:, P:d], x[:, d]
@@ -180,6 +181,8 @@ def pwlin_cell(sd, cell, x, P, n_bins, train, stats=None):
     C = torch.cat((torch.zeros_like(norm), Qsum / norm), -1)   # :123-124 cdf at left edges
     a = xB * n_bins
     bins = torch.floor(a)
+    if edges is not None:
+        edges.append(((a - torch.round(a)).abs() / n_bins).detach())
     alpha = (a - bins) / n_bins                         # :130-131
     k = bins.long().unsqueeze(-1)
     Qk = torch.gather(Q, -1, k).squeeze(-1)
@@ -189,8 +192,9 @@ def pwlin_cell(sd, cell, x, P, n_bins, train, stats=None):
     return torch.cat((xA, y, J.unsqueeze(-1)), -1), bins.long()
 
 
-def pwquad_cell(sd, cell, x, P, n_bins, train, stats=None):
-    """coupling_cells.py:159-228.  Returns (out [B, d+1], bins [B, T])."""
+def pwquad_cell(sd, cell, x, P, n_bins, train, stats=None, edges=None):
+    """coupling_cells.py:159-228.  Returns (out [B, d+1], bins [B, T]).
+    ``edges`` (list) receives the distance [B, T] of every transformed coordinate to its nearest bin edge."""
     d = x.shape[1] - 1
     T = d - P
     nb = n_bins
@@ -208,6 +212,8 @@ def pwquad_cell(sd, cell, x, P, n_bins, train, stats=None):
     E = torch.cat((torch.zeros_like(Wn), Wsum), -1)     # :198 left edges E_0..E_nb
     # :199-202 — argmax(cat(1e-30, (Wsum<=xB)*Wsum)) == number of right edges <= xB
     k = (Wsum <= xB.unsqueeze(-1)).sum(-1, keepdim=True)
+    if edges is not None:
+        edges.append((E - xB.unsqueeze(-1)).abs().min(-1).values.detach())
     Wk = torch.gather(W, -1, k).squeeze(-1)
     alpha = (xB - torch.gather(E, -1, k).squeeze(-1)) / Wk                  # :206-207
     S = torch.cat((torch.zeros_like(Wn),
@@ -222,9 +228,10 @@ def pwquad_cell(sd, cell, x, P, n_bins, train, stats=None):
 # ----------------------------------------------------------------------------------------------
 # whole flow, layer by layer like the reference Sequential
 # ----------------------------------------------------------------------------------------------
-def flow_forward(layers, sd, xj, kind, n_bins, train=True, stats=None, trace=None):
+def flow_forward(layers, sd, xj, kind, n_bins, train=True, stats=None, trace=None, edges=None):
     """Run the reference Sequential.  xj: [B, d+1] float64.  Returns (XJ [B, d+1], bins [B, C, T_c]
-    as a list of per-cell LongTensors).  ``trace`` (dict) receives each module's output by name."""
+    as a list of per-cell LongTensors).  ``trace`` (dict) receives each module's output by name, ``edges`` (list)
+    each cell's [B, T_c] distances to the nearest bin edge."""
     d = xj.shape[1] - 1
     cell_fn = pwlin_cell if kind == "lin" else pwquad_cell
     x = xj
@@ -232,7 +239,7 @@ def flow_forward(layers, sd, xj, kind, n_bins, train=True, stats=None, trace=Non
     for L in layers:
         t = L["type"]
         if t == "cell":
-            x, b = cell_fn(sd, L["name"], x, L["P"], n_bins, train, stats)
+            x, b = cell_fn(sd, L["name"], x, L["P"], n_bins, train, stats, edges)
             all_bins.append(b)
         elif t == "roll":
             x = torch.cat((torch.roll(x[:, :-1], L["shift"], -1), x[:, -1:]), -1)

@@ -42,6 +42,28 @@ def _worker(rank, world, port, out):
         expect = [world * (world + 1) / 2] * len(params)
         expect[1] = 1.0                                    # rank 1 had no gradient there
         grads_ok = all(torch.allclose(p.grad, torch.full_like(p, e)) for p, e in zip(params, expect))
+        # fast path: the gradients are views of ONE flat buffer (what nis_flow_backward + autograd leave behind):
+        # a single in-place collective, the views stay views
+        flat = torch.arange(sum(p.numel() for p in params), dtype=torch.float32) * (rank + 1)
+        off = 0
+        for p in params:
+            p.grad = flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        ptrs = [p.grad.data_ptr() for p in params]
+        BasicManager._allreduce_grads(params)
+        want = torch.arange(flat.numel(), dtype=torch.float32) * (world * (world + 1) / 2)
+        grads_ok = grads_ok and torch.equal(flat, want) and ptrs == [p.grad.data_ptr() for p in params] and \
+            torch.equal(torch.cat([p.grad.reshape(-1) for p in params]), want)
+        # latent-point streams: identical user seed on every rank -> different points per rank, same on re-run
+        torch.manual_seed(5)
+        g1 = BasicManager._rank_generator(torch.device("cpu"), rank, world)
+        pts = torch.rand(64, 3, generator=g1)
+        torch.manual_seed(5)
+        g2 = BasicManager._rank_generator(torch.device("cpu"), rank, world)
+        again = torch.rand(64, 3, generator=g2)
+        allpts = [torch.zeros_like(pts) for _ in range(world)]
+        dist.all_gather(allpts, pts)
+        grads_ok = grads_ok and torch.equal(pts, again) and not torch.equal(allpts[0], allpts[1])
         # sharded moments == single-process moments
         g = torch.Generator().manual_seed(7)
         v = torch.rand(1003, generator=g, dtype=torch.float64)

@@ -24,7 +24,12 @@ def test_forward_matches_reference_golden(golden, case, mode, io):
     XJ, bins = model.forward_with_bins(xj)
     assert XJ.dtype == io and XJ.shape == xj.shape
     ref_bins = [g["%s/bins/%d" % (mode, i)] for i in range(model.spec().n_cells)]
-    compare_flow(XJ.cpu(), bins.cpu(), g.t(mode + "/XJ"), ref_bins, "%s/%s" % (case, mode))
+    edges = []                              # distances to the nearest bin edge, from the oracle (== reference to 1e-12)
+    with torch.no_grad():
+        oflow.flow_forward(oracle_layers(g.meta), g.state_dict(), g.t("xj"), g.meta["kind"], g.meta["n_bins"],
+                           train=(mode == "train"), edges=edges)
+    compare_flow(XJ.cpu(), bins.cpu(), g.t(mode + "/XJ"), ref_bins, "%s/%s" % (case, mode),
+                 ref_edges=[e.numpy() for e in edges])
     if mode == "train":                      # running statistics updated like torch BatchNorm1d
         sd = model.state_dict()
         for k in g.keys("train/stats/"):
@@ -63,7 +68,7 @@ BIG = [
 
 @pytest.mark.parametrize("cfg", BIG, ids=[c["name"] for c in BIG])
 @pytest.mark.parametrize("mode", ["eval", "train"])
-def test_forward_matches_oracle_at_size(cfg, mode):
+def test_forward_matches_oracle_at_size(cfg, mode, max_log_j=None):
     torch.manual_seed(5)
     NF = make_manager(cfg)
     model = NF._model
@@ -77,14 +82,22 @@ def test_forward_matches_oracle_at_size(cfg, mode):
     xj = NF.format_input(x, torch.device("cuda"))
     XJ, bins = model.forward_with_bins(xj)
     sd64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    edges = []
     with torch.no_grad():
         ref, ref_bins = oflow.flow_forward(oracle_layers(cfg), sd64, xj.cpu(), cfg["kind"], cfg["n_bins"],
-                                           train=(mode == "train"))
+                                           train=(mode == "train"), edges=edges)
         sd32 = {k: (v.float() if v.dtype.is_floating_point else v) for k, v in sd.items()}
         ref32, _ = oflow.flow_forward(oracle_layers(cfg), sd32, xj.cpu().float(), cfg["kind"], cfg["n_bins"],
                                       train=(mode == "train"))
     compare_flow(XJ.cpu(), bins.cpu(), ref, [b.numpy() for b in ref_bins], "%s/%s" % (cfg["name"], mode),
-                 fp32_yardstick=ref32)
+                 fp32_yardstick=ref32, ref_edges=[e.numpy() for e in edges], max_log_j=max_log_j)
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_bench_configuration_against_the_oracle_at_a_million_points(mode):
+    """cfg2 (the bench workload) at 2^20 points, every point against the float64 oracle: bins (each difference
+    proven to sit on an edge), transformed points, and the log-Jacobian with its MAXIMUM bounded (printed)."""
+    test_forward_matches_oracle_at_size(dict(BIG[0], B=1 << 20), mode, max_log_j=1e-4)
 
 
 @pytest.mark.parametrize("backend", ["tcgen05", "fp32_tiled_4x8", "fp32_tiled_8x8", "generic"])
