@@ -247,8 +247,10 @@ class FlowSpec:
 
 class _FlowFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xj, spec, train, *params):
-        need = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+    def forward(ctx, xj, spec, train, need, *params):
+        # ``need`` comes from flow_apply: grad mode is always off inside Function.forward and
+        # ctx.needs_input_grad only reflects requires_grad, so under torch.no_grad() (integrate, the tail
+        # integration, create_model's trial pass) neither can tell that no backward will follow
         out, saved, bn_saved, _ = spec.forward(xj, train, want_saved=need)
         ctx.spec, ctx.train = spec, train
         ctx.in_cols, ctx.in_dtype, ctx.in_device = xj.shape[1], xj.dtype, xj.device
@@ -266,9 +268,9 @@ class _FlowFn(torch.autograd.Function):
         if gin is not None:
             gin = gin[:, :ctx.in_cols].to(device=ctx.in_device, dtype=ctx.in_dtype)
         grads = []
-        for p, off, need in zip(spec.params, spec.param_arena.offsets, ctx.needs_input_grad[3:]):
+        for p, off, need in zip(spec.params, spec.param_arena.offsets, ctx.needs_input_grad[4:]):
             grads.append(gparams[off:off + p.numel()].view(p.shape).to(p.dtype) if need else None)
-        return (gin, None, None) + tuple(grads)
+        return (gin, None, None, None) + tuple(grads)
 
 
 def flow_apply(spec, xj, train):
@@ -278,7 +280,8 @@ def flow_apply(spec, xj, train):
         # before autograd records them as inputs, or the first backward after a device change sees gradients
         # on another device than the one it noted for the parameters.
         spec.param_arena.get(xj.device)
-    return _FlowFn.apply(xj, spec, bool(train), *spec.params)
+    need = torch.is_grad_enabled() and (xj.requires_grad or any(p.requires_grad for p in spec.params))
+    return _FlowFn.apply(xj, spec, bool(train), need, *spec.params)
 
 
 class FlowSequential(torch.nn.Sequential):
