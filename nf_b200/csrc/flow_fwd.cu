@@ -231,6 +231,9 @@ bool nis_tc_supported(const DevFlow& F, int64_t B, int bn_mode);
 int nis_tc_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream_t s);
 int nis_launch_tc(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaStream_t s);
 bool nis_tc_split_eval(const DevFlow& F);
+bool nis_h_supported(const DevFlow& F, int64_t B, int bn_mode);
+int nis_h_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream_t s);
+int nis_launch_h(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaStream_t s);
 bool nis_bwd_tc_supported(const DevFlow& F, int64_t B, int bn_mode);
 bool nis_wide_supported(const DevFlow& F, int64_t B, int bn_mode);
 int nis_wide_pack(const DevFlow& F, const float* params, float* widepack, cudaStream_t s);
@@ -326,9 +329,10 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr;
     // per-cell launch sequences: tcgen05 kernel where it applies, else the FP32 register-tiled kernel
     const bool tc = nis_tc_supported(F, B, bn_mode);
+    const bool hp = tc && nis_h_supported(F, B, bn_mode);              // fp16-split, four-group kernel (flow_tc_h.cu)
     const bool wide = !tc && nis_wide_supported(F, B, bn_mode);       // streamed-weights tcgen05 kernel (flow_wide.cu)
     const bool tiled = tc || wide || nis_tiled_supported(F, B);
-    if (tc) { rc = nis_tc_pack(F, params, ws.tcpack, s); if (rc) return rc; }
+    if (tc) { rc = hp ? nis_h_pack(F, params, ws.tcpack, s) : nis_tc_pack(F, params, ws.tcpack, s); if (rc) return rc; }
     if (wide) { rc = nis_wide_pack(F, params, ws.tcpack, s); if (rc) return rc; }
     const long long rows = (long long)B * (F.d + 1);
     if (bn_mode == NIS_BN_EVAL && !tiled) {
@@ -361,7 +365,8 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
                     // layer pass: reads the pre-BN activations of layer l-1, writes those of layer l
                     A.zin = (l >= 2 && !(moments && l == 2)) ? zb[(l - 1) & 1] : nullptr;
                     A.zout = zb[l & 1];
-                    rc = tc ? nis_launch_tc(F, A, ws.tcpack, s) : wide ? nis_launch_wide(F, A, ws.tcpack, s) : nis_launch_tiled(F, A, s);
+                    rc = hp ? nis_launch_h(F, A, ws.tcpack, s) : tc ? nis_launch_tc(F, A, ws.tcpack, s)
+                            : wide ? nis_launch_wide(F, A, ws.tcpack, s) : nis_launch_tiled(F, A, s);
                 } else if (tiled && l == 0) {
                     rc = nis_launch_col_stats(F, A, s);
                 } else {
@@ -395,7 +400,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
         const bool last = c == F.n_cells - 1;
         A.to_out = last;
         A.state_out = saved ? saved + (long long)(c + 1) * rows : (last ? nullptr : ws.state);
-        rc = tc ? nis_launch_tc(F, A, ws.tcpack, s) : wide ? nis_launch_wide(F, A, ws.tcpack, s)
+        rc = hp ? nis_launch_h(F, A, ws.tcpack, s) : tc ? nis_launch_tc(F, A, ws.tcpack, s) : wide ? nis_launch_wide(F, A, ws.tcpack, s)
                 : (tiled ? nis_launch_tiled(F, A, s) : launch_fwd_any(F, A, s));
         if (rc) return rc;
     }

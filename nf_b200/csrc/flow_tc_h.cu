@@ -1,0 +1,535 @@
+// Fused coupling-cell forward, width-64 PWLin cells, on tcgen05 with a HALF-PRECISION SPLIT of the operands —
+// the round-2 successor of flow_tc.cu's 3xTF32 kernel (which stays for PWQuad cells and as the A/B reference).
+//
+// Why: ncu on the 3xTF32 kernel (profiles/r01_ncu_tc.md) showed a latency-bound chain epilogue -> MMA -> epilogue
+// with only TWO 128-point groups per SM to overlap (warp slots 14 % occupied, 52 % of the stall samples on the
+// mbarrier / tcgen05.ld hand-over): TF32 operands in tensor memory take 64 + 64 columns per group next to a 128-
+// column accumulator, i.e. all 512 columns for two groups.  Here
+//   * activations and weights are split as x = x_hi + x_lo with BOTH parts in fp16 (11-bit significands: the same
+//     22 bits as the TF32 split) after an exact power-of-two scaling that keeps x_lo out of fp16's subnormal range
+//     (activations x 2^3, clamped at 65504 / 8 = 8188 — a BatchNorm output that large does not occur; weights by a
+//     per-layer 2^k chosen at pack time so that max |w| lands in [2^13, 2^14)); D += a_hi w_lo + a_lo w_hi + a_hi w_hi
+//     as tcgen05.mma.kind::f16 with fp32 accumulation, K = 16 per instruction: 12 instructions per 64x64 layer
+//     instead of 24 (tools/tc_f16_probe.cu: same 44.7 cycles per M128 N64 instruction as kind::tf32);
+//   * the packed A operand takes 32 + 32 columns and every MMA block is N = 64 (the 128 logits of the output layer
+//     are two blocks into the same accumulator columns, the splines of the first pair run while the second block's
+//     MMAs execute), so a group needs 128 columns and FOUR groups (16 warps) share an SM;
+//   * there is no issuer warp: thread 0 of a group issues the group's own MMAs once the group's 128 "my operand row
+//     is in tensor memory" arrivals are in (a 17th warp would cap the kernel at 96 registers per thread, and a
+//     group never queues behind a slower one).
+// The layer-pass scheme for train-mode BatchNorm, the tile-blocked activation buffers and the statistics fold are
+// those of flow_tc.cu / flow_tiled.cu.  Reference: coupling_cells.py:84-142 (PWLin + conditioner).
+#include <stdlib.h>
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "spline.cuh"
+#include "flow_fwd_common.cuh"
+#include "tc_common.cuh"
+
+#define H_SA 8.0f                                  // activation scale before the split (exact power of two)
+#define H_AMAX 65504.0f                            // largest finite fp16
+#define H_HID_BYTES (2 * TCH * TCH * 2)            // hi + lo of a 64x64 layer in fp16: 16 KB
+#define H_OUT_ROWS 128
+#define H_OUT_BYTES (2 * H_OUT_ROWS * TCH * 2)     // hi + lo of the [128 logits x 64] output layer: 32 KB
+#define H_COLS 128                                 // tensor-memory columns per group: D 64 | A_hi 32 | A_lo 32
+#define H_COL_AHI 64
+#define H_COL_ALO 96
+#define H_MAXG 4
+
+// byte offset of (row, k) in a [rows x 64] fp16 K-major operand: 128 B per row, 8-row groups of 1024 B, 16-byte
+// chunks XOR-swizzled with row % 8 (the canonical SWIZZLE_128B layout; one 128-byte row holds all of K = 64)
+__host__ __device__ static inline int h_off(int row, int k) {
+    return (row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) << 4) | ((k & 7) << 1));
+}
+// instruction descriptor for kind::f16: c_format F32 (1) at [4,6), a/b format F16 (0) at [7,10)/[10,13), K-major,
+// N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t h_idesc(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ static inline size_t h_cell_bytes(const DevFlow& F) {
+    return (size_t)(F.depth - 1) * H_HID_BYTES + H_OUT_BYTES + 64;      // + the per-layer 1 / (SA * SW) factors
+}
+
+__device__ __forceinline__ void h_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// ---- weight pack: one CTA per (MMA layer, cell): max |w| -> power-of-two scale -> fp16 hi / lo in UMMA layout -------
+__global__ void __launch_bounds__(256) flow_h_pack_kernel(DevFlow F, const float* __restrict__ params, char* __restrict__ hpack) {
+    __shared__ float red[8];
+    __shared__ float sw_s;
+    const int c = blockIdx.y, li = blockIdx.x, tid = threadIdx.x;
+    const DevCell& q = F.cells[c];
+    const bool outl = li == F.depth - 1;
+    const int l = li + 1;                                            // MMA layer 1..depth (depth = output layer)
+    const float* w = params + q.param_off + F.p_lin(c, l);           // hidden: [64][64]; output: [T*32][64] (out, in)
+    const int rows_src = outl ? q.T * F.K : TCH, rows = outl ? H_OUT_ROWS : TCH;
+    float m = 0.f;
+    for (int i = tid; i < rows_src * TCH; i += 256) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) red[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+        int e = 14;
+        if (m > 0.f && m < 3.0e38f) frexpf(m, &e);                   // m = f * 2^e, f in [0.5, 1)
+        e = e < -100 ? -100 : (e > 100 ? 100 : e);
+        sw_s = ldexpf(1.f, 14 - e);                                  // max |w| * SW in [2^13, 2^14)
+    }
+    __syncthreads();
+    const float SW = sw_s;
+    char* dst = hpack + (size_t)c * h_cell_bytes(F);
+    char* hi = dst + (size_t)li * H_HID_BYTES;                       // (the output layer follows the depth-1 hidden ones)
+    char* lo = hi + (size_t)rows * TCH * 2;
+    for (int i = tid; i < rows * TCH; i += 256) {
+        const int n = i / TCH, k = i - n * TCH;
+        const float v = n < rows_src ? w[(size_t)n * TCH + k] * SW : 0.f;
+        const __half h = __float2half_rn(v);
+        const int o = h_off(n, k);
+        *reinterpret_cast<__half*>(hi + o) = h;
+        *reinterpret_cast<__half*>(lo + o) = __float2half_rn(v - __half2float(h));
+    }
+    if (tid == 0) reinterpret_cast<float*>(dst + h_cell_bytes(F) - 64)[l] = 1.f / (H_SA * SW);
+}
+
+struct HSmem {      // byte offsets from the 1024-aligned base
+    int w0, aff, bias, st, sst, red, zb, total;
+    int wl[NIS_MAX_HIDDEN + 1];     // per MMA layer l (1..depth): offset of (hi, lo), or -1 when not staged
+};
+__host__ __device__ static inline HSmem h_layout(const DevFlow& F, int P, int l_begin, int l_end, bool zstage, int NG) {
+    HSmem s;
+    int o = 0;
+    for (int l = 0; l <= F.depth; ++l) {
+        s.wl[l] = -1;
+        if (l >= 1 && l >= l_begin && l <= l_end) { s.wl[l] = o; o += l == F.depth ? H_OUT_BYTES : H_HID_BYTES; }
+    }
+    s.w0 = o; o += pad8(P) * TCH * 4;
+    s.aff = o; o += (F.depth + 1) * 2 * TCH * 4;
+    s.bias = o; o += H_OUT_ROWS * 4;
+    s.st = o; o += NG * (F.d + 1) * TCM * 4;
+    o = (o + 15) & ~15;
+    s.sst = o; o += NG * (F.d + 1) * TCM * 4;          // landing zone of the next tile's state rows (bulk copy), per group
+    o = (o + 7) & ~7;
+    s.red = o; o += (NG * TCM * 2 + 2 * F.maxW) * 8;
+    o = (o + 127) & ~127;
+    s.zb = o;                                          // [NG][64][128] floats: stored-activation tile in, then out
+    if (zstage) o += NG * TCH * TCM * 4;
+    s.total = o;
+    return s;
+}
+
+// 32 activations: a = min(max(v * sc + sh, 0), 65504) with sc / sh pre-multiplied by SA, split a = hi + lo with hi
+// rounded to an 11-bit significand (the integer add-and-mask of tf32_rn: exactly fp16's precision in its normal
+// range), both packed two per 32-bit column (even feature in the low half) into the group's A operand.
+__device__ __forceinline__ void h_store_act32(const float* v, const float* sc, const float* sh, uint32_t t_hi, uint32_t t_lo) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 s4 = reinterpret_cast<const float4*>(sc)[j4], h4 = reinterpret_cast<const float4*>(sh)[j4];
+        const float a0 = fminf(fmaxf(fmaf(v[4 * j4], s4.x, h4.x), 0.f), H_AMAX);
+        const float a1 = fminf(fmaxf(fmaf(v[4 * j4 + 1], s4.y, h4.y), 0.f), H_AMAX);
+        const float a2 = fminf(fmaxf(fmaf(v[4 * j4 + 2], s4.z, h4.z), 0.f), H_AMAX);
+        const float a3 = fminf(fmaxf(fmaf(v[4 * j4 + 3], s4.w, h4.w), 0.f), H_AMAX);
+        const float b0 = tf32_rn(a0), b1 = tf32_rn(a1), b2 = tf32_rn(a2), b3 = tf32_rn(a3);
+        __half2 p;
+        p = __floats2half2_rn(b0, b1); hi[2 * j4] = *reinterpret_cast<uint32_t*>(&p);
+        p = __floats2half2_rn(b2, b3); hi[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&p);
+        p = __floats2half2_rn(a0 - b0, a1 - b1); lo[2 * j4] = *reinterpret_cast<uint32_t*>(&p);
+        p = __floats2half2_rn(a2 - b2, a3 - b3); lo[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&p);
+    }
+    tc_st16(t_hi, hi);
+    tc_st16(t_lo, lo);
+}
+
+// one N = 64 block of a layer: D (+)= a_hi w_lo + a_lo w_hi (cross terms first: the tensor core truncates when it adds
+// into the accumulator, so the small terms go in while it is small), then a_hi w_hi; K = 16 per step
+__device__ __forceinline__ void h_issue_block(uint32_t tmem_d, uint32_t t_hi, uint32_t t_lo, uint32_t w_hi, uint32_t w_lo, uint32_t idesc) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        h_mma_ts(tmem_d, t_hi + ks * 8, tc_desc(w_lo + ks * 32), idesc, ks > 0);
+        h_mma_ts(tmem_d, t_lo + ks * 8, tc_desc(w_hi + ks * 32), idesc, 1);
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) h_mma_ts(tmem_d, t_hi + ks * 8, tc_desc(w_hi + ks * 32), idesc, 1);
+}
+
+template <int NG>
+__global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_constant__ DevFlow F, const FwdArgs A,
+                                                                        const char* __restrict__ hpack) {
+    constexpr int NT = NG * TCM;
+    extern __shared__ char smraw[];
+    __shared__ uint64_t a_ready[NG], d_ready[NG], z_full[NG], s_full[NG];
+    __shared__ uint32_t tmem_base_s;
+    char* sm = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = A.c_begin;
+    const DevCell& q = F.cells[c];
+    const int d = F.d, depth = F.depth;
+    // which slice of the cell this launch computes (same table as flow_tc.cu)
+    const bool stats = A.stats_layer >= 1;
+    const bool from_z = A.zin != nullptr;
+    const int lz = from_z ? (stats ? A.stats_layer - 1 : depth) : 1;      // the first A operand is made of z_{lz}
+    const int l_end = stats ? A.stats_layer - 1 : depth;                   // MMA layers lz .. l_end
+    const bool zst = from_z || stats;
+    const HSmem L = h_layout(F, q.P, lz, l_end, zst, NG);
+    float* w0s = reinterpret_cast<float*>(sm + L.w0);
+    float* affs = reinterpret_cast<float*>(sm + L.aff);
+    float* biass = reinterpret_cast<float*>(sm + L.bias);
+    const float* pk = A.wpack + q.pk_off;
+    const char* cellpack = hpack + (size_t)c * h_cell_bytes(F);
+    const float* inv_scale = reinterpret_cast<const float*>(cellpack + h_cell_bytes(F) - 64);    // [l] = 1 / (SA * SW_l)
+
+    // ---- one-time setup: weights, barriers, tensor memory ---------------------------------------------
+    for (int l = lz; l <= l_end; ++l) {
+        if (L.wl[l] < 0) continue;
+        const int n16 = (l == depth ? H_OUT_BYTES : H_HID_BYTES) / 16;
+        const uint4* src = reinterpret_cast<const uint4*>(cellpack + (size_t)(l - 1) * H_HID_BYTES);
+        uint4* dst = reinterpret_cast<uint4*>(sm + L.wl[l]);
+        for (int i = tid; i < n16; i += NT) dst[i] = src[i];
+    }
+    if (!from_z) {
+        const float* s0 = pk + q.wt_off[0];                       // layer 0, [P][64] k-major
+        for (int i = tid; i < q.P * TCH; i += NT) w0s[i] = s0[i];
+    }
+    for (int l = 0; l <= depth; ++l) {                            // BN scale / shift; layers feeding an MMA carry the SA factor
+        const int W = l == 0 ? q.P : TCH, Wp = pad8(W);
+        const float* s = pk + q.aff_off[l];
+        const float f = l == 0 ? 1.f : H_SA;
+        for (int i = tid; i < W; i += NT) { affs[l * 2 * TCH + i] = f * s[i]; affs[l * 2 * TCH + TCH + i] = f * s[Wp + i]; }
+    }
+    for (int i = tid; i < H_OUT_ROWS; i += NT) {
+        const int t = i >> 5, jj = i & 31;
+        biass[i] = t < q.T ? pk[q.bo_off + t * F.Kpad + jj] : 0.f;
+    }
+    if (tid == 0) {
+        for (int g = 0; g < NG; ++g) {
+            mbar_init(&a_ready[g], TCM); mbar_init(&d_ready[g], 1); mbar_init(&z_full[g], 1); mbar_init(&s_full[g], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const long long ntiles = (A.B + TCM - 1) / TCM;
+    const long long rowlen = d + 1;
+    const int nblk = (q.T + 1) >> 1;                              // output layer: N = 64 blocks of two transformed dimensions
+    const bool has_out = l_end == depth;
+    double dsum = 0.0, dsq = 0.0;
+
+    const uint32_t idesc = h_idesc(TCM, TCH);
+    {
+        // ===================== point groups ====================================================
+        const int g = warp >> 2, gt = tid & (TCM - 1);
+        float* st = reinterpret_cast<float*>(sm + L.st) + g * (d + 1) * TCM + gt;   // this thread's state column
+        const uint32_t tg = tmem_base + g * H_COLS + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t pd = 0, pa = 0, zph = 0, sph = 0;
+        float* zs = reinterpret_cast<float*>(sm + L.zb) + g * TCH * TCM;
+        constexpr uint32_t ZBYTES = TCH * TCM * 4;
+        // the state rows of a full tile are one contiguous block: they arrive by bulk copy, issued one tile ahead
+        // (the landing zone is free as soon as every thread has moved its row into its state column)
+        float* sst = reinterpret_cast<float*>(sm + L.sst) + g * (d + 1) * TCM;
+        const uint32_t SBYTES = (uint32_t)((d + 1) * TCM * 4);
+        const bool st_bulk = A.from_state && (reinterpret_cast<uintptr_t>(A.state_in) & 15) == 0 && (SBYTES & 15) == 0;
+        if (st_bulk && gt == 0) {
+            const long long t0 = (long long)blockIdx.x * NG + g;
+            if ((t0 + 1) * TCM <= A.B) bulk_load(sst, A.state_in + t0 * TCM * rowlen, SBYTES, &s_full[g]);
+        }
+        const float inv_out = has_out ? inv_scale[depth] : 0.f;
+        for (long long it = 0;; ++it) {
+            const long long tile = ((long long)blockIdx.x + it * gridDim.x) * NG + g;
+            if (tile >= ntiles) break;
+            const long long tn = tile + (long long)gridDim.x * NG;
+            if (from_z && gt == 0) {
+                // single staging buffer per group: the previous tile's output (if any) must have left it
+                if (A.zout) bulk_store_wait_read();
+                bulk_load(zs, A.zin + (size_t)tile * TCH * TCM, ZBYTES, &z_full[g]);
+                if (tn < ntiles) bulk_prefetch_l2(A.zin + (size_t)tn * TCH * TCM, ZBYTES);
+            }
+            const long long pt = tile * TCM + gt;
+            const bool valid = pt < A.B;
+            // ---- this thread's point --------------------------------------------------------------
+            if (st_bulk && (tile + 1) * TCM <= A.B) {
+                mbar_wait(&s_full[g], sph);
+                sph ^= 1;
+                for (int i = 0; i <= d; ++i) st[i * TCM] = sst[gt * rowlen + i];
+                proxy_fence();                       // our reads of the landing zone precede the next bulk write into it
+                group_sync(g);
+                if (gt == 0 && (tn + 1) * TCM <= A.B) bulk_load(sst, A.state_in + tn * TCM * rowlen, SBYTES, &s_full[g]);
+            } else if (valid) {
+                if (A.from_state) {
+                    for (int i = 0; i <= d; ++i) st[i * TCM] = A.state_in[pt * rowlen + i];
+                } else {
+                    for (int i = 0; i < d; ++i) st[i * TCM] = load_io(A.in, A.in_dtype, pt * A.in_cols + i);
+                    st[d * TCM] = A.in_cols > d ? load_io(A.in, A.in_dtype, pt * A.in_cols + d) : 1.f;
+                }
+                if (!stats && A.saved && !A.from_state) {
+                    float* sv = A.saved + ((long long)c * A.B + pt) * rowlen;
+                    for (int i = 0; i <= d; ++i) sv[i] = st[i * TCM];
+                }
+            } else {
+                for (int i = 0; i < d; ++i) st[i * TCM] = 0.5f;
+                st[d * TCM] = 1.f;
+            }
+            if (from_z) { mbar_wait(&z_full[g], zph); zph ^= 1; }
+            // ---- MMA layers lz .. l_end: build the A operand of layer l from z_l, 32 features at a time -----------
+            float inv_prev = 1.f;                                 // D of the previous layer = z * SA * SW
+            for (int l = lz; l <= l_end; ++l) {
+                const float* sc = affs + l * 2 * TCH;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v[32];
+                    if (l > lz) {                                 // chained: the accumulator of layer l-1
+                        tc_ld32(tg + 32 * h, v);
+                        tc_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= inv_prev;
+                    } else if (from_z) {                          // stored pre-BN activations
+                        const float* zr = zs + (32 * h) * TCM + gt;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = zr[j * TCM];
+                    } else {                                      // layer 0 (K = P) on the FP32 pipe
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        for (int k = 0; k < q.P; ++k) {
+                            const float a = fmaf(st[q.feed[k] * TCM], affs[k], affs[TCH + k]);
+                            const float4* wr = reinterpret_cast<const float4*>(w0s + k * TCH + 32 * h);
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 w = wr[j4];
+                                v[4 * j4] = fmaf(a, w.x, v[4 * j4]); v[4 * j4 + 1] = fmaf(a, w.y, v[4 * j4 + 1]);
+                                v[4 * j4 + 2] = fmaf(a, w.z, v[4 * j4 + 2]); v[4 * j4 + 3] = fmaf(a, w.w, v[4 * j4 + 3]);
+                            }
+                        }
+                    }
+                    h_store_act32(v, sc + 32 * h, sc + TCH + 32 * h, tg + H_COL_AHI + 16 * h, tg + H_COL_ALO + 16 * h);
+                }
+                if (l == lz && from_z) proxy_fence();             // our reads of the staging tile precede the next bulk write into it
+                tc_st_wait();
+                tc_fence_before();
+                mbar_arrive(&a_ready[g]);
+                if (gt == 0) {                                    // the group's issuer: all 128 operand rows are in place
+                    mbar_wait(&a_ready[g], pa);
+                    tc_fence_after();
+                    const uint32_t whi = smem_u32(sm + L.wl[l]);
+                    const uint32_t tb = tmem_base + g * H_COLS;
+                    h_issue_block(tb, tb + H_COL_AHI, tb + H_COL_ALO, whi, whi + (l == depth ? H_OUT_ROWS : TCH) * TCH * 2, idesc);
+                    tc_commit(&d_ready[g]);
+                }
+                pa ^= 1;
+                if (l < depth) {
+                    mbar_wait(&d_ready[g], pd);
+                    pd ^= 1;
+                    tc_fence_after();
+                    inv_prev = inv_scale[l];
+                }
+            }
+            if (stats) {
+                // ---- statistics pass: z_L goes to the staging tile [64][128] (over the input tile), from there to HBM by
+                //      ONE bulk store, and its per-feature sums are row sums of the tile
+                if (!from_z) {
+                    if (gt == 0) bulk_store_wait_read();          // the previous tile's store has read the buffer
+                    group_sync(g);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v[32];
+                    tc_ld32(tg + 32 * h, v);
+                    tc_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) zs[(32 * h + j) * TCM + gt] = valid ? v[j] * inv_prev : 0.f;
+                }
+                proxy_fence();
+                group_sync(g);
+                if (gt == 0 && A.zout) bulk_store(A.zout + (size_t)tile * TCH * TCM, zs, ZBYTES);
+                if (!A.no_stats) {
+                    // thread gt sums half a row (64 points) of feature gt & 63, 16 bytes at a time; the start is
+                    // rotated by the lane so that a warp's 32 rows do not hit the same banks
+                    const float4* row = reinterpret_cast<const float4*>(zs + (gt & 63) * TCM + (gt >> 6) * 64);
+                    float s_ = 0.f, q_ = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float4 x = row[(i + lane) & 15];
+                        s_ += (x.x + x.y) + (x.z + x.w);
+                        q_ = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, q_))));
+                    }
+                    dsum += (double)s_; dsq += (double)q_;
+                }
+                proxy_fence();
+                group_sync(g);
+                continue;
+            }
+            // ---- output layer: N = 64 blocks of two transformed dimensions; PWLin with 32 bins on the thread's logits
+            //      in registers (coupling_cells.py:114-141)
+            float jfac = 1.f;
+            for (int b = 0; b < nblk; ++b) {
+                mbar_wait(&d_ready[g], pd);
+                pd ^= 1;
+                tc_fence_after();
+                float z[64];
+                tc_ld32(tg, z);
+                tc_ld32(tg + 32, z + 32);
+                tc_ld_wait();
+                if (b + 1 < nblk) {                  // accumulator consumed: the next block's MMAs may overwrite it
+                    tc_fence_before();
+                    mbar_arrive(&a_ready[g]);
+                    if (gt == 0) {
+                        mbar_wait(&a_ready[g], pa);
+                        tc_fence_after();
+                        const uint32_t whi = smem_u32(sm + L.wl[depth]) + (uint32_t)(b + 1) * (TCH * 128);
+                        const uint32_t tb = tmem_base + g * H_COLS;
+                        h_issue_block(tb, tb + H_COL_AHI, tb + H_COL_ALO, whi, whi + H_OUT_ROWS * TCH * 2, idesc);
+                        tc_commit(&d_ready[g]);
+                    }
+                    pa ^= 1;
+                }
+#pragma unroll
+                for (int tt = 0; tt < 2; ++tt) {
+                    const int t = 2 * b + tt;
+                    if (t >= q.T) break;
+                    const float xv = st[q.trafo[t] * TCM];
+                    const float a = xv * 32.f;
+                    int kb = (int)floorf(a);
+                    kb = kb < 0 ? 0 : (kb > 31 ? 31 : kb);
+                    const float alpha = a - (float)kb;
+                    const float* bs = biass + t * 32;
+                    float m = -3.0e38f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { z[32 * tt + j] = fmaf(z[32 * tt + j], inv_out, bs[j]); m = fmaxf(m, z[32 * tt + j]); }
+                    float S = 0.f, C = 0.f, ek = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float e = __expf(z[32 * tt + j] - m);
+                        S += e;
+                        C += j < kb ? e : 0.f;
+                        ek = j == kb ? e : ek;
+                    }
+                    const float inv = 1.f / S;
+                    st[q.trafo[t] * TCM] = (ek * alpha + C) * inv;
+                    jfac *= ek * inv * 32.f;
+                    if (A.bins && valid) A.bins[((long long)c * A.B + pt) * d + t] = kb;
+                }
+            }
+            st[d * TCM] *= jfac;
+            // ---- store ----------------------------------------------------------------------------------
+            if (valid) {
+                if (A.state_out) {
+                    float* so = A.state_out + pt * rowlen;
+                    for (int i = 0; i <= d; ++i) so[i] = st[i * TCM];
+                }
+                if (A.to_out) {
+                    for (int i = 0; i < d; ++i) store_io(A.out, A.out_dtype, pt * rowlen + i, st[F.out_perm[i] * TCM]);
+                    store_io(A.out, A.out_dtype, pt * rowlen + d, st[d * TCM]);
+                }
+            }
+        }
+    }
+    bulk_store_wait_read();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (!stats || A.no_stats) return;
+    // ---- fold: thread gt of a group holds the sums of feature gt & 63 over half of each of its tiles -----------
+    double* red = reinterpret_cast<double*>(sm + L.red);          // [2][NG * 128]: sum / sum of squares per group thread
+    double* sacc = red + NG * TCM * 2;                            // [2 * maxW]
+    red[tid] = dsum; red[NG * TCM + tid] = dsq;
+    for (int i = tid; i < 2 * F.maxW; i += NT) sacc[i] = 0.0;
+    __syncthreads();
+    if (tid < TCH) {
+        double s = 0.0, s2 = 0.0;
+        for (int k = 0; k < 2 * NG; ++k) { s += red[tid + 64 * k]; s2 += red[NG * TCM + tid + 64 * k]; }
+        sacc[tid] = s; sacc[F.maxW + tid] = s2;
+    }
+    bn_stats_finalize(F, A, sacc, NT);
+}
+
+// ---------------------------------------------------------------------------------------------------
+size_t nis_h_pack_floats(const DevFlow& F) {
+    if (F.depth < 1) return 0;
+    return (size_t)F.n_cells * (h_cell_bytes(F) / 4);
+}
+
+int64_t nis_tc_min_batch(int64_t dflt);
+
+static int h_groups(const DevFlow& F) {
+    // the largest group count whose three launch shapes fit the shared memory of an SM
+    const size_t lim = 226 * 1024;
+    for (int ng = H_MAXG; ng >= 2; --ng) {
+        bool ok = true;
+        for (int c = 0; c < F.n_cells && ok; ++c) {
+            const int P = F.cells[c].P;
+            ok = (size_t)h_layout(F, P, 1, F.depth, false, ng).total + 1024 <= lim               // fused eval cell
+                 && (size_t)h_layout(F, P, F.depth - 1, F.depth - 1, true, ng).total + 1024 <= lim   // a layer pass
+                 && (size_t)h_layout(F, P, F.depth, F.depth, true, ng).total + 1024 <= lim;      // final pass
+        }
+        if (ok) return ng;
+    }
+    return 0;
+}
+
+// Width-64 PWLin cells with 32 bins (BASELINE configs[1]); NIS_TC_H=0 keeps the 3xTF32 kernel (A/B test knob)
+bool nis_h_supported(const DevFlow& F, int64_t B, int bn_mode) {
+    (void)bn_mode;
+    const char* off = getenv("NIS_TC_H");
+    if (off && off[0] == '0') return false;
+    const char* tcoff = getenv("NIS_TC");
+    if (tcoff && tcoff[0] == '0') return false;
+    if (F.kind != NIS_KIND_PWLIN || F.K != 32 || F.nb != 32 || F.depth < 1 || F.maxW != TCH) return false;
+    if (B < nis_tc_min_batch(256)) return false;
+    for (int l = 0; l < F.depth; ++l) if (F.widths[l] != TCH) return false;
+    for (int c = 0; c < F.n_cells; ++c)
+        if (F.cells[c].P > 16 || F.cells[c].T * 32 > H_OUT_ROWS) return false;
+    return h_groups(F) >= 2;
+}
+
+int nis_h_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream_t s) {
+    flow_h_pack_kernel<<<dim3(F.depth, F.n_cells), 256, 0, s>>>(F, params, reinterpret_cast<char*>(tcpack));
+    NIS_CUDA_CHECK_LAUNCH();
+    return NIS_OK;
+}
+
+template <int NG>
+static int h_launch(const DevFlow& F, const FwdArgs& A, const char* hpack, size_t smem, int sms, cudaStream_t s) {
+    static int attr_smem = 0;                            // cudaFuncSetAttribute only when the requirement grows
+    if ((int)smem > attr_smem) {
+        if (cudaFuncSetAttribute(flow_cell_h_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return NIS_ECUDA;
+        attr_smem = (int)smem;
+    }
+    const long long nsets = ((A.B + TCM - 1) / TCM + NG - 1) / NG;
+    const int grid = (int)(nsets < sms ? nsets : sms);
+    flow_cell_h_kernel<NG><<<grid, NG * TCM, smem, s>>>(F, A, hpack);
+    NIS_CUDA_CHECK_LAUNCH();
+    return NIS_OK;
+}
+
+int nis_launch_h(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaStream_t s) {
+    static int sms = 0;
+    if (sms <= 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const bool stats = A.stats_layer >= 1;
+    const int lz = A.zin ? (stats ? A.stats_layer - 1 : F.depth) : 1;
+    const int l_end = stats ? A.stats_layer - 1 : F.depth;
+    const int ng = h_groups(F);
+    const size_t smem = (size_t)h_layout(F, F.cells[A.c_begin].P, lz, l_end, A.zin != nullptr || stats, ng).total + 1024;
+    const char* hp = reinterpret_cast<const char*>(tcpack);
+    switch (ng) {
+        case 4: return h_launch<4>(F, A, hp, smem, sms, s);
+        case 3: return h_launch<3>(F, A, hp, smem, sms, s);
+        case 2: return h_launch<2>(F, A, hp, smem, sms, s);
+    }
+    return NIS_EUNSUPPORTED;
+}

@@ -167,9 +167,12 @@ def rectnn(sd, cell, xA, train, stats=None):
 # ----------------------------------------------------------------------------------------------
 # coupling cells
 # ----------------------------------------------------------------------------------------------
-def pwlin_cell(sd, cell, x, P, n_bins, train, stats=None, edges=None):
+def pwlin_cell(sd, cell, x, P, n_bins, train, stats=None, edges=None, clamp_bins=False):
     """coupling_cells.py:107-142.  x: [B, d+1].  Returns (out [B, d+1], bins [B, T]).
-    ``edges`` (list) receives the distance [B, T] of every transformed coordinate to its nearest bin edge."""
+    ``edges`` (list) receives the distance [B, T] of every transformed coordinate to its nearest bin edge.
+    ``clamp_bins``: a coordinate of exactly 1.0 (the output of a previous cell can round to it) makes the reference
+    gather out of range and raise (:126-133, no clamp); with this flag the bin is clamped to n_bins-1 like the
+    CUDA kernels do (known divergences) so that large batches can be compared point by point."""
     d = x.shape[1] - 1
     T = d - P
     xA, xB, J = x[:, :P], x[:, P:d], x[:, d]
@@ -181,6 +184,8 @@ def pwlin_cell(sd, cell, x, P, n_bins, train, stats=None, edges=None):
     C = torch.cat((torch.zeros_like(norm), Qsum / norm), -1)   # :123-124 cdf at left edges
     a = xB * n_bins
     bins = torch.floor(a)
+    if clamp_bins:
+        bins = bins.clamp(0, n_bins - 1)
     if edges is not None:
         edges.append(((a - torch.round(a)).abs() / n_bins).detach())
     alpha = (a - bins) / n_bins                         # :130-131
@@ -228,7 +233,7 @@ def pwquad_cell(sd, cell, x, P, n_bins, train, stats=None, edges=None):
 # ----------------------------------------------------------------------------------------------
 # whole flow, layer by layer like the reference Sequential
 # ----------------------------------------------------------------------------------------------
-def flow_forward(layers, sd, xj, kind, n_bins, train=True, stats=None, trace=None, edges=None):
+def flow_forward(layers, sd, xj, kind, n_bins, train=True, stats=None, trace=None, edges=None, clamp_bins=False):
     """Run the reference Sequential.  xj: [B, d+1] float64.  Returns (XJ [B, d+1], bins [B, C, T_c]
     as a list of per-cell LongTensors).  ``trace`` (dict) receives each module's output by name, ``edges`` (list)
     each cell's [B, T_c] distances to the nearest bin edge."""
@@ -239,7 +244,7 @@ def flow_forward(layers, sd, xj, kind, n_bins, train=True, stats=None, trace=Non
     for L in layers:
         t = L["type"]
         if t == "cell":
-            x, b = cell_fn(sd, L["name"], x, L["P"], n_bins, train, stats, edges)
+            x, b = cell_fn(sd, L["name"], x, L["P"], n_bins, train, stats, edges, **({"clamp_bins": True} if clamp_bins and kind == "lin" else {}))
             all_bins.append(b)
         elif t == "roll":
             x = torch.cat((torch.roll(x[:, :-1], L["shift"], -1), x[:, -1:]), -1)

@@ -85,10 +85,10 @@ def test_forward_matches_oracle_at_size(cfg, mode, max_log_j=None):
     edges = []
     with torch.no_grad():
         ref, ref_bins = oflow.flow_forward(oracle_layers(cfg), sd64, xj.cpu(), cfg["kind"], cfg["n_bins"],
-                                           train=(mode == "train"), edges=edges)
+                                           train=(mode == "train"), edges=edges, clamp_bins=True)
         sd32 = {k: (v.float() if v.dtype.is_floating_point else v) for k, v in sd.items()}
         ref32, _ = oflow.flow_forward(oracle_layers(cfg), sd32, xj.cpu().float(), cfg["kind"], cfg["n_bins"],
-                                      train=(mode == "train"))
+                                      train=(mode == "train"), clamp_bins=True)
     compare_flow(XJ.cpu(), bins.cpu(), ref, [b.numpy() for b in ref_bins], "%s/%s" % (cfg["name"], mode),
                  fp32_yardstick=ref32, ref_edges=[e.numpy() for e in edges], max_log_j=max_log_j)
 
@@ -100,7 +100,7 @@ def test_bench_configuration_against_the_oracle_at_a_million_points(mode):
     test_forward_matches_oracle_at_size(dict(BIG[0], B=1 << 20), mode, max_log_j=1e-4)
 
 
-@pytest.mark.parametrize("backend", ["tcgen05", "fp32_tiled_4x8", "fp32_tiled_8x8", "generic"])
+@pytest.mark.parametrize("backend", ["tcgen05", "tcgen05_3xtf32", "fp32_tiled_4x8", "fp32_tiled_8x8", "generic"])
 @pytest.mark.parametrize("mode", ["eval", "train"])
 @pytest.mark.parametrize("which", [0, 1, 3], ids=["cfg2", "cfg4", "cfg5_small"])
 def test_every_kernel_family_agrees_with_the_oracle(monkeypatch, backend, mode, which):
@@ -109,9 +109,11 @@ def test_every_kernel_family_agrees_with_the_oracle(monkeypatch, backend, mode, 
     kernel stay selectable (library test knobs) and must meet the same parity bar."""
     if which == 3 and backend.startswith("fp32_tiled"):
         pytest.skip("the register-tiled FP32 kernels are width-64 only")
-    env = {"tcgen05": {}, "fp32_tiled_4x8": {"NIS_TC": "0"}, "fp32_tiled_8x8": {"NIS_TC": "0", "NIS_TILED_VARIANT": "8"},
+    if backend == "tcgen05_3xtf32" and which != 0:
+        pytest.skip("only the PWLin width-64 cells have two tensor-core kernels (fp16-split default, 3xTF32 with NIS_TC_H=0)")
+    env = {"tcgen05": {}, "tcgen05_3xtf32": {"NIS_TC_H": "0"}, "fp32_tiled_4x8": {"NIS_TC": "0"}, "fp32_tiled_8x8": {"NIS_TC": "0", "NIS_TILED_VARIANT": "8"},
            "generic": {"NIS_TC": "0", "NIS_DISABLE_TILED": "1"}}[backend]
-    for k in ("NIS_TC", "NIS_TILED_VARIANT", "NIS_DISABLE_TILED"):
+    for k in ("NIS_TC", "NIS_TC_H", "NIS_TILED_VARIANT", "NIS_DISABLE_TILED"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)

@@ -44,8 +44,10 @@ def test_ends_of_the_unit_interval_match_reference(golden, case):
     rows = rambo_edge_rows(ref_mom, g["r"], len(g.meta["final"]))
     assert np.array_equal(mask[rows], (ref_w != 0)[rows]), "cut mask must be bit-exact"
     cmp = rows | (mask & (ref_w != 0))
-    rt = rambo_edge_weight_rtol(g["r"], len(g.meta["final"]))
-    assert (np.abs(w - ref_w)[cmp] <= (rt * np.abs(ref_w))[cmp]).all(), np.abs(w / ref_w - 1)[cmp & (ref_w != 0)].max()
+    rt = rambo_edge_weight_rtol(g["r"], g.meta)
+    bad = cmp & ~(np.abs(w - ref_w) <= rt * np.abs(ref_w))
+    assert not bad.any(), (np.nonzero(bad)[0], (w / ref_w - 1)[bad], rt[bad])
+    assert np.isfinite(rt[cmp]).mean() > 0.8
     np.testing.assert_allclose(mom[rows], ref_mom[rows], rtol=1e-9, atol=1e-9 * m["E_cm"])
     # the float32 grid: the same uniforms as float32 input give the same events
     mom32, w32 = ps.generateKinematics_batch(m["E_cm"], g.t("r").float().cuda(), **m["cuts"])

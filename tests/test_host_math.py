@@ -203,7 +203,9 @@ def test_rambo_event_on_the_ends_of_the_unit_interval(host, golden, case):
     # rows on which the reference's momenta overflowed: its cuts compared NaNs (all pass); only the pre-cut weight
     # is comparable there, and only when we did not cut the event
     cmp = rows | (ok.astype(bool) & (ref_w != 0))
-    rt = rambo_edge_weight_rtol(g["r"], len(g.meta["final"]))
-    assert (np.abs(w - ref_w)[cmp] <= (rt * np.abs(ref_w))[cmp]).all(), np.abs(w / ref_w - 1)[cmp & (ref_w != 0)].max()
+    rt = rambo_edge_weight_rtol(g["r"], g.meta)
+    bad = cmp & ~(np.abs(w - ref_w) <= rt * np.abs(ref_w))
+    assert not bad.any(), (np.nonzero(bad)[0], (w / ref_w - 1)[bad], rt[bad])
+    assert np.isfinite(rt[cmp]).mean() > 0.8
     np.testing.assert_allclose(mom[rows], ref_mom[rows], rtol=1e-9, atol=1e-9 * g.meta["E_cm"])
     assert cmp.sum() >= 0.5 * len(w)
