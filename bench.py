@@ -142,6 +142,72 @@ def fma_peak_tflops():
     return best
 
 
+def tensor_peak_tflops(kind, n):
+    """Measured tcgen05.mma peak (TFLOP/s, all SMs) for kind 0 = kind::tf32 / 1 = kind::f16 at M = 128, N = n, A in
+    tensor memory: nis_probe_tensor issues 8192 back-to-back MMAs per SM; best of 5 after one warm-up."""
+    from nf_b200 import _cabi
+    lib = _cabi.lib()
+    best = 0.0
+    for it in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        flop = lib.nis_probe_tensor(kind, n, 1024, _cabi.stream_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        if flop <= 0:
+            return None
+        if it:
+            best = max(best, flop / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def parity_checks(rank, world, dev):
+    """Run by every `bench.py --gpus N`: the N-rank paths checked in the driver's own run.
+    (a) data-parallel gradient == single-GPU gradient: every rank backpropagates the variance loss of ITS minibatch
+        (per-rank BN statistics), the flat gradient is sum-allreduced; rank 0 also computes all `world` minibatches
+        one after the other on its own GPU and sums — the two must agree (SURVEY 8e);
+    (b) per-rank latent streams differ under identical seeding;
+    (c) the configs[3] integrate result is finite and within one honest standard error (filled in by main)."""
+    from nf_b200.normalizing_flows.manager import BasicManager, PWLinManager
+    torch.manual_seed(77)
+    NF = PWLinManager(n_flow=8)
+    NF.create_model(4, 3, 32, [64, 64], 4)
+    NF._model.to(dev)
+    model = NF._model.train()
+    params = list(model.parameters())
+
+    def minibatch(r):
+        g = torch.Generator().manual_seed(4242 + r)
+        return torch.rand(4096, 8, generator=g, dtype=torch.float32).to(dev)
+
+    def grad_of(x):
+        model.zero_grad()
+        XJ = model(x)
+        f = torch.exp(-((XJ[:, :-1].detach() - 0.5) ** 2).sum(-1) / 0.3)
+        (torch.var(f * XJ[:, -1]) / world).backward()
+        return torch.cat([p.grad.reshape(-1) for p in params]).clone()
+
+    out = {}
+    mine = grad_of(minibatch(rank))
+    if world > 1:
+        BasicManager._allreduce_grads(params)
+        reduced = torch.cat([p.grad.reshape(-1) for p in params]).clone()
+    else:
+        reduced = mine
+    if rank == 0:
+        ref = sum(grad_of(minibatch(r)) for r in range(world))
+        out["dp_gradient_max_err_over_scale"] = float((reduced - ref).abs().max() / ref.abs().max())
+        out["dp_gradient_ok"] = out["dp_gradient_max_err_over_scale"] <= 2e-4
+    torch.manual_seed(99)
+    gen = BasicManager._rank_generator(dev, rank, world)
+    pts = torch.rand(8, device=dev, generator=gen)
+    if world > 1:
+        allp = [torch.zeros_like(pts) for _ in range(world)]
+        dist.all_gather(allp, pts)
+        out["rank_streams_differ"] = all(not torch.equal(allp[0], a) for a in allp[1:])
+    return out
+
+
 def reference_flow(threads):
     """The reference's CPU path for this workload as a callable [B,9] float64 -> [B,9] (train-mode BN like
     the reference's integrate).  kind "reference": the UNMODIFIED reference package installed under
@@ -374,7 +440,10 @@ def bench_rambo(steps, warmup, world, hbm_peak, peak_kind):
                                    "pT>20, dR>0.4, |eta|<2.5 cuts", "events_per_step_per_gpu": RAMBO_EVENTS},
             "dtype": "f64",
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                         "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes_per_event": RAMBO_BYTES_PER_EVENT},
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^24 events from the committed
+                         # ncu --set full capture (profiles/r01_ncu_rambo.md: 1.074 GB + 3.300 GB); not re-measured per run
+                         "traffic": 4374426000 if RAMBO_EVENTS == 1 << 24 else None,
+                         "peak_kind": peak_kind, "algorithmic_bytes_per_event": RAMBO_BYTES_PER_EVENT},
             "weight_only": {"value": world * RAMBO_EVENTS / (ms_w * 1e-3), "unit": "events/s", "ms_per_step": ms_w}}
 
 
@@ -496,7 +565,10 @@ def main():
         # dominant kernel: flow_cell_tc_kernel (tcgen05.mma kind::tf32, 3 products per conditioner MAC)
         tensor_flop_pt = n_cells * 3 * 2 * (64 * 64 * (depth - 1) + 64 * 128)      # executed on the tensor pipe
         tfl_exec = N_POINTS * tensor_flop_pt / (ms * 1e-3) / 1e12
-        tf32_peak = pk["bf16_tflops"] / 2.0
+        f16_peak = tensor_peak_tflops(1, 128) or pk["bf16_tflops"]
+        f16_peak_n64 = tensor_peak_tflops(1, 64)
+        tf32_meas = tensor_peak_tflops(0, 128)
+        tf32_peak = f16_peak                     # the dominant kernel issues kind::f16 MMAs (fp16-split operands)
         tfl = N_POINTS * FLOP_PER_POINT / (ms * 1e-3) / 1e12
         # moments pass reads the rows; first layer pass reads rows, writes z2; later passes read+write 256 B; final
         train_bytes_pt = n_cells * (36 + (36 + 256) + 2 * (depth - 2) * 256 + (256 + 36 + 36))
@@ -507,11 +579,13 @@ def main():
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE train-mode layer-pass launch of flow_cell_tc_kernel at
             # 2^22 points, from the committed ncu --set full capture (profiles/r01_ncu_tc.md); not re-measured per run
             "traffic": 2250729000 if N_POINTS == 1 << 22 else None,
-            "peak_kind": "%s bf16 cuBLAS peak / 2 (kind::tf32 runs at half the bf16 rate)" % peak_kind,
-            "kernel": "flow_cell_tc_kernel: %d launches per step (per cell %d train-mode layer passes + 1 final pass) "
+            "peak_kind": "tcgen05.mma kind::f16 M128 N128 K16 issued back to back on every SM, measured in this run "
+                         "(nis_probe_tensor); MEASURED_PEAKS.json bf16 cuBLAS: %s TFLOP/s" % pk.get("bf16_tflops"),
+            "measured_tensor_peaks_tflops": {"f16_n128": f16_peak, "f16_n64": f16_peak_n64, "tf32_n128": tf32_meas},
+            "kernel": "flow_cell_h_kernel: %d launches per step (per cell %d train-mode layer passes + 1 final pass) "
                       "+ %d flow_col_moments_kernel" % (n_cells * depth, depth - 1, n_cells),
             "tensor_flop_per_point": tensor_flop_pt,
-            "note": "executed TF32 flops (3xTF32 split: 3 tensor MACs per conditioner MAC); the step is not "
+            "note": "executed fp16 flops (fp16-split operands: 3 tensor MACs per conditioner MAC); the step is not "
                     "tensor-bound: see hbm_design and fp32_equivalent",
             "fp32_equivalent": {"achieved": tfl, "peak": fma, "unit": "TFLOP/s", "frac": tfl / fma,
                                 "algorithmic_flop_per_point": FLOP_PER_POINT,
@@ -542,6 +616,10 @@ def main():
         line["train_step"] = bench_train_step(max(3, args.steps // 2), args.warmup, world, dev)
         line["train_step_large"] = bench_train_step(max(3, args.steps // 2), args.warmup, world, dev, log2n=20)
         line["integrate"] = bench_integrate(world, dev)
+        par = parity_checks(rank, world, dev)
+        par["integrate_finite"] = line["integrate"]["finite"]
+        par["integrate_within_one_honest_error"] = line["integrate"]["within_one_honest_error"]
+        line["parity"] = par
         line["wide_flow"] = bench_wide(max(3, args.steps // 2), args.warmup, world, dev)
         if world == 1:
             line["readme_example"] = bench_readme(dev)

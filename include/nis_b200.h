@@ -145,7 +145,8 @@ typedef struct NisRamboDesc {
 } NisRamboDesc;
 
 /* r[B, 3n-4] (dtype r_dtype) -> momenta[B, 2+n, 4] float64 (E,px,py,pz; CM frame; optional),
- * weight[B] float64 (cuts applied, divided by 2 s), cutmask[B] uint8 (1 = passed; optional). */
+ * weight[B] float64 (cuts applied, divided by 2 s), cutmask[B] uint8 (1 = passed; optional).
+ * r and momenta must be 16-byte aligned (rows are moved as 16-byte vectors). */
 int nis_rambo_generate(const NisRamboDesc* desc, const void* r, int32_t r_dtype, double* momenta,
                        double* weight, uint8_t* cutmask, int64_t B, void* stream);
 
@@ -157,6 +158,12 @@ int nis_uniform_fill(void* out, int32_t dtype, int64_t n, uint64_t seed, uint64_
  * number of floating-point operations it performs (or a negative error).  Timing it with CUDA events
  * gives the measured FP32-pipe peak the compute-bound flow kernels are quoted against. */
 int64_t nis_probe_fp32_fma(float* out, int32_t iters, void* stream);
+
+/* Measurement aid for bench.py: launches `iters` x 8 back-to-back tcgen05.mma (cta_group::1, M = 128, N = n in
+ * {64, 128, 256}, A in tensor memory, fp32 accumulate) per SM on `stream` and returns the floating-point operations
+ * performed (or a negative error).  kind 0 = kind::tf32 (K = 8), 1 = kind::f16 (K = 16).  Timing it with CUDA events
+ * gives the MEASURED tensor-pipe peak the tcgen05 flow kernels are quoted against. */
+int64_t nis_probe_tensor(int32_t kind, int32_t n, int32_t iters, void* stream);
 
 /* sizeof(NisFlowDesc) / sizeof(NisRamboDesc) as compiled, so a foreign-language binding can verify its
  * struct layout at load time. */

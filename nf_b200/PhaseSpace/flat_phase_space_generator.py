@@ -105,6 +105,8 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
         rd = r.detach().to(dev).contiguous()
         if rd.dtype not in (torch.float32, torch.float64):
             rd = rd.double()
+        if rd.data_ptr() % 16:                     # the kernel moves rows 16 bytes at a time (a slice can start anywhere)
+            rd = rd.clone()
         B = rd.shape[0]
         desc = self._desc(E_cm, pT_mincut, delR_mincut, rap_maxcut)
         with torch.cuda.device(dev):

@@ -11,6 +11,7 @@
 //
 // Reference semantics: coupling_cells.py:107-142 (PWLin), :159-228 (PWQuad), :230-254 (RectNN),
 // layers.py:27-32,43-51,75-77,90-91 (Mask/DeMask/AddJacobian/Roll, folded into column tables).
+#include <stdlib.h>
 #include "common.cuh"
 #include "spline.cuh"
 #include "flow_fwd_common.cuh"
@@ -332,6 +333,10 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     const bool hp = tc && nis_h_supported(F, B, bn_mode);              // fp16-split, four-group kernel (flow_tc_h.cu)
     const bool wide = !tc && nis_wide_supported(F, B, bn_mode);       // streamed-weights tcgen05 kernel (flow_wide.cu)
     const bool tiled = tc || wide || nis_tiled_supported(F, B);
+    // train-mode layer passes either hand their pre-BN activations to the next pass through HBM (256 B/point/pass) or
+    // recompute them from the state (more tensor work, ~7x less traffic); NIS_TRAIN_RECOMPUTE=0/1 overrides the default
+    static const int recompute_env = [] { const char* e = getenv("NIS_TRAIN_RECOMPUTE"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    const bool recompute = hp && (recompute_env >= 0 ? recompute_env == 1 : false);
     if (tc) { rc = hp ? nis_h_pack(F, params, ws.tcpack, s) : nis_tc_pack(F, params, ws.tcpack, s); if (rc) return rc; }
     if (wide) { rc = nis_wide_pack(F, params, ws.tcpack, s); if (rc) return rc; }
     const long long rows = (long long)B * (F.d + 1);
@@ -363,8 +368,8 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
                 A.stats_layer = l;
                 if (tiled && l >= 1) {
                     // layer pass: reads the pre-BN activations of layer l-1, writes those of layer l
-                    A.zin = (l >= 2 && !(moments && l == 2)) ? zb[(l - 1) & 1] : nullptr;
-                    A.zout = zb[l & 1];
+                    A.zin = (l >= 2 && !(moments && l == 2) && !recompute) ? zb[(l - 1) & 1] : nullptr;
+                    A.zout = recompute ? nullptr : zb[l & 1];
                     rc = hp ? nis_launch_h(F, A, ws.tcpack, s) : tc ? nis_launch_tc(F, A, ws.tcpack, s)
                             : wide ? nis_launch_wide(F, A, ws.tcpack, s) : nis_launch_tiled(F, A, s);
                 } else if (tiled && l == 0) {
@@ -376,7 +381,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
             }
         }
         A.stats_layer = -1;
-        A.zin = (tiled && bn_mode == NIS_BN_TRAIN && !(moments && F.depth == 1)) ? zb[F.depth & 1] : nullptr;
+        A.zin = (tiled && bn_mode == NIS_BN_TRAIN && !(moments && F.depth == 1) && !recompute) ? zb[F.depth & 1] : nullptr;
         A.zout = nullptr;
         if (tc && bn_mode == NIS_BN_EVAL && nis_tc_split_eval(F)) {
             // eval, PWQuad: hidden layers in one launch (activations of the last hidden layer to HBM), then the final pass

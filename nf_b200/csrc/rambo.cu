@@ -21,32 +21,54 @@ __global__ void __launch_bounds__(RAMBO_NT) rambo_kernel(const __grid_constant__
     double* rs = smd;                       // [NT][NDP]
     double* mo = smd + RAMBO_NT * NDP;      // [NT][NMP]  (scratch even when momenta are not requested)
     const int tid = threadIdx.x;
-    // i / ND and i / NM by multiplication (exact for i < 2^14, divisor <= 128: i * (M d - 2^24) < 2^24)
-    const unsigned long long magD = (1u << 24) / ND + 1, magM = (1u << 24) / NM + 1;
+    // the kinematics are needed for the momenta and for the cuts; a weight-only call without cuts stops after the masses
+    const bool kin = momenta != nullptr || C.pT_min > 0.0 || C.dR_min > 0.0 || C.rap_max > 0.0;
+    // copy-out: the tile's momenta are one contiguous block of cnt * NM doubles; thread tid moves the 16-byte pairs
+    // tid, tid + 128, ... (coalesced 512 B per warp instruction).  Pair p sits in event p / (NM/2) at component
+    // 2 * (p % (NM/2)): both are carried incrementally (no division in the loop).
+    const int HP = NM >> 1, dq = RAMBO_NT / HP, dr = RAMBO_NT - dq * HP;
+    const int ev0 = tid / HP, c0 = tid - ev0 * HP;
     const long long ntiles = (B + RAMBO_NT - 1) / RAMBO_NT;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long base = tile * RAMBO_NT;
         const int cnt = (int)((B - base) < RAMBO_NT ? (B - base) : RAMBO_NT);
-        const RT* src = r + base * ND;
-        for (int i = tid; i < cnt * ND; i += RAMBO_NT) {
-            const int ev = (int)(((unsigned long long)i * magD) >> 24), c = i - ev * ND;
-            rs[ev * NDP + c] = (double)src[i];
-        }
-        __syncthreads();
         if (tid < cnt) {
+            // this thread's uniforms: one contiguous row, loaded 16 bytes at a time where the row allows it; it is
+            // staged in the thread's own (odd-stride) shared-memory row only because rambo_event indexes it at run time
+            const RT* src = r + (base + tid) * ND;
+            double* row = rs + tid * NDP;
+            if (sizeof(RT) == 8 && (ND & 1) == 0) {
+                for (int i = 0; i < ND; i += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(reinterpret_cast<const double*>(src) + i);
+                    row[i] = v.x; row[i + 1] = v.y;
+                }
+            } else if (sizeof(RT) == 4 && (ND & 3) == 0) {
+                for (int i = 0; i < ND; i += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + i);
+                    row[i] = (double)v.x; row[i + 1] = (double)v.y; row[i + 2] = (double)v.z; row[i + 3] = (double)v.w;
+                }
+            } else {
+                for (int i = 0; i < ND; ++i) row[i] = (double)src[i];
+            }
             double w;
             uint8_t pass;
-            rambo_event(C, rs + tid * NDP, 1, mo + tid * NMP, 1, w, pass);
+            if (kin) rambo_event<true>(C, row, 1, mo + tid * NMP, 1, w, pass);
+            else rambo_event<false>(C, row, 1, mo + tid * NMP, 1, w, pass);
             weight[base + tid] = w;
             if (cutmask) cutmask[base + tid] = pass;
         }
-        __syncthreads();
         if (momenta) {
+            __syncthreads();
             double* dst = momenta + base * NM;
-            for (int i = tid; i < cnt * NM; i += RAMBO_NT) {
-                const int ev = (int)(((unsigned long long)i * magM) >> 24), c = i - ev * NM;
-                dst[i] = mo[ev * NMP + c];
+            const int npairs = cnt * HP;
+            int ev = ev0, c = c0;
+            for (int p = tid; p < npairs; p += RAMBO_NT) {
+                const double* srow = mo + ev * NMP + 2 * c;
+                *reinterpret_cast<double2*>(dst + 2 * (long long)p) = make_double2(srow[0], srow[1]);
+                ev += dq; c += dr;
+                if (c >= HP) { c -= HP; ++ev; }
             }
+            __syncthreads();
         }
     }
 }
@@ -68,6 +90,8 @@ extern "C" int nis_rambo_generate(const NisRamboDesc* desc, const void* r, int32
                                   double* weight, uint8_t* cutmask, int64_t B, void* stream) {
     if (!desc || B < 0 || (B > 0 && (!r || !weight))) return NIS_EINVAL;
     if (r_dtype != NIS_F32 && r_dtype != NIS_F64) return NIS_EINVAL;
+    // rows are moved 16 bytes at a time
+    if ((reinterpret_cast<uintptr_t>(r) & 15) || (reinterpret_cast<uintptr_t>(momenta) & 15)) return NIS_EINVAL;
     RamboConst C;
     int rc = rambo_fill_const(desc, &C);
     if (rc) return rc;

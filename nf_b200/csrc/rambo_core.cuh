@@ -236,6 +236,8 @@ NIS_DEV double rambo_root_dyn(int e, double r) { return rambo_root(e, r, rambo_l
 //     all but a ~1e-4-wide shell around deltaR = cut, where the reference's log/acos formula runs.
 // All differences to the reference are at float64 rounding level (tests: momenta / weights rtol 1e-9,
 // cut masks bit-exact on the golden vectors).
+// KIN = false (weight-only call without cuts): only the intermediate masses and the reweighting run.
+template <bool KIN>
 NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* mo, int ms, double& weight,
                          uint8_t& pass) {
     const int n = C.n;
@@ -261,6 +263,7 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
             num *= sl;
             den *= M2;
         }
+        if (!KIN) { Kj = Kn; Mj = Mn; continue; }
         const double i2M = nis_div(0.5, Mj);
         const double q = sl * i2M;                              // :228
         const double ct = 2.0 * r[(n - 2 + 2 * j) * rs] - 1.0;  // :233-243
@@ -279,11 +282,12 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
         Q1 -= p1; Q2 -= p2; Q3 -= p3; Q0 -= e;                  // :271-275
         Kj = Kn; Mj = Mn;
     }
+    const double w = C.wconst * nis_div(num, den);
+    if (!KIN) { pass = 1; weight = w; return; }
     {
         double* o = mo + (n + 1) * 4 * ms;                      // :278
         o[0] = Q0; o[ms] = Q1; o[2 * ms] = Q2; o[3 * ms] = Q3;
     }
-    const double w = C.wconst * nis_div(num, den);
     // ---- cuts (:285-301); x1 = x2 = 1 so the lab frame is the CM frame -------------------------
     bool ok = true;
     const double* fin = mo + 8 * ms;                            // final-state particle j at fin + 4*j*ms

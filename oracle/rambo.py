@@ -101,21 +101,75 @@ def delta_r(p1, p2):
     return torch.sqrt((_pseudorap(p1) - _pseudorap(p2)) ** 2 + _delphi(p1, p2) ** 2)
 
 
-def generate_kinematics(E_cm, r, initial_masses, final_masses,
-                        pT_mincut=-1, delR_mincut=-1, rap_maxcut=-1, return_parts=False):
-    """flat_phase_space_generator.py:139-308 with pdf inactive.
+def pdf_density(pdf, pdg, x, scale2):
+    """get_pdfQ2, flat_phase_space_generator.py:120-137: xf(x, Q^2) / x for gluons and quarks, 1 otherwise."""
+    if pdf is None:
+        return torch.ones_like(x)
+    if pdg not in [21] and abs(pdg) not in range(1, 7):
+        return torch.ones_like(x)
+    f = pdf.xfxQ2(pdg, x, scale2)
+    return torch.tensor(f, dtype=torch.float64) / x
 
-    r: [B, 3n-4] float64.  Returns (momenta [B, 2+n, 4] (E,px,py,pz; CM frame), weight [B]); with
-    ``return_parts`` also (flat*massive weight before cuts, cut factor in {0,1})."""
+
+def lab_boost(momenta, xb_1, xb_2):
+    """boost_to_lab_frame, utils.py:134-146 with boost_tt :83-106.  The reference decides batch-wide: if ANY event has
+    a reference vector x1 p1 + x2 p2 at rest (x1 == x2 for equal beams) nothing is boosted, otherwise every event
+    is (its torch.where sees the tensor boost_tt already changed in place)."""
+    ref = momenta[:, 0, :] * xb_1.unsqueeze(-1) + momenta[:, 1, :] * xb_2.unsqueeze(-1)
+    if bool(((ref[:, 1:] ** 2).sum(-1) == 0).any()):
+        return momenta
+    bv = (ref[:, 1:] / ref[:, 0:1]).unsqueeze(1)                    # boostVector_t, [B,1,3]
+    b2 = (bv * bv).sum(-1)                                           # [B,1]
+    gamma = 1.0 / torch.sqrt(1.0 - b2)
+    bp = (momenta[:, :, 1:] * bv).sum(-1)
+    gamma2 = torch.where(b2 > 0, (gamma - 1.0) / b2, torch.zeros_like(b2))
+    factor = gamma2 * bp + gamma * momenta[:, :, 0]
+    space = momenta[:, :, 1:] + factor.unsqueeze(-1) * bv
+    e = gamma * (momenta[:, :, 0] + bp)
+    return torch.cat((e.unsqueeze(-1), space), -1)
+
+
+def generate_kinematics(E_cm, r, initial_masses, final_masses,
+                        pT_mincut=-1, delR_mincut=-1, rap_maxcut=-1, return_parts=False,
+                        pdf=None, pdf_active=False, tau=True, pdgs=(0, 0), absolute_Ecm_min=1.0):
+    """flat_phase_space_generator.py:139-308.
+
+    r: [B, 3n-4] float64 (+ 2 columns when ``pdf_active``: tau / y_cm, or x2 / x1 with ``tau=False``).  Returns
+    (momenta [B, 2+n, 4] (E,px,py,pz; CM frame), weight [B]); with ``return_parts`` also (flat*massive weight
+    before cuts, cut factor in {0,1})."""
     r = torch.as_tensor(r, dtype=torch.float64)
     n = len(final_masses)
     if len(initial_masses) != 2:                                    # :76-79
         raise PhaseSpaceGeneratorError("only 2 incoming particles")
     if torch.isnan(r).any():                                        # :147-149
         raise PhaseSpaceGeneratorError("NaN random variables")
-    assert r.shape[1] == n_dim_phase_space(n)                       # :191
-    B = r.shape[0]
     m = torch.tensor(final_masses, dtype=torch.float64)
+    collider_energy = E_cm
+    B = r.shape[0]
+    wgt_jac = torch.ones(B, dtype=torch.float64)
+    xb_1 = torch.ones(B, dtype=torch.float64)
+    xb_2 = torch.ones(B, dtype=torch.float64)
+    if pdf_active:                                                  # :157-187
+        full = r
+        r = full[:, :-2]
+        if tau:
+            tau_min = (max(float(m.sum()), absolute_Ecm_min) / E_cm) ** 2
+            tau_v = tau_min + (1.0 - tau_min) * full[:, -2]         # uniform_distr utils.py:124-132
+            ycm_min = 0.5 * torch.log(tau_v)
+            ycm = ycm_min + (-ycm_min - ycm_min) * full[:, -1]
+            xb_1 = torch.sqrt(tau_v) * torch.exp(ycm)
+            xb_2 = torch.sqrt(tau_v) * torch.exp(-ycm)
+            E_cm = torch.sqrt(tau_v) * E_cm
+            wgt_jac = wgt_jac * ((1.0 - tau_min) * (-ycm_min - ycm_min))
+        else:
+            xb_1 = full[:, -1]
+            xb_2 = full[:, -2]
+            E_cm = torch.sqrt(xb_1 * xb_2) * E_cm
+        q2 = torch.ones_like(xb_1) * 91.188 ** 2
+        x_cut = torch.where(xb_1 < 1e-4, torch.zeros_like(xb_1), torch.ones_like(xb_1))
+        x_cut = torch.where(xb_2 < 1e-4, torch.zeros_like(x_cut), x_cut)
+        wgt_jac = wgt_jac * (pdf_density(pdf, pdgs[0], xb_1, q2) * pdf_density(pdf, pdgs[1], xb_2, q2) * x_cut)
+    assert r.shape[1] == n_dim_phase_space(n)                       # :191
 
     # (1) massless intermediate masses K_j, :204-210,:384,:363-370
     K = torch.zeros(B, n - 1, dtype=torch.float64)
@@ -124,7 +178,12 @@ def generate_kinematics(E_cm, r, initial_masses, final_masses,
     for i in range(2, n):
         K[:, i - 1] = torch.sqrt(u[:, i - 2] * K[:, i - 2] ** 2)
     # (2) flat weight, :372
-    w = torch.full((B,), flat_weight(E_cm, n), dtype=torch.float64)
+    if torch.is_tensor(E_cm):                                       # :95-97
+        w = math.pow(2 * math.pi, 4 - 3 * n) * math.pow(math.pi / 2.0, n - 1) * \
+            (torch.pow(E_cm ** 2, n - 2) / (math.factorial(n - 1) * math.factorial(n - 2)))
+    else:
+        w = torch.full((B,), flat_weight(E_cm, n), dtype=torch.float64)
+    w = w * wgt_jac
     # (3) massive intermediates and reweighting, :389-403
     msum = torch.flip(torch.cumsum(torch.flip(m, (-1,)), -1), (-1,))
     M = K + msum[:-1]

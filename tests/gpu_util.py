@@ -68,7 +68,19 @@ def compare_flow(XJ, bins, ref_XJ, ref_bins, what="", fp32_yardstick=None, ref_e
     assert nflip <= max(2, int(FLIP_BUDGET * total)), "%s: %d of %d bins differ" % (what, nflip, total)
     keep = ~flipped
     y, ry = XJ[keep, :-1], ref_XJ[keep, :-1]
-    assert torch.allclose(y, ry, rtol=RTOL, atol=ATOL_Y), "%s: points, max abs err %g" % (what, float((y - ry).abs().max()))
+    yn = ((y - ry).abs() / (ATOL_Y + RTOL * ry.abs())).reshape(-1)         # error in units of the tolerance
+    if fp32_yardstick is None:
+        assert float(yn.max()) <= 1.0, "%s: points, max abs err %g" % (what, float((y - ry).abs().max()))
+    else:
+        # large batches: like the log-Jacobian below, the worst of ~10^7 float32 spline evaluations sits in a narrow bin
+        yy = ((fp32_yardstick.double()[keep, :-1] - ry).abs() / (ATOL_Y + RTOL * ry.abs())).reshape(-1)
+        yy = yy[torch.isfinite(yy)]
+        k = max(1, int(1e-4 * yn.numel()))
+        q = float(torch.topk(yn, k).values[-1]) if yn.numel() > 1 else float(yn.max())
+        msg = "%s: points, error / tolerance: ours q99.99 %.2f max %.2f | float32 oracle max %.2f" % (
+            what, q, float(yn.max()), float(yy.max()))
+        print(msg)
+        assert q <= 1.0 and float(yn.max()) <= max(1.0, 2 * float(yy.max())), msg
     lj, rlj = torch.log(XJ[keep, -1]), torch.log(ref_XJ[keep, -1])
     err = (lj - rlj).abs() / rlj.abs().clamp_min(1.0)
     if fp32_yardstick is None:

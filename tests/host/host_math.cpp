@@ -36,7 +36,7 @@ int host_rambo(const NisRamboDesc* d, long long B, const double* r, double* mom,
     if (rc) return rc;
     const int n = d->n_final, nd = 3 * n - 4, nm = (n + 2) * 4;
     double scratch[(NIS_MAX_FINAL + 2) * 4];
-    for (long long i = 0; i < B; ++i) rambo_event(C, r + i * nd, 1, mom ? mom + i * nm : scratch, 1, w[i], pass[i]);
+    for (long long i = 0; i < B; ++i) rambo_event<true>(C, r + i * nd, 1, mom ? mom + i * nm : scratch, 1, w[i], pass[i]);
     return 0;
 }
 
