@@ -138,13 +138,30 @@ typedef struct NisRamboDesc {
     int32_t n_final;
     double initial_masses[2];
     double final_masses[NIS_MAX_FINAL];
-    double E_cm;
+    double E_cm;        /* collider energy; the partonic energy is sqrt(x1 x2) E_cm when pdf_active */
     double pT_mincut;   /* event weight -> 0 if min_j pT_j < pT_mincut      (:285-288) */
     double delR_mincut; /* ... if any pair |deltaR| < delR_mincut           (:290-296) */
     double rap_maxcut;  /* ... if rap_maxcut > 0 and rap_maxcut < |max eta| (:298-301) */
+    /* ---- parton-density mode (:157-187, 213-219, 283; utils.py:83-146) -------------------------------------------
+     * pdf_active != 0: r has two more columns (3n-2 in all) that sample the Bjorken x of the beams; the event is
+     * generated at E = sqrt(x1 x2) E_cm, the weight carries the sampling Jacobian, the two parton densities
+     * f(x) = xf(x, Q2) / x, the x cut and 1 / (2 x1 x2 E_cm^2), and the cuts act on the momenta boosted to the lab
+     * frame (the momenta returned stay in the partonic CM frame, like the reference's).
+     *   tau_mode != 0: column 3n-4 samples tau in [tau_min, 1], column 3n-3 samples y_cm in [ln(tau)/2, -ln(tau)/2],
+     *                  x1,2 = sqrt(tau) exp(+-y_cm);   tau_mode == 0: x2 = column 3n-4, x1 = column 3n-3.
+     *   pdf_grid[i]: DEVICE pointer to pdf_nodes float64 values of x f_i(x, Q2 = 91.188^2) on nodes uniform in ln x
+     *                over [pdf_lnx_lo, 0] (4-point Lagrange interpolation in ln x), or NULL for density 1
+     *                (what get_pdfQ2 returns without a PDF set or for a non-parton pdg code, :124-128). */
+    int32_t pdf_active;
+    int32_t tau_mode;
+    double tau_min;     /* (max(sum of final masses, absolute_Ecm_min) / E_cm)^2  (:163-164) */
+    double x_cut;       /* weight -> 0 if x1 or x2 < x_cut; the reference uses 1e-4 (:185-186) */
+    const double* pdf_grid[2];
+    int32_t pdf_nodes;
+    double pdf_lnx_lo;
 } NisRamboDesc;
 
-/* r[B, 3n-4] (dtype r_dtype) -> momenta[B, 2+n, 4] float64 (E,px,py,pz; CM frame; optional),
+/* r[B, 3n-4 (+2 when pdf_active)] (dtype r_dtype) -> momenta[B, 2+n, 4] float64 (E,px,py,pz; CM frame; optional),
  * weight[B] float64 (cuts applied, divided by 2 s), cutmask[B] uint8 (1 = passed; optional).
  * r and momenta must be 16-byte aligned (rows are moved as 16-byte vectors). */
 int nis_rambo_generate(const NisRamboDesc* desc, const void* r, int32_t r_dtype, double* momenta,

@@ -5,8 +5,11 @@ masses, massive reweighting, sequential two-body decays with boosts, the pT / de
 the 1/(2 s) flux factor in ONE pass per event (the reference: a 120-180 level batched bisection plus
 ~600 ATen launches).
 
-Scope: the ``pdf_active=False`` path (what BASELINE.json names).  ``pdf_active=True`` needs LHAPDF,
-which is neither in this image nor under /root/reference; it raises NotImplementedError.
+Both modes of the reference: ``pdf_active=False`` (what BASELINE.json names) and ``pdf_active=True`` (two more
+uniforms sample the Bjorken x of the beams, per-event partonic energy, parton densities, lab-frame cuts;
+flat_phase_space_generator.py:157-187).  The densities come from any object with the reference's
+``pdf.xfxQ2(pdg, x, Q2)`` call (an ``lhapdf.PDF``; LHAPDF itself is not needed to construct the generator), sampled
+once per parton into a device grid the kernel interpolates (pdf_grid.py).
 """
 import ctypes
 import math
@@ -14,6 +17,7 @@ import math
 import torch
 
 from .. import _cabi
+from .pdf_grid import PdfGrid, X_CUT, is_parton
 
 
 class PhaseSpaceGeneratorError(Exception):
@@ -32,8 +36,7 @@ class VirtualPhaseSpaceGenerator(object):
         self.pdf = pdf
         self.pdf_active = pdf_active
         self.tau = tau
-        if pdf_active:
-            raise NotImplementedError("pdf_active=True needs LHAPDF; only the pdf-inactive path is built")
+        self._pdf_grids = {}
 
     def generateKinematics(self, E_cm, random_variables):
         raise NotImplementedError
@@ -71,6 +74,30 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
             return norm * torch.pow(E_cm ** 2, n - 2)
         return norm * math.pow(E_cm ** 2, n - 2)
 
+    def nDimInput(self):
+        """Columns of the uniforms handed to generateKinematics_batch: nDimPhaseSpace() + 2 in pdf-active mode (:159)."""
+        return self.nDimPhaseSpace() + (2 if self.pdf_active else 0)
+
+    def _pdf_desc(self, d, E_cm, pdgs, dev):
+        """Parton-density part of the descriptor (:157-187).  Returns the device grids (kept alive by the caller)."""
+        d.pdf_active, d.tau_mode = 1, 1 if self.tau else 0
+        tot = float(torch.sum(self.masses_t))
+        d.tau_min = (max(tot, self.absolute_Ecm_min) / float(E_cm)) ** 2          # :163-164
+        d.x_cut = X_CUT
+        keep = []
+        for i, pdg in enumerate(pdgs[:2]):
+            if self.pdf is None or not is_parton(pdg):                           # get_pdfQ2 :124-128 -> density 1
+                d.pdf_grid[i] = None
+                continue
+            if pdg not in self._pdf_grids:
+                self._pdf_grids[pdg] = PdfGrid(self.pdf, pdg)
+            g = self._pdf_grids[pdg]
+            t = g.on(dev)
+            keep.append(t)
+            d.pdf_grid[i] = t.data_ptr()
+            d.pdf_nodes, d.pdf_lnx_lo = g.n_nodes, g.lnx_lo
+        return keep
+
     def _desc(self, E_cm, pT_mincut, delR_mincut, rap_maxcut):
         d = _cabi.NisRamboDesc()
         d.n_final = self.n_final
@@ -85,6 +112,8 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
                                  pdgs=[0, 0], return_cutmask=False, momenta=True):
         """r[B, 3 n_final - 4] uniforms -> (momenta[B, 2+n_final, 4] float64 in the CM frame, weight[B]
         float64 = flat weight x massive Jacobian x cuts / (2 s))  (flat_phase_space_generator.py:139-308).
+        In pdf-active mode r has two more columns (tau, y_cm; or x2, x1 with ``tau=False``), ``pdgs`` name the two
+        partons, and the weight also carries the sampling Jacobian, both parton densities and the x cut (:157-187).
 
         Extras over the reference signature: ``return_cutmask`` appends the uint8 pass mask,
         ``momenta=False`` skips writing the momenta (weight-only mode) and returns None for them.
@@ -96,9 +125,10 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
         self.collider_energy = E_cm
         if self.check_nan and torch.isnan(r).any():
             raise PhaseSpaceGeneratorError("Some of the random variables passed to the phase-space generator are NaN")
-        assert r.dim() == 2 and r.shape[1] == self.nDimPhaseSpace()
+        assert r.dim() == 2 and r.shape[1] == self.nDimInput()
         if torch.is_tensor(E_cm):
-            raise NotImplementedError("per-event E_cm belongs to the PDF path, which is not built")
+            raise TypeError("E_cm is the (scalar) collider energy; the per-event partonic energy sqrt(x1 x2) E_cm "
+                            "is formed inside the kernel in pdf-active mode")
         lib = _cabi.lib()
         home = r.device
         dev = home if home.type == "cuda" else self.masses_t.device
@@ -109,6 +139,7 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
             rd = rd.clone()
         B = rd.shape[0]
         desc = self._desc(E_cm, pT_mincut, delR_mincut, rap_maxcut)
+        grids = self._pdf_desc(desc, E_cm, pdgs, dev) if self.pdf_active else None      # noqa: F841 (keeps the grids alive)
         with torch.cuda.device(dev):
             mom = torch.empty(B, 2 + self.n_final, 4, dtype=torch.double, device=dev) if momenta else None
             weight = torch.empty(B, dtype=torch.double, device=dev)

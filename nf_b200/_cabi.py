@@ -47,7 +47,10 @@ class NisRamboDesc(ctypes.Structure):
                 ("initial_masses", ctypes.c_double * 2),
                 ("final_masses", ctypes.c_double * NIS_MAX_FINAL),
                 ("E_cm", ctypes.c_double), ("pT_mincut", ctypes.c_double),
-                ("delR_mincut", ctypes.c_double), ("rap_maxcut", ctypes.c_double)]
+                ("delR_mincut", ctypes.c_double), ("rap_maxcut", ctypes.c_double),
+                ("pdf_active", ctypes.c_int32), ("tau_mode", ctypes.c_int32),
+                ("tau_min", ctypes.c_double), ("x_cut", ctypes.c_double),
+                ("pdf_grid", ctypes.c_void_p * 2), ("pdf_nodes", ctypes.c_int32), ("pdf_lnx_lo", ctypes.c_double)]
 
 
 _P = ctypes.c_void_p

@@ -13,7 +13,7 @@ template <typename RT>
 __global__ void __launch_bounds__(RAMBO_NT) rambo_kernel(const __grid_constant__ RamboConst C, const RT* __restrict__ r,
                                                          double* __restrict__ momenta, double* __restrict__ weight,
                                                          uint8_t* __restrict__ cutmask, long long B) {
-    const int ND = 3 * C.n - 4;             // uniforms per event
+    const int ND = 3 * C.n - 4 + (C.pdf_active ? 2 : 0);    // uniforms per event
     const int NDP = ND | 1;                 // odd row stride (doubles): conflict-free per-thread rows
     const int NM = (C.n + 2) * 4;           // momentum components per event
     const int NMP = NM | 1;
@@ -52,8 +52,11 @@ __global__ void __launch_bounds__(RAMBO_NT) rambo_kernel(const __grid_constant__
             }
             double w;
             uint8_t pass;
-            if (kin) rambo_event<true>(C, row, 1, mo + tid * NMP, 1, w, pass);
-            else rambo_event<false>(C, row, 1, mo + tid * NMP, 1, w, pass);
+            if (C.pdf_active) {
+                if (kin) rambo_event<true, true>(C, row, 1, mo + tid * NMP, 1, w, pass);
+                else rambo_event<false, true>(C, row, 1, mo + tid * NMP, 1, w, pass);
+            } else if (kin) rambo_event<true, false>(C, row, 1, mo + tid * NMP, 1, w, pass);
+            else rambo_event<false, false>(C, row, 1, mo + tid * NMP, 1, w, pass);
             weight[base + tid] = w;
             if (cutmask) cutmask[base + tid] = pass;
         }
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(RAMBO_NT) rambo_kernel(const __grid_constant__
 template <typename RT>
 static int rambo_launch(const RamboConst& C, const void* r, double* momenta, double* weight, uint8_t* cutmask,
                         long long B, cudaStream_t s) {
-    const int NDP = (3 * C.n - 4) | 1, NMP = ((C.n + 2) * 4) | 1;
+    const int NDP = (3 * C.n - 4 + (C.pdf_active ? 2 : 0)) | 1, NMP = ((C.n + 2) * 4) | 1;
     const size_t smem = sizeof(double) * RAMBO_NT * (NDP + NMP);
     cudaFuncSetAttribute(rambo_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long long ntiles = (B + RAMBO_NT - 1) / RAMBO_NT;

@@ -74,6 +74,14 @@ struct RamboConst {
     double cos_dR;                // cos(min(dR_min, pi))
     int dR_ge_pi;                 // dR_min >= pi: the d-phi quick reject never fires
     double u_one[NIS_MAX_FINAL];  // u_one[e]: what the reference's lattice bisection returns for r == 1
+    // parton-density mode (flat_phase_space_generator.py:157-187): per-event partonic energy
+    int pdf_active, tau_mode;
+    double E_coll, tau_min, x_cut;
+    double flat_norm;             // (2 pi)^(4-3n) (pi/2)^(n-1) / ((n-1)! (n-2)!)
+    double m_in2[2];              // squared beam masses (0, 0 when either beam is massless, :415)
+    const double* pdf_grid[2];
+    int pdf_nodes;
+    double pdf_lnx_lo, pdf_inv_h;
 };
 
 // The reference's root finder (flat_phase_space_generator.py:333-348) never returns u = 0 or u = 1:
@@ -113,9 +121,21 @@ static inline int rambo_fill_const(const NisRamboDesc* d, RamboConst* C) {
     double fact1 = 1.0, fact2 = 1.0;
     for (int i = 2; i <= n - 1; ++i) fact1 *= i;
     for (int i = 2; i <= n - 2; ++i) fact2 *= i;
+    C->flat_norm = pow(2 * NIS_PI, 4 - 3 * n) * pow(NIS_PI / 2.0, n - 1) / (fact1 * fact2);
     const double flat = pow(2 * NIS_PI, 4 - 3 * n) * pow(NIS_PI / 2.0, n - 1) * (pow(E * E, n - 2) / (fact1 * fact2));
     C->wconst = flat * pow(C->K0 / E, 2 * n - 4) / (2.0 * E * E);   // :403, :307-308 (M_0 = E_cm)
+    C->pdf_active = d->pdf_active != 0; C->tau_mode = d->tau_mode != 0;
+    C->E_coll = E; C->tau_min = d->tau_min; C->x_cut = d->x_cut;
+    C->pdf_grid[0] = d->pdf_grid[0]; C->pdf_grid[1] = d->pdf_grid[1];
+    C->pdf_nodes = d->pdf_nodes; C->pdf_lnx_lo = d->pdf_lnx_lo;
+    C->pdf_inv_h = d->pdf_nodes > 1 ? (double)(d->pdf_nodes - 1) / (0.0 - d->pdf_lnx_lo) : 0.0;
+    if (C->pdf_active) {
+        if ((d->pdf_grid[0] || d->pdf_grid[1]) && (d->pdf_nodes < 4 || !(d->pdf_lnx_lo < 0.0))) return NIS_EINVAL;
+        if (C->tau_mode && !(d->tau_min > 0.0 && d->tau_min < 1.0)) return NIS_EINVAL;
+    }
     const double m1 = d->initial_masses[0], m2 = d->initial_masses[1];
+    C->m_in2[0] = (m1 == 0.0 || m2 == 0.0) ? 0.0 : m1 * m1;
+    C->m_in2[1] = (m1 == 0.0 || m2 == 0.0) ? 0.0 : m2 * m2;
     if (m1 == 0.0 || m2 == 0.0) {                                    // :415-419
         const double b[2][4] = {{E / 2.0, 0.0, 0.0, E / 2.0}, {E / 2.0, 0.0, 0.0, -E / 2.0}};
         for (int i = 0; i < 8; ++i) C->beam[i / 4][i % 4] = b[i / 4][i % 4];
@@ -218,6 +238,22 @@ NIS_DEV double rambo_root(int e, double r, double u_one) {
 
 NIS_DEV double rambo_root_dyn(int e, double r) { return rambo_root(e, r, rambo_lattice_at_one(e)); }
 
+// x f(x) from the caller's grid (nodes uniform in ln x over [lnx_lo, 0]) by 4-point Lagrange interpolation in ln x,
+// divided by x: the density get_pdfQ2 returns (flat_phase_space_generator.py:120-137).  NULL grid: 1.
+NIS_DEV double rambo_pdf_density(const double* grid, int nodes, double lnx_lo, double inv_h, double x) {
+    if (!grid) return 1.0;
+    double t = log(x);
+    t = t < lnx_lo ? lnx_lo : (t > 0.0 ? 0.0 : t);
+    const double s = (t - lnx_lo) * inv_h;
+    int i = (int)s;
+    i = i < 1 ? 1 : (i > nodes - 3 ? nodes - 3 : i);
+    const double f = s - (double)i;                             // in [0,1) inside the table, up to +-1 at its ends
+    const double ym = grid[i - 1], y0 = grid[i], y1 = grid[i + 1], y2 = grid[i + 2];
+    const double v = -f * (f - 1.0) * (f - 2.0) * (1.0 / 6.0) * ym + (f + 1.0) * (f - 1.0) * (f - 2.0) * 0.5 * y0
+                     - (f + 1.0) * f * (f - 2.0) * 0.5 * y1 + (f + 1.0) * f * (f - 1.0) * (1.0 / 6.0) * y2;
+    return v / x;
+}
+
 // One event, runtime multiplicity n = C.n.  r: 3n-4 uniforms at stride rs.  mo: scratch AND output row of
 // (n+2)*4 doubles at stride ms (beams, final-state momenta; the two beam slots double as scratch for
 // exp(2 eta_j) until the end).
@@ -237,11 +273,39 @@ NIS_DEV double rambo_root_dyn(int e, double r) { return rambo_root(e, r, rambo_l
 // All differences to the reference are at float64 rounding level (tests: momenta / weights rtol 1e-9,
 // cut masks bit-exact on the golden vectors).
 // KIN = false (weight-only call without cuts): only the intermediate masses and the reweighting run.
-template <bool KIN>
+// PDF = true: two more uniforms sample the Bjorken x; the event is generated at E = sqrt(x1 x2) E_coll, the cuts see the
+// lab frame (:157-187, 213-219, 283).
+template <bool KIN, bool PDF>
 NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* mo, int ms, double& weight,
                          uint8_t& pass) {
     const int n = C.n;
-    double Kj = C.K0, Mj = Kj + C.msum[0];
+    double K0 = C.K0, wconst = C.wconst, E = C.E_coll, x1 = 1.0, x2 = 1.0;
+    if (PDF) {
+        const double ra = r[(3 * n - 4) * rs], rb = r[(3 * n - 3) * rs];
+        double jac = 1.0, rt;
+        if (C.tau_mode) {                                       // :161-176, uniform_distr utils.py:124-132
+            const double tau = C.tau_min + (1.0 - C.tau_min) * ra;
+            const double ymin = 0.5 * log(tau);
+            const double ycm = ymin + (-ymin - ymin) * rb;
+            rt = sqrt(tau);
+            const double ey = exp(ycm);
+            x1 = rt * ey; x2 = rt / ey;
+            jac = (1.0 - C.tau_min) * (-ymin - ymin);
+        } else {                                                // :177-182
+            x1 = rb; x2 = ra;
+            rt = sqrt(x1 * x2);
+        }
+        E = rt * C.E_coll;
+        const double xc = (x1 < C.x_cut || x2 < C.x_cut) ? 0.0 : 1.0;      // :185-186
+        jac *= rambo_pdf_density(C.pdf_grid[0], C.pdf_nodes, C.pdf_lnx_lo, C.pdf_inv_h, x1)
+               * rambo_pdf_density(C.pdf_grid[1], C.pdf_nodes, C.pdf_lnx_lo, C.pdf_inv_h, x2) * xc;
+        K0 = E - C.msum[0];
+        double e2p = 1.0, kp = 1.0;                             // (E^2)^(n-2), (K0/E)^(2n-4)  (:95-97, :403)
+        const double E2 = E * E, k2 = (K0 / E) * (K0 / E);
+        for (int i = 0; i < n - 2; ++i) { e2p *= E2; kp *= k2; }
+        wconst = C.flat_norm * e2p * kp * jac / (2.0 * (x1 * x2 * (C.E_coll * C.E_coll)));   // :306-308
+    }
+    double Kj = K0, Mj = Kj + C.msum[0];
     double num = 1.0, den = 1.0;
     double Q0 = Mj, Q1 = 0.0, Q2 = 0.0, Q3 = 0.0;
 #pragma unroll 1
@@ -282,7 +346,7 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
         Q1 -= p1; Q2 -= p2; Q3 -= p3; Q0 -= e;                  // :271-275
         Kj = Kn; Mj = Mn;
     }
-    const double w = C.wconst * nis_div(num, den);
+    const double w = wconst * nis_div(num, den);
     if (!KIN) { pass = 1; weight = w; return; }
     {
         double* o = mo + (n + 1) * 4 * ms;                      // :278
@@ -290,6 +354,25 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
     }
     // ---- cuts (:285-301); x1 = x2 = 1 so the lab frame is the CM frame -------------------------
     bool ok = true;
+    // lab frame (boost_to_lab_frame utils.py:134-146): the beams' x1 p1 + x2 p2 moves along z with beta; only p_z
+    // enters the cuts (pT and d-phi are invariant): p_z' = gamma (p_z + beta E).  The reference skips the boost for the
+    // WHOLE batch when any event has beta = 0 (x1 == x2); here every event is boosted by its own beta (identity then).
+    double lb_g = 1.0, lb_gb = 0.0;
+    if (PDF) {
+        double e1, e2_, z;
+        if (C.m_in2[0] == 0.0 && C.m_in2[1] == 0.0) { e1 = 0.5 * E; e2_ = e1; z = e1; }
+        else {
+            const double E2 = E * E, M1 = C.m_in2[0], M2 = C.m_in2[1];
+            e1 = 0.5 * (E2 + M1 - M2) / E; e2_ = 0.5 * (E2 - M1 + M2) / E;
+            z = 0.5 * sqrt(E2 * E2 - 2 * E2 * M1 - 2 * E2 * M2 + M1 * M1 - 2 * M1 * M2 + M2 * M2) / E;
+        }
+        const double r0 = x1 * e1 + x2 * e2_, rz = (x1 - x2) * z;
+        if (rz != 0.0) {
+            const double beta = rz / r0;
+            lb_g = 1.0 / sqrt(1.0 - beta * beta);
+            lb_gb = lb_g * beta;
+        }
+    }
     const double* fin = mo + 8 * ms;                            // final-state particle j at fin + 4*j*ms
     double* e2 = mo;                                            // exp(2 eta_j), j < n <= 8 (beam slots)
     const bool need_eta = C.rap_max > 0.0 || C.dR_min > 0.0;
@@ -297,7 +380,8 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
         double pt2min = NIS_HUGE, e2max = 0.0;
 #pragma unroll 1
         for (int j = 0; j < n; ++j) {
-            const double px = fin[(4 * j + 1) * ms], py = fin[(4 * j + 2) * ms], pz = fin[(4 * j + 3) * ms];
+            const double px = fin[(4 * j + 1) * ms], py = fin[(4 * j + 2) * ms];
+            const double pz = PDF ? lb_g * fin[(4 * j + 3) * ms] + lb_gb * fin[4 * j * ms] : fin[(4 * j + 3) * ms];
             const double pt2 = px * px + py * py;
             pt2min = fmin(pt2min, pt2);
             if (need_eta) {
@@ -368,8 +452,20 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
             }
         }
     }
+    if (PDF) {                                                  // setInitialStateMomenta_batch with a tensor E_cm, :420-441
+        double e1, e2_, z;
+        if (C.m_in2[0] == 0.0 && C.m_in2[1] == 0.0) { e1 = 0.5 * E; e2_ = e1; z = e1; }
+        else {
+            const double E2 = E * E, M1 = C.m_in2[0], M2 = C.m_in2[1];
+            e1 = 0.5 * (E2 + M1 - M2) / E; e2_ = 0.5 * (E2 - M1 + M2) / E;
+            z = 0.5 * sqrt(E2 * E2 - 2 * E2 * M1 - 2 * E2 * M2 + M1 * M1 - 2 * M1 * M2 + M2 * M2) / E;
+        }
+        mo[0] = e1; mo[ms] = 0.0; mo[2 * ms] = 0.0; mo[3 * ms] = z;
+        mo[4 * ms] = e2_; mo[5 * ms] = 0.0; mo[6 * ms] = 0.0; mo[7 * ms] = -z;
+    } else {
 #pragma unroll 1
-    for (int i = 0; i < 8; ++i) mo[i * ms] = C.beam[i >> 2][i & 3];
+        for (int i = 0; i < 8; ++i) mo[i * ms] = C.beam[i >> 2][i & 3];
+    }
     pass = ok ? 1 : 0;
     weight = ok ? w : 0.0;
 }

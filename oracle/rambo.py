@@ -224,19 +224,24 @@ def generate_kinematics(E_cm, r, initial_masses, final_masses,
         Qs = Q[:, 1:] - p[:, 1:]
         Q = torch.cat((torch.sqrt((Qs ** 2).sum(-1) + Mx[:, j + 1] ** 2).unsqueeze(1), Qs), -1)  # :271-275
     out[:, -1] = Q                                                   # :278
-    # (7) beams, :408-441
+    # (7) beams, :408-441 (per event when E_cm is a tensor)
     m1, m2 = float(initial_masses[0]), float(initial_masses[1])
+    Ev = E_cm if torch.is_tensor(E_cm) else torch.full((B,), float(E_cm), dtype=torch.float64)
+    zero = torch.zeros_like(Ev)
     if m1 == 0.0 or m2 == 0.0:
-        out[:, 0] = torch.tensor([E_cm / 2.0, 0.0, 0.0, +E_cm / 2.0], dtype=torch.float64)
-        out[:, 1] = torch.tensor([E_cm / 2.0, 0.0, 0.0, -E_cm / 2.0], dtype=torch.float64)
+        out[:, 0] = torch.stack((Ev / 2.0, zero, zero, Ev / 2.0), -1)
+        out[:, 1] = torch.stack((Ev / 2.0, zero, zero, -Ev / 2.0), -1)
     else:
         M1, M2 = m1 ** 2, m2 ** 2
-        E1 = (E_cm ** 2 + M1 - M2) / E_cm
-        E2 = (E_cm ** 2 - M1 + M2) / E_cm
-        Z = math.sqrt(E_cm ** 4 - 2 * E_cm ** 2 * M1 - 2 * E_cm ** 2 * M2 + M1 ** 2 - 2 * M1 * M2 + M2 ** 2) / E_cm
-        out[:, 0] = torch.tensor([E1 / 2.0, 0.0, 0.0, +Z / 2.0], dtype=torch.float64)
-        out[:, 1] = torch.tensor([E2 / 2.0, 0.0, 0.0, -Z / 2.0], dtype=torch.float64)
-    # (8) cuts on the final state (x1=x2=1: boost_to_lab_frame is the identity, utils.py:134-146)
+        E1 = (Ev ** 2 + M1 - M2) / Ev
+        E2 = (Ev ** 2 - M1 + M2) / Ev
+        Z = torch.sqrt(Ev ** 4 - 2 * Ev ** 2 * M1 - 2 * Ev ** 2 * M2 + M1 ** 2 - 2 * M1 * M2 + M2 ** 2) / Ev
+        out[:, 0] = torch.stack((E1 / 2.0, zero, zero, Z / 2.0), -1)
+        out[:, 1] = torch.stack((E2 / 2.0, zero, zero, -Z / 2.0), -1)
+    cm = out                                                         # returned: the CM-frame clone (:282,:308)
+    if pdf_active:
+        out = lab_boost(out, xb_1, xb_2)                             # :283
+    # (8) cuts on the (lab-frame) final state; pdf inactive: x1 = x2 = 1 and boost_to_lab_frame is the identity
     fin = out[:, 2:]
     ptmin = torch.sqrt(fin[:, :, 1] ** 2 + fin[:, :, 2] ** 2).abs().min(1).values
     cut = torch.where(ptmin < pT_mincut, torch.zeros_like(w), torch.ones_like(w))     # :285-288
@@ -249,7 +254,7 @@ def generate_kinematics(E_cm, r, initial_masses, final_masses,
         cut = cut * torch.where(rap_maxcut < _pseudorap(fin).max(1).values.abs(),
                                 torch.zeros_like(w), torch.ones_like(w))
     # (9) :304-308
-    weight = w * cut / (2.0 * E_cm ** 2)
+    weight = w * cut / (2.0 * (xb_1 * xb_2 * collider_energy ** 2))   # shat = x1 x2 s
     if return_parts:
-        return out, weight, w, cut
-    return out, weight
+        return cm, weight, w, cut
+    return cm, weight

@@ -58,6 +58,11 @@ RAMBO_CASES = ["m4_cuts", "m4_nocuts", "m0_4", "m2", "mixed3", "m5_cuts", "m0_6"
 RAMBO_EDGE_CASES = [t + c for t in ("edge0_", "edge1_") for c in ("m0_4", "m4", "m4_cuts", "m0_4_cuts", "m5", "m0_3")]
 
 
+# pdf-active phase space (tau / y_cm or x1, x2 sampling, per-event E_cm, lab boost before the cuts), dumped from the
+# reference with the analytic stand-in PDF of tests/pdf_stub.py
+RAMBO_PDF_CASES = ["pdf_tau_m0_3", "pdf_tau_m4", "pdf_x_m0_4", "pdf_x_m3_nocuts", "pdf_tau_nopdf"]
+
+
 def rambo_edge_rows(ref_mom, r, n_final):
     """Rows of an edge fixture on which momenta / cut decisions are comparable with the reference's.  The
     reference boosts with gamma = 1/sqrt(1 - beta^2) (utils.py:66-81), which loses eps * gamma^2 and overflows for a

@@ -229,6 +229,29 @@ def rambo_edge_case(name, initial, final, E_cm, seed, with_zero, **cuts):
           int((~torch.isfinite(mom).all(-1).all(-1)).sum()))
 
 
+def rambo_pdf_case(name, initial, final, E_cm, B, seed, tau, pdgs, **cuts):
+    """pdf-active phase space (flat_phase_space_generator.py:157-187, 213-219, 283): the reference needs `import
+    lhapdf` only to construct (:37-38) and then calls ``pdf.xfxQ2`` - an empty module of that name and the analytic
+    stand-in of tests/pdf_stub.py let it run unmodified."""
+    import types
+    sys.modules.setdefault("lhapdf", types.ModuleType("lhapdf"))
+    sys.path.insert(0, os.path.dirname(HERE))
+    from pdf_stub import StubPdf
+    gen = FlatInvertiblePhasespace(initial, final, pdf=StubPdf(), pdf_active=True, tau=tau)
+    g = torch.Generator().manual_seed(seed)
+    r = torch.rand(B, gen.nDimPhaseSpace() + 2, generator=g, dtype=torch.float64)
+    if not tau:
+        # the last two columns ARE x2, x1: keep sqrt(x1 x2) E_cm above the final-state masses
+        lo = (sum(final) / E_cm) ** 2 + 0.02
+        r[:, -2:] = lo ** 0.5 + (1.0 - lo ** 0.5) * r[:, -2:]
+    mom, w = gen.generateKinematics_batch(E_cm, r.clone(), pdgs=list(pdgs), **cuts)
+    assert bool(torch.isfinite(w).all())
+    meta = dict(name=name, initial=initial, final=final, E_cm=E_cm, B=B, seed=seed, cuts=cuts, tau=tau, pdgs=list(pdgs))
+    np.savez_compressed(os.path.join(HERE, "rambo_%s.npz" % name), r=r.numpy(), momenta=mom.numpy(),
+                        weight=w.numpy(), meta=np.array(json.dumps(meta)))
+    print("rambo", name, "pass fraction", float((w != 0).double().mean()), "w range", float(w.min()), float(w.max()))
+
+
 class FakeRun:
     """Stand-in for the Sacred run object the reference logs to (manager.py:89-93,197-198,286-288)."""
     _id = "run"
@@ -308,6 +331,12 @@ if __name__ == "__main__":
             rambo_edge_case(t + "_m0_4_cuts", [0.0] * 2, [0.0] * 4, 1000.0, 64, z, **cuts)
             rambo_edge_case(t + "_m5", [50.0, 100.0], [10.0, 20.0, 30.0, 40.0, 50.0], 2000.0, 65, z)
             rambo_edge_case(t + "_m0_3", [0.0] * 2, [0.0, 0.0, 0.0], 500.0, 66, z)
+    if "rambo_pdf" in what or "rambo" in what:
+        rambo_pdf_case("pdf_tau_m0_3", [0.0] * 2, [0.0] * 3, 13000.0, 256, 71, True, (21, 2), **cuts)
+        rambo_pdf_case("pdf_tau_m4", [0.938, 0.938], [10.0, 20.0, 30.0, 40.0], 13000.0, 256, 72, True, (2, -1), **cuts)
+        rambo_pdf_case("pdf_x_m0_4", [0.0] * 2, [0.0] * 4, 13000.0, 256, 73, False, (21, 21), **cuts)
+        rambo_pdf_case("pdf_x_m3_nocuts", [0.0] * 2, [0.0, 80.4, 91.2], 1000.0, 192, 74, False, (1, -1))
+        rambo_pdf_case("pdf_tau_nopdf", [0.0] * 2, [0.0] * 4, 13000.0, 128, 75, True, (0, 22), pT_mincut=20, delR_mincut=-1, rap_maxcut=2.5)
     if "train" in what:
         train_case("a", 41, 40, 2000, 1000, preburn_time=10, kill_counter=7)
         train_case("b", 42, 60, 2000, 1000, preburn_time=5, kill_counter=1)

@@ -34,9 +34,9 @@ int host_rambo(const NisRamboDesc* d, long long B, const double* r, double* mom,
     RamboConst C;
     int rc = rambo_fill_const(d, &C);
     if (rc) return rc;
-    const int n = d->n_final, nd = 3 * n - 4, nm = (n + 2) * 4;
+    const int n = d->n_final, nd = 3 * n - 4 + (d->pdf_active ? 2 : 0), nm = (n + 2) * 4;
     double scratch[(NIS_MAX_FINAL + 2) * 4];
-    for (long long i = 0; i < B; ++i) rambo_event<true>(C, r + i * nd, 1, mom ? mom + i * nm : scratch, 1, w[i], pass[i]);
+    for (long long i = 0; i < B; ++i) { if (C.pdf_active) rambo_event<true, true>(C, r + i * nd, 1, mom ? mom + i * nm : scratch, 1, w[i], pass[i]); else rambo_event<true, false>(C, r + i * nd, 1, mom ? mom + i * nm : scratch, 1, w[i], pass[i]); }
     return 0;
 }
 

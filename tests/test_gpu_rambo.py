@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import RAMBO_CASES, RAMBO_EDGE_CASES, rambo_edge_rows, rambo_edge_weight_rtol
+from conftest import RAMBO_CASES, RAMBO_EDGE_CASES, RAMBO_PDF_CASES, rambo_edge_rows, rambo_edge_weight_rtol
 from oracle import rambo as orambo
 
 from nf_b200.PhaseSpace.flat_phase_space_generator import FlatInvertiblePhasespace
@@ -55,6 +55,40 @@ def test_ends_of_the_unit_interval_match_reference(golden, case):
     same = (r32 == g.t("r")).all(1).numpy()
     assert np.isfinite(w32.cpu().numpy()).all()
     assert np.array_equal(w32.cpu().numpy()[same], w[same])
+
+
+@pytest.mark.parametrize("case", RAMBO_PDF_CASES)
+def test_pdf_active_matches_reference(golden, case):
+    """pdf-active phase space through the public API (same constructor arguments as the reference, any object with
+    ``xfxQ2``): vectors dumped from the reference with the stand-in PDF of tests/pdf_stub.py.  Cut masks bit-exact
+    (the cuts act on lab-frame momenta), CM-frame momenta to 1e-9, weights to 1e-7 (densities are interpolated)."""
+    from pdf_stub import StubPdf
+    g = golden("rambo_" + case)
+    m = g.meta
+    ps = FlatInvertiblePhasespace(m["initial"], m["final"], pdf=StubPdf(), pdf_active=True, tau=m["tau"])
+    assert ps.nDimInput() == g["r"].shape[1]
+    mom, w, mask = ps.generateKinematics_batch(m["E_cm"], g.t("r").cuda(), pdgs=m["pdgs"], return_cutmask=True, **m["cuts"])
+    ref_w, ref_mom = g.t("weight"), g.t("momenta")
+    assert np.array_equal(mask.cpu().numpy().astype(bool), (ref_w != 0).numpy()), "cut mask must be bit-exact"
+    assert torch.allclose(mom.cpu(), ref_mom, rtol=1e-9, atol=1e-9 * m["E_cm"])
+    assert torch.allclose(w.cpu(), ref_w, rtol=1e-7, atol=1e-12 * float(ref_w.abs().max()))
+    # weight-only mode and float32 uniforms run the same events
+    _, w2 = ps.generateKinematics_batch(m["E_cm"], g.t("r").cuda(), pdgs=m["pdgs"], momenta=False, **m["cuts"])
+    assert torch.equal(w2, w)
+
+
+def test_pdf_active_at_size_matches_oracle():
+    from pdf_stub import StubPdf
+    B = 1 << 15
+    r = torch.rand(B, 10, generator=torch.Generator().manual_seed(8), dtype=torch.float64)
+    cuts = dict(pT_mincut=20, delR_mincut=0.4, rap_maxcut=2.5)
+    ps = FlatInvertiblePhasespace([0.0] * 2, [0.0, 0.0, 80.4, 91.2], pdf=StubPdf(), pdf_active=True, tau=True)
+    mom, w, mask = ps.generateKinematics_batch(13000.0, r.cuda(), pdgs=[21, 2], return_cutmask=True, **cuts)
+    rmom, rw = orambo.generate_kinematics(13000.0, r, [0.0] * 2, [0.0, 0.0, 80.4, 91.2], pdf=StubPdf(), pdf_active=True,
+                                          tau=True, pdgs=[21, 2], **cuts)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), (rw != 0).numpy())
+    assert torch.allclose(mom.cpu(), rmom, rtol=1e-8, atol=1e-6)
+    assert torch.allclose(w.cpu(), rw, rtol=1e-7, atol=1e-12 * float(rw.abs().max()))
 
 
 def test_float32_uniforms_and_weight_only_mode():

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import RAMBO_CASES, RAMBO_EDGE_CASES, ROOT, rambo_edge_rows, rambo_edge_weight_rtol
+from conftest import RAMBO_CASES, RAMBO_EDGE_CASES, RAMBO_PDF_CASES, ROOT, rambo_edge_rows, rambo_edge_weight_rtol
 from oracle import rambo as orambo
 
 SRC = os.path.join(ROOT, "tests", "host", "host_math.cpp")
@@ -148,7 +148,10 @@ def test_rambo_root_solves_the_mass_polynomial(host, e):
 class RamboDesc(ctypes.Structure):
     _fields_ = [("n_final", ctypes.c_int32), ("initial_masses", ctypes.c_double * 2),
                 ("final_masses", ctypes.c_double * 8), ("E_cm", ctypes.c_double), ("pT_mincut", ctypes.c_double),
-                ("delR_mincut", ctypes.c_double), ("rap_maxcut", ctypes.c_double)]
+                ("delR_mincut", ctypes.c_double), ("rap_maxcut", ctypes.c_double),
+                ("pdf_active", ctypes.c_int32), ("tau_mode", ctypes.c_int32),
+                ("tau_min", ctypes.c_double), ("x_cut", ctypes.c_double),
+                ("pdf_grid", ctypes.c_void_p * 2), ("pdf_nodes", ctypes.c_int32), ("pdf_lnx_lo", ctypes.c_double)]
 
 
 @pytest.mark.parametrize("case", RAMBO_CASES)
@@ -209,3 +212,39 @@ def test_rambo_event_on_the_ends_of_the_unit_interval(host, golden, case):
     assert np.isfinite(rt[cmp]).mean() > 0.8
     np.testing.assert_allclose(mom[rows], ref_mom[rows], rtol=1e-9, atol=1e-9 * g.meta["E_cm"])
     assert cmp.sum() >= 0.5 * len(w)
+
+
+@pytest.mark.parametrize("case", RAMBO_PDF_CASES)
+def test_rambo_event_pdf_active_matches_reference(host, golden, case):
+    """The pdf-active path of the kernel source (host build) against vectors dumped from the reference with the stand-in
+    PDF: Bjorken-x sampling, densities from the interpolation grid, per-event energy, lab-frame cuts."""
+    from pdf_stub import StubPdf
+    from nf_b200.PhaseSpace.pdf_grid import PdfGrid, X_CUT, is_parton
+    g = golden("rambo_" + case)
+    m = g.meta
+    n = len(m["final"])
+    cuts = dict(pT_mincut=-1, delR_mincut=-1, rap_maxcut=-1)
+    cuts.update(m["cuts"])
+    d = RamboDesc(n, (ctypes.c_double * 2)(*m["initial"]), (ctypes.c_double * 8)(*(m["final"] + [0.0] * (8 - n))),
+                  m["E_cm"], cuts["pT_mincut"], cuts["delR_mincut"], cuts["rap_maxcut"])
+    d.pdf_active, d.tau_mode = 1, int(m["tau"])
+    d.tau_min, d.x_cut = (max(sum(m["final"]), 1.0) / m["E_cm"]) ** 2, X_CUT
+    grids = []
+    for i, pdg in enumerate(m["pdgs"]):
+        if is_parton(pdg):
+            gr = PdfGrid(StubPdf(), pdg)
+            grids.append(gr.host.numpy())
+            d.pdf_grid[i] = grids[-1].ctypes.data
+            d.pdf_nodes, d.pdf_lnx_lo = gr.n_nodes, gr.lnx_lo
+    r = np.ascontiguousarray(g["r"])
+    B = r.shape[0]
+    mom = np.zeros((B, n + 2, 4))
+    w = np.zeros(B)
+    ok = np.zeros(B, np.uint8)
+    assert host.host_rambo(ctypes.byref(d), ctypes.c_longlong(B), fp(r, D), fp(mom, D), fp(w, D),
+                           ok.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))) == 0
+    ref_w, ref_mom = g["weight"], g["momenta"]
+    assert np.array_equal(ok.astype(bool), ref_w != 0), "cut mask"
+    np.testing.assert_allclose(mom, ref_mom, rtol=1e-9, atol=1e-9 * m["E_cm"])
+    # the densities are interpolated from 16384 nodes in ln x: 1e-8 away from x = 1, where x f ~ (1-x)^b vanishes
+    np.testing.assert_allclose(w, ref_w, rtol=1e-7, atol=1e-12 * np.abs(ref_w).max())

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import RAMBO_EDGE_CASES, FLOW_CASES, GRAD_CASES, RAMBO_CASES
+from conftest import RAMBO_EDGE_CASES, RAMBO_PDF_CASES, FLOW_CASES, GRAD_CASES, RAMBO_CASES
 from oracle import flow as oflow
 from oracle import nis as onis
 from oracle import rambo as orambo
@@ -123,6 +123,21 @@ def test_rambo_edges_match_reference(golden, case):
     assert np.array_equal((w != 0).numpy(), (ref_w != 0).numpy()), "cut mask"
     assert torch.allclose(w, ref_w, rtol=1e-12, atol=0)
     assert torch.allclose(mom, ref_mom, rtol=1e-12, atol=1e-13 * m["E_cm"], equal_nan=True)
+
+
+@pytest.mark.parametrize("case", RAMBO_PDF_CASES)
+def test_rambo_pdf_active_matches_reference(golden, case):
+    """flat_phase_space_generator.py:157-187,213-219,283 with the stand-in PDF: Bjorken x sampling, PDF densities, x
+    cut, per-event E_cm, lab-frame cuts, 1 / (2 x1 x2 s)."""
+    from pdf_stub import StubPdf
+    g = golden("rambo_" + case)
+    m = g.meta
+    mom, w = orambo.generate_kinematics(m["E_cm"], g.t("r"), m["initial"], m["final"], pdf=StubPdf(), pdf_active=True,
+                                        tau=m["tau"], pdgs=m["pdgs"], **m["cuts"])
+    ref_mom, ref_w = g.t("momenta"), g.t("weight")
+    assert np.array_equal((w != 0).numpy(), (ref_w != 0).numpy()), "cut mask"
+    assert torch.allclose(w, ref_w, rtol=1e-12, atol=0)
+    assert torch.allclose(mom, ref_mom, rtol=1e-12, atol=1e-13 * m["E_cm"])
 
 
 def test_rambo_known_answers():
