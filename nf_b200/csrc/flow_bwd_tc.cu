@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_head_kernel(const _
     extern __shared__ char smraw[];
     __shared__ uint64_t a_ready[2], d_ready[2];
     __shared__ uint32_t tmem_base_s;
-    char* sm = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+    char* sm = smem_align1024(smraw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c = A.c;
     const DevCell& q = F.cells[c];
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
     __shared__ uint64_t a_ready, done[2], hdone, acc_ready, acc_free;
     __shared__ uint32_t tmem_base_s;
     __shared__ bool s_last;
-    char* sm = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+    char* sm = smem_align1024(smraw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c = A.c, lam = A.lam;
     const DevCell& q = F.cells[c];

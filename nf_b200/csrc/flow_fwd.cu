@@ -383,7 +383,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
         A.stats_layer = -1;
         A.zin = (tiled && bn_mode == NIS_BN_TRAIN && !(moments && F.depth == 1) && !recompute) ? zb[F.depth & 1] : nullptr;
         A.zout = nullptr;
-        if (tc && bn_mode == NIS_BN_EVAL && nis_tc_split_eval(F)) {
+        if (tc && !hp && bn_mode == NIS_BN_EVAL && nis_tc_split_eval(F)) {
             // eval, PWQuad: hidden layers in one launch (activations of the last hidden layer to HBM), then the final pass
             A.stats_layer = F.depth; A.no_stats = 1; A.zin = nullptr; A.zout = zb[F.depth & 1];
             rc = nis_launch_tc(F, A, ws.tcpack, s);

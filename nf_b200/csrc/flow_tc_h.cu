@@ -25,16 +25,33 @@
 #include "spline.cuh"
 #include "flow_fwd_common.cuh"
 #include "tc_common.cuh"
+#include "tc_spline.cuh"
 
 #define H_SA 8.0f                                  // activation scale before the split (exact power of two)
 #define H_AMAX 65504.0f                            // largest finite fp16
 #define H_HID_BYTES (2 * TCH * TCH * 2)            // hi + lo of a 64x64 layer in fp16: 16 KB
-#define H_OUT_ROWS 128
-#define H_OUT_BYTES (2 * H_OUT_ROWS * TCH * 2)     // hi + lo of the [128 logits x 64] output layer: 32 KB
-#define H_COLS 128                                 // tensor-memory columns per group: D 64 | A_hi 32 | A_lo 32
-#define H_COL_AHI 64
-#define H_COL_ALO 96
 #define H_MAXG 4
+// Output layer as N-wide MMA blocks into the same accumulator columns.  PWLin, 32 bins: N = 64 = two transformed
+// dimensions per block, 128 rows in all; tensor-memory columns per group: D 64 | A_hi 32 | A_lo 32 = 128 -> four groups.
+// PWQuad, 32 bins (65 logits per dimension): N = 80 = one dimension per block (rows 65..79 zero); D 80 | pad 16 |
+// A_hi 32 | A_lo 32 = 160 -> three groups.
+template <int KIND> struct HK {
+    static constexpr int OUT_N = KIND == NIS_KIND_PWLIN ? 64 : 80;          // MMA N of an output block
+    static constexpr int TPER = KIND == NIS_KIND_PWLIN ? 2 : 1;             // transformed dimensions per block
+    static constexpr int SLOT = KIND == NIS_KIND_PWLIN ? 32 : 80;           // rows per dimension
+    static constexpr int COLS = KIND == NIS_KIND_PWLIN ? 128 : 160;
+    static constexpr int COL_AHI = KIND == NIS_KIND_PWLIN ? 64 : 96;
+    static constexpr int COL_ALO = COL_AHI + 32;
+    static constexpr int MAXG = KIND == NIS_KIND_PWLIN ? 4 : 3;
+};
+__host__ __device__ static inline int h_slot(const DevFlow& F) { return F.kind == NIS_KIND_PWLIN ? 32 : 80; }
+__host__ __device__ static inline int h_out_rows(const DevFlow& F) {      // rows of the staged output-layer operand
+    int mt = 1;
+    for (int c = 0; c < F.n_cells; ++c) mt = F.cells[c].T > mt ? F.cells[c].T : mt;
+    const int r = mt * h_slot(F);
+    return F.kind == NIS_KIND_PWLIN ? (r < 128 ? 128 : r) : r;
+}
+__host__ __device__ static inline int h_out_bytes(const DevFlow& F) { return 2 * h_out_rows(F) * TCH * 2; }
 
 // byte offset of (row, k) in a [rows x 64] fp16 K-major operand: 128 B per row, 8-row groups of 1024 B, 16-byte
 // chunks XOR-swizzled with row % 8 (the canonical SWIZZLE_128B layout; one 128-byte row holds all of K = 64)
@@ -47,7 +64,13 @@ __host__ __device__ constexpr uint32_t h_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __host__ __device__ static inline size_t h_cell_bytes(const DevFlow& F) {
-    return (size_t)(F.depth - 1) * H_HID_BYTES + H_OUT_BYTES + 64;      // + the per-layer 1 / (SA * SW) factors
+    return (size_t)(F.depth - 1) * H_HID_BYTES + h_out_bytes(F) + 64;      // + the per-layer 1 / (SA * SW) factors
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 __device__ __forceinline__ void h_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -65,8 +88,8 @@ __global__ void __launch_bounds__(256) flow_h_pack_kernel(DevFlow F, const float
     const DevCell& q = F.cells[c];
     const bool outl = li == F.depth - 1;
     const int l = li + 1;                                            // MMA layer 1..depth (depth = output layer)
-    const float* w = params + q.param_off + F.p_lin(c, l);           // hidden: [64][64]; output: [T*32][64] (out, in)
-    const int rows_src = outl ? q.T * F.K : TCH, rows = outl ? H_OUT_ROWS : TCH;
+    const float* w = params + q.param_off + F.p_lin(c, l);           // hidden: [64][64]; output: [T*K][64] (out, in)
+    const int rows_src = outl ? q.T * F.K : TCH, rows = outl ? h_out_rows(F) : TCH, slot = h_slot(F);
     float m = 0.f;
     for (int i = tid; i < rows_src * TCH; i += 256) m = fmaxf(m, fabsf(w[i]));
 #pragma unroll
@@ -87,7 +110,10 @@ __global__ void __launch_bounds__(256) flow_h_pack_kernel(DevFlow F, const float
     char* lo = hi + (size_t)rows * TCH * 2;
     for (int i = tid; i < rows * TCH; i += 256) {
         const int n = i / TCH, k = i - n * TCH;
-        const float v = n < rows_src ? w[(size_t)n * TCH + k] * SW : 0.f;
+        // staged row n = dimension n / slot, logit n % slot (PWLin: slot = K = 32, the torch row order itself)
+        const int t = outl ? n / slot : 0, jj = outl ? n - t * slot : n;
+        const bool live = outl ? (t < q.T && jj < F.K) : true;
+        const float v = live ? w[(size_t)(outl ? t * F.K + jj : n) * TCH + k] * SW : 0.f;
         const __half h = __float2half_rn(v);
         const int o = h_off(n, k);
         *reinterpret_cast<__half*>(hi + o) = h;
@@ -105,11 +131,11 @@ __host__ __device__ static inline HSmem h_layout(const DevFlow& F, int P, int l_
     int o = 0;
     for (int l = 0; l <= F.depth; ++l) {
         s.wl[l] = -1;
-        if (l >= 1 && l >= l_begin && l <= l_end) { s.wl[l] = o; o += l == F.depth ? H_OUT_BYTES : H_HID_BYTES; }
+        if (l >= 1 && l >= l_begin && l <= l_end) { s.wl[l] = o; o += l == F.depth ? h_out_bytes(F) : H_HID_BYTES; }
     }
     s.w0 = o; o += pad8(P) * TCH * 4;
     s.aff = o; o += (F.depth + 1) * 2 * TCH * 4;
-    s.bias = o; o += H_OUT_ROWS * 4;
+    s.bias = o; o += h_out_rows(F) * 4;
     s.st = o; o += NG * (F.d + 1) * TCM * 4;
     o = (o + 15) & ~15;
     s.sst = o; o += NG * (F.d + 1) * TCM * 4;          // landing zone of the next tile's state rows (bulk copy), per group
@@ -157,21 +183,26 @@ __device__ __forceinline__ void h_issue_block(uint32_t tmem_d, uint32_t t_hi, ui
     for (int ks = 0; ks < 4; ++ks) h_mma_ts(tmem_d, t_hi + ks * 8, tc_desc(w_hi + ks * 32), idesc, 1);
 }
 
-template <int NG>
+// MODE: bit 0 = statistics (layer) pass, bit 1 = the first operand comes from stored activations.  Compile-time, so that
+// every instantiation carries only its own path: the all-in-one kernel was 64 KB of SASS and its four groups, each in
+// another phase, missed the instruction cache (ncu: `no_instruction` 0.8 stalled warps per issue).
+template <int NG, int KIND, int MODE>
 __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_constant__ DevFlow F, const FwdArgs A,
                                                                         const char* __restrict__ hpack) {
     constexpr int NT = NG * TCM;
+    typedef HK<KIND> K_;
+    constexpr int H_COLS = K_::COLS, H_COL_AHI = K_::COL_AHI, H_COL_ALO = K_::COL_ALO;
     extern __shared__ char smraw[];
     __shared__ uint64_t a_ready[NG], d_ready[NG], z_full[NG], s_full[NG];
     __shared__ uint32_t tmem_base_s;
-    char* sm = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+    char* sm = smem_align1024(smraw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c = A.c_begin;
     const DevCell& q = F.cells[c];
     const int d = F.d, depth = F.depth;
     // which slice of the cell this launch computes (same table as flow_tc.cu)
-    const bool stats = A.stats_layer >= 1;
-    const bool from_z = A.zin != nullptr;
+    constexpr bool stats = (MODE & 1) != 0;
+    constexpr bool from_z = (MODE & 2) != 0;
     const int lz = from_z ? (stats ? A.stats_layer - 1 : depth) : 1;      // the first A operand is made of z_{lz}
     const int l_end = stats ? A.stats_layer - 1 : depth;                   // MMA layers lz .. l_end
     const bool zst = from_z || stats;
@@ -186,7 +217,7 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
     // ---- one-time setup: weights, barriers, tensor memory ---------------------------------------------
     for (int l = lz; l <= l_end; ++l) {
         if (L.wl[l] < 0) continue;
-        const int n16 = (l == depth ? H_OUT_BYTES : H_HID_BYTES) / 16;
+        const int n16 = (l == depth ? h_out_bytes(F) : H_HID_BYTES) / 16;
         const uint4* src = reinterpret_cast<const uint4*>(cellpack + (size_t)(l - 1) * H_HID_BYTES);
         uint4* dst = reinterpret_cast<uint4*>(sm + L.wl[l]);
         for (int i = tid; i < n16; i += NT) dst[i] = src[i];
@@ -199,11 +230,17 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
         const int W = l == 0 ? q.P : TCH, Wp = pad8(W);
         const float* s = pk + q.aff_off[l];
         const float f = l == 0 ? 1.f : H_SA;
-        for (int i = tid; i < W; i += NT) { affs[l * 2 * TCH + i] = f * s[i]; affs[l * 2 * TCH + TCH + i] = f * s[Wp + i]; }
+        // a layer fed by the accumulator of the layer below (D = z * SA * SW) takes that factor into its scale
+        const float fs = (l > lz && l <= l_end) ? f * inv_scale[l - 1] : f;
+        for (int i = tid; i < W; i += NT) { affs[l * 2 * TCH + i] = fs * s[i]; affs[l * 2 * TCH + TCH + i] = f * s[Wp + i]; }
     }
-    for (int i = tid; i < H_OUT_ROWS; i += NT) {
-        const int t = i >> 5, jj = i & 31;
-        biass[i] = t < q.T ? pk[q.bo_off + t * F.Kpad + jj] : 0.f;
+    const int out_rows = h_out_rows(F);
+    // PWLin only needs exp(logit - max): the logits are kept in units of log2 (scale and bias carry log2(e)) so that
+    // the exponential is a bare ex2
+    constexpr float LOGIT_UNIT = KIND == NIS_KIND_PWLIN ? 1.4426950408889634f : 1.f;
+    for (int i = tid; i < out_rows; i += NT) {
+        const int t = i / K_::SLOT, jj = i - t * K_::SLOT;
+        biass[i] = (t < q.T && jj < F.K) ? LOGIT_UNIT * pk[q.bo_off + t * F.Kpad + jj] : 0.f;
     }
     if (tid == 0) {
         for (int g = 0; g < NG; ++g) {
@@ -222,11 +259,11 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
     const uint32_t tmem_base = tmem_base_s;
     const long long ntiles = (A.B + TCM - 1) / TCM;
     const long long rowlen = d + 1;
-    const int nblk = (q.T + 1) >> 1;                              // output layer: N = 64 blocks of two transformed dimensions
+    const int nblk = (q.T + K_::TPER - 1) / K_::TPER;            // output layer: MMA blocks of TPER transformed dimensions
     const bool has_out = l_end == depth;
     double dsum = 0.0, dsq = 0.0;
 
-    const uint32_t idesc = h_idesc(TCM, TCH);
+    const uint32_t idesc = h_idesc(TCM, TCH), idesc_out = h_idesc(TCM, K_::OUT_N);
     {
         // ===================== point groups ====================================================
         const int g = warp >> 2, gt = tid & (TCM - 1);
@@ -244,7 +281,7 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
             const long long t0 = (long long)blockIdx.x * NG + g;
             if ((t0 + 1) * TCM <= A.B) bulk_load(sst, A.state_in + t0 * TCM * rowlen, SBYTES, &s_full[g]);
         }
-        const float inv_out = has_out ? inv_scale[depth] : 0.f;
+        const float inv_out = has_out ? LOGIT_UNIT * inv_scale[depth] : 0.f;
         for (long long it = 0;; ++it) {
             const long long tile = ((long long)blockIdx.x + it * gridDim.x) * NG + g;
             if (tile >= ntiles) break;
@@ -285,14 +322,12 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
             float inv_prev = 1.f;                                 // D of the previous layer = z * SA * SW
             for (int l = lz; l <= l_end; ++l) {
                 const float* sc = affs + l * 2 * TCH;
-#pragma unroll
+#pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     float v[32];
                     if (l > lz) {                                 // chained: the accumulator of layer l-1
                         tc_ld32(tg + 32 * h, v);
                         tc_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= inv_prev;
                     } else if (from_z) {                          // stored pre-BN activations
                         const float* zr = zs + (32 * h) * TCM + gt;
 #pragma unroll
@@ -322,7 +357,8 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
                     tc_fence_after();
                     const uint32_t whi = smem_u32(sm + L.wl[l]);
                     const uint32_t tb = tmem_base + g * H_COLS;
-                    h_issue_block(tb, tb + H_COL_AHI, tb + H_COL_ALO, whi, whi + (l == depth ? H_OUT_ROWS : TCH) * TCH * 2, idesc);
+                    h_issue_block(tb, tb + H_COL_AHI, tb + H_COL_ALO, whi, whi + (l == depth ? out_rows : TCH) * TCH * 2,
+                                  l == depth ? idesc_out : idesc);
                     tc_commit(&d_ready[g]);
                 }
                 pa ^= 1;
@@ -340,7 +376,7 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
                     if (gt == 0) bulk_store_wait_read();          // the previous tile's store has read the buffer
                     group_sync(g);
                 }
-#pragma unroll
+#pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     float v[32];
                     tc_ld32(tg + 32 * h, v);
@@ -368,16 +404,17 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
                 group_sync(g);
                 continue;
             }
-            // ---- output layer: N = 64 blocks of two transformed dimensions; PWLin with 32 bins on the thread's logits
-            //      in registers (coupling_cells.py:114-141)
+            // ---- output layer, one MMA block at a time; the splines run on the thread's logits in registers while the
+            //      next block's MMAs execute (the accumulator is released as soon as tcgen05.ld has returned)
             float jfac = 1.f;
             for (int b = 0; b < nblk; ++b) {
                 mbar_wait(&d_ready[g], pd);
                 pd ^= 1;
                 tc_fence_after();
-                float z[64];
+                float z[K_::OUT_N];
                 tc_ld32(tg, z);
                 tc_ld32(tg + 32, z + 32);
+                if (KIND != NIS_KIND_PWLIN) tc_ld16(tg + 64, z + 64);
                 tc_ld_wait();
                 if (b + 1 < nblk) {                  // accumulator consumed: the next block's MMAs may overwrite it
                     tc_fence_before();
@@ -385,38 +422,53 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
                     if (gt == 0) {
                         mbar_wait(&a_ready[g], pa);
                         tc_fence_after();
-                        const uint32_t whi = smem_u32(sm + L.wl[depth]) + (uint32_t)(b + 1) * (TCH * 128);
+                        const uint32_t whi = smem_u32(sm + L.wl[depth]) + (uint32_t)(b + 1) * (K_::OUT_N * 128);
                         const uint32_t tb = tmem_base + g * H_COLS;
-                        h_issue_block(tb, tb + H_COL_AHI, tb + H_COL_ALO, whi, whi + H_OUT_ROWS * TCH * 2, idesc);
+                        h_issue_block(tb, tb + H_COL_AHI, tb + H_COL_ALO, whi, whi + out_rows * TCH * 2, idesc_out);
                         tc_commit(&d_ready[g]);
                     }
                     pa ^= 1;
                 }
+                if (KIND == NIS_KIND_PWLIN) {
+                    // PWLin, 32 bins (coupling_cells.py:114-141): two transformed dimensions per block
 #pragma unroll
-                for (int tt = 0; tt < 2; ++tt) {
-                    const int t = 2 * b + tt;
-                    if (t >= q.T) break;
-                    const float xv = st[q.trafo[t] * TCM];
-                    const float a = xv * 32.f;
-                    int kb = (int)floorf(a);
-                    kb = kb < 0 ? 0 : (kb > 31 ? 31 : kb);
-                    const float alpha = a - (float)kb;
-                    const float* bs = biass + t * 32;
-                    float m = -3.0e38f;
+                    for (int tt = 0; tt < 2; ++tt) {
+                        const int t = 2 * b + tt;
+                        if (t >= q.T) break;
+                        const float xv = st[q.trafo[t] * TCM];
+                        const float a = xv * 32.f;
+                        int kb = (int)floorf(a);
+                        kb = kb < 0 ? 0 : (kb > 31 ? 31 : kb);
+                        const float alpha = a - (float)kb;
+                        const float* bs = biass + t * 32;
+                        float m = -3.0e38f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { z[32 * tt + j] = fmaf(z[32 * tt + j], inv_out, bs[j]); m = fmaxf(m, z[32 * tt + j]); }
-                    float S = 0.f, C = 0.f, ek = 0.f;
+                        for (int j = 0; j < 32; ++j) { z[32 * tt + j] = fmaf(z[32 * tt + j], inv_out, bs[j]); m = fmaxf(m, z[32 * tt + j]); }
+                        float S = 0.f, C = 0.f, ek = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float e = __expf(z[32 * tt + j] - m);
-                        S += e;
-                        C += j < kb ? e : 0.f;
-                        ek = j == kb ? e : ek;
+                        for (int j = 0; j < 32; ++j) {
+                            const float e = ex2_approx(z[32 * tt + j] - m);
+                            S += e;
+                            C += j < kb ? e : 0.f;
+                            ek = j == kb ? e : ek;
+                        }
+                        const float inv = 1.f / S;
+                        st[q.trafo[t] * TCM] = (ek * alpha + C) * inv;
+                        jfac *= ek * inv * 32.f;
+                        if (A.bins && valid) A.bins[((long long)c * A.B + pt) * d + t] = kb;
                     }
-                    const float inv = 1.f / S;
-                    st[q.trafo[t] * TCM] = (ek * alpha + C) * inv;
-                    jfac *= ek * inv * 32.f;
-                    if (A.bins && valid) A.bins[((long long)c * A.B + pt) * d + t] = kb;
+                } else {
+                    // PWQuad, 32 bins (coupling_cells.py:159-228): one transformed dimension per block, 65 logits
+                    const float xv = st[q.trafo[b] * TCM];
+                    const float* bs = biass + b * K_::SLOT;
+#pragma unroll
+                    for (int j = 0; j < 65; ++j) z[j] = fmaf(z[j], inv_out, bs[j]);
+                    float y, f;
+                    int kb;
+                    pwquad32_regs(z, xv, y, f, kb);
+                    st[q.trafo[b] * TCM] = y;
+                    jfac *= f;
+                    if (A.bins && valid) A.bins[((long long)c * A.B + pt) * d + b] = kb;
                 }
             }
             st[d * TCM] *= jfac;
@@ -463,7 +515,7 @@ int64_t nis_tc_min_batch(int64_t dflt);
 static int h_groups(const DevFlow& F) {
     // the largest group count whose three launch shapes fit the shared memory of an SM
     const size_t lim = 226 * 1024;
-    for (int ng = H_MAXG; ng >= 2; --ng) {
+    for (int ng = F.kind == NIS_KIND_PWLIN ? HK<NIS_KIND_PWLIN>::MAXG : HK<NIS_KIND_PWQUAD>::MAXG; ng >= 2; --ng) {
         bool ok = true;
         for (int c = 0; c < F.n_cells && ok; ++c) {
             const int P = F.cells[c].P;
@@ -476,18 +528,20 @@ static int h_groups(const DevFlow& F) {
     return 0;
 }
 
-// Width-64 PWLin cells with 32 bins (BASELINE configs[1]); NIS_TC_H=0 keeps the 3xTF32 kernel (A/B test knob)
+// Width-64 cells with 32 bins: PWLin (BASELINE configs[1]) and PWQuad (configs[3]); NIS_TC_H=0 keeps the 3xTF32 kernel
+// (A/B test knob)
 bool nis_h_supported(const DevFlow& F, int64_t B, int bn_mode) {
     (void)bn_mode;
     const char* off = getenv("NIS_TC_H");
     if (off && off[0] == '0') return false;
     const char* tcoff = getenv("NIS_TC");
     if (tcoff && tcoff[0] == '0') return false;
-    if (F.kind != NIS_KIND_PWLIN || F.K != 32 || F.nb != 32 || F.depth < 1 || F.maxW != TCH) return false;
+    if (F.nb != 32 || F.depth < 1 || F.maxW != TCH) return false;
+    if (F.kind == NIS_KIND_PWLIN ? F.K != 32 : F.K != 65) return false;
     if (B < nis_tc_min_batch(256)) return false;
     for (int l = 0; l < F.depth; ++l) if (F.widths[l] != TCH) return false;
     for (int c = 0; c < F.n_cells; ++c)
-        if (F.cells[c].P > 16 || F.cells[c].T * 32 > H_OUT_ROWS) return false;
+        if (F.cells[c].P > 16 || (F.kind == NIS_KIND_PWLIN && F.cells[c].T * 32 > 128)) return false;
     return h_groups(F) >= 2;
 }
 
@@ -497,19 +551,29 @@ int nis_h_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream_
     return NIS_OK;
 }
 
-template <int NG>
-static int h_launch(const DevFlow& F, const FwdArgs& A, const char* hpack, size_t smem, int sms, cudaStream_t s) {
+template <int NG, int KIND, int MODE>
+static int h_launch_mode(const DevFlow& F, const FwdArgs& A, const char* hpack, size_t smem, int sms, cudaStream_t s) {
     static int attr_smem = 0;                            // cudaFuncSetAttribute only when the requirement grows
     if ((int)smem > attr_smem) {
-        if (cudaFuncSetAttribute(flow_cell_h_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(flow_cell_h_kernel<NG, KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return NIS_ECUDA;
         attr_smem = (int)smem;
     }
     const long long nsets = ((A.B + TCM - 1) / TCM + NG - 1) / NG;
     const int grid = (int)(nsets < sms ? nsets : sms);
-    flow_cell_h_kernel<NG><<<grid, NG * TCM, smem, s>>>(F, A, hpack);
+    flow_cell_h_kernel<NG, KIND, MODE><<<grid, NG * TCM, smem, s>>>(F, A, hpack);
     NIS_CUDA_CHECK_LAUNCH();
     return NIS_OK;
+}
+
+template <int NG, int KIND>
+static int h_launch(const DevFlow& F, const FwdArgs& A, const char* hpack, size_t smem, int sms, cudaStream_t s) {
+    switch ((A.stats_layer >= 1 ? 1 : 0) | (A.zin != nullptr ? 2 : 0)) {
+        case 0: return h_launch_mode<NG, KIND, 0>(F, A, hpack, smem, sms, s);
+        case 1: return h_launch_mode<NG, KIND, 1>(F, A, hpack, smem, sms, s);
+        case 2: return h_launch_mode<NG, KIND, 2>(F, A, hpack, smem, sms, s);
+    }
+    return h_launch_mode<NG, KIND, 3>(F, A, hpack, smem, sms, s);
 }
 
 int nis_launch_h(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaStream_t s) {
@@ -526,10 +590,17 @@ int nis_launch_h(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaSt
     const int ng = h_groups(F);
     const size_t smem = (size_t)h_layout(F, F.cells[A.c_begin].P, lz, l_end, A.zin != nullptr || stats, ng).total + 1024;
     const char* hp = reinterpret_cast<const char*>(tcpack);
-    switch (ng) {
-        case 4: return h_launch<4>(F, A, hp, smem, sms, s);
-        case 3: return h_launch<3>(F, A, hp, smem, sms, s);
-        case 2: return h_launch<2>(F, A, hp, smem, sms, s);
+    if (F.kind == NIS_KIND_PWLIN) {
+        switch (ng) {
+            case 4: return h_launch<4, NIS_KIND_PWLIN>(F, A, hp, smem, sms, s);
+            case 3: return h_launch<3, NIS_KIND_PWLIN>(F, A, hp, smem, sms, s);
+            case 2: return h_launch<2, NIS_KIND_PWLIN>(F, A, hp, smem, sms, s);
+        }
+    } else {
+        switch (ng) {
+            case 3: return h_launch<3, NIS_KIND_PWQUAD>(F, A, hp, smem, sms, s);
+            case 2: return h_launch<2, NIS_KIND_PWQUAD>(F, A, hp, smem, sms, s);
+        }
     }
     return NIS_EUNSUPPORTED;
 }

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
     extern __shared__ char smraw[];
     __shared__ uint64_t full[WD_MAX_SLOTS], empty[WD_MAX_SLOTS], a_ready[2], a_free[2], d_ready, d_free;
     __shared__ uint32_t tmem_base_s;
-    char* sm = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+    char* sm = smem_align1024(smraw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c = A.c_begin;
     const DevCell& q = F.cells[c];

@@ -10,7 +10,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int iters) {
     extern __shared__ char smraw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tb_s;
-    char* sm = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+    char* sm = smem_align1024(smraw);
     for (int i = threadIdx.x; i < 256 * 128 / 4; i += blockDim.x) reinterpret_cast<float*>(sm)[i] = 0.f;
     if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (threadIdx.x < 32) {

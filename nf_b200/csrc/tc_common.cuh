@@ -21,6 +21,10 @@ __device__ __forceinline__ float tf32_rn(float a) {
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 1024-byte aligned start inside the dynamic shared-memory window, formed as base + offset: a pointer rebuilt from an
+// integer loses its address space and every access through it becomes a generic LD / ST instead of LDS / STS
+__device__ __forceinline__ char* smem_align1024(char* smraw) { return smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
