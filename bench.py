@@ -161,6 +161,32 @@ def tensor_peak_tflops(kind, n):
     return best
 
 
+def pcie_probe(dev, nbytes=1 << 28):
+    """Host<->device copy bandwidth of this box from pinned memory (GB/s): H2D alone, D2H alone, and both at once on
+    two streams - the ceiling of the end-to-end number, which moves 285 MB per step across PCIe."""
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def timed(do_in, do_out):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            if do_in:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if do_out:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        return 3 * nbytes * (int(do_in) + int(do_out)) / (time.perf_counter() - t0) / 1e9
+
+    timed(True, True)
+    return {"h2d_gbs": timed(True, False), "d2h_gbs": timed(False, True), "both_directions_total_gbs": timed(True, True)}
+
+
 def parity_checks(rank, world, dev):
     """Run by every `bench.py --gpus N`: the N-rank paths checked in the driver's own run.
     (a) data-parallel gradient == single-GPU gradient: every rank backpropagates the variance loss of ITS minibatch
@@ -554,6 +580,10 @@ def main():
            "api": "FlowSequential.__call__ (PWLinManager._model); pinned host float32 points in, pinned host "
                   "[N,9] result out, copies on a side stream inside the timed region"}
     del xh, oh, xd
+    if rank == 0:
+        e2e["pcie"] = pcie_probe(dev)
+        e2e["pcie_bound_ms_per_step"] = (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) / \
+            (e2e["pcie"]["both_directions_total_gbs"] * 1e9) * 1e3
 
     line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",

@@ -168,15 +168,15 @@ __global__ void __launch_bounds__(NT) flow_bwd_generic_kernel(const __grid_const
     int rows = 0;
     float* st0 = sm + rows * NT; rows += d + 1;
     float* g0 = sm + rows * NT; rows += d + 1;
-    float* act0[NIS_MAX_HIDDEN + 1];
+    int acto[NIS_MAX_HIDDEN + 1];      // offsets, not pointers: a pointer read back from a local array is generic (LD instead of LDS)
     if (A.rotate) {
         // a launch that runs ONE step touches a_l and a_{l-1} only: layer l lives in buffer l % 3, so the
         // recompute never overwrites the two it still needs
-        for (int l = 0; l <= depth; ++l) act0[l] = sm + (rows + (l % 3) * maxW) * NT;
+        for (int l = 0; l <= depth; ++l) acto[l] = (rows + (l % 3) * maxW) * NT;
         rows += 3 * maxW;
     } else {
-        act0[0] = sm + rows * NT; rows += maxW;           // a_0 (BN0 output), P <= maxW rows used
-        for (int l = 1; l <= depth; ++l) { act0[l] = sm + rows * NT; rows += pad8(F.widths[l - 1]); }
+        acto[0] = rows * NT; rows += maxW;                // a_0 (BN0 output), P <= maxW rows used
+        for (int l = 1; l <= depth; ++l) { acto[l] = rows * NT; rows += pad8(F.widths[l - 1]); }
     }
     float* lg0 = sm + rows * NT; rows += F.Kpad;
     float* GA0 = sm + rows * NT; rows += maxW;
@@ -224,17 +224,17 @@ __global__ void __launch_bounds__(NT) flow_bwd_generic_kernel(const __grid_const
         {
             const float* sc = pk + q.aff_off[0];
             const float* sh = sc + pad8(q.P);
-            float* a0 = act0[0] + tid;
+            float* a0 = (sm + acto[0]) + tid;
             for (int k = 0; k < q.P; ++k) a0[k * NT] = fmaf(st[q.feed[k] * NT], sc[k], sh[k]);
             int in = q.P;
             for (int l = 0; l < fwd_upto; ++l) {
                 const int H = F.widths[l], Hp = pad8(H);
                 const float* scl = pk + q.aff_off[l + 1];
                 const float* shl = scl + Hp;
-                float* an = act0[l + 1] + tid;
+                float* an = (sm + acto[l + 1]) + tid;
                 auto epi = [&](int j, float z) { an[j * NT] = fmaf(z, scl[j], shl[j]); };   // signed: ReLU on read
-                if (l == 0) dense8b<NT, false>(pk + q.wt_off[l], in, Hp, act0[l] + tid, epi);
-                else dense8b<NT, true>(pk + q.wt_off[l], in, Hp, act0[l] + tid, epi);
+                if (l == 0) dense8b<NT, false>(pk + q.wt_off[l], in, Hp, (sm + acto[l]) + tid, epi);
+                else dense8b<NT, true>(pk + q.wt_off[l], in, Hp, (sm + acto[l]) + tid, epi);
                 in = H;
             }
         }
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(NT) flow_bwd_generic_kernel(const __grid_const
         for (int step = A.step_begin; step >= A.step_end; --step) {
             if (step == OUT) {
                 // ================= output layer + splines =====================================
-                const float* ad = act0[depth] + tid;
+                const float* ad = (sm + acto[depth]) + tid;
                 const int inp = pad8(in_last);
                 for (int k = 0; k < in_last; ++k) GA[k * NT] = 0.f;
                 const float gJ = g[d * NT];
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(NT) flow_bwd_generic_kernel(const __grid_const
                     dense8b<NT, false>(wbc + wb_layer_off(F, c, depth) + (size_t)t * F.K * inp, F.K, inp, lg,
                                 [&](int k, float v) { if (k < in_last) GA[k * NT] += v; });
                     __syncthreads();
-                    outer_accum<NT>(lg0, F.K, act0[depth], in_last, gp + F.p_out_w(c) + (size_t)t * F.K * in_last, depth > 0);
+                    outer_accum<NT>(lg0, F.K, (sm + acto[depth]), in_last, gp + F.p_out_w(c) + (size_t)t * F.K * in_last, depth > 0);
                     rowsum_accum<NT>(lg0, F.K, gp + F.p_out_b(c) + t * F.K);
                     __syncthreads();
                 }
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(NT) flow_bwd_generic_kernel(const __grid_const
                 const float* sc = pk + q.aff_off[l];
                 const float* gam = prm + F.p_bn_gamma(c, l);
                 const float* bet = gam + W;
-                const float* al = act0[l] + tid;
+                const float* al = (sm + acto[l]) + tid;
                 const float* m1 = A.bnb + l * 2 * maxW;
                 const float* m2 = m1 + maxW;
                 if (!A.train) {    // eval: dgamma / dbeta are plain sums over points
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(NT) flow_bwd_generic_kernel(const __grid_const
                     for (int j = W; j < Wp; ++j) GA[j * NT] = 0.f;
                     dense8b<NT, false>(wbc + wb_layer_off(F, c, l - 1), W, inp, GA, [&](int k, float v) { if (k < in) GB[k * NT] = v; });
                     __syncthreads();
-                    outer_accum<NT>(GAb, W, act0[l - 1], in, gp + F.p_lin(c, l - 1), l - 1 > 0);
+                    outer_accum<NT>(GAb, W, (sm + acto[l - 1]), in, gp + F.p_lin(c, l - 1), l - 1 > 0);
                     __syncthreads();
                     float* t_ = GA; GA = GB; GB = t_;
                     t_ = GAb; GAb = GBb; GBb = t_;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(NT) flow_bwd_generic_kernel(const __grid_const
             const int W = F.W(c, l);
             const float* gam = prm + F.p_bn_gamma(c, l);
             const float* bet = gam + W;
-            const float* al = act0[l] + tid;
+            const float* al = (sm + acto[l]) + tid;
             float* dst = A.dact + (size_t)tile * maxW * NT + tid;
             for (int j = 0; j < W; ++j) {
                 const float a = al[j * NT];
