@@ -10,6 +10,21 @@
         if (e__ != cudaSuccess) return NIS_ECUDA;        \
     } while (0)
 
+// Opt a kernel in to `bytes` of dynamic shared memory: cudaFuncSetAttribute once per device and per growth of the
+// requirement instead of on every launch (a driver call of a few microseconds each: the latency-bound small-batch
+// steps launch ~20 kernels per forward/backward pair).
+#define NIS_ENSURE_SMEM(kernel, bytes)                                                                    \
+    do {                                                                                                  \
+        static int have__[16] = {0};                                                                      \
+        int dev__ = 0;                                                                                    \
+        cudaGetDevice(&dev__);                                                                            \
+        dev__ &= 15;                                                                                      \
+        if ((int)(bytes) > have__[dev__]) {                                                               \
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));      \
+            have__[dev__] = (int)(bytes);                                                                 \
+        }                                                                                                 \
+    } while (0)
+
 static inline __host__ __device__ int pad8(int x) { return (x + 7) & ~7; }
 static inline __host__ __device__ int pad4(int x) { return (x + 3) & ~3; }
 

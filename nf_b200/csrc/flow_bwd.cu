@@ -483,7 +483,7 @@ size_t nis_flow_bwd_scratch_floats(const DevFlow& F, int64_t B) {
 template <int NT>
 static int launch_bwd(const DevFlow& F, const BwdArgs& A, int grid, cudaStream_t s) {
     const size_t smem = bwd_smem_bytes(F, NT, A.rotate != 0);
-    cudaFuncSetAttribute(flow_bwd_generic_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    NIS_ENSURE_SMEM((flow_bwd_generic_kernel<NT>), (int)smem);
     flow_bwd_generic_kernel<NT><<<grid, NT, smem, s>>>(F, A);
     NIS_CUDA_CHECK_LAUNCH();
     return NIS_OK;

@@ -879,8 +879,8 @@ int nis_flow_backward_tc(const DevFlow& F, const FlowWorkspace& ws, const float*
         A.flush_every = fe ? atoi(fe) : BT_FLUSH;
     }
     const size_t smem64 = (size_t)bt_layout(64).total + 1024, smem128 = (size_t)bt_layout(128).total + 1024;
-    cudaFuncSetAttribute(flow_bwd_tc_layer_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64);
-    cudaFuncSetAttribute(flow_bwd_tc_layer_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128);
+    NIS_ENSURE_SMEM((flow_bwd_tc_layer_kernel<64>), (int)smem64);
+    NIS_ENSURE_SMEM((flow_bwd_tc_layer_kernel<128>), (int)smem128);
     int sms1 = 0, dev1 = 0;
     cudaGetDevice(&dev1);
     cudaDeviceGetAttribute(&sms1, cudaDevAttrMultiProcessorCount, dev1);
@@ -892,7 +892,7 @@ int nis_flow_backward_tc(const DevFlow& F, const FlowWorkspace& ws, const float*
     for (int c = F.n_cells - 1; c >= 0; --c) {
         A.c = c; A.first = c == F.n_cells - 1;
         const size_t smem_head = (size_t)tc_layout(F, F.cells[c].P, 1, F.depth, false).total + 2 * (F.d + 1) * TCM * 4 + 1024;
-        cudaFuncSetAttribute(flow_bwd_tc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head);
+        NIS_ENSURE_SMEM((flow_bwd_tc_head_kernel), (int)smem_head);
         flow_bwd_tc_head_kernel<<<grid, TC_THREADS, smem_head, s>>>(F, A);
         NIS_CUDA_CHECK_LAUNCH();
         int pp = 0;

@@ -947,8 +947,8 @@ int nis_flow_backward_wide(const DevFlow& F, const FlowWorkspace& ws, const floa
     const size_t tile_fl = (size_t)W * TCM;
     const long long rows = (long long)B * (F.d + 1);
     auto headk = F.kind == NIS_KIND_PWLIN ? flow_bwd_wide_head_kernel<NIS_KIND_PWLIN> : flow_bwd_wide_head_kernel<NIS_KIND_PWQUAD>;
-    cudaFuncSetAttribute(flow_bwd_wide_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608 + 1024 + 1024);
-    cudaFuncSetAttribute(flow_bwd_wide_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608 + 1024 + 1024);
+    NIS_ENSURE_SMEM((flow_bwd_wide_wgrad_kernel<true>), 196608 + 1024 + 1024);
+    NIS_ENSURE_SMEM((flow_bwd_wide_wgrad_kernel<false>), 196608 + 1024 + 1024);
     for (int c = F.n_cells - 1; c >= 0; --c) {
         const DevCell& q = F.cells[c];
         A.c = c; A.first = c == F.n_cells - 1;
@@ -973,7 +973,8 @@ int nis_flow_backward_wide(const DevFlow& F, const FlowWorkspace& ws, const floa
         // ---- head ----------------------------------------------------------------------------------------------------
         {
             const size_t smem = (size_t)bw_head_layout(F, q.P, depth == 1).total + 1024;
-            cudaFuncSetAttribute(headk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (F.kind == NIS_KIND_PWLIN) NIS_ENSURE_SMEM((flow_bwd_wide_head_kernel<NIS_KIND_PWLIN>), (int)smem);
+            else NIS_ENSURE_SMEM((flow_bwd_wide_head_kernel<NIS_KIND_PWQUAD>), (int)smem);
             headk<<<grid, WD_THREADS, smem, s>>>(F, A);
             NIS_CUDA_CHECK_LAUNCH();
         }
@@ -984,10 +985,10 @@ int nis_flow_backward_wide(const DevFlow& F, const FlowWorkspace& ws, const floa
             A.dh_in = sc.dh[pp]; A.dh_out = sc.dh[pp ^ 1];
             const size_t smem = (size_t)bw_dg_layout(F, lam).total + 1024;
             if (lam == depth) {
-                cudaFuncSetAttribute(flow_bwd_wide_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                NIS_ENSURE_SMEM((flow_bwd_wide_dgrad_kernel<true>), (int)smem);
                 flow_bwd_wide_dgrad_kernel<true><<<grid, WD_THREADS, smem, s>>>(F, A);
             } else {
-                cudaFuncSetAttribute(flow_bwd_wide_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                NIS_ENSURE_SMEM((flow_bwd_wide_dgrad_kernel<false>), (int)smem);
                 flow_bwd_wide_dgrad_kernel<false><<<grid, WD_THREADS, smem, s>>>(F, A);
             }
             NIS_CUDA_CHECK_LAUNCH();

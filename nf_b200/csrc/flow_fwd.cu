@@ -276,7 +276,7 @@ extern "C" size_t nis_flow_workspace_bytes(const NisFlowDesc* desc, int64_t B) {
 template <int NT>
 static int launch_fwd(const DevFlow& F, const FwdArgs& A, cudaStream_t s) {
     const size_t smem = fwd_smem_bytes(F, NT);
-    cudaFuncSetAttribute(flow_fwd_generic_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    NIS_ENSURE_SMEM((flow_fwd_generic_kernel<NT>), (int)smem);
     long long ntiles = (A.B + NT - 1) / NT;
     int grid = (int)(ntiles < NIS_MAX_GRID ? ntiles : NIS_MAX_GRID);
     flow_fwd_generic_kernel<NT><<<grid, NT, smem, s>>>(F, A);

@@ -424,17 +424,21 @@ int nis_tc_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream
 }
 
 int nis_launch_tc(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaStream_t s) {
-    int sms = 0, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+    static int sms = 0;
+    if (sms <= 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
     const bool stats = A.stats_layer >= 1;
     const int lz = A.zin ? (stats ? A.stats_layer - 1 : F.depth) : 1;
     const int l_end = stats ? A.stats_layer - 1 : F.depth;
     const bool zst = (A.zin != nullptr || A.zout != nullptr) && (stats || F.K == 32);
     const size_t smem = (size_t)tc_layout(F, F.cells[A.c_begin].P, lz, l_end, zst).total + 1024;
     auto kern = F.kind == NIS_KIND_PWLIN ? flow_cell_tc_kernel<NIS_KIND_PWLIN> : flow_cell_tc_kernel<NIS_KIND_PWQUAD>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (F.kind == NIS_KIND_PWLIN) NIS_ENSURE_SMEM((flow_cell_tc_kernel<NIS_KIND_PWLIN>), (int)smem);
+    else NIS_ENSURE_SMEM((flow_cell_tc_kernel<NIS_KIND_PWQUAD>), (int)smem);
     long long npairs = ((A.B + TCM - 1) / TCM + 1) / 2;
     int grid = (int)(npairs < sms ? npairs : sms);
     kern<<<grid, TC_THREADS, smem, s>>>(F, A, tcpack);

@@ -549,7 +549,7 @@ static int launch_tiled_m(const DevFlow& F, const FwdArgs& A, int sms, cudaStrea
     const int first = A.zin ? last - (stats ? 1 : 0) : 0;
     TiledSmem L = tiled_layout(F, A.c_begin, M, first, last, !stats);
     const size_t smem = (size_t)L.total * sizeof(float);
-    cudaFuncSetAttribute(flow_cell_tiled_kernel<M, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    NIS_ENSURE_SMEM((flow_cell_tiled_kernel<M, TM>), (int)smem);
     long long ntiles = (A.B + M - 1) / M;
     const int per_sm = (M == 128 && TM == 4 && smem <= 110 * 1024) ? 2 : 1;
     int grid = (int)(ntiles < (long long)sms * per_sm ? ntiles : (long long)sms * per_sm);

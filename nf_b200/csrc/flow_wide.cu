@@ -409,7 +409,8 @@ int nis_launch_wide(const DevFlow& F, const FwdArgs& A, const float* widepack, c
     const WdSmem L = wd_layout(F, F.cells[A.c_begin].P, final_pass, A.zin == nullptr);
     const size_t smem = (size_t)L.total + 1024;
     auto kern = F.kind == NIS_KIND_PWLIN ? flow_wide_tc_kernel<NIS_KIND_PWLIN> : flow_wide_tc_kernel<NIS_KIND_PWQUAD>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (F.kind == NIS_KIND_PWLIN) NIS_ENSURE_SMEM((flow_wide_tc_kernel<NIS_KIND_PWLIN>), (int)smem);
+    else NIS_ENSURE_SMEM((flow_wide_tc_kernel<NIS_KIND_PWQUAD>), (int)smem);
     const long long ntiles = (A.B + TCM - 1) / TCM;
     const int grid = (int)(ntiles < sms ? ntiles : sms);
     kern<<<grid, WD_THREADS, smem, s>>>(F, A, widepack);

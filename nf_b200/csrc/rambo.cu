@@ -81,7 +81,7 @@ static int rambo_launch(const RamboConst& C, const void* r, double* momenta, dou
                         long long B, cudaStream_t s) {
     const int NDP = (3 * C.n - 4 + (C.pdf_active ? 2 : 0)) | 1, NMP = ((C.n + 2) * 4) | 1;
     const size_t smem = sizeof(double) * RAMBO_NT * (NDP + NMP);
-    cudaFuncSetAttribute(rambo_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    NIS_ENSURE_SMEM((rambo_kernel<RT>), (int)smem);
     long long ntiles = (B + RAMBO_NT - 1) / RAMBO_NT;
     int grid = (int)(ntiles < 148 * 16 ? ntiles : 148 * 16);
     rambo_kernel<RT><<<grid, RAMBO_NT, smem, s>>>(C, (const RT*)r, momenta, weight, cutmask, B);

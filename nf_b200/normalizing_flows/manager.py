@@ -239,35 +239,80 @@ class BasicManager(ModelAPI):
         state = EpochState(self.int_loss, preburn_time, kill_counter, impr_ratio)
         params = [p for p in self.model.parameters() if p.requires_grad]
         i = epoch_start - 1
-        for i in epoch_progress:
-            loss = 0
-            var = 0
-            optimizer_object.zero_grad()
-            for j in minibatch_progress:
+        def epoch_body(preburn, batches):
+            """One epoch up to and including backward (manager.py:219-278): fresh uniform minibatches, the variance of
+            f J / maxf per minibatch, one backward of their mean.  Returns (loss, var, integ, err) tensors."""
+            loss, var, integ_e, err_e = 0, 0, 0, 0
+            for _ in batches:
                 w = self._uniform(mini_batch_size, dev, generator=gen)
                 XJ = self.model(self.format_input(w, dev))
                 X = XJ[:, :-1].detach()                 # the sample is fixed, the Jacobian is optimised
-                if state.preburner:
+                if preburn:
                     fres = f(w)
                     fXJ = torch.mul(fres, XJ[:, -1]) / maxf
-                    integ[i + 1] += torch.mean(fres) / n_minibatches
-                    err[i + 1] += torch.var(fres) / n_minibatches
+                    integ_e = integ_e + torch.mean(fres) / n_minibatches
+                    err_e = err_e + torch.var(fres) / n_minibatches
                 else:
                     fres = torch.mul(f(X), XJ[:, -1])
                     fXJ = fres / maxf
-                    integ[i + 1] += torch.mean(fres.detach()) / n_minibatches
-                    err[i + 1] += torch.var(fres.detach()) / n_minibatches
+                    integ_e = integ_e + torch.mean(fres.detach()) / n_minibatches
+                    err_e = err_e + torch.var(fres.detach()) / n_minibatches
                 if loss_mode == "var":
                     loss = loss + torch.var(fXJ)
                 else:
                     loss = loss + torch.mean((fXJ * maxf) ** 2)
                 var = var + (torch.var(fXJ.detach() ** 2) / mini_batch_size)
                 del X, fXJ, XJ
+            if torch.is_tensor(loss):
+                loss = loss / n_minibatches
+                loss.backward()
+            return loss, var, integ_e, err_e
+
+        # The epoch body is latency-bound for small minibatches (README example: ~40 launches per minibatch, more
+        # host time than device time).  After two eager epochs in the current mode it is captured into a CUDA graph
+        # and replayed (the optimizer step and the bookkeeping stay eager).  A user integrand that cannot be
+        # captured (host synchronisation, Python-side state) makes the capture fail, and training continues eagerly;
+        # ``cuda_graph_epochs = False`` on the manager (or NIS_TRAIN_GRAPH=0) turns it off.
+        graphs = {}                                    # preburner flag -> (CUDAGraph, static outputs)
+        eager_epochs = {True: 0, False: 0}
+        use_graph = world == 1 and getattr(self, "cuda_graph_epochs", True) and \
+            os.environ.get("NIS_TRAIN_GRAPH", "1") != "0" and len(my_minibatches) > 0
+
+        for i in epoch_progress:
+            mode = bool(state.preburner)
+            if use_graph and mode not in graphs and eager_epochs[mode] >= 2:
+                optimizer_object.zero_grad(set_to_none=True)
+                try:
+                    torch.cuda.synchronize(dev)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        outs = epoch_body(mode, my_minibatches)
+                    graphs[mode] = (g, outs, [p.grad for p in params])
+                except Exception as exc:               # not capturable: stay eager for good
+                    use_graph = False
+                    graphs.clear()
+                    optimizer_object.zero_grad(set_to_none=True)
+                    torch.cuda.synchronize(dev)
+                    warnings.warn("the training epoch could not be captured into a CUDA graph (%s); continuing "
+                                  "eagerly" % (str(exc).splitlines()[0] if str(exc) else type(exc).__name__))
+            if use_graph and mode in graphs:
+                g, outs, grads = graphs[mode]
+                for p, gr in zip(params, grads):       # the graph writes its gradients into these very tensors
+                    p.grad = gr
+                g.replay()
+                loss, var, integ_e, err_e = outs
+                loss = loss.clone()
+            else:
+                optimizer_object.zero_grad()
+                loss, var, integ_e, err_e = epoch_body(mode, minibatch_progress)
+                eager_epochs[mode] += 1
+            if torch.is_tensor(integ_e):
+                integ[i + 1] += integ_e
+                err[i + 1] += err_e
             if not torch.is_tensor(loss):              # a rank without minibatches this epoch
                 loss = sum(p.sum() for p in params) * 0.0
                 var = torch.zeros((), device=dev, dtype=torch.double)
-            loss = loss / n_minibatches
-            loss.backward()
+                loss.backward()
             if world > 1:
                 self._allreduce_grads(params)
                 stats = torch.stack((loss.detach().double(), var.double(), integ[i + 1].double(), err[i + 1].double()))
