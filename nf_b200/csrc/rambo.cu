@@ -4,6 +4,7 @@
 // an odd number of doubles so the per-thread row accesses are bank-conflict free.
 // Reference: nisrep/PhaseSpace/flat_phase_space_generator.py:139-308 (see rambo_core.cuh).
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "rambo_core.cuh"
 
@@ -98,6 +99,10 @@ extern "C" int nis_rambo_generate(const NisRamboDesc* desc, const void* r, int32
     RamboConst C;
     int rc = rambo_fill_const(desc, &C);
     if (rc) return rc;
+    {
+        const char* e = getenv("NIS_RAMBO_SCREEN");        // test knob: 0 = every event through the exact float64 cuts
+        if (e && e[0] == '0') C.screen = 0;
+    }
     if (B == 0) return NIS_OK;
     cudaStream_t s = (cudaStream_t)stream;
     return r_dtype == NIS_F64 ? rambo_launch<double>(C, r, momenta, weight, cutmask, B, s)

@@ -73,6 +73,7 @@ struct RamboConst {
     double e2_dR;                 // exp(2 dR_min)
     double cos_dR;                // cos(min(dR_min, pi))
     int dR_ge_pi;                 // dR_min >= pi: the d-phi quick reject never fires
+    int screen;                   // float32 screening of the cuts (NIS_RAMBO_SCREEN=0 turns it off: test knob)
     double u_one[NIS_MAX_FINAL];  // u_one[e]: what the reference's lattice bisection returns for r == 1
     // parton-density mode (flat_phase_space_generator.py:157-187): per-event partonic energy
     int pdf_active, tau_mode;
@@ -151,6 +152,7 @@ static inline int rambo_fill_const(const NisRamboDesc* d, RamboConst* C) {
     C->e2_dR = exp(2.0 * d->delR_mincut);
     C->dR_ge_pi = d->delR_mincut >= NIS_PI;
     C->cos_dR = cos(d->delR_mincut < NIS_PI ? d->delR_mincut : NIS_PI);
+    C->screen = 1;
     C->u_one[0] = 1.0;
     for (int e = 1; e < NIS_MAX_FINAL; ++e) C->u_one[e] = rambo_lattice_at_one(e);
     return NIS_OK;
@@ -252,6 +254,84 @@ NIS_DEV double rambo_pdf_density(const double* grid, int nodes, double lnx_lo, d
     const double v = -f * (f - 1.0) * (f - 2.0) * (1.0 / 6.0) * ym + (f + 1.0) * (f - 1.0) * (f - 2.0) * 0.5 * y0
                      - (f + 1.0) * f * (f - 2.0) * 0.5 * y1 + (f + 1.0) * f * (f - 1.0) * (1.0 / 6.0) * y2;
     return v / x;
+}
+
+// ---- cuts, first in float32 ---------------------------------------------------------------------------------------
+// The cut decisions (:285-301) are comparisons of pT, eta and deltaR with thresholds; the float64 evaluation above all
+// of the pair loop was a third of the kernel's instructions (ncu source view, profiles/r02_ncu_rambo.md).  They are
+// taken here from a float32 evaluation with rigorous guard bands: a quantity closer to its threshold than the float32
+// error bound (times >= 5) makes the event "unsure" and the exact float64 code below decides it (a few events in 10^4),
+// so the masks stay bit-identical to the float64 reference.  Returns 1 = passes every cut, 0 = cut, -1 = unsure.
+// Error bounds: converted momenta 6e-8 relative; pT^2 2e-7; eta = sign(pz) log((|p|+|pz|)/pT) 2e-6 absolute for
+// |eta| < 14 (beyond, and for the reference's `huge` case, unsure); unit transverse vectors 3e-7, cos / sin of d-phi
+// 1e-6, d-phi = atan2(|sin|, cos) 3e-6; deltaR^2 <= 1.4e-5 max(|d eta|, |d phi|).
+#ifndef __CUDACC__
+static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
+#endif
+template <int N, bool PDF>
+NIS_DEV int rambo_cuts_screen(const RamboConst& C, const double* fin, int ms, double lb_g, double lb_gb) {
+    float eta[N], ux[N], uy[N];
+    float pt2min = 3.0e38f, etamax = -3.0e38f;
+    bool unsure = false;
+    const bool need_eta = C.rap_max > 0.0 || C.dR_min > 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const float px = (float)fin[(4 * j + 1) * ms], py = (float)fin[(4 * j + 2) * ms];
+        const float pz = (float)(PDF ? lb_g * fin[(4 * j + 3) * ms] + lb_gb * fin[4 * j * ms] : fin[(4 * j + 3) * ms]);
+        const float pt2 = px * px + py * py, pz2 = pz * pz;
+        pt2min = fminf(pt2min, pt2);
+        if (need_eta) {
+            if (!(pt2 > 1e-12f * pz2) || !(pt2 > 1e-30f) || !(pt2 + pz2 < 1e37f)) unsure = true;   // |eta| > 14, underflow, overflow
+            const float ipt = rsqrtf(pt2);
+            const float t = (sqrtf(pt2 + pz2) + fabsf(pz)) * ipt;             // exp(|eta|)
+            eta[j] = copysignf(logf(t), pz);
+            ux[j] = px * ipt; uy[j] = py * ipt;
+            etamax = fmaxf(etamax, eta[j]);
+        }
+    }
+    if (C.pT_min > 0.0) {                                                     // :285-288
+        const float c2 = (float)(C.pT_min * C.pT_min);
+        if (!(pt2min < 3.0e37f)) unsure = true;
+        else if (pt2min < c2 * (1.f - 1e-5f)) return 0;
+        else if (!(pt2min > c2 * (1.f + 1e-5f))) unsure = true;
+    }
+    if (C.rap_max > 0.0) {                                                    // :298-301, |max eta|
+        const float a = fabsf(etamax), c = (float)C.rap_max;
+        if (a > c + 2e-5f) { if (!unsure) return 0; }                         // (an unsure eta may be the `huge` one: let the exact path say)
+        else if (!(a < c - 2e-5f)) unsure = true;
+    }
+    if (C.dR_min > 0.0) {                                                     // :290-296
+        const float cut = (float)C.dR_min, cut2 = cut * cut;
+        const float g2 = 1e-4f * fmaxf(cut2, cut);
+#pragma unroll
+        for (int i = 1; i < N; ++i) {
+#pragma unroll
+            for (int j = 0; j < i; ++j) {
+                const float de = eta[i] - eta[j];
+                if (fabsf(de) >= cut + 2e-5f) continue;
+                const float cs = ux[i] * ux[j] + uy[i] * uy[j], sn = fabsf(ux[i] * uy[j] - uy[i] * ux[j]);
+                const float dphi = atan2f(sn, cs);
+                const float dr2 = de * de + dphi * dphi;
+                if (dr2 < cut2 - g2) { if (!unsure) return 0; }
+                else if (!(dr2 > cut2 + g2)) unsure = true;
+            }
+        }
+    }
+    return unsure ? -1 : 1;
+}
+
+template <bool PDF>
+NIS_DEV int rambo_cuts_screen_n(const RamboConst& C, const double* fin, int ms, double lb_g, double lb_gb) {
+    switch (C.n) {
+        case 2: return rambo_cuts_screen<2, PDF>(C, fin, ms, lb_g, lb_gb);
+        case 3: return rambo_cuts_screen<3, PDF>(C, fin, ms, lb_g, lb_gb);
+        case 4: return rambo_cuts_screen<4, PDF>(C, fin, ms, lb_g, lb_gb);
+        case 5: return rambo_cuts_screen<5, PDF>(C, fin, ms, lb_g, lb_gb);
+        case 6: return rambo_cuts_screen<6, PDF>(C, fin, ms, lb_g, lb_gb);
+        case 7: return rambo_cuts_screen<7, PDF>(C, fin, ms, lb_g, lb_gb);
+        case 8: return rambo_cuts_screen<8, PDF>(C, fin, ms, lb_g, lb_gb);
+    }
+    return -1;
 }
 
 // One event, runtime multiplicity n = C.n.  r: 3n-4 uniforms at stride rs.  mo: scratch AND output row of
@@ -376,7 +456,11 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
     const double* fin = mo + 8 * ms;                            // final-state particle j at fin + 4*j*ms
     double* e2 = mo;                                            // exp(2 eta_j), j < n <= 8 (beam slots)
     const bool need_eta = C.rap_max > 0.0 || C.dR_min > 0.0;
-    if (C.pT_min > 0.0 || need_eta) {
+    const bool any_cut = C.pT_min > 0.0 || need_eta;
+    // float32 screen first; the exact float64 evaluation only for events within a guard band of a threshold
+    const int scr = (any_cut && C.screen) ? rambo_cuts_screen_n<PDF>(C, fin, ms, lb_g, lb_gb) : -1;
+    if (scr >= 0) ok = scr == 1;
+    if (scr < 0 && (C.pT_min > 0.0 || need_eta)) {
         double pt2min = NIS_HUGE, e2max = 0.0;
 #pragma unroll 1
         for (int j = 0; j < n; ++j) {
@@ -402,7 +486,7 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
         // rap_max < |max_j eta_j|  (|max eta|, not max |eta|, :298-301)
         if (C.rap_max > 0.0 && (e2max > C.e2_rap || e2max < C.e2_rap_inv)) ok = false;
     }
-    if (C.dR_min > 0.0) {                                       // :290-296
+    if (scr < 0 && C.dR_min > 0.0) {                            // :290-296
         const double cut2 = C.dR_min * C.dR_min;
 #pragma unroll 1
         for (int i = 1; i < n; ++i) {

@@ -85,5 +85,6 @@ class AddJacobian(torch.nn.Module):
 
     def forward(self, input, dev=torch.device("cpu")):
         x = input.to(dev)
-        j = self.jacobian_value.to(device=x.device, dtype=torch.double).expand(x.shape[0], 1)
+        # filled on the device (no host-to-device copy per call: that would also break CUDA-graph capture of the epoch)
+        j = torch.full((x.shape[0], 1), float(self.jacobian_value), dtype=torch.double, device=x.device)
         return torch.cat((x, j), dim=1)
