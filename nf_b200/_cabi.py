@@ -9,7 +9,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnisb200.so")
+LIB_PATH = os.environ.get("NIS_LIB_PATH") or os.path.join(HERE, "libnisb200.so")     # override: development A/B builds
 
 NIS_MAX_DIM = 32
 NIS_MAX_CELLS = 32

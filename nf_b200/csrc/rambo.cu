@@ -10,8 +10,10 @@
 
 #define RAMBO_NT 128
 
+// six CTAs per SM (what the shared-memory tile allows): without the bound ptxas takes 255 registers for the four inlined
+// event variants and the kernel runs at half speed
 template <typename RT>
-__global__ void __launch_bounds__(RAMBO_NT) rambo_kernel(const __grid_constant__ RamboConst C, const RT* __restrict__ r,
+__global__ void __launch_bounds__(RAMBO_NT, 6) rambo_kernel(const __grid_constant__ RamboConst C, const RT* __restrict__ r,
                                                          double* __restrict__ momenta, double* __restrict__ weight,
                                                          uint8_t* __restrict__ cutmask, long long B) {
     const int ND = 3 * C.n - 4 + (C.pdf_active ? 2 : 0);    // uniforms per event
@@ -99,10 +101,6 @@ extern "C" int nis_rambo_generate(const NisRamboDesc* desc, const void* r, int32
     RamboConst C;
     int rc = rambo_fill_const(desc, &C);
     if (rc) return rc;
-    {
-        const char* e = getenv("NIS_RAMBO_SCREEN");        // test knob: 0 = every event through the exact float64 cuts
-        if (e && e[0] == '0') C.screen = 0;
-    }
     if (B == 0) return NIS_OK;
     cudaStream_t s = (cudaStream_t)stream;
     return r_dtype == NIS_F64 ? rambo_launch<double>(C, r, momenta, weight, cutmask, B, s)

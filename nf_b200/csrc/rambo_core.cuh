@@ -17,6 +17,11 @@
 #include <stdint.h>
 #include "../../include/nis_b200.h"
 
+#ifdef __CUDACC__
+#define nis_fdiv(a, b) __fdividef((a), (b))       /* 2-ulp float division: only steers a Newton iterate */
+#else
+#define nis_fdiv(a, b) ((a) / (b))
+#endif
 #ifndef __CUDACC__
 // host build (tests only): glibc has no sincospi
 static inline void sincospi(double x, double* s, double* c) { *s = sin(3.141592653589793 * x); *c = cos(3.141592653589793 * x); }
@@ -56,6 +61,36 @@ static inline double nis_div(double a, double b) { return a / b; }
 static inline double nis_sqrt(double x) { return x > 0.0 ? sqrt(x) : 0.0; }
 #endif
 
+// sin and cos of 2 pi r for r in [0, 1] (the azimuth of a decay, :236-243): quadrant k = round(4 r), a = 2 pi (r - k/4)
+// in [-pi/4, pi/4] (the subtraction is exact), Taylor polynomials to a^15 / a^16 (remainders 5e-17 / 2e-18), quadrant
+// fix-up.  ~40 instructions; the library sincospi, which also handles arbitrary arguments, was 8.7 % of the kernel.
+NIS_DEV void rambo_sincos2pi(double r, double* s, double* c) {
+    const double k = rint(4.0 * r);
+    const double a = (r - 0.25 * k) * 6.283185307179586;
+    const double a2 = a * a;
+    double sp = -7.6471637318198164759e-13;                    // -1/15!
+    sp = fma(sp, a2, 1.6059043836821614599e-10);               //  1/13!
+    sp = fma(sp, a2, -2.5052108385441718775e-08);              // -1/11!
+    sp = fma(sp, a2, 2.7557319223985890653e-06);               //  1/9!
+    sp = fma(sp, a2, -1.9841269841269841270e-04);              // -1/7!
+    sp = fma(sp, a2, 8.3333333333333333333e-03);               //  1/5!
+    sp = fma(sp, a2, -1.6666666666666666667e-01);              // -1/3!
+    sp = fma(sp * a2, a, a);
+    double cp = 4.7794773323873852974e-14;                     //  1/16!
+    cp = fma(cp, a2, -1.1470745597729724714e-11);              // -1/14!
+    cp = fma(cp, a2, 2.0876756987868098979e-09);               //  1/12!
+    cp = fma(cp, a2, -2.7557319223985890653e-07);              // -1/10!
+    cp = fma(cp, a2, 2.4801587301587301587e-05);               //  1/8!
+    cp = fma(cp, a2, -1.3888888888888888889e-03);              // -1/6!
+    cp = fma(cp, a2, 4.1666666666666666667e-02);               //  1/4!
+    cp = fma(cp, a2, -0.5);
+    cp = fma(cp, a2, 1.0);
+    const int q = (int)k & 3;
+    const double s0 = (q & 1) ? cp : sp, c0 = (q & 1) ? sp : cp;
+    *s = (q & 2) ? -s0 : s0;
+    *c = ((q + 1) & 2) ? -c0 : c0;
+}
+
 #define NIS_TWO_PI 6.283185307179586
 #define NIS_PI 3.141592653589793
 #define NIS_SQRT_EPS 1.4901161193847656e-08   /* np.finfo(float).eps**0.5, utils.py:151 */
@@ -73,7 +108,6 @@ struct RamboConst {
     double e2_dR;                 // exp(2 dR_min)
     double cos_dR;                // cos(min(dR_min, pi))
     int dR_ge_pi;                 // dR_min >= pi: the d-phi quick reject never fires
-    int screen;                   // float32 screening of the cuts (NIS_RAMBO_SCREEN=0 turns it off: test knob)
     double u_one[NIS_MAX_FINAL];  // u_one[e]: what the reference's lattice bisection returns for r == 1
     // parton-density mode (flat_phase_space_generator.py:157-187): per-event partonic energy
     int pdf_active, tau_mode;
@@ -152,7 +186,6 @@ static inline int rambo_fill_const(const NisRamboDesc* d, RamboConst* C) {
     C->e2_dR = exp(2.0 * d->delR_mincut);
     C->dR_ge_pi = d->delR_mincut >= NIS_PI;
     C->cos_dR = cos(d->delR_mincut < NIS_PI ? d->delR_mincut : NIS_PI);
-    C->screen = 1;
     C->u_one[0] = 1.0;
     for (int e = 1; e < NIS_MAX_FINAL; ++e) C->u_one[e] = rambo_lattice_at_one(e);
     return NIS_OK;
@@ -216,7 +249,7 @@ NIS_DEV double rambo_root(int e, double r, double u_one) {
         for (int i = 2; i < e; ++i) xe1 *= x;
         const float g = xe1 * x * ((ef + 1.f) - ef * x) - rf;
         const float dg = ef * (ef + 1.f) * xe1 * (1.f - x);
-        const float xn = x - g / dg;
+        const float xn = x - nis_fdiv(g, dg);
         if (xn > 0.f && xn < 1.f) x = xn;
     }
     // float64 polish.  The float32 iterate is within ~1e-7 of the root, so two Newton steps reach float64
@@ -254,84 +287,6 @@ NIS_DEV double rambo_pdf_density(const double* grid, int nodes, double lnx_lo, d
     const double v = -f * (f - 1.0) * (f - 2.0) * (1.0 / 6.0) * ym + (f + 1.0) * (f - 1.0) * (f - 2.0) * 0.5 * y0
                      - (f + 1.0) * f * (f - 2.0) * 0.5 * y1 + (f + 1.0) * f * (f - 1.0) * (1.0 / 6.0) * y2;
     return v / x;
-}
-
-// ---- cuts, first in float32 ---------------------------------------------------------------------------------------
-// The cut decisions (:285-301) are comparisons of pT, eta and deltaR with thresholds; the float64 evaluation above all
-// of the pair loop was a third of the kernel's instructions (ncu source view, profiles/r02_ncu_rambo.md).  They are
-// taken here from a float32 evaluation with rigorous guard bands: a quantity closer to its threshold than the float32
-// error bound (times >= 5) makes the event "unsure" and the exact float64 code below decides it (a few events in 10^4),
-// so the masks stay bit-identical to the float64 reference.  Returns 1 = passes every cut, 0 = cut, -1 = unsure.
-// Error bounds: converted momenta 6e-8 relative; pT^2 2e-7; eta = sign(pz) log((|p|+|pz|)/pT) 2e-6 absolute for
-// |eta| < 14 (beyond, and for the reference's `huge` case, unsure); unit transverse vectors 3e-7, cos / sin of d-phi
-// 1e-6, d-phi = atan2(|sin|, cos) 3e-6; deltaR^2 <= 1.4e-5 max(|d eta|, |d phi|).
-#ifndef __CUDACC__
-static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
-#endif
-template <int N, bool PDF>
-NIS_DEV int rambo_cuts_screen(const RamboConst& C, const double* fin, int ms, double lb_g, double lb_gb) {
-    float eta[N], ux[N], uy[N];
-    float pt2min = 3.0e38f, etamax = -3.0e38f;
-    bool unsure = false;
-    const bool need_eta = C.rap_max > 0.0 || C.dR_min > 0.0;
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        const float px = (float)fin[(4 * j + 1) * ms], py = (float)fin[(4 * j + 2) * ms];
-        const float pz = (float)(PDF ? lb_g * fin[(4 * j + 3) * ms] + lb_gb * fin[4 * j * ms] : fin[(4 * j + 3) * ms]);
-        const float pt2 = px * px + py * py, pz2 = pz * pz;
-        pt2min = fminf(pt2min, pt2);
-        if (need_eta) {
-            if (!(pt2 > 1e-12f * pz2) || !(pt2 > 1e-30f) || !(pt2 + pz2 < 1e37f)) unsure = true;   // |eta| > 14, underflow, overflow
-            const float ipt = rsqrtf(pt2);
-            const float t = (sqrtf(pt2 + pz2) + fabsf(pz)) * ipt;             // exp(|eta|)
-            eta[j] = copysignf(logf(t), pz);
-            ux[j] = px * ipt; uy[j] = py * ipt;
-            etamax = fmaxf(etamax, eta[j]);
-        }
-    }
-    if (C.pT_min > 0.0) {                                                     // :285-288
-        const float c2 = (float)(C.pT_min * C.pT_min);
-        if (!(pt2min < 3.0e37f)) unsure = true;
-        else if (pt2min < c2 * (1.f - 1e-5f)) return 0;
-        else if (!(pt2min > c2 * (1.f + 1e-5f))) unsure = true;
-    }
-    if (C.rap_max > 0.0) {                                                    // :298-301, |max eta|
-        const float a = fabsf(etamax), c = (float)C.rap_max;
-        if (a > c + 2e-5f) { if (!unsure) return 0; }                         // (an unsure eta may be the `huge` one: let the exact path say)
-        else if (!(a < c - 2e-5f)) unsure = true;
-    }
-    if (C.dR_min > 0.0) {                                                     // :290-296
-        const float cut = (float)C.dR_min, cut2 = cut * cut;
-        const float g2 = 1e-4f * fmaxf(cut2, cut);
-#pragma unroll
-        for (int i = 1; i < N; ++i) {
-#pragma unroll
-            for (int j = 0; j < i; ++j) {
-                const float de = eta[i] - eta[j];
-                if (fabsf(de) >= cut + 2e-5f) continue;
-                const float cs = ux[i] * ux[j] + uy[i] * uy[j], sn = fabsf(ux[i] * uy[j] - uy[i] * ux[j]);
-                const float dphi = atan2f(sn, cs);
-                const float dr2 = de * de + dphi * dphi;
-                if (dr2 < cut2 - g2) { if (!unsure) return 0; }
-                else if (!(dr2 > cut2 + g2)) unsure = true;
-            }
-        }
-    }
-    return unsure ? -1 : 1;
-}
-
-template <bool PDF>
-NIS_DEV int rambo_cuts_screen_n(const RamboConst& C, const double* fin, int ms, double lb_g, double lb_gb) {
-    switch (C.n) {
-        case 2: return rambo_cuts_screen<2, PDF>(C, fin, ms, lb_g, lb_gb);
-        case 3: return rambo_cuts_screen<3, PDF>(C, fin, ms, lb_g, lb_gb);
-        case 4: return rambo_cuts_screen<4, PDF>(C, fin, ms, lb_g, lb_gb);
-        case 5: return rambo_cuts_screen<5, PDF>(C, fin, ms, lb_g, lb_gb);
-        case 6: return rambo_cuts_screen<6, PDF>(C, fin, ms, lb_g, lb_gb);
-        case 7: return rambo_cuts_screen<7, PDF>(C, fin, ms, lb_g, lb_gb);
-        case 8: return rambo_cuts_screen<8, PDF>(C, fin, ms, lb_g, lb_gb);
-    }
-    return -1;
 }
 
 // One event, runtime multiplicity n = C.n.  r: 3n-4 uniforms at stride rs.  mo: scratch AND output row of
@@ -413,7 +368,7 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
         const double ct = 2.0 * r[(n - 2 + 2 * j) * rs] - 1.0;  // :233-243
         const double st = nis_sqrt(1.0 - ct * ct);
         double sp, cp;
-        sincospi(2.0 * r[(n - 1 + 2 * j) * rs], &sp, &cp);
+        rambo_sincos2pi(r[(n - 1 + 2 * j) * rs], &sp, &cp);
         double p1 = q * st * cp, p2 = q * st * sp, p3 = q * ct;
         const double p0 = (M2 + mj * mj - Mn * Mn) * i2M;
         const double pQ = p1 * Q1 + p2 * Q2 + p3 * Q3;
@@ -456,11 +411,7 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
     const double* fin = mo + 8 * ms;                            // final-state particle j at fin + 4*j*ms
     double* e2 = mo;                                            // exp(2 eta_j), j < n <= 8 (beam slots)
     const bool need_eta = C.rap_max > 0.0 || C.dR_min > 0.0;
-    const bool any_cut = C.pT_min > 0.0 || need_eta;
-    // float32 screen first; the exact float64 evaluation only for events within a guard band of a threshold
-    const int scr = (any_cut && C.screen) ? rambo_cuts_screen_n<PDF>(C, fin, ms, lb_g, lb_gb) : -1;
-    if (scr >= 0) ok = scr == 1;
-    if (scr < 0 && (C.pT_min > 0.0 || need_eta)) {
+    if (C.pT_min > 0.0 || need_eta) {
         double pt2min = NIS_HUGE, e2max = 0.0;
 #pragma unroll 1
         for (int j = 0; j < n; ++j) {
@@ -486,7 +437,7 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
         // rap_max < |max_j eta_j|  (|max eta|, not max |eta|, :298-301)
         if (C.rap_max > 0.0 && (e2max > C.e2_rap || e2max < C.e2_rap_inv)) ok = false;
     }
-    if (scr < 0 && C.dR_min > 0.0) {                            // :290-296
+    if (C.dR_min > 0.0) {                                       // :290-296
         const double cut2 = C.dR_min * C.dR_min;
 #pragma unroll 1
         for (int i = 1; i < n; ++i) {

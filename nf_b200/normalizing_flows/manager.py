@@ -21,6 +21,7 @@ import datetime
 import math
 import os
 import warnings
+import weakref
 
 import numpy as np
 import torch
@@ -140,6 +141,33 @@ class BasicManager(ModelAPI):
         torch.distributed the per-rank generator of ``_rank_generator``."""
         return torch.rand(n, self.n_flow, device=dev, dtype=dtype, generator=generator)
 
+    def _snapshot_best(self):
+        """``best_model = deepcopy(model)`` (manager.py:299) without rebuilding the module tree on every improving
+        epoch (a deepcopy of the Sequential costs ~6 ms: most of the README example's wall time once the kernels are
+        fast).  After the first deepcopy the snapshot is refreshed by copying the three flat arenas (parameters, BN
+        running statistics, batch counters) - three small device copies."""
+        src, dst = self.model, self.best_model
+        fast = isinstance(src, FlowSequential) and isinstance(dst, FlowSequential) and dst is not src and \
+            getattr(self, "_best_src", None) is not None and self._best_src() is src and dst.training == src.training
+        if fast:
+            try:
+                ss, ds = src.spec(), dst.spec()
+                dev = ss.params[0].device
+                pairs = []
+                for a, b in ((ss.param_arena, ds.param_arena), (ss.bn_arena, ds.bn_arena), (ss.nbt_arena, ds.nbt_arena)):
+                    fa, fb = a.get(dev), b.get(dev)
+                    if a.flat is None or b.flat is None or fa.shape != fb.shape:
+                        raise RuntimeError("arena not linked")
+                    pairs.append((fb, fa))
+                with torch.no_grad():
+                    for fb, fa in pairs:
+                        fb.copy_(fa)
+                return
+            except Exception:
+                pass
+        self.best_model = copy.deepcopy(src)
+        self._best_src = weakref.ref(src)
+
     @staticmethod
     def _rank_generator(dev, rank, world):
         """Ranks seeded alike (the usual ``torch.manual_seed(s)`` on every rank) would all draw the same latent
@@ -225,7 +253,8 @@ class BasicManager(ModelAPI):
             X, J = XJ[:, :-1], XJ[:, -1]
             self.varJ = torch.mean(J ** 2).detach()
             self.DKL = torch.nn.KLDivLoss(reduction='batchmean')(torch.log(X + 1e-45), w).detach()
-            self.best_model = copy.deepcopy(self.model)
+            self._best_src = None
+            self._snapshot_best()
             self.best_epoch = 0
             self.best_time = 0
             self.best_loss_rel = torch.ones_like(self.best_loss)
@@ -275,6 +304,8 @@ class BasicManager(ModelAPI):
         # ``cuda_graph_epochs = False`` on the manager (or NIS_TRAIN_GRAPH=0) turns it off.
         graphs = {}                                    # preburner flag -> (CUDAGraph, static outputs)
         eager_epochs = {True: 0, False: 0}
+        side = None                                    # warm-up epochs and capture share one side stream (so that the
+                                                       # parameters' AccumulateGrad nodes live on the capture stream)
         use_graph = world == 1 and getattr(self, "cuda_graph_epochs", True) and \
             os.environ.get("NIS_TRAIN_GRAPH", "1") != "0" and len(my_minibatches) > 0
 
@@ -285,7 +316,7 @@ class BasicManager(ModelAPI):
                 try:
                     torch.cuda.synchronize(dev)
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, stream=side):
                         outs = epoch_body(mode, my_minibatches)
                     graphs[mode] = (g, outs, [p.grad for p in params])
                 except Exception as exc:               # not capturable: stay eager for good
@@ -302,10 +333,18 @@ class BasicManager(ModelAPI):
                 g.replay()
                 loss, var, integ_e, err_e = outs
                 loss = loss.clone()
+            elif use_graph:
+                if side is None:
+                    side = torch.cuda.Stream(device=dev)
+                optimizer_object.zero_grad()
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    loss, var, integ_e, err_e = epoch_body(mode, minibatch_progress)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                eager_epochs[mode] += 1
             else:
                 optimizer_object.zero_grad()
                 loss, var, integ_e, err_e = epoch_body(mode, minibatch_progress)
-                eager_epochs[mode] += 1
             if torch.is_tensor(integ_e):
                 integ[i + 1] += integ_e
                 err[i + 1] += err_e
@@ -337,7 +376,7 @@ class BasicManager(ModelAPI):
                 self.best_loss = loss
                 self.best_var = var
                 self.best_loss_rel = loss / self.int_loss
-                self.best_model = copy.deepcopy(self.model)
+                self._snapshot_best()
                 self.best_epoch = i
                 self.best_time = (datetime.datetime.utcnow() - run.start_time).total_seconds() if run is not None else 0
             if state.advance(i, loss):

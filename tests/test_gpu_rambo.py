@@ -146,3 +146,17 @@ def test_cut_quirks_of_the_reference():
     expect = ~(1.0 < eta.max(1).values.abs())
     assert torch.equal(w_rap != 0, expect)
     assert bool(((eta.abs().max(1).values > 1.0) & (w_rap != 0)).any())     # very negative eta passes, like the reference
+
+
+@pytest.mark.parametrize("masses,E", [(100.0, 1000.0), (0.0, 1000.0)])
+def test_cut_masks_bit_exact_at_a_million_events(masses, E):
+    """Cut masks over 2^20 events against the float64 oracle: bit-exact (the kernel decides the cuts on squared
+    quantities with series bounds and runs the reference's own formula only inside a thin shell around a threshold)."""
+    B = 1 << 20
+    r = torch.rand(B, 8, generator=torch.Generator().manual_seed(17), dtype=torch.float64)
+    cuts = dict(pT_mincut=20, delR_mincut=0.4, rap_maxcut=2.5)
+    ps = FlatInvertiblePhasespace([masses] * 2, [masses] * 4)
+    _, w, mask = ps.generateKinematics_batch(E, r.cuda(), return_cutmask=True, **cuts)
+    _, rw = orambo.generate_kinematics(E, r, [masses] * 2, [masses] * 4, **cuts)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), (rw != 0).numpy())
+    assert 0.3 < float(mask.float().mean()) < 0.99
