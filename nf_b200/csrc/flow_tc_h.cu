@@ -7,7 +7,7 @@
 // column accumulator, i.e. all 512 columns for two groups.  Here
 //   * activations and weights are split as x = x_hi + x_lo with BOTH parts in fp16 (11-bit significands: the same
 //     22 bits as the TF32 split) after an exact power-of-two scaling that keeps x_lo out of fp16's subnormal range
-//     (activations x 2^3, clamped at 65504 / 8 = 8188 — a BatchNorm output that large does not occur; weights by a
+//     (activations x 2^3, saturating at 65504 / 8 = 8188 — a BatchNorm output that large does not occur; weights by a
 //     per-layer 2^k chosen at pack time so that max |w| lands in [2^13, 2^14)); D += a_hi w_lo + a_lo w_hi + a_hi w_hi
 //     as tcgen05.mma.kind::f16 with fp32 accumulation, K = 16 per instruction: 12 instructions per 64x64 layer
 //     instead of 24 (tools/tc_f16_probe.cu: same 44.7 cycles per M128 N64 instruction as kind::tf32);
@@ -71,6 +71,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// two floats -> packed fp16 pair (x in the low half), round to nearest, saturating to +-65504 instead of infinity
+__device__ __forceinline__ uint32_t h_pack_sat(float x, float y) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(y), "f"(x));
+    return d;
 }
 
 __device__ __forceinline__ void h_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -148,24 +155,24 @@ __host__ __device__ static inline HSmem h_layout(const DevFlow& F, int P, int l_
     return s;
 }
 
-// 32 activations: a = min(max(v * sc + sh, 0), 65504) with sc / sh pre-multiplied by SA, split a = hi + lo with hi
-// rounded to an 11-bit significand (the integer add-and-mask of tf32_rn: exactly fp16's precision in its normal
-// range), both packed two per 32-bit column (even feature in the low half) into the group's A operand.
+// 32 activations: a = min(max(v * sc + sh, 0), 65504) with sc / sh pre-multiplied by SA, split a = hi + lo (both fp16),
+// packed two per 32-bit column (even feature in the low half) into the group's A operand.
 __device__ __forceinline__ void h_store_act32(const float* v, const float* sc, const float* sh, uint32_t t_hi, uint32_t t_lo) {
     uint32_t hi[16], lo[16];
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
         const float4 s4 = reinterpret_cast<const float4*>(sc)[j4], h4 = reinterpret_cast<const float4*>(sh)[j4];
-        const float a0 = fminf(fmaxf(fmaf(v[4 * j4], s4.x, h4.x), 0.f), H_AMAX);
-        const float a1 = fminf(fmaxf(fmaf(v[4 * j4 + 1], s4.y, h4.y), 0.f), H_AMAX);
-        const float a2 = fminf(fmaxf(fmaf(v[4 * j4 + 2], s4.z, h4.z), 0.f), H_AMAX);
-        const float a3 = fminf(fmaxf(fmaf(v[4 * j4 + 3], s4.w, h4.w), 0.f), H_AMAX);
-        const float b0 = tf32_rn(a0), b1 = tf32_rn(a1), b2 = tf32_rn(a2), b3 = tf32_rn(a3);
-        __half2 p;
-        p = __floats2half2_rn(b0, b1); hi[2 * j4] = *reinterpret_cast<uint32_t*>(&p);
-        p = __floats2half2_rn(b2, b3); hi[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&p);
-        p = __floats2half2_rn(a0 - b0, a1 - b1); lo[2 * j4] = *reinterpret_cast<uint32_t*>(&p);
-        p = __floats2half2_rn(a2 - b2, a3 - b3); lo[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&p);
+        const float a0 = fmaxf(fmaf(v[4 * j4], s4.x, h4.x), 0.f), a1 = fmaxf(fmaf(v[4 * j4 + 1], s4.y, h4.y), 0.f);
+        const float a2 = fmaxf(fmaf(v[4 * j4 + 2], s4.z, h4.z), 0.f), a3 = fmaxf(fmaf(v[4 * j4 + 3], s4.w, h4.w), 0.f);
+        // hi = fp16(a) (round to nearest, saturating at 65504: one packed conversion per pair), lo = fp16(a - hi) with
+        // the subtraction exact in float32; even feature in the low half
+        const uint32_t p01 = h_pack_sat(a0, a1), p23 = h_pack_sat(a2, a3);
+        const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&p01));
+        const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&p23));
+        hi[2 * j4] = p01;
+        hi[2 * j4 + 1] = p23;
+        lo[2 * j4] = h_pack_sat(a0 - f01.x, a1 - f01.y);
+        lo[2 * j4 + 1] = h_pack_sat(a2 - f23.x, a3 - f23.y);
     }
     tc_st16(t_hi, hi);
     tc_st16(t_lo, lo);
@@ -230,8 +237,9 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
         const int W = l == 0 ? q.P : TCH, Wp = pad8(W);
         const float* s = pk + q.aff_off[l];
         const float f = l == 0 ? 1.f : H_SA;
-        // a layer fed by the accumulator of the layer below (D = z * SA * SW) takes that factor into its scale
-        const float fs = (l > lz && l <= l_end) ? f * inv_scale[l - 1] : f;
+        // a layer fed by the accumulator of the layer below (D = z * SA * SW: chained in this launch, or stored as it is
+        // by the statistics pass of that layer) takes that factor into its scale
+        const float fs = (l <= l_end && (l > lz || (from_z && l == lz))) ? f * inv_scale[l - 1] : f;
         for (int i = tid; i < W; i += NT) { affs[l * 2 * TCH + i] = fs * s[i]; affs[l * 2 * TCH + TCH + i] = f * s[Wp + i]; }
     }
     const int out_rows = h_out_rows(F);
@@ -319,7 +327,6 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
             }
             if (from_z) { mbar_wait(&z_full[g], zph); zph ^= 1; }
             // ---- MMA layers lz .. l_end: build the A operand of layer l from z_l, 32 features at a time -----------
-            float inv_prev = 1.f;                                 // D of the previous layer = z * SA * SW
             for (int l = lz; l <= l_end; ++l) {
                 const float* sc = affs + l * 2 * TCH;
 #pragma unroll 1
@@ -366,7 +373,6 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
                     mbar_wait(&d_ready[g], pd);
                     pd ^= 1;
                     tc_fence_after();
-                    inv_prev = inv_scale[l];
                 }
             }
             if (stats) {
@@ -376,13 +382,21 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
                     if (gt == 0) bulk_store_wait_read();          // the previous tile's store has read the buffer
                     group_sync(g);
                 }
+                // the accumulator is stored as it is (z * SA * SW: the next pass and the statistics fold carry the factor);
+                // rows beyond the batch (ragged last tile only) are stored as zeros
+                const bool full = (tile + 1) * TCM <= A.B;
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     float v[32];
                     tc_ld32(tg + 32 * h, v);
                     tc_ld_wait();
+                    if (full) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) zs[(32 * h + j) * TCM + gt] = valid ? v[j] * inv_prev : 0.f;
+                        for (int j = 0; j < 32; ++j) zs[(32 * h + j) * TCM + gt] = v[j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) zs[(32 * h + j) * TCM + gt] = valid ? v[j] : 0.f;
+                    }
                 }
                 proxy_fence();
                 group_sync(g);
@@ -444,14 +458,46 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
                         float m = -3.0e38f;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) { z[32 * tt + j] = fmaf(z[32 * tt + j], inv_out, bs[j]); m = fmaxf(m, z[32 * tt + j]); }
-                        float S = 0.f, C = 0.f, ek = 0.f;
+                        // S = sum of the 32 exponentials, C = the kb below the bin, ek = the bin's own: a pairwise sum tree, then
+                        // a descent along the bits of kb that keeps the half / quarter / ... holding the bin (53 selects + 36
+                        // adds; the predicated running sums `C += j < kb ? e : 0`, `ek = j == kb ? e : ek` were 128 + 32)
+                        float e[32], s1[16], s2[8], s4[4];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float e = ex2_approx(z[32 * tt + j] - m);
-                            S += e;
-                            C += j < kb ? e : 0.f;
-                            ek = j == kb ? e : ek;
-                        }
+                        for (int j = 0; j < 32; ++j) e[j] = ex2_approx(z[32 * tt + j] - m);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) s1[j] = e[2 * j] + e[2 * j + 1];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) s2[j] = s1[2 * j] + s1[2 * j + 1];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) s4[j] = s2[2 * j] + s2[2 * j + 1];
+                        const float s8a = s4[0] + s4[1], s8b = s4[2] + s4[3];
+                        const float S = s8a + s8b;
+                        const bool b4 = kb & 16, b3 = kb & 8, b2 = kb & 4, b1 = kb & 2, b0 = kb & 1;
+                        float C = b4 ? s8a : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) e[j] = b4 ? e[16 + j] : e[j];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) s1[j] = b4 ? s1[8 + j] : s1[j];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) s2[j] = b4 ? s2[4 + j] : s2[j];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) s4[j] = b4 ? s4[2 + j] : s4[j];
+                        C += b3 ? s4[0] : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) e[j] = b3 ? e[8 + j] : e[j];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) s1[j] = b3 ? s1[4 + j] : s1[j];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) s2[j] = b3 ? s2[2 + j] : s2[j];
+                        C += b2 ? s2[0] : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) e[j] = b2 ? e[4 + j] : e[j];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) s1[j] = b2 ? s1[2 + j] : s1[j];
+                        C += b1 ? s1[0] : 0.f;
+                        const float e0 = b1 ? e[2] : e[0], e1 = b1 ? e[3] : e[1];
+                        C += b0 ? e0 : 0.f;
+                        const float ek = b0 ? e1 : e0;
                         const float inv = 1.f / S;
                         st[q.trafo[t] * TCM] = (ek * alpha + C) * inv;
                         jfac *= ek * inv * 32.f;
@@ -499,7 +545,8 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
     if (tid < TCH) {
         double s = 0.0, s2 = 0.0;
         for (int k = 0; k < 2 * NG; ++k) { s += red[tid + 64 * k]; s2 += red[NG * TCM + tid + 64 * k]; }
-        sacc[tid] = s; sacc[F.maxW + tid] = s2;
+        const double k1 = (double)inv_scale[l_end];               // the sums are of z * SA * SW (a power of two: exact)
+        sacc[tid] = s * k1; sacc[F.maxW + tid] = s2 * k1 * k1;
     }
     bn_stats_finalize(F, A, sacc, NT);
 }
