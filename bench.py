@@ -187,6 +187,41 @@ def pcie_probe(dev, nbytes=1 << 28):
     return {"h2d_gbs": timed(True, False), "d2h_gbs": timed(False, True), "both_directions_total_gbs": timed(True, True)}
 
 
+LAUNCH_NAMES = {0: "weight packs", 1: "flow_col_moments_kernel", 11: "flow_cell_h_kernel<.,.,1> layer pass from the state",
+                13: "flow_cell_h_kernel<.,.,3> layer pass from stored activations",
+                12: "flow_cell_h_kernel<.,.,2> final pass (output layer + splines)", 10: "flow_cell_h_kernel<.,.,0> fused cell",
+                2: "other"}
+
+
+def flow_launch_times(model, x, dev, n_points, hbm_peak, abytes, traffic=None):
+    """Per-launch device times of ONE forward, from CUDA events the library records on the launch stream around every
+    kernel (nis_flow_timing_begin / _end), grouped by kernel: launches, average ms, share of the step and - with the
+    algorithmic bytes per point of each launch - the achieved GB/s against the measured HBM peak."""
+    import ctypes
+    from nf_b200 import _cabi
+    lib = _cabi.lib()
+    lib.nis_flow_timing_begin(_cabi.stream_ptr(dev))
+    with torch.no_grad():
+        model(x)
+    lms = (ctypes.c_float * 512)()
+    ltag = (ctypes.c_int32 * 512)()
+    nl = lib.nis_flow_timing_end(lms, ltag, 512)
+    per = {}
+    for i in range(max(nl, 0)):
+        per.setdefault(int(ltag[i]), []).append(float(lms[i]))
+    tot_ms = sum(sum(v) for v in per.values()) or 1.0
+    kernels = []
+    for tag, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
+        k = {"kernel": LAUNCH_NAMES.get(tag, str(tag)), "launches_per_step": len(v), "avg_ms": sum(v) / len(v),
+             "share_of_step": sum(v) / tot_ms}
+        if tag in abytes:
+            g = n_points * abytes[tag] / (k["avg_ms"] * 1e-3) / 1e9
+            k.update({"algorithmic_bytes_per_point": abytes[tag], "achieved_gbs": g, "frac_of_hbm_peak": g / hbm_peak,
+                      "traffic": (traffic or {}).get(tag)})
+        kernels.append(k)
+    return kernels
+
+
 def parity_checks(rank, world, dev):
     """Run by every `bench.py --gpus N`: the N-rank paths checked in the driver's own run.
     (a) data-parallel gradient == single-GPU gradient: every rank backpropagates the variance loss of ITS minibatch
@@ -396,14 +431,15 @@ def bench_wide(steps, warmup, world, dev):
 
     ms_f = time_steps(fwd, steps, warmup, world)
     ms_s = time_steps(step, steps, warmup, world)
-    pk, _ = peaks()
-    tf32_peak = pk.get("bf16_tflops", 1590.0) / 2
+    tf32_peak = tensor_peak_tflops(0, 128) or peaks()[0].get("bf16_tflops", 1590.0) / 2     # measured kind::tf32 peak
     ach = world * n * flop * 3 / (ms_f * 1e-3) / 1e12         # executed TF32 flops (3xTF32 split)
     return {"metric": "nis_flow_fwd_logdet_points_per_sec", "value": world * n / (ms_f * 1e-3), "unit": "points/s",
             "ms_per_step": ms_f,
             "config": {"workload": "configs[4]: 16-D PWQuad flow, 8 cells, 64 bins, MLP [256]*4, train-mode BN, 2^16 points per rank"},
             "roofline": {"bound": "tensor", "achieved": ach / world, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / world / tf32_peak,
-                         "algorithmic_tflops": ach / 3 / world, "note": "3xTF32: three tensor MACs per conditioner MAC"},
+                         "algorithmic_tflops": ach / 3 / world,
+                         "peak_kind": "tcgen05.mma kind::tf32 M128 N128 K8 back to back on every SM, measured in this run",
+                         "note": "3xTF32: three tensor MACs per conditioner MAC"},
             "train_step": {"metric": "nis_train_step_points_per_sec", "value": world * n / (ms_s * 1e-3), "unit": "points/s",
                            "ms_per_step": ms_s}}
 
@@ -434,7 +470,12 @@ def bench_integrate(world, dev):
     dt = time.perf_counter() - t0
     honest = float(err) * nitn ** 0.5                          # manager.py:403 under-reports by sqrt(nitn)
     known = 0.06648282151394422
+    xq = torch.rand(1 << 22, 8, device=dev, dtype=torch.float32)
+    flow_k = flow_launch_times(NF.best_model, xq, dev, 1 << 22, peaks()[0]["hbm_gbs"],
+                               {1: 36, 11: 36 + 256, 13: 512, 12: 256 + 72, 10: 72})
+    del xq
     return {"metric": "nis_integrate_points_per_sec", "value": nitn * neval / dt, "unit": "points/s",
+            "flow_kernels_at_2p22_points": flow_k,
             "estimate": float(sig), "reported_error": float(err), "honest_error": honest, "known_answer": known,
             "finite": bool(torch.isfinite(sig)), "within_one_honest_error": bool(abs(float(sig) - known) <= honest),
             "n_nonfinite_weights": NF.n_nonfinite,
@@ -607,35 +648,49 @@ def main():
         f16_peak = tensor_peak_tflops(1, 128) or pk["bf16_tflops"]
         f16_peak_n64 = tensor_peak_tflops(1, 64)
         tf32_meas = tensor_peak_tflops(0, 128)
-        tf32_peak = f16_peak                     # the dominant kernel issues kind::f16 MMAs (fp16-split operands)
         tfl = N_POINTS * FLOP_PER_POINT / (ms * 1e-3) / 1e12
         # moments pass reads the rows; first layer pass reads rows, writes z2; later passes read+write 256 B; final
         train_bytes_pt = n_cells * (36 + (36 + 256) + 2 * (depth - 2) * 256 + (256 + 36 + 36))
         gbs_design = N_POINTS * train_bytes_pt / (ms * 1e-3) / 1e9
         gbs = N_POINTS * IO_BYTES_PER_POINT / (ms * 1e-3) / 1e9
+        # ---- per-launch device times of one more forward (CUDA events recorded on the launch stream by the library:
+        #      nis_flow_timing_begin / _end), outside the timed region -----------------------------------------------
+        # algorithmic bytes per point of each launch: what the kernel has to read and write once
+        abytes = {1: 36, 11: 36 + 256, 13: 256 + 256, 12: 256 + 36 + 36, 10: 36 + 36}
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch at 2^22 points, ncu --set full (profiles/r02_ncu_h_kernel.md)
+        traffic = {11: 1176675000, 13: 2407364000, 12: 1378160000, 10: 264708000} if N_POINTS == 1 << 22 else None
+        kernels = flow_launch_times(model, x, dev, N_POINTS, pk["hbm_gbs"], abytes, traffic)
+        dom = next((k for k in kernels if "achieved_gbs" in k), None)
         line["roofline"] = {
-            "bound": "tensor", "achieved": tfl_exec, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tfl_exec / tf32_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE train-mode layer-pass launch of flow_cell_tc_kernel at
-            # 2^22 points, from the committed ncu --set full capture (profiles/r01_ncu_tc.md); not re-measured per run
-            "traffic": 2250729000 if N_POINTS == 1 << 22 else None,
-            "peak_kind": "tcgen05.mma kind::f16 M128 N128 K16 issued back to back on every SM, measured in this run "
-                         "(nis_probe_tensor); MEASURED_PEAKS.json bf16 cuBLAS: %s TFLOP/s" % pk.get("bf16_tflops"),
-            "measured_tensor_peaks_tflops": {"f16_n128": f16_peak, "f16_n64": f16_peak_n64, "tf32_n128": tf32_meas},
-            "kernel": "flow_cell_h_kernel: %d launches per step (per cell %d train-mode layer passes + 1 final pass) "
-                      "+ %d flow_col_moments_kernel" % (n_cells * depth, depth - 1, n_cells),
-            "tensor_flop_per_point": tensor_flop_pt,
-            "note": "executed fp16 flops (fp16-split operands: 3 tensor MACs per conditioner MAC); the step is not "
-                    "tensor-bound: see hbm_design and fp32_equivalent",
-            "fp32_equivalent": {"achieved": tfl, "peak": fma, "unit": "TFLOP/s", "frac": tfl / fma,
-                                "algorithmic_flop_per_point": FLOP_PER_POINT,
-                                "peak_kind": "FP32 FMA pipe measured in this run (nis_probe_fp32_fma); the stated "
-                                             "roofline of SURVEY.md 8(d) for this config"},
-            "hbm_design": {"achieved": gbs_design, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs_design / pk["hbm_gbs"],
-                           "bytes_per_point": train_bytes_pt, "peak_kind": peak_kind,
-                           "note": "traffic of the train-mode layer-pass design (pre-BN activations round-trip "
-                                   "through HBM once per BN layer), not the algorithmic minimum"},
-            "hbm": {"achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                    "peak_kind": peak_kind, "algorithmic_bytes_per_point": IO_BYTES_PER_POINT}}
+            # the dominant kernel of the train-mode step: an HBM-bound layer pass (reads one 256 B/point activation tile,
+            # writes the next); achieved = algorithmic bytes of ONE launch / its device time measured in this run
+            "bound": "hbm", "achieved": dom["achieved_gbs"] if dom else None, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": dom["frac_of_hbm_peak"] if dom else None, "traffic": dom.get("traffic") if dom else None,
+            "peak_kind": "%s (MEASURED_PEAKS.json copy bandwidth)" % peak_kind,
+            "kernel": dom["kernel"] if dom else None,
+            "algorithmic_bytes_per_launch": N_POINTS * dom["algorithmic_bytes_per_point"] if dom else None,
+            "kernels": kernels,
+            "step": {
+                "hbm_design": {"achieved": gbs_design, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs_design / pk["hbm_gbs"],
+                               "bytes_per_point": train_bytes_pt,
+                               "note": "all launches of the step: the train-mode layer-pass design moves the pre-BN activations "
+                                       "through HBM once per BatchNorm layer (grid-wide statistics)"},
+                "hbm_algorithmic": {"achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                                    "algorithmic_bytes_per_point": IO_BYTES_PER_POINT,
+                                    "note": "SURVEY 8(d) I/O of the whole forward (32 B in + 36 B out)"},
+                "tensor": {"achieved": tfl_exec, "peak": f16_peak, "unit": "TFLOP/s", "frac": tfl_exec / f16_peak,
+                           "tensor_flop_per_point": tensor_flop_pt,
+                           "peak_kind": "tcgen05.mma kind::f16 M128 N128 K16 back to back on every SM, measured in this run "
+                                        "(nis_probe_tensor)",
+                           "measured_tensor_peaks_tflops": {"f16_n128": f16_peak, "f16_n64": f16_peak_n64, "tf32_n128": tf32_meas,
+                                                            "bf16_cublas_MEASURED_PEAKS": pk.get("bf16_tflops")},
+                           "note": "executed fp16 flops (fp16-split operands: 3 tensor MACs per conditioner MAC); the step is "
+                                   "not tensor-bound"},
+                "fp32_equivalent": {"achieved": tfl, "peak": fma, "unit": "TFLOP/s", "frac": tfl / fma,
+                                    "algorithmic_flop_per_point": FLOP_PER_POINT,
+                                    "peak_kind": "FP32 FMA pipe measured in this run (nis_probe_fp32_fma): the roofline SURVEY 8(d) "
+                                                 "states for this config; above 1 because the conditioner runs on the tensor pipe"}}}
+        line["roofline"]["tensor_flop_per_point"] = tensor_flop_pt
 
     if not args.no_extras:
         model.eval()
@@ -644,10 +699,13 @@ def main():
         tfl_e_exec = N_POINTS * line["roofline"]["tensor_flop_per_point"] / (ms_eval * 1e-3) / 1e12
         line["eval_mode"] = {"value": world * N_POINTS / (ms_eval * 1e-3), "unit": "points/s", "ms_per_step": ms_eval,
                              "launches_per_step": 2 + n_cells,
-                             "roofline": {"bound": "tensor", "achieved": tfl_e_exec, "peak": line["roofline"]["peak"],
-                                          "unit": "TFLOP/s", "frac": tfl_e_exec / line["roofline"]["peak"],
-                                          "fp32_equivalent": {"achieved": tfl_e, "peak": line["roofline"]["fp32_equivalent"]["peak"],
-                                                              "frac": tfl_e / line["roofline"]["fp32_equivalent"]["peak"]}}}
+                             "roofline": {"bound": "tensor", "achieved": tfl_e_exec,
+                                          "peak": line["roofline"]["step"]["tensor"]["peak"], "unit": "TFLOP/s",
+                                          "frac": tfl_e_exec / line["roofline"]["step"]["tensor"]["peak"],
+                                          "note": "fused eval cell: instruction-issue bound (profiles/r02_ncu_h_kernel.md), "
+                                                  "neither tensor- nor HBM-bound",
+                                          "fp32_equivalent": {"achieved": tfl_e, "peak": line["roofline"]["step"]["fp32_equivalent"]["peak"],
+                                                              "frac": tfl_e / line["roofline"]["step"]["fp32_equivalent"]["peak"]}}}
         model.train()
         del x
         torch.cuda.empty_cache()

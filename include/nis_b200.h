@@ -182,6 +182,14 @@ int64_t nis_probe_fp32_fma(float* out, int32_t iters, void* stream);
  * gives the MEASURED tensor-pipe peak the tcgen05 flow kernels are quoted against. */
 int64_t nis_probe_tensor(int32_t kind, int32_t n, int32_t iters, void* stream);
 
+/* Measurement aid for bench.py: per-launch device times of nis_flow_forward.  After nis_flow_timing_begin(stream) every
+ * kernel launch of the nis_flow_forward calls made by THIS thread is bracketed by CUDA events recorded on the launch
+ * stream; nis_flow_timing_end synchronises them and returns the number of launches written to ms[] / tags[] (tags: 0 weight
+ * packs, 1 column moments, 10 fused eval cell, 11 layer pass from the state, 13 layer pass from stored activations, 12
+ * final pass from stored activations, 2 other), or a negative error. */
+int nis_flow_timing_begin(void* stream);
+int nis_flow_timing_end(float* ms, int32_t* tags, int32_t max_n);
+
 /* sizeof(NisFlowDesc) / sizeof(NisRamboDesc) as compiled, so a foreign-language binding can verify its
  * struct layout at load time. */
 size_t nis_sizeof_flow_desc(void);

@@ -74,6 +74,8 @@ _PROTOS = {
     "nis_uniform_fill": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, _P]),
     "nis_probe_fp32_fma": (ctypes.c_int64, [_P, ctypes.c_int32, _P]),
     "nis_probe_tensor": (ctypes.c_int64, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P]),
+    "nis_flow_timing_begin": (ctypes.c_int, [_P]),
+    "nis_flow_timing_end": (ctypes.c_int, [_P, _P, ctypes.c_int32]),
     "nis_sizeof_flow_desc": (ctypes.c_size_t, []),
     "nis_sizeof_rambo_desc": (ctypes.c_size_t, []),
     "nis_strerror": (ctypes.c_char_p, [ctypes.c_int]),

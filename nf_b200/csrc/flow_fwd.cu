@@ -249,6 +249,43 @@ int nis_launch_col_stats(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 bool nis_moments_supported(const DevFlow& F, int c);
 int nis_launch_col_moments(const DevFlow& F, const FwdArgs& A, cudaStream_t s);
 
+// ---- measurement aid: per-launch device times of nis_flow_forward (bench.py's roofline object) ---------------------------
+// nis_flow_timing_begin() arms a per-thread sink; every kernel launch of the following nis_flow_forward calls is then
+// bracketed by CUDA events recorded on the launch stream; nis_flow_timing_end() synchronises those events and returns the
+// elapsed time and a tag per launch (0 pack, 1 column moments, 10 + mode for the tensor-core cell kernel: 10 fused cell,
+// 11 layer pass from the state, 12 final pass from stored activations, 13 layer pass from stored activations; 2 other).
+#define NIS_TIMING_MAX 512
+struct TimingSink { bool on; int n; cudaEvent_t ev[NIS_TIMING_MAX + 1]; int tag[NIS_TIMING_MAX]; bool made; };
+static thread_local TimingSink g_timing = {false, 0, {}, {}, false};
+static inline void timing_mark(cudaStream_t s, int tag) {
+    TimingSink& T = g_timing;
+    if (!T.on || T.n >= NIS_TIMING_MAX) return;
+    if (tag >= 0) T.tag[T.n++] = tag;
+    cudaEventRecord(T.ev[T.n], s);         // ev[n] closes launch n-1 and opens launch n
+}
+extern "C" int nis_flow_timing_begin(void* stream) {
+    TimingSink& T = g_timing;
+    if (!T.made) {
+        for (int i = 0; i <= NIS_TIMING_MAX; ++i) if (cudaEventCreate(&T.ev[i]) != cudaSuccess) return NIS_ECUDA;
+        T.made = true;
+    }
+    T.on = true; T.n = 0;
+    cudaEventRecord(T.ev[0], (cudaStream_t)stream);
+    return NIS_OK;
+}
+extern "C" int nis_flow_timing_end(float* ms, int32_t* tags, int32_t max_n) {
+    TimingSink& T = g_timing;
+    if (!T.on) return NIS_EINVAL;
+    T.on = false;
+    if (cudaEventSynchronize(T.ev[T.n]) != cudaSuccess) return NIS_ECUDA;
+    const int n = T.n < max_n ? T.n : max_n;
+    for (int i = 0; i < n; ++i) {
+        if (cudaEventElapsedTime(&ms[i], T.ev[i], T.ev[i + 1]) != cudaSuccess) return NIS_ECUDA;
+        tags[i] = T.tag[i];
+    }
+    return n;
+}
+
 static size_t fwd_smem_bytes(const DevFlow& F, int NT) {
     const int bw = F.maxW > F.Kpad ? F.maxW : F.Kpad;
     size_t fl = (size_t)((F.d + 1) + 2 * bw) * NT;
@@ -318,8 +355,10 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
         }
         int bx = (mx + 255) / 256;
         if (bx > 64) bx = 64;
+        timing_mark(s, -1);                 // open the first interval on this stream (after the counter memset)
         flow_pack_kernel<<<dim3(bx, F.n_cells), 256, 0, s>>>(F, params, bn_running, ws.wpack, bn_mode);
         NIS_CUDA_CHECK_LAUNCH();
+        timing_mark(s, 0);
     }
     FwdArgs A;
     A.in = xj_in; A.in_dtype = in_dtype; A.in_cols = in_cols;
@@ -337,7 +376,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     // recompute them from the state (more tensor work, ~7x less traffic); NIS_TRAIN_RECOMPUTE=0/1 overrides the default
     static const int recompute_env = [] { const char* e = getenv("NIS_TRAIN_RECOMPUTE"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
     const bool recompute = hp && (recompute_env >= 0 ? recompute_env == 1 : false);
-    if (tc) { rc = hp ? nis_h_pack(F, params, ws.tcpack, s) : nis_tc_pack(F, params, ws.tcpack, s); if (rc) return rc; }
+    if (tc) { rc = hp ? nis_h_pack(F, params, ws.tcpack, s) : nis_tc_pack(F, params, ws.tcpack, s); if (rc) return rc; timing_mark(s, 0); }
     if (wide) { rc = nis_wide_pack(F, params, ws.tcpack, s); if (rc) return rc; }
     const long long rows = (long long)B * (F.d + 1);
     if (bn_mode == NIS_BN_EVAL && !tiled) {
@@ -362,6 +401,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
                 A.stats_layer = 0;
                 rc = nis_launch_col_moments(F, A, s);
                 if (rc) return rc;
+                timing_mark(s, 1);
                 l0 = 2;
             }
             for (int l = l0; l <= F.depth; ++l) {
@@ -378,6 +418,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
                     rc = launch_fwd_any(F, A, s);
                 }
                 if (rc) return rc;
+                timing_mark(s, (tc || wide) && l >= 1 ? 10 + 1 + (A.zin ? 2 : 0) : 2);
             }
         }
         A.stats_layer = -1;
@@ -408,6 +449,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
         rc = hp ? nis_launch_h(F, A, ws.tcpack, s) : tc ? nis_launch_tc(F, A, ws.tcpack, s) : wide ? nis_launch_wide(F, A, ws.tcpack, s)
                 : (tiled ? nis_launch_tiled(F, A, s) : launch_fwd_any(F, A, s));
         if (rc) return rc;
+        timing_mark(s, (tc || wide) ? 10 + (A.zin ? 2 : 0) : 2);
     }
     return NIS_OK;
 }
