@@ -669,7 +669,7 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
     extern __shared__ char smraw[];
     __shared__ uint64_t a_ready, done;
     __shared__ uint32_t tmem_base_s;
-    char* sm = smem_align1024(smraw);
+    char* sm = smem_align1024_generic(smraw);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int c = A.c, lam = A.lam;
     const DevCell& q = F.cells[c];
