@@ -733,6 +733,16 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
         for (long long tile = part; tile < ntiles; tile += gridDim.z, ++n) {
             const long long pt = tile * TCM + gt;
             const bool valid = pt < A.B;
+            // the kernel is latency-bound (5 warps per SM, operands loaded in dependent batches of 32 values): pull the next
+            // tile's two operand blocks (contiguous in the tile-blocked buffers) into L2 while this one is processed
+            if (gt == 0 && tile + gridDim.z < ntiles) {
+                const long long tn = tile + gridDim.z;
+                const int rows_here = nrows - 64 * rb < 64 ? nrows - 64 * rb : 64;
+                if (rows_here > 0)
+                    bulk_prefetch_l2((OUTL ? A.dl + (size_t)tn * nlog * TCM : A.dz + (size_t)tn * W * TCM) + (size_t)(64 * rb) * TCM,
+                                     (uint32_t)rows_here * TCM * 4);
+                if (lam > 0) bulk_prefetch_l2(A.zbuf + (((size_t)(lam - 1) * ntiles + tn) * W + 128 * nh) * TCM, (uint32_t)N * TCM * 4);
+            }
             // A: 64 upstream features [64 rb, 64 rb + 64)
             {
                 const float* up = (OUTL ? A.dl + (size_t)tile * nlog * TCM : A.dz + (size_t)tile * W * TCM) + (size_t)(64 * rb) * TCM + gt;
