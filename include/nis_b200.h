@@ -11,15 +11,21 @@
  *                             layers/layers.py:27-32,43-51,75-77,90-91; called at manager.py:174,225,341,397)
  *   nis_flow_backward     <- loss.backward() through the same modules (manager.py:278)
  *   nis_reduce_moments    <- torch.var / torch.mean of f*J (manager.py:255,399-400)
- *   nis_rambo_generate    <- FlatInvertiblePhasespace.generateKinematics_batch, pdf inactive
- *                            (nisrep/PhaseSpace/flat_phase_space_generator.py:139-308, 313-441;
- *                             PhaseSpace/utils.py:5-81,134-187)
+ *   nis_reduce_stats      <- the same plus torch.max / torch.min and a non-finite count
+ *                            (nisrep/utils/experiment_mg.py:73-76,101)
+ *   nis_rambo_generate    <- FlatInvertiblePhasespace.generateKinematics_batch, pdf inactive and pdf active
+ *                            (nisrep/PhaseSpace/flat_phase_space_generator.py:81-137, 139-308, 313-441;
+ *                             PhaseSpace/utils.py:5-146, 151-187)
  *   nis_uniform_fill      <- torch.nn.init.uniform_(w) (manager.py:222,395)
  *
  * Conventions: plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
  * unless marked host; work is enqueued on `stream` and the call returns without synchronising; no
- * allocation; no global state (re-entrant).  Return value: 0 on success, a negative NIS_E* code
- * otherwise (nis_strerror() gives text).  `stream` is a cudaStream_t passed as void*.
+ * allocation; re-entrant.  Process-wide state is limited to caches of launch attributes (the dynamic
+ * shared-memory opt-in per kernel and device, the SM count) and to environment variables that select a
+ * kernel family for tests and A/B measurements (NIS_TC, NIS_TC_H, NIS_BWD_TC, ... - INTEGRATION.md section 7;
+ * read on every call, unset in production); the measurement aid nis_flow_timing_* keeps a per-thread
+ * event list.  Return value: 0 on success, a negative NIS_E* code otherwise (nis_strerror() gives
+ * text).  `stream` is a cudaStream_t passed as void*.
  */
 #ifndef NIS_B200_H
 #define NIS_B200_H
