@@ -17,6 +17,8 @@
 // Autograd semantics reproduced: torch.autograd through coupling_cells.py:107-142,159-228,230-254 as
 // the reference's loss.backward() does (manager.py:278); bin indices carry no gradient, the PWQuad
 // clamp (:167) passes gradient only to unclamped points.
+#include <stdlib.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "spline.cuh"
 
@@ -158,8 +160,7 @@ __device__ __forceinline__ float load_g(const void* p, int dtype, long long idx)
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) flow_bwd_generic_kernel(const __grid_constant__ DevFlow F, const BwdArgs A) {
-    extern __shared__ __align__(16) float sm[];
+__device__ __forceinline__ void bwd_generic_body(const DevFlow& F, const BwdArgs& A, float* sm) {
     const int tid = threadIdx.x;
     const int d = F.d, maxW = F.maxW, depth = F.depth, OUT = depth + 1;
     const int c = A.c;
@@ -321,7 +322,8 @@ __global__ void __launch_bounds__(NT) flow_bwd_generic_kernel(const __grid_const
                         const bool on = l == 0 || a > 0.f;
                         const float dh = on ? GA[j * NT] : 0.f;
                         const float xh = gam[j] != 0.f ? (a - bet[j]) / gam[j] : 0.f;
-                        GA[j * NT] = valid ? sc[j] * (dh - m1[j] - xh * m2[j]) : 0.f;
+                        // (m1 / m2 through L2: in the cooperative launch another CTA has just written them)
+                        GA[j * NT] = valid ? sc[j] * (dh - __ldcg(m1 + j) - xh * __ldcg(m2 + j)) : 0.f;
                     }
                 }
                 if (l == 0) {
@@ -406,6 +408,44 @@ __global__ void __launch_bounds__(NT) flow_bwd_generic_kernel(const __grid_const
         gg[W + j] += (float)s1;      // dL/dbeta
     }
     if (tid == 0) *A.counter = 0u;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) flow_bwd_generic_kernel(const __grid_constant__ DevFlow F, const BwdArgs A) {
+    extern __shared__ __align__(16) float sm[];
+    bwd_generic_body<NT>(F, A, sm);
+}
+
+// Small batches in train mode: the per-step launches of every cell (output layer, each BatchNorm layer: the next step needs
+// the batch means the previous one folds), the zeroing of the per-CTA gradient slices and their reduction run inside ONE
+// cooperative launch with grid-wide barriers (README example: 16 launches of ~20 us -> one).
+template <int NT>
+__global__ void __launch_bounds__(NT) flow_bwd_coop_kernel(const __grid_constant__ DevFlow F, const BwdArgs A0) {
+    extern __shared__ __align__(16) float sm[];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int tid = threadIdx.x, OUT = F.depth + 1;
+    BwdArgs A = A0;
+    for (int c = F.n_cells - 1; c >= 0; --c) {
+        const int np = (int)(F.p_out_b(c) + (long long)F.cells[c].T * F.K);
+        float* gp = A0.gpart + (size_t)blockIdx.x * np;
+        for (int i = tid; i < np; i += NT) gp[i] = 0.f;
+        __syncthreads();
+        A.c = c; A.cell_params = np; A.first = c == F.n_cells - 1;
+        for (int L = OUT; L >= 0; --L) {
+            A.step_begin = A.step_end = L;
+            A.grad_in = (c == 0 && L == 0) ? A0.grad_in : nullptr;
+            bwd_generic_body<NT>(F, A, sm);
+            grid.sync();
+        }
+        // grad_params[cell block] += sum over CTAs of their slices, in CTA order (deterministic)
+        float* out = A0.grad_params + F.cells[c].param_off;
+        for (int i = blockIdx.x * NT + tid; i < np; i += gridDim.x * NT) {
+            float s_ = 0.f;
+            for (unsigned b = 0; b < gridDim.x; ++b) s_ += __ldcg(A0.gpart + (size_t)b * np + i);
+            out[i] += s_;
+        }
+        grid.sync();                                   // the slices are free for the next cell
+    }
 }
 
 // grad_params[cell block] += sum over CTAs of their slices (fixed order)
@@ -560,6 +600,31 @@ extern "C" int nis_flow_backward(const NisFlowDesc* desc, const float* params, c
     A.bnb = sc.bnb; A.gpart = sc.gpart; A.grad_params = grad_params;
     A.partials = ws.partials; A.counter = ws.counter; A.B = B; A.train = train; A.rotate = rotate;
     const int OUT = F.depth + 1;
+    if (train && NT == 128 && !rotate) {
+        // small batch: the whole backward in one cooperative launch when every tile has its own resident CTA
+        static const int coop_env = [] { const char* e = getenv("NIS_COOP"); return e && e[0] == '0' ? 0 : 1; }();
+        const long long ntiles = (B + NT - 1) / NT;
+        const size_t smem = bwd_smem_bytes(F, 128, false);
+        static int maxg[16] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 15;
+        if (coop_env && maxg[dev] == 0) {
+            int per_sm = 0, sms = 0;
+            NIS_ENSURE_SMEM((flow_bwd_coop_kernel<128>), (int)smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flow_bwd_coop_kernel<128>, 128, smem);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            maxg[dev] = per_sm * sms > 0 ? per_sm * sms : -1;
+        }
+        if (coop_env && ntiles == grid && ntiles <= maxg[dev]) {
+            NIS_ENSURE_SMEM((flow_bwd_coop_kernel<128>), (int)smem);
+            A.grad_in = grad_in; A.c = 0; A.cell_params = 0; A.first = 1; A.step_begin = A.step_end = OUT;
+            void* args[] = {(void*)&F, (void*)&A};
+            if (cudaLaunchCooperativeKernel((const void*)flow_bwd_coop_kernel<128>, dim3((unsigned)grid), dim3(128), args, smem, s) == cudaSuccess)
+                return NIS_OK;
+            cudaGetLastError();
+        }
+    }
     for (int c = F.n_cells - 1; c >= 0; --c) {
         const int np = (int)(F.p_out_b(c) + (long long)F.cells[c].T * F.K);
         cudaMemsetAsync(sc.gpart, 0, sizeof(float) * (size_t)grid * np, s);

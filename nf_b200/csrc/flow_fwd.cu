@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "spline.cuh"
+#include <cooperative_groups.h>
 #include "flow_fwd_common.cuh"
 
 // ---------------------------------------------------------------------------------------------------
@@ -108,8 +109,7 @@ __device__ __forceinline__ void reduce_rows(const float* buf, int W, double* sac
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) flow_fwd_generic_kernel(const __grid_constant__ DevFlow F, const FwdArgs A) {
-    extern __shared__ __align__(16) float sm[];
+__device__ __forceinline__ void fwd_generic_body(const DevFlow& F, const FwdArgs& A, float* sm) {
     const int tid = threadIdx.x;
     const int d = F.d, maxW = F.maxW;
     const int bw = maxW > F.Kpad ? maxW : F.Kpad;
@@ -157,7 +157,9 @@ __global__ void __launch_bounds__(NT) flow_fwd_generic_kernel(const __grid_const
             {
                 const float* sc = pk + q.aff_off[0];
                 const float* sh = sc + pad8(q.P);
-                for (int k = 0; k < q.P; ++k) bufA[k * NT] = fmaf(st[q.feed[k] * NT], sc[k], sh[k]);
+                // (scale / shift through L2: in the cooperative launch another CTA has just written them, and an L1 line
+                //  holding a neighbouring layer's values may be stale)
+                for (int k = 0; k < q.P; ++k) bufA[k * NT] = fmaf(st[q.feed[k] * NT], __ldcg(sc + k), __ldcg(sh + k));
             }
             float* cur = bufA;
             float* nxt = bufB;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(NT) flow_fwd_generic_kernel(const __grid_const
                 }
                 const float* sc = pk + q.aff_off[l + 1];
                 const float* sh = sc + Hp;
-                dense8<NT>(Wt, in, Hp, cur, [&](int j, float z) { nxt[j * NT] = fmaxf(fmaf(z, sc[j], sh[j]), 0.f); });
+                dense8<NT>(Wt, in, Hp, cur, [&](int j, float z) { nxt[j * NT] = fmaxf(fmaf(z, __ldcg(sc + j), __ldcg(sh + j)), 0.f); });
                 float* t_ = cur; cur = nxt; nxt = t_;
                 in = H;
             }
@@ -220,6 +222,41 @@ __global__ void __launch_bounds__(NT) flow_fwd_generic_kernel(const __grid_const
     }
     if (!stats) return;
     bn_stats_finalize(F, A, sacc, NT);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) flow_fwd_generic_kernel(const __grid_constant__ DevFlow F, const FwdArgs A) {
+    extern __shared__ __align__(16) float sm[];
+    fwd_generic_body<NT>(F, A, sm);
+}
+
+// Small batches in train mode (the README example: 2000-point minibatches, 2 cells x 5 BatchNorm layers): the launch
+// sequence above is one statistics pass per BN layer plus a final pass per cell - 11 launches of ~9 us each for a few
+// microseconds of arithmetic.  When the whole batch is co-resident (one tile per CTA slot) the same passes run inside ONE
+// cooperative launch with a grid-wide barrier where the next pass needs the folded statistics.
+template <int NT>
+__global__ void __launch_bounds__(NT) flow_fwd_coop_kernel(const __grid_constant__ DevFlow F, const FwdArgs A0) {
+    extern __shared__ __align__(16) float sm[];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const long long rows = A0.B * (F.d + 1);
+    FwdArgs A = A0;
+    for (int c = 0; c < F.n_cells; ++c) {
+        A.c_begin = c; A.c_end = c + 1;
+        A.from_state = c > 0;
+        A.state_in = c > 0 ? (A0.saved ? A0.saved + (long long)c * rows : A0.scratch_state) : nullptr;
+        A.state_out = nullptr; A.to_out = 0;
+        for (int l = 0; l <= F.depth; ++l) {
+            A.stats_layer = l;
+            fwd_generic_body<NT>(F, A, sm);
+            grid.sync();                               // the folded scale / shift of layer l is visible to every CTA
+        }
+        const bool last = c == F.n_cells - 1;
+        A.stats_layer = -1;
+        A.to_out = last;
+        A.state_out = A0.saved ? A0.saved + (long long)(c + 1) * rows : (last ? nullptr : A0.scratch_state);
+        fwd_generic_body<NT>(F, A, sm);
+        // (the next cell's passes read the rows this CTA's threads have just written: no barrier needed)
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -321,6 +358,41 @@ static int launch_fwd(const DevFlow& F, const FwdArgs& A, cudaStream_t s) {
     return NIS_OK;
 }
 
+// Co-residency: every CTA of a cooperative launch must be resident at once.
+template <int NT>
+static int coop_max_grid(size_t smem) {
+    static int cached[16] = {0};
+    static size_t cached_smem[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 15;
+    if (cached[dev] == 0 || cached_smem[dev] != smem) {
+        int per_sm = 0, sms = 0;
+        NIS_ENSURE_SMEM((flow_fwd_coop_kernel<NT>), (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flow_fwd_coop_kernel<NT>, NT, smem);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = per_sm * sms > 0 ? per_sm * sms : -1;
+        cached_smem[dev] = smem;
+    }
+    return cached[dev];
+}
+
+// the whole train-mode forward in one cooperative launch, or NIS_EUNSUPPORTED when the batch is not co-resident
+static int launch_fwd_coop(const DevFlow& F, FwdArgs A, cudaStream_t s) {
+    constexpr int NT = 128;
+    const size_t smem = fwd_smem_bytes(F, NT);
+    if (smem > 200 * 1024) return NIS_EUNSUPPORTED;
+    const long long ntiles = (A.B + NT - 1) / NT;
+    const int maxg = coop_max_grid<NT>(smem);
+    if (maxg <= 0 || ntiles > maxg) return NIS_EUNSUPPORTED;
+    void* args[] = {(void*)&F, (void*)&A};
+    if (cudaLaunchCooperativeKernel((const void*)flow_fwd_coop_kernel<NT>, dim3((unsigned)ntiles), dim3(NT), args, smem, s) != cudaSuccess) {
+        cudaGetLastError();
+        return NIS_EUNSUPPORTED;
+    }
+    return NIS_OK;
+}
+
 static int launch_fwd_any(const DevFlow& F, const FwdArgs& A, cudaStream_t s) {
     const size_t lim = 200 * 1024;
     if (fwd_smem_bytes(F, 128) <= lim / 2) return launch_fwd<128>(F, A, s);   // >= 2 CTAs per SM
@@ -366,7 +438,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     A.saved = saved; A.bins = bins_out;
     A.params = params; A.wpack = ws.wpack; A.bn_running = bn_running; A.bn_saved = bn_saved;
     A.partials = ws.partials; A.counter = ws.counter; A.B = B;
-    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr;
+    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr; A.scratch_state = nullptr;
     // per-cell launch sequences: tcgen05 kernel where it applies, else the FP32 register-tiled kernel
     const bool tc = nis_tc_supported(F, B, bn_mode);
     const bool hp = tc && nis_h_supported(F, B, bn_mode);              // fp16-split, four-group kernel (flow_tc_h.cu)
@@ -383,6 +455,17 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
         A.state_in = nullptr; A.state_out = nullptr; A.from_state = 0; A.to_out = 1;
         A.c_begin = 0; A.c_end = F.n_cells; A.stats_layer = -1;
         return launch_fwd_any(F, A, s);
+    }
+    if (bn_mode == NIS_BN_TRAIN && !tiled) {
+        // small batch: every pass of every cell inside one cooperative launch (falls through when not co-resident)
+        static const int coop_env = [] { const char* e = getenv("NIS_COOP"); return e && e[0] == '0' ? 0 : 1; }();
+        if (coop_env) {
+            A.scratch_state = ws.state;
+            A.state_in = nullptr; A.state_out = nullptr; A.from_state = 0; A.to_out = 0;
+            A.c_begin = 0; A.c_end = 1; A.stats_layer = 0;
+            rc = launch_fwd_coop(F, A, s);
+            if (rc == NIS_OK) { timing_mark(s, 2); return NIS_OK; }
+        }
     }
     // One launch sequence per cell.  TRAIN: a statistics pass per BN layer, then the full pass.
     // (EVAL reaches here only on the register-tiled path, whose launches are per cell.)

@@ -17,6 +17,7 @@ struct FwdArgs {
     float* zout;                                 // tile-blocked [tile][64][M] (written by a statistics pass)
     int no_stats;                                // layer pass that only stores its activations (eval-mode split cell)
     float* z1out;                          // wide kernel, pass from the state: also store z_1 (backward recompute) or null
+    float* scratch_state;                  // cooperative small-batch kernel: fp32 [B][d+1] state between cells when `saved` is null
 };
 
 
