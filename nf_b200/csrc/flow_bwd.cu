@@ -22,6 +22,10 @@
 #include "common.cuh"
 #include "spline.cuh"
 
+// floats between the BN-backward means of consecutive layers: whole 128-byte lines per layer (a layer's block is rewritten by
+// one CTA of the cooperative kernel while the others may hold its neighbours in L1)
+__host__ __device__ static inline int bnb_stride(int maxW) { return (2 * maxW + 31) & ~31; }
+
 struct BwdArgs {
     const float* saved;                    // [C+1][B][d+1]
     const void* grad_out; int grad_dtype;  // external upstream gradient (first launch of the last cell)
@@ -29,7 +33,7 @@ struct BwdArgs {
     float* gstate;                         // [B][d+1] gradient state, physical column order
     float* dact;                           // [tiles][maxW][NT] dL/da between train-mode launches
     const float* params; const float* wpack; const float* wb;
-    float* bnb;                            // [depth+1][2][maxW] mean(dh), mean(dh*xhat) of the current cell
+    float* bnb;                            // [depth+1][bnb_stride]: mean(dh)[maxW], mean(dh*xhat)[maxW] of the current cell
     float* gpart;                          // [grid][cell_params]
     float* grad_params;
     double* partials; unsigned* counter;
@@ -300,7 +304,7 @@ __device__ __forceinline__ void bwd_generic_body(const DevFlow& F, const BwdArgs
                 const float* gam = prm + F.p_bn_gamma(c, l);
                 const float* bet = gam + W;
                 const float* al = (sm + acto[l]) + tid;
-                const float* m1 = A.bnb + l * 2 * maxW;
+                const float* m1 = A.bnb + l * bnb_stride(maxW);
                 const float* m2 = m1 + maxW;
                 if (!A.train) {    // eval: dgamma / dbeta are plain sums over points
                     for (int j = 0; j < W; ++j) {
@@ -322,8 +326,7 @@ __device__ __forceinline__ void bwd_generic_body(const DevFlow& F, const BwdArgs
                         const bool on = l == 0 || a > 0.f;
                         const float dh = on ? GA[j * NT] : 0.f;
                         const float xh = gam[j] != 0.f ? (a - bet[j]) / gam[j] : 0.f;
-                        // (m1 / m2 through L2: in the cooperative launch another CTA has just written them)
-                        GA[j * NT] = valid ? sc[j] * (dh - __ldcg(m1 + j) - xh * __ldcg(m2 + j)) : 0.f;
+                        GA[j * NT] = valid ? sc[j] * (dh - m1[j] - xh * m2[j]) : 0.f;
                     }
                 }
                 if (l == 0) {
@@ -402,10 +405,12 @@ __device__ __forceinline__ void bwd_generic_body(const DevFlow& F, const BwdArgs
             s1 += __ldcg(A.partials + (size_t)b * 2 * maxW + j);
             s2 += __ldcg(A.partials + (size_t)b * 2 * maxW + maxW + j);
         }
-        A.bnb[l * 2 * maxW + j] = (float)(s1 / (double)A.B);
-        A.bnb[l * 2 * maxW + maxW + j] = (float)(s2 / (double)A.B);
-        gg[j] += (float)s2;          // dL/dgamma
-        gg[W + j] += (float)s1;      // dL/dbeta
+        A.bnb[l * bnb_stride(maxW) + j] = (float)(s1 / (double)A.B);
+        A.bnb[l * bnb_stride(maxW) + maxW + j] = (float)(s2 / (double)A.B);
+        // (read through L2: in the cooperative kernel another CTA may have updated a neighbouring cell's gradients on the
+        //  same 128-byte line earlier in the launch)
+        gg[j] = __ldcg(gg + j) + (float)s2;          // dL/dgamma
+        gg[W + j] = __ldcg(gg + W + j) + (float)s1;  // dL/dbeta
     }
     if (tid == 0) *A.counter = 0u;
 }
@@ -442,7 +447,7 @@ __global__ void __launch_bounds__(NT) flow_bwd_coop_kernel(const __grid_constant
         for (int i = blockIdx.x * NT + tid; i < np; i += gridDim.x * NT) {
             float s_ = 0.f;
             for (unsigned b = 0; b < gridDim.x; ++b) s_ += __ldcg(A0.gpart + (size_t)b * np + i);
-            out[i] += s_;
+            out[i] = __ldcg(out + i) + s_;
         }
         grid.sync();                                   // the slices are free for the next cell
     }
@@ -506,7 +511,7 @@ static void bwd_carve(const DevFlow& F, int64_t B, float* base, BwdScratch* s) {
     s->wb = base + off; off = up(off + wb_total(F));
     s->gstate = base + off; off = up(off + (size_t)B * (F.d + 1));
     s->dact = base + off; off = up(off + (size_t)((B + 127) / 128) * 128 * F.maxW);
-    s->bnb = base + off; off = up(off + (size_t)(F.depth + 1) * 2 * F.maxW);
+    s->bnb = base + off; off = up(off + (size_t)(F.depth + 1) * bnb_stride(F.maxW));
     s->gpart = base + off;
     bool rot = false;
     int NT = bwd_pick_nt(F, true, &rot);

@@ -65,12 +65,14 @@ int nis_build_dev_flow(const NisFlowDesc* d, DevFlow* F) {
         q.param_off = s.param_off; q.bn_off = s.bn_off;
         q.pk_off = pk;
         int o = 0;
-        for (int l = 0; l <= d->depth; ++l) { q.aff_off[l] = o; o += 2 * F->Wp(c, l); }
+        // each layer's scale / shift block starts on its own 128-byte line: the cooperative small-batch kernels let one CTA
+        // rewrite a block while the others still hold its neighbours in L1 (no stale line may be shared)
+        for (int l = 0; l <= d->depth; ++l) { q.aff_off[l] = o; o += 2 * F->Wp(c, l); o = (o + 31) & ~31; }
         int in = q.P;
         for (int l = 0; l < d->depth; ++l) { q.wt_off[l] = o; o += in * pad8(d->widths[l]); in = d->widths[l]; }
         q.wo_off = o; o += q.T * in * F->Kpad;
         q.bo_off = o; o += q.T * F->Kpad;
-        pk += pad8(o);
+        pk += (o + 31) & ~31;
         q.sv_off = c * (d->depth + 1) * 2 * maxW;
     }
     F->pack_total = pk;

@@ -157,9 +157,7 @@ __device__ __forceinline__ void fwd_generic_body(const DevFlow& F, const FwdArgs
             {
                 const float* sc = pk + q.aff_off[0];
                 const float* sh = sc + pad8(q.P);
-                // (scale / shift through L2: in the cooperative launch another CTA has just written them, and an L1 line
-                //  holding a neighbouring layer's values may be stale)
-                for (int k = 0; k < q.P; ++k) bufA[k * NT] = fmaf(st[q.feed[k] * NT], __ldcg(sc + k), __ldcg(sh + k));
+                for (int k = 0; k < q.P; ++k) bufA[k * NT] = fmaf(st[q.feed[k] * NT], sc[k], sh[k]);
             }
             float* cur = bufA;
             float* nxt = bufB;
@@ -176,7 +174,7 @@ __device__ __forceinline__ void fwd_generic_body(const DevFlow& F, const FwdArgs
                 }
                 const float* sc = pk + q.aff_off[l + 1];
                 const float* sh = sc + Hp;
-                dense8<NT>(Wt, in, Hp, cur, [&](int j, float z) { nxt[j * NT] = fmaxf(fmaf(z, __ldcg(sc + j), __ldcg(sh + j)), 0.f); });
+                dense8<NT>(Wt, in, Hp, cur, [&](int j, float z) { nxt[j * NT] = fmaxf(fmaf(z, sc[j], sh[j]), 0.f); });
                 float* t_ = cur; cur = nxt; nxt = t_;
                 in = H;
             }
@@ -248,7 +246,8 @@ __global__ void __launch_bounds__(NT) flow_fwd_coop_kernel(const __grid_constant
         for (int l = 0; l <= F.depth; ++l) {
             A.stats_layer = l;
             fwd_generic_body<NT>(F, A, sm);
-            grid.sync();                               // the folded scale / shift of layer l is visible to every CTA
+            grid.sync();                               // the folded scale / shift of layer l (its own 128-byte lines in wpack,
+                                                       // not read before in this launch) is visible to every CTA
         }
         const bool last = c == F.n_cells - 1;
         A.stats_layer = -1;
