@@ -113,6 +113,16 @@ int nis_flow_forward(const NisFlowDesc* desc, const float* params, float* bn_run
                      float* saved, float* bn_saved, int32_t bn_mode,
                      void* workspace, size_t workspace_bytes, int64_t B, void* stream);
 
+/* Inverse flow (the reference lists it as to do, README.md:68-69): yj_in [B, n_flow(+1)] in the flow's OUTPUT
+ * column order -> xj_out [B, n_flow+1] with column n_flow = J_in / prod of the densities, so that
+ * nis_flow_inverse(nis_flow_forward(x)) == x with Jacobian 1 (away from PWQuad's clamp at 1 - 1e-6).  EVAL: running
+ * statistics; TRAIN: batch statistics of what each cell sees on the way back (running statistics are not updated).
+ * Shape-generic FP32 kernels; bins_out as in nis_flow_forward. */
+int nis_flow_inverse(const NisFlowDesc* desc, const float* params, const float* bn_running,
+                     const void* yj_in, int32_t in_dtype, int32_t in_cols,
+                     void* xj_out, int32_t out_dtype, int32_t* bins_out, int32_t bn_mode,
+                     void* workspace, size_t workspace_bytes, int64_t B, void* stream);
+
 /* Backward: given dL/d(xj_out) computes dL/d(params) (accumulated into grad_params, which the caller
  * zeroes when it wants a fresh gradient) and optionally dL/d(xj_in).
  *   bn_running  running statistics (EVAL mode; may be NULL in TRAIN mode)

@@ -132,7 +132,8 @@ __device__ __forceinline__ void fwd_generic_body(const DevFlow& F, const FwdArgs
             if (A.from_state) {
                 for (int i = 0; i <= d; ++i) st[i * NT] = A.state_in[pt * rowlen + i];
             } else {
-                for (int i = 0; i < d; ++i) st[i * NT] = load_io(A.in, A.in_dtype, pt * A.in_cols + i);
+                // (inverse: the input is in the reference's OUTPUT column order, out_perm scatters it back)
+                for (int i = 0; i < d; ++i) st[(A.inverse ? F.out_perm[i] : i) * NT] = load_io(A.in, A.in_dtype, pt * A.in_cols + i);
                 st[d * NT] = A.in_cols > d ? load_io(A.in, A.in_dtype, pt * A.in_cols + d) : 1.f;
             }
         } else {
@@ -140,7 +141,8 @@ __device__ __forceinline__ void fwd_generic_body(const DevFlow& F, const FwdArgs
             st[d * NT] = 1.f;
         }
         bool tile_done = false;
-        for (int c = A.c_begin; c < A.c_end && !tile_done; ++c) {
+        for (int ci = A.c_begin; ci < A.c_end && !tile_done; ++ci) {
+            const int c = A.inverse ? A.c_end - 1 - (ci - A.c_begin) : ci;
             const DevCell& q = F.cells[c];
             const float* pk = A.wpack + q.pk_off;
             if (!stats && A.saved && valid && (!A.from_state || c > A.c_begin)) {
@@ -189,7 +191,10 @@ __device__ __forceinline__ void fwd_generic_body(const DevFlow& F, const FwdArgs
                 const float x = st[col * NT];
                 float y, f;
                 int k;
-                if (F.kind == NIS_KIND_PWLIN) {
+                if (A.inverse) {
+                    y = F.kind == NIS_KIND_PWLIN ? pwlin_inv(nxt, NT, F.nb, x, f, k) : pwquad_inv(nxt, NT, F.nb, x, f, k);
+                    f = 1.f / f;
+                } else if (F.kind == NIS_KIND_PWLIN) {
                     float S, al;
                     y = pwlin_fwd(nxt, NT, F.nb, x, f, k, S, al);
                 } else {
@@ -214,7 +219,7 @@ __device__ __forceinline__ void fwd_generic_body(const DevFlow& F, const FwdArgs
             for (int i = 0; i <= d; ++i) so[i] = st[i * NT];
         }
         if (A.to_out) {
-            for (int i = 0; i < d; ++i) store_io(A.out, A.out_dtype, pt * rowlen + i, st[F.out_perm[i] * NT]);
+            for (int i = 0; i < d; ++i) store_io(A.out, A.out_dtype, pt * rowlen + i, st[(A.inverse ? i : F.out_perm[i]) * NT]);
             store_io(A.out, A.out_dtype, pt * rowlen + d, st[d * NT]);
         }
     }
@@ -437,7 +442,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     A.saved = saved; A.bins = bins_out;
     A.params = params; A.wpack = ws.wpack; A.bn_running = bn_running; A.bn_saved = bn_saved;
     A.partials = ws.partials; A.counter = ws.counter; A.B = B;
-    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr; A.scratch_state = nullptr;
+    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr; A.scratch_state = nullptr; A.inverse = 0;
     // per-cell launch sequences: tcgen05 kernel where it applies, else the FP32 register-tiled kernel
     const bool tc = nis_tc_supported(F, B, bn_mode);
     const bool hp = tc && nis_h_supported(F, B, bn_mode);              // fp16-split, four-group kernel (flow_tc_h.cu)
@@ -532,6 +537,71 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
                 : (tiled ? nis_launch_tiled(F, A, s) : launch_fwd_any(F, A, s));
         if (rc) return rc;
         timing_mark(s, (tc || wide) ? 10 + (A.zin ? 2 : 0) : 2);
+    }
+    return NIS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Inverse flow: y -> x with the Jacobian column divided by the product of the densities, so that
+// nis_flow_inverse(nis_flow_forward(x)) = x with Jacobian 1.  Shape-generic kernel only (any shape); eval-mode BN uses
+// the running statistics, train-mode BN the batch statistics of the pass-through columns each cell sees on the way back
+// (the same values as in the forward pass of the same batch); running statistics are not updated.
+// ---------------------------------------------------------------------------------------------------
+extern "C" int nis_flow_inverse(const NisFlowDesc* desc, const float* params, const float* bn_running,
+                                const void* yj_in, int32_t in_dtype, int32_t in_cols,
+                                void* xj_out, int32_t out_dtype, int32_t* bins_out, int32_t bn_mode,
+                                void* workspace, size_t workspace_bytes, int64_t B, void* stream) {
+    DevFlow F;
+    int rc = nis_build_dev_flow(desc, &F);
+    if (rc) return rc;
+    if (!params || !workspace || B < 0 || (B > 0 && (!yj_in || !xj_out))) return NIS_EINVAL;
+    if (in_cols != F.d && in_cols != F.d + 1) return NIS_EINVAL;
+    if ((in_dtype != NIS_F32 && in_dtype != NIS_F64) || (out_dtype != NIS_F32 && out_dtype != NIS_F64)) return NIS_EINVAL;
+    if (bn_mode == NIS_BN_EVAL && !bn_running) return NIS_EINVAL;
+    if (workspace_bytes < nis_flow_workspace_bytes(desc, B)) return NIS_EWORKSPACE;
+    if (B == 0) return NIS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    FlowWorkspace ws;
+    nis_flow_carve(F, B, workspace, &ws);
+    cudaMemsetAsync(ws.counter, 0, 256, s);
+    {
+        int mx = 0;
+        for (int c = 0; c < F.n_cells; ++c) {
+            int sz = (c + 1 < F.n_cells ? F.cells[c + 1].pk_off : F.pack_total) - F.cells[c].pk_off;
+            if (sz > mx) mx = sz;
+        }
+        int bx = (mx + 255) / 256;
+        if (bx > 64) bx = 64;
+        flow_pack_kernel<<<dim3(bx, F.n_cells), 256, 0, s>>>(F, params, bn_running, ws.wpack, bn_mode);
+        NIS_CUDA_CHECK_LAUNCH();
+    }
+    FwdArgs A;
+    A.in = yj_in; A.in_dtype = in_dtype; A.in_cols = in_cols;
+    A.out = xj_out; A.out_dtype = out_dtype;
+    A.saved = nullptr; A.bins = bins_out;
+    A.params = params; A.wpack = ws.wpack; A.bn_running = nullptr; A.bn_saved = nullptr;
+    A.partials = ws.partials; A.counter = ws.counter; A.B = B;
+    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr; A.scratch_state = nullptr; A.inverse = 1;
+    if (bn_mode == NIS_BN_EVAL) {
+        A.state_in = nullptr; A.state_out = nullptr; A.from_state = 0; A.to_out = 1;
+        A.c_begin = 0; A.c_end = F.n_cells; A.stats_layer = -1;
+        return launch_fwd_any(F, A, s);
+    }
+    for (int c = F.n_cells - 1; c >= 0; --c) {
+        A.c_begin = c; A.c_end = c + 1;
+        A.from_state = c < F.n_cells - 1;
+        A.state_in = A.from_state ? ws.state : nullptr;
+        A.state_out = nullptr; A.to_out = 0;
+        for (int l = 0; l <= F.depth; ++l) {
+            A.stats_layer = l;
+            rc = launch_fwd_any(F, A, s);
+            if (rc) return rc;
+        }
+        A.stats_layer = -1;
+        A.to_out = c == 0;
+        A.state_out = c == 0 ? nullptr : ws.state;
+        rc = launch_fwd_any(F, A, s);
+        if (rc) return rc;
     }
     return NIS_OK;
 }

@@ -53,6 +53,27 @@ NIS_DEV float pwlin_fwd(float* z, int zs, int nb, float x, float& f, int& k, flo
     return pwlin_fwd_z(c, nb, x, f, k, S_out, alpha_out);
 }
 
+// Inverse of the PWLin map (the reference lists the inverse as to do, README.md:68-69): given y, the bin is the
+// largest k with C_k <= y and x = (k + (y S - sum_{j<k} e_j) / e_k) / nb; f = bin height at x (the inverse's Jacobian
+// factor is 1/f).  Same float32 running sum as pwlin_fwd_z, so a round trip lands in the same bin.
+NIS_DEV float pwlin_inv(float* z, int zs, int nb, float y, float& f, int& k) {
+    float m = z[0];
+    for (int j = 1; j < nb; ++j) m = fmaxf(m, z[j * zs]);
+    float S = 0.f;
+    for (int j = 0; j < nb; ++j) { float e = expf(z[j * zs] - m); z[j * zs] = e; S += e; }
+    const float target = y * S;
+    float C = 0.f;
+    k = 0;
+    for (int j = 0; j < nb - 1; ++j) {
+        const float nc = C + z[j * zs];
+        if (nc <= target) { C = nc; k = j + 1; } else break;
+    }
+    const float ek = z[k * zs];
+    f = ek / S * (float)nb;
+    float x = ((float)k + (target - C) / ek) / (float)nb;
+    return x < 0.f ? 0.f : (x > 1.f ? 1.f : x);
+}
+
 // z holds e_j (after pwlin_fwd).  Overwrites z[j] with dL/dz_j.  Returns dL/dx.
 //   gy = dL/dy, gJJ = dL/dJ_out * J_out (= dL/df * f)
 NIS_DEV float pwlin_bwd(float* z, int zs, int nb, int k, float S, float alpha, float y,
@@ -117,6 +138,47 @@ NIS_DEV void pwquad_fwd(float* z, int zs, int nb, float x, QuadCtx& c) {
     c.k = k; c.xb = xb; c.Sw = (float)Sw; c.A = (float)(Araw / Sw); c.alpha = alpha; c.Wk = Wk; c.Vk = Vk; c.Vk1 = Vk1;
     c.y = alpha * alpha * 0.5f * (Vk1 - Vk) * Wk + alpha * Vk * Wk + (float)(ca / Araw);
     c.f = Vk + alpha * (Vk1 - Vk);
+}
+
+// Inverse of the PWQuad map: the bin is the largest k with S_k <= y (S = cdf at the edges); inside it
+// y - S_k = alpha V_k W_k + alpha^2 (V_{k+1} - V_k) W_k / 2 is solved for alpha in its cancellation-free form.
+// Returns x; f = density at x (the inverse's Jacobian factor is 1/f).  Float64 sums as in pwquad_fwd.
+NIS_DEV float pwquad_inv(float* z, int zs, int nb, float y, float& f, int& kout) {
+    float* zv = z;
+    float* zw = z + (nb + 1) * zs;
+    float mv = zv[0], mw = zw[0];
+    for (int j = 1; j <= nb; ++j) mv = fmaxf(mv, zv[j * zs]);
+    for (int j = 1; j < nb; ++j) mw = fmaxf(mw, zw[j * zs]);
+    double Sw = 0.0;
+    for (int j = 0; j < nb; ++j) { float e = expf(zw[j * zs] - mw); zw[j * zs] = e; Sw += (double)e; }
+    float vprev = expf(zv[0] - mv);
+    zv[0] = vprev;
+    double Araw = 0.0;
+    for (int j = 0; j < nb; ++j) {
+        float vn = expf(zv[(j + 1) * zs] - mv);
+        zv[(j + 1) * zs] = vn;
+        Araw += 0.5 * ((double)vprev + (double)vn) * (double)zw[j * zs];
+        vprev = vn;
+    }
+    const double target = (double)y * Araw;
+    int k = 0;
+    double cw = 0.0, ca = 0.0;
+    for (int j = 0; j < nb - 1; ++j) {
+        const double na = ca + 0.5 * ((double)zv[j * zs] + (double)zv[(j + 1) * zs]) * (double)zw[j * zs];
+        if (na <= target) { ca = na; cw += (double)zw[j * zs]; k = j + 1; } else break;
+    }
+    const double wk = (double)zw[k * zs], vk = (double)zv[k * zs], vk1 = (double)zv[(k + 1) * zs];
+    double c = target - ca;
+    c = c > 0.0 ? c : 0.0;
+    const double a = 0.5 * (vk1 - vk) * wk, b = vk * wk;
+    double disc = b * b + 4.0 * a * c;
+    disc = disc > 0.0 ? disc : 0.0;
+    double alpha = 2.0 * c / (b + sqrt(disc));
+    alpha = alpha < 0.0 ? 0.0 : (alpha > 1.0 ? 1.0 : alpha);
+    f = (float)((vk + alpha * (vk1 - vk)) * (Sw / Araw));
+    kout = k;
+    const double x = (cw + alpha * wk) / Sw;
+    return (float)(x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x));
 }
 
 // z holds v_j / w_j (after pwquad_fwd).  Overwrites with dL/dz.  Returns dL/dx.

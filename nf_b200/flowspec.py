@@ -222,6 +222,39 @@ class FlowSpec:
                 self.nbt_arena.write_back(nbt)
         return out, saved, bn_saved, bins
 
+    def inverse(self, yj, train, want_bins=False, out_dtype=None):
+        """Runs nis_flow_inverse: yj [B, d(+1)] in the flow's output column order -> (XJ [B, d+1], bins or None), with
+        XJ[:, -1] = J_in / prod of the densities (no autograd; train-mode BN uses batch statistics without updating the
+        running ones)."""
+        lib = _cabi.lib()
+        self._self_check(lib)
+        if yj.dim() != 2 or yj.shape[1] not in (self.n_flow, self.n_flow + 1):
+            raise ValueError("expected a [B, %d] or [B, %d] tensor" % (self.n_flow, self.n_flow + 1))
+        if not yj.is_cuda:
+            dev = self.params[0].device
+            if dev.type != "cuda":
+                dev = torch.device("cuda", torch.cuda.current_device())
+            yj = yj.to(dev)
+        dev = yj.device
+        yj = yj.detach().contiguous()
+        if yj.dtype not in (torch.float32, torch.float64):
+            yj = yj.double()
+        B, d = yj.shape[0], self.n_flow
+        if train and B == 1:
+            raise ValueError("Expected more than 1 value per channel when training, got input size [1, %d]" % d)
+        with torch.cuda.device(dev):
+            params = self.param_arena.get(dev)
+            bn = self.bn_arena.get(dev)
+            out = torch.empty(B, d + 1, dtype=out_dtype or yj.dtype, device=dev)
+            bins = torch.full((self.n_cells, B, d), -1, dtype=torch.int32, device=dev) if want_bins else None
+            ws = self.workspace(lib, B, dev)
+            rc = lib.nis_flow_inverse(ctypes.byref(self.desc), _cabi.ptr(params), _cabi.ptr(bn), _cabi.ptr(yj),
+                                      _cabi.dtype_code(yj), yj.shape[1], _cabi.ptr(out), _cabi.dtype_code(out),
+                                      _cabi.ptr(bins), _cabi.BN_TRAIN if train else _cabi.BN_EVAL, _cabi.ptr(ws),
+                                      ws.numel(), B, _cabi.stream_ptr(dev))
+            _cabi.check(rc, "nis_flow_inverse")
+        return out, bins
+
     def backward(self, saved, bn_saved, grad_out, train, need_grad_in):
         """Runs nis_flow_backward.  Returns (grad_params flat float32, grad_in or None)."""
         lib = _cabi.lib()
@@ -304,6 +337,13 @@ class FlowSequential(torch.nn.Sequential):
 
     def forward(self, input):
         return flow_apply(self.spec(), input, self.training)
+
+    def inverse(self, input):
+        """The inverse map (a to-do in the reference, README.md:68-69): [B, d(+1)] points in the flow's
+        output space -> [B, d+1] latent points with the Jacobian column divided by the product of the densities, so that
+        ``model.inverse(model(x))`` returns x with Jacobian 1.  Not differentiable."""
+        with torch.no_grad():
+            return self.spec().inverse(input, self.training)[0]
 
     def forward_with_bins(self, input):
         """(XJ, bins[n_cells, B, n_flow] int32) without autograd — for parity checks."""

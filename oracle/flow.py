@@ -231,6 +231,82 @@ def pwquad_cell(sd, cell, x, P, n_bins, train, stats=None, edges=None):
 
 
 # ----------------------------------------------------------------------------------------------
+# inverse cells.  The reference has no inverse (its README lists it as to do, README.md:68-69); these are
+# the algebraic inverses of the two maps above, validated by round trips against the reference-pinned forward.
+# ----------------------------------------------------------------------------------------------
+def pwlin_cell_inverse(sd, cell, yj, P, n_bins, train, stats=None):
+    """Inverse of pwlin_cell: yj = (xA, y, J) -> (xA, x, J / prod Q_k).  The conditioner sees the same xA."""
+    d = yj.shape[1] - 1
+    T = d - P
+    xA, yB, J = yj[:, :P], yj[:, P:d], yj[:, d]
+    Z = rectnn(sd, cell, xA, train, stats).reshape(-1, T, n_bins)
+    Q = torch.exp(Z)
+    Qsum = torch.cumsum(Q, -1)
+    norm = Qsum[:, :, -1:]
+    Q = Q / (norm / n_bins)
+    C = torch.cat((torch.zeros_like(norm), Qsum / norm), -1)         # cdf at left edges, C[..., n_bins] = 1
+    k = ((C[:, :, 1:-1] <= yB.unsqueeze(-1)).sum(-1)).clamp(0, n_bins - 1).unsqueeze(-1)   # largest k with C_k <= y
+    Qk = torch.gather(Q, -1, k).squeeze(-1)
+    Ck = torch.gather(C, -1, k).squeeze(-1)
+    x = k.squeeze(-1).to(yB.dtype) / n_bins + (yB - Ck) / Qk
+    J = J / torch.prod(Qk, -1)
+    return torch.cat((xA, x, J.unsqueeze(-1)), -1), k.squeeze(-1)
+
+
+def pwquad_cell_inverse(sd, cell, yj, P, n_bins, train, stats=None):
+    """Inverse of pwquad_cell (away from the forward's clamp at 1 - 1e-6): solve the bin's quadratic for alpha."""
+    d = yj.shape[1] - 1
+    T = d - P
+    nb = n_bins
+    xA, yB, J = yj[:, :P], yj[:, P:d], yj[:, d]
+    Z = rectnn(sd, cell, xA, train, stats).reshape(-1, T, 2 * nb + 1)
+    V = torch.exp(Z[:, :, :nb + 1])
+    W = torch.exp(Z[:, :, nb + 1:])
+    Wsum = torch.cumsum(W, -1)
+    Wn = Wsum[:, :, -1:]
+    W = W / Wn
+    Wsum = Wsum / Wn
+    area = torch.cumsum((V[:, :, :-1] + V[:, :, 1:]) / 2 * W, -1)
+    V = V / area[:, :, -1:]
+    E = torch.cat((torch.zeros_like(Wn), Wsum), -1)
+    S = torch.cat((torch.zeros_like(Wn), torch.cumsum((V[:, :, :-1] + V[:, :, 1:]) / 2 * W, -1)), -1)   # cdf at the edges
+    k = ((S[:, :, 1:-1] <= yB.unsqueeze(-1)).sum(-1)).clamp(0, nb - 1).unsqueeze(-1)
+    Wk = torch.gather(W, -1, k).squeeze(-1)
+    Vk = torch.gather(V, -1, k).squeeze(-1)
+    Vk1 = torch.gather(V, -1, k + 1).squeeze(-1)
+    c = yB - torch.gather(S, -1, k).squeeze(-1)
+    a = (Vk1 - Vk) * Wk / 2
+    b = Vk * Wk
+    alpha = 2 * c / (b + torch.sqrt(b * b + 4 * a * c))
+    x = torch.gather(E, -1, k).squeeze(-1) + alpha * Wk
+    J = J / torch.prod(torch.lerp(Vk, Vk1, alpha), -1)
+    return torch.cat((xA, x, J.unsqueeze(-1)), -1), k.squeeze(-1)
+
+
+def flow_inverse(layers, sd, yj, kind, n_bins, train=False, stats=None):
+    """Inverse of flow_forward: the Sequential backwards (inverse rolls / masks, inverse cells).  yj: [B, d+1] in
+    the reference's output column order; returns (XJ, bins) with XJ[:, -1] = J_in / prod f, so that
+    flow_inverse(flow_forward(x)) = x with Jacobian 1."""
+    cell_fn = pwlin_cell_inverse if kind == "lin" else pwquad_cell_inverse
+    x = yj
+    all_bins = []
+    for L in reversed(layers):
+        t = L["type"]
+        if t == "cell":
+            x, b = cell_fn(sd, L["name"], x, L["P"], n_bins, train, stats)
+            all_bins.append(b)
+        elif t == "roll":
+            x = torch.cat((torch.roll(x[:, :-1], -L["shift"], -1), x[:, -1:]), -1)
+        elif t == "demask":                 # forward demask scattered (feeder, trafoer) back: undo = mask
+            x = torch.cat((x[:, L["feeder"]], x[:, L["trafoer"]], x[:, -1:]), -1)
+        elif t == "mask":                   # forward mask gathered: undo = scatter back
+            ret = torch.empty_like(x[:, :-1])
+            ret[:, L["feeder"] + L["trafoer"]] = x[:, :-1]
+            x = torch.cat((ret, x[:, -1:]), -1)
+    return x, all_bins[::-1]
+
+
+# ----------------------------------------------------------------------------------------------
 # whole flow, layer by layer like the reference Sequential
 # ----------------------------------------------------------------------------------------------
 def flow_forward(layers, sd, xj, kind, n_bins, train=True, stats=None, trace=None, edges=None, clamp_bins=False):

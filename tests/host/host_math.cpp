@@ -30,6 +30,16 @@ void host_pwquad(int n, int nb, float* z, const float* x, const float* gy, const
     }
 }
 
+// inverse spline maps: z [n][K] logits (left untouched: a copy is transformed), y -> x, f = density at x, k = bin
+void host_spline_inv(int kind, int n, int nb, const float* z, const float* y, float* x, float* f, int* k) {
+    const int K = kind == 0 ? nb : 2 * nb + 1;
+    float buf[2 * 512 + 1];
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < K; ++j) buf[j] = z[(size_t)i * K + j];
+        x[i] = kind == 0 ? pwlin_inv(buf, 1, nb, y[i], f[i], k[i]) : pwquad_inv(buf, 1, nb, y[i], f[i], k[i]);
+    }
+}
+
 int host_rambo(const NisRamboDesc* d, long long B, const double* r, double* mom, double* w, uint8_t* pass) {
     RamboConst C;
     int rc = rambo_fill_const(d, &C);

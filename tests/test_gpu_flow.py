@@ -162,3 +162,55 @@ def test_tensor_core_kernels_at_small_batches(which, mode):
     """The tensor-core kernels take over from 256 points (a training minibatch of a few hundred points is common in
     the reference's examples): three tiles, the last one ragged, a grid of two or three CTAs."""
     test_forward_matches_oracle_at_size(dict(BIG[which], B=300), mode)
+
+
+INV = [
+    dict(name="lin8d", kind="lin", n_flow=8, n_pass_through=4, n_cells=6, n_bins=32, NN=[64] * 3, roll_step=4, B=3000),
+    dict(name="quad8d", kind="quad", n_flow=8, n_cells=6, n_bins=32, NN=[64] * 3, B=3000),
+    dict(name="quad2d", kind="quad", n_flow=2, n_cells=2, n_bins=4, NN=[3] * 3, B=2000),
+    dict(name="quad9d_extra", kind="quad", n_flow=9, n_cells=10, n_bins=6, NN=[16, 16], B=777),
+    dict(name="lin5d", kind="lin", n_flow=5, n_pass_through=1, n_cells=4, n_bins=7, NN=[12], roll_step=2, B=1025),
+]
+
+
+@pytest.mark.parametrize("cfg", INV, ids=[c["name"] for c in INV])
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_inverse_flow(cfg, mode):
+    """FlowSequential.inverse (nis_flow_inverse).  (a) against the float64 inverse of the oracle on the same
+    points: same bins (except on an edge), latent points and log-Jacobian within the forward's bars scaled by the local
+    stretch; (b) round trip through the CUDA forward (tensor-core kernels where they apply): inverse(forward(x)) = x,
+    Jacobian 1."""
+    torch.manual_seed(9)
+    NF = make_manager(cfg)
+    model = NF._model
+    cells, out_perm = oflow.compile_layers(oracle_layers(cfg), cfg["n_flow"])
+    sd = oflow.init_state_dict(cells, cfg["n_flow"], cfg["kind"], cfg["n_bins"], cfg["NN"], seed=11,
+                               dtype=torch.float32, bn_jitter=0.2)
+    model.load_state_dict(sd)
+    model.train(mode == "train")
+    sd64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    gen = torch.Generator().manual_seed(77)
+    y = (0.002 + 0.996 * torch.rand(cfg["B"], cfg["n_flow"], generator=gen, dtype=torch.float32)).double()
+    yj = torch.cat((y, torch.ones(cfg["B"], 1, dtype=torch.float64)), 1)
+    X, bins = model.spec().inverse(yj.cuda(), model.training, want_bins=True)
+    with torch.no_grad():
+        ref, ref_bins = oflow.flow_inverse(oracle_layers(cfg), sd64, yj, cfg["kind"], cfg["n_bins"], train=(mode == "train"))
+    X, bins = X.cpu(), bins.cpu()
+    same = torch.ones(cfg["B"], dtype=torch.bool)
+    for c, rb in enumerate(ref_bins):
+        same &= (bins[c, :, :rb.shape[1]].long() == rb).all(1)
+    assert float(same.float().mean()) > 0.995, float(same.float().mean())
+    # |dx| = |dy| / density: compare in units of the local stretch (the Jacobian column holds 1 / prod density)
+    stretch = ref[:, -1].clamp_min(1.0)
+    err = ((X[:, :-1] - ref[:, :-1]).abs().max(1).values / stretch)[same]
+    assert float(err.max()) < 2e-5, float(err.max())
+    lj = (torch.log(X[:, -1]) - torch.log(ref[:, -1])).abs()[same]
+    assert float(torch.quantile(lj, 0.99)) < 1e-4 and float(lj.median()) < 1e-5, (float(lj.median()), float(lj.max()))
+    # round trip through the CUDA forward
+    x = (0.002 + 0.996 * torch.rand(cfg["B"], cfg["n_flow"], generator=gen, dtype=torch.float32)).double().cuda()
+    with torch.no_grad():
+        Y = model(NF.format_input(x, torch.device("cuda")))
+        back = model.inverse(Y)
+    rt = (back[:, :-1] - x).abs().max(1).values * Y[:, -1].clamp_max(1.0)      # stretch of the inverse = 1 / J
+    assert float(torch.quantile(rt, 0.999)) < 2e-5, float(rt.max())
+    assert float(torch.quantile((torch.log(back[:, -1])).abs(), 0.99)) < 2e-4

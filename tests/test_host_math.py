@@ -248,3 +248,49 @@ def test_rambo_event_pdf_active_matches_reference(host, golden, case):
     np.testing.assert_allclose(mom, ref_mom, rtol=1e-9, atol=1e-9 * m["E_cm"])
     # the densities are interpolated from 16384 nodes in ln x: 1e-8 away from x = 1, where x f ~ (1-x)^b vanishes
     np.testing.assert_allclose(w, ref_w, rtol=1e-7, atol=1e-12 * np.abs(ref_w).max())
+
+
+@pytest.mark.parametrize("kind,nb", [(0, 4), (0, 32), (1, 4), (1, 32), (1, 64)])
+def test_inverse_splines_round_trip_and_match_the_oracle(host, kind, nb):
+    """spline.cuh's pwlin_inv / pwquad_inv (the reference has no inverse: README.md:68-69 lists it as to do)
+    undo the forward maps of the same source - same bin, x back to float32 accuracy, density at x equal to the forward's -
+    and agree with the float64 inverse cells of oracle/flow.py."""
+    g = torch.Generator().manual_seed(7 * nb + kind)
+    n = 500
+    K = nb if kind == 0 else 2 * nb + 1
+    z = (1.5 * torch.randn(n, K, generator=g)).float()
+    x = (0.001 + 0.998 * torch.rand(n, generator=g)).float()
+    yo, fo, dx = (np.zeros(n, np.float32) for _ in range(3))
+    ko = np.zeros(n, np.int32)
+    zz = np.ascontiguousarray(z.numpy().copy())
+    zero = np.zeros(n, np.float32)
+    (host.host_pwlin if kind == 0 else host.host_pwquad)(n, nb, fp(zz), fp(x.numpy()), fp(zero), fp(zero), fp(yo), fp(fo),
+                                                          fp(ko, I), fp(dx))
+    xi, fi = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    ki = np.zeros(n, np.int32)
+    host.host_spline_inv(kind, n, nb, fp(np.ascontiguousarray(z.numpy())), fp(yo), fp(xi), fp(fi), fp(ki, I))
+    same = ki == ko                                          # a y within float32 rounding of an edge may land next door
+    assert same.mean() > 0.99
+    # y is a float32: x comes back to delta_y / f (a low-density bin stretches the rounding of y)
+    assert (np.abs(xi - x.numpy())[same] * fo[same]).max() < 1e-6
+    np.testing.assert_allclose(fi[same], fo[same], rtol=2e-3)
+    # float64 oracle inverse on the same logits
+    from oracle import flow as oflow
+    zd, yd = z.double(), torch.from_numpy(yo).double()
+    if kind == 0:
+        Q = torch.exp(zd)
+        Qs = torch.cumsum(Q, -1)
+        norm = Qs[:, -1:]
+        Qn = Q / (norm / nb)
+        C = torch.cat((torch.zeros_like(norm), Qs / norm), -1)
+        k = (C[:, 1:-1] <= yd.unsqueeze(-1)).sum(-1).clamp(0, nb - 1)
+        Qk = torch.gather(Qn, -1, k.unsqueeze(-1)).squeeze(-1)
+        xo = k.double() / nb + (yd - torch.gather(C, -1, k.unsqueeze(-1)).squeeze(-1)) / Qk
+        fo64 = Qk
+    else:
+        yq, fq, kq = oracle_pwquad(zd, x.double(), nb)       # forward oracle at the true x: inverse must return (x, f)
+        xo, fo64, k = x.double(), fq, kq
+    ok = same & (ki == k.numpy())
+    assert ok.mean() > 0.98
+    assert (np.abs(xi - xo.numpy())[ok] * fo64.numpy()[ok]).max() < 2e-6
+    np.testing.assert_allclose(fi[ok], fo64.numpy()[ok], rtol=2e-3)

@@ -100,6 +100,27 @@ def test_autograd_of_oracle_matches_reference_gradients(golden, case, mode):
         assert torch.allclose(gr, ref, rtol=1e-8, atol=1e-11 * max(1.0, float(ref.abs().max()))), k
 
 
+@pytest.mark.parametrize("case", FLOW_CASES)
+@pytest.mark.parametrize("train", [False, True])
+def test_inverse_flow_undoes_the_reference_pinned_forward(golden, case, train):
+    """SURVEY 8 f4.  The reference has no inverse (README.md:68-69: to do), so the oracle's inverse cells are pinned through
+    the forward that IS pinned to the reference: flow_inverse(flow_forward(x)) = x with Jacobian 1, on every golden model
+    (all topologies: rolls, masks, extra cells), for points off the bin edges and below PWQuad's clamp at 1 - 1e-6."""
+    g = golden("flow_" + case)
+    m = g.meta
+    layers = oflow.pwlin_layers(m["n_flow"], m["n_pass_through"], m["n_cells"], m["roll_step"]) if m["kind"] == "lin" \
+        else oflow.pwquad_layers(m["n_flow"], m["n_cells"])
+    sd = g.state_dict()
+    x = 0.001 + 0.998 * torch.rand(300, m["n_flow"], generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    xj = torch.cat((x, torch.full((300, 1), 1.7, dtype=torch.float64)), 1)
+    with torch.no_grad():
+        y, bins = oflow.flow_forward(layers, sd, xj, m["kind"], m["n_bins"], train=train)
+        xb, ibins = oflow.flow_inverse(layers, sd, y, m["kind"], m["n_bins"], train=train)
+    assert all(torch.equal(a, b) for a, b in zip(bins, ibins))
+    assert torch.allclose(xb[:, :-1], x, rtol=0, atol=1e-9)
+    assert torch.allclose(xb[:, -1], xj[:, -1], rtol=1e-9)
+
+
 @pytest.mark.parametrize("case", RAMBO_CASES)
 def test_rambo_matches_reference(golden, case):
     g = golden("rambo_" + case)
