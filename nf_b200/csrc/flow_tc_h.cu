@@ -243,9 +243,9 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
         for (int i = tid; i < W; i += NT) { affs[l * 2 * TCH + i] = fs * s[i]; affs[l * 2 * TCH + TCH + i] = f * s[Wp + i]; }
     }
     const int out_rows = h_out_rows(F);
-    // PWLin only needs exp(logit - max): the logits are kept in units of log2 (scale and bias carry log2(e)) so that
-    // the exponential is a bare ex2
-    constexpr float LOGIT_UNIT = KIND == NIS_KIND_PWLIN ? 1.4426950408889634f : 1.f;
+    // the splines only need exp(logit - max): the logits are kept in units of log 2 (scale and bias carry log2(e)) so
+    // that the exponential is a bare ex2
+    constexpr float LOGIT_UNIT = 1.4426950408889634f;
     for (int i = tid; i < out_rows; i += NT) {
         const int t = i / K_::SLOT, jj = i - t * K_::SLOT;
         biass[i] = (t < q.T && jj < F.K) ? LOGIT_UNIT * pk[q.bo_off + t * F.Kpad + jj] : 0.f;
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
                     for (int j = 0; j < 65; ++j) z[j] = fmaf(z[j], inv_out, bs[j]);
                     float y, f;
                     int kb;
-                    pwquad32_regs(z, xv, y, f, kb);
+                    pwquad32_tree<true>(z, xv, y, f, kb);
                     st[q.trafo[b] * TCM] = y;
                     jfac *= f;
                     if (A.bins && valid) A.bins[((long long)c * A.B + pt) * d + b] = kb;
