@@ -379,9 +379,11 @@ __global__ void __launch_bounds__(256) flow_col_stats_kernel(const __grid_consta
 // the batch (the BN0 statistics pass and the layer-1 statistics pass with its 256 B/point store) by one
 // streaming read of P columns.  Used when P <= 8.
 // ---------------------------------------------------------------------------------------------------
-#define MOM_P 8
-#define MOM_N (MOM_P + MOM_P * (MOM_P + 1) / 2)      // 44 sums
-__global__ void __launch_bounds__(256) flow_col_moments_kernel(const __grid_constant__ DevFlow F, const FwdArgs A) {
+#define MOM_PMAX 8
+// PM = compile-time bound on the pass-through width (4: 14 sums, the bench shapes; 8: 44 sums)
+template <int MOM_P>
+__global__ void __launch_bounds__(256, MOM_P <= 4 ? 4 : 2) flow_col_moments_kernel(const __grid_constant__ DevFlow F, const FwdArgs A) {
+    constexpr int MOM_N = MOM_P + MOM_P * (MOM_P + 1) / 2;
     __shared__ double red[8][MOM_N];
     __shared__ double tot[MOM_N];
     __shared__ double sc0s[MOM_P];
@@ -389,11 +391,12 @@ __global__ void __launch_bounds__(256) flow_col_moments_kernel(const __grid_cons
     const int c = A.c_begin;
     const DevCell& q = F.cells[c];
     const int d = F.d, P = q.P, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double acc[MOM_N];
+    // Per-thread partial sums in float32 (a thread sees B / (grid * 256) ~ 30 points of magnitude <= 1: 3e-7 relative, averaged
+    // down over the ~150 000 threads), everything across threads in float64.  (Round 1 kept 44 float64 accumulators per
+    // thread: 88 registers, two blocks per SM, 1.7 TB/s.)
+    float acc[MOM_N];
 #pragma unroll
-    for (int i = 0; i < MOM_N; ++i) acc[i] = 0.0;
-    // four points per thread and iteration: their loads are issued together (the kernel is latency-bound: 88
-    // accumulator registers leave two blocks per SM)
+    for (int i = 0; i < MOM_N; ++i) acc[i] = 0.f;
     constexpr int MOM_U = 4;
     const long long stride = (long long)gridDim.x * 256;
     for (long long pt0 = (long long)blockIdx.x * 256 + tid; pt0 < A.B; pt0 += MOM_U * stride) {
@@ -411,17 +414,18 @@ __global__ void __launch_bounds__(256) flow_col_moments_kernel(const __grid_cons
             int o = MOM_P;
 #pragma unroll
             for (int k = 0; k < MOM_P; ++k) {
-                acc[k] += (double)x[u][k];
+                acc[k] += x[u][k];
 #pragma unroll
-                for (int k2 = k; k2 < MOM_P; ++k2) acc[o++] += (double)x[u][k] * (double)x[u][k2];
+                for (int k2 = k; k2 < MOM_P; ++k2) { acc[o] = fmaf(x[u][k], x[u][k2], acc[o]); ++o; }
             }
         }
     }
 #pragma unroll
     for (int i = 0; i < MOM_N; ++i) {
+        double a = (double)acc[i];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-        if (lane == 0) red[warp][i] = acc[i];
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) red[warp][i] = a;
     }
     __syncthreads();
     double* mine = A.partials + (size_t)blockIdx.x * MOM_N;
@@ -508,12 +512,13 @@ __global__ void __launch_bounds__(256) flow_col_moments_kernel(const __grid_cons
     if (tid == 0) *A.counter = 0u;
 }
 
-bool nis_moments_supported(const DevFlow& F, int c) { return F.depth >= 1 && F.cells[c].P <= MOM_P; }
+bool nis_moments_supported(const DevFlow& F, int c) { return F.depth >= 1 && F.cells[c].P <= MOM_PMAX; }
 
 int nis_launch_col_moments(const DevFlow& F, const FwdArgs& A, cudaStream_t s) {
     long long blocks = (A.B + 255) / 256;
     int grid = (int)(blocks < 592 ? blocks : 592);
-    flow_col_moments_kernel<<<grid, 256, 0, s>>>(F, A);
+    if (F.cells[A.c_begin].P <= 4) flow_col_moments_kernel<4><<<grid, 256, 0, s>>>(F, A);
+    else flow_col_moments_kernel<8><<<grid, 256, 0, s>>>(F, A);
     NIS_CUDA_CHECK_LAUNCH();
     return NIS_OK;
 }
