@@ -179,7 +179,7 @@ typedef struct NisRamboDesc {
 
 /* r[B, 3n-4 (+2 when pdf_active)] (dtype r_dtype) -> momenta[B, 2+n, 4] float64 (E,px,py,pz; CM frame; optional),
  * weight[B] float64 (cuts applied, divided by 2 s), cutmask[B] uint8 (1 = passed; optional).
- * r and momenta must be 16-byte aligned (rows are moved as 16-byte vectors). */
+ * r must be 16-byte and momenta 32-byte aligned (rows are moved as 16- / 32-byte vectors). */
 int nis_rambo_generate(const NisRamboDesc* desc, const void* r, int32_t r_dtype, double* momenta,
                        double* weight, uint8_t* cutmask, int64_t B, void* stream);
 
