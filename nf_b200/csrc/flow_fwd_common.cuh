@@ -35,7 +35,11 @@ __device__ __forceinline__ void store_io(void* p, int dtype, long long idx, floa
 // the per-CTA partials in index order (deterministic) and folds them into the layer's scale/shift
 // (wpack), the saved batch statistics (backward) and the running statistics (torch BatchNorm1d
 // semantics: biased variance for normalisation, unbiased for the running estimate, momentum 0.1).
-__device__ __forceinline__ void bn_stats_finalize(const DevFlow& F, const FwdArgs& A, const double* sacc, int NT) {
+// `scratch` (optional, 2 * NT doubles of shared memory): the last CTA then adds the per-CTA partials with all its threads
+// (NT / Wp slices per feature, combined in slice order - still a fixed order) instead of one thread per feature walking
+// all gridDim.x partials: 148 x 2 dependent-latency loads per feature were ~25 us at the tail of every statistics pass.
+__device__ __forceinline__ void bn_stats_finalize(const DevFlow& F, const FwdArgs& A, const double* sacc, int NT,
+                                                  double* scratch = nullptr) {
     const int tid = threadIdx.x;
     const int maxW = F.maxW;
     __syncthreads();
@@ -53,13 +57,31 @@ __device__ __forceinline__ void bn_stats_finalize(const DevFlow& F, const FwdArg
     __threadfence();
     const float* p = A.params + q.param_off + F.p_bn_gamma(c, l);
     float* aff = A.wpack + q.pk_off + q.aff_off[l];
+    const int slices = scratch ? NT / Wp : 0;
+    if (slices > 1) {
+        const int sl = tid / Wp, j = tid - sl * Wp;
+        if (sl < slices) {
+            double s = 0.0, s2 = 0.0;
+            for (unsigned b = sl; b < gridDim.x; b += slices) {
+                s += __ldcg(A.partials + (size_t)b * 2 * maxW + j);
+                s2 += __ldcg(A.partials + (size_t)b * 2 * maxW + maxW + j);
+            }
+            scratch[sl * Wp + j] = s;
+            scratch[NT + sl * Wp + j] = s2;
+        }
+        __syncthreads();
+    }
     for (int j = tid; j < Wp; j += NT) {
         float sc = 0.f, sh = 0.f;
         if (j < W) {
             double s = 0.0, s2 = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) {
-                s += __ldcg(A.partials + (size_t)b * 2 * maxW + j);
-                s2 += __ldcg(A.partials + (size_t)b * 2 * maxW + maxW + j);
+            if (slices > 1) {
+                for (int sl = 0; sl < slices; ++sl) { s += scratch[sl * Wp + j]; s2 += scratch[NT + sl * Wp + j]; }
+            } else {
+                for (unsigned b = 0; b < gridDim.x; ++b) {
+                    s += __ldcg(A.partials + (size_t)b * 2 * maxW + j);
+                    s2 += __ldcg(A.partials + (size_t)b * 2 * maxW + maxW + j);
+                }
             }
             const double n = (double)A.B;
             const double mean = s / n;

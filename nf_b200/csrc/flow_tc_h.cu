@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
         const double k1 = (double)inv_scale[l_end];               // the sums are of z * SA * SW (a power of two: exact)
         sacc[tid] = s * k1; sacc[F.maxW + tid] = s2 * k1 * k1;
     }
-    bn_stats_finalize(F, A, sacc, NT);
+    bn_stats_finalize(F, A, sacc, NT, red);           // (red: 2 * NT doubles, free again once sacc is formed)
 }
 
 // ---------------------------------------------------------------------------------------------------
