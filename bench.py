@@ -472,7 +472,7 @@ def bench_integrate(world, dev):
     known = 0.06648282151394422
     xq = torch.rand(1 << 22, 8, device=dev, dtype=torch.float32)
     flow_k = flow_launch_times(NF.best_model, xq, dev, 1 << 22, peaks()[0]["hbm_gbs"],
-                               {1: 36, 11: 36 + 256, 13: 512, 12: 256 + 72, 10: 72})
+                               {1: 36, 11: 36 + 256, 13: 256, 12: 256 + 72, 10: 72})
     del xq
     return {"metric": "nis_integrate_points_per_sec", "value": nitn * neval / dt, "unit": "points/s",
             "flow_kernels_at_2p22_points": flow_k,
@@ -650,13 +650,14 @@ def main():
         tf32_meas = tensor_peak_tflops(0, 128)
         tfl = N_POINTS * FLOP_PER_POINT / (ms * 1e-3) / 1e12
         # moments pass reads the rows; first layer pass reads rows, writes z2; later passes read+write 256 B; final
-        train_bytes_pt = n_cells * (36 + (36 + 256) + 2 * (depth - 2) * 256 + (256 + 36 + 36))
+        train_bytes_pt = n_cells * (36 + (36 + 256) + (2 * (depth - 2) - 1) * 256 + (256 + 36 + 36))
         gbs_design = N_POINTS * train_bytes_pt / (ms * 1e-3) / 1e9
         gbs = N_POINTS * IO_BYTES_PER_POINT / (ms * 1e-3) / 1e9
         # ---- per-launch device times of one more forward (CUDA events recorded on the launch stream by the library:
         #      nis_flow_timing_begin / _end), outside the timed region -----------------------------------------------
         # algorithmic bytes per point of each launch: what the kernel has to read and write once
-        abytes = {1: 36, 11: 36 + 256, 13: 256 + 256, 12: 256 + 36 + 36, 10: 36 + 36}
+        # (the last layer pass only takes statistics: it reads its 256 B/point tile and stores nothing)
+        abytes = {1: 36, 11: 36 + 256, 13: 256, 12: 256 + 36 + 36, 10: 36 + 36}
         # dram__bytes_read.sum + dram__bytes_write.sum per launch at 2^22 points, ncu --set full (profiles/r02_ncu_h_kernel.md)
         traffic = {11: 1176675000, 13: 2407364000, 12: 1378160000, 10: 264708000} if N_POINTS == 1 << 22 else None
         kernels = flow_launch_times(model, x, dev, N_POINTS, pk["hbm_gbs"], abytes, traffic)

@@ -442,7 +442,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     A.saved = saved; A.bins = bins_out;
     A.params = params; A.wpack = ws.wpack; A.bn_running = bn_running; A.bn_saved = bn_saved;
     A.partials = ws.partials; A.counter = ws.counter; A.B = B;
-    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr; A.scratch_state = nullptr; A.inverse = 0;
+    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr; A.scratch_state = nullptr; A.inverse = 0; A.zin_layer = 0;
     // per-cell launch sequences: tcgen05 kernel where it applies, else the FP32 register-tiled kernel
     const bool tc = nis_tc_supported(F, B, bn_mode);
     const bool hp = tc && nis_h_supported(F, B, bn_mode);              // fp16-split, four-group kernel (flow_tc_h.cu)
@@ -452,6 +452,11 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     // recompute them from the state (more tensor work, ~7x less traffic); NIS_TRAIN_RECOMPUTE=0/1 overrides the default
     static const int recompute_env = [] { const char* e = getenv("NIS_TRAIN_RECOMPUTE"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
     const bool recompute = hp && (recompute_env >= 0 ? recompute_env == 1 : false);
+    // fp16-split kernel, depth >= 3: the last layer pass only takes the statistics of z_depth (no 256 B/point store) and the final
+    // pass starts from z_{depth-1} and runs the last hidden layer again (one more MMA block per tile, 256 B/point less traffic
+    // per cell); NIS_SKIP_LAST_STORE=0 keeps the store (A/B knob)
+    static const int skip_env = [] { const char* e = getenv("NIS_SKIP_LAST_STORE"); return e && e[0] == '0' ? 0 : 1; }();
+    const bool skip_last = hp && !recompute && skip_env && F.depth >= 3;
     if (tc) { rc = hp ? nis_h_pack(F, params, ws.tcpack, s) : nis_tc_pack(F, params, ws.tcpack, s); if (rc) return rc; timing_mark(s, 0); }
     if (wide) { rc = nis_wide_pack(F, params, ws.tcpack, s); if (rc) return rc; }
     const long long rows = (long long)B * (F.d + 1);
@@ -496,7 +501,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
                 if (tiled && l >= 1) {
                     // layer pass: reads the pre-BN activations of layer l-1, writes those of layer l
                     A.zin = (l >= 2 && !(moments && l == 2) && !recompute) ? zb[(l - 1) & 1] : nullptr;
-                    A.zout = recompute ? nullptr : zb[l & 1];
+                    A.zout = (recompute || (skip_last && moments && l == F.depth)) ? nullptr : zb[l & 1];
                     rc = hp ? nis_launch_h(F, A, ws.tcpack, s) : tc ? nis_launch_tc(F, A, ws.tcpack, s)
                             : wide ? nis_launch_wide(F, A, ws.tcpack, s) : nis_launch_tiled(F, A, s);
                 } else if (tiled && l == 0) {
@@ -511,6 +516,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
         A.stats_layer = -1;
         A.zin = (tiled && bn_mode == NIS_BN_TRAIN && !(moments && F.depth == 1) && !recompute) ? zb[F.depth & 1] : nullptr;
         A.zout = nullptr;
+        if (skip_last && moments && bn_mode == NIS_BN_TRAIN) { A.zin = zb[(F.depth - 1) & 1]; A.zin_layer = F.depth - 1; }
         if (tc && !hp && bn_mode == NIS_BN_EVAL && nis_tc_split_eval(F)) {
             // eval, PWQuad: hidden layers in one launch (activations of the last hidden layer to HBM), then the final pass
             A.stats_layer = F.depth; A.no_stats = 1; A.zin = nullptr; A.zout = zb[F.depth & 1];
@@ -537,6 +543,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
                 : (tiled ? nis_launch_tiled(F, A, s) : launch_fwd_any(F, A, s));
         if (rc) return rc;
         timing_mark(s, (tc || wide) ? 10 + (A.zin ? 2 : 0) : 2);
+        A.zin_layer = 0;
     }
     return NIS_OK;
 }
@@ -581,7 +588,7 @@ extern "C" int nis_flow_inverse(const NisFlowDesc* desc, const float* params, co
     A.saved = nullptr; A.bins = bins_out;
     A.params = params; A.wpack = ws.wpack; A.bn_running = nullptr; A.bn_saved = nullptr;
     A.partials = ws.partials; A.counter = ws.counter; A.B = B;
-    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr; A.scratch_state = nullptr; A.inverse = 1;
+    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr; A.scratch_state = nullptr; A.inverse = 1; A.zin_layer = 0;
     if (bn_mode == NIS_BN_EVAL) {
         A.state_in = nullptr; A.state_out = nullptr; A.from_state = 0; A.to_out = 1;
         A.c_begin = 0; A.c_end = F.n_cells; A.stats_layer = -1;

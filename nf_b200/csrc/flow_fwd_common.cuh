@@ -18,6 +18,8 @@ struct FwdArgs {
     int no_stats;                                // layer pass that only stores its activations (eval-mode split cell)
     float* z1out;                          // wide kernel, pass from the state: also store z_1 (backward recompute) or null
     float* scratch_state;                  // cooperative small-batch kernel: fp32 [B][d+1] state between cells when `saved` is null
+    int zin_layer;                         // fp16-split kernel: which layer's pre-activations `zin` holds (0: the default,
+                                           // stats_layer - 1 for a layer pass, depth for the final pass)
     int inverse;                           // nis_flow_inverse: cells backwards, inverse splines, J divided (shape-generic kernel only)
 };
 

@@ -133,21 +133,22 @@ struct HSmem {      // byte offsets from the 1024-aligned base
     int w0, aff, bias, st, sst, red, zb, total;
     int wl[NIS_MAX_HIDDEN + 1];     // per MMA layer l (1..depth): offset of (hi, lo), or -1 when not staged
 };
-__host__ __device__ static inline HSmem h_layout(const DevFlow& F, int P, int l_begin, int l_end, bool zstage, int NG) {
+__host__ __device__ static inline HSmem h_layout(const DevFlow& F, int P, int l_begin, int l_end, bool zstage, int NG,
+                                                 bool layer0 = true, bool stats = true) {
     HSmem s;
     int o = 0;
     for (int l = 0; l <= F.depth; ++l) {
         s.wl[l] = -1;
         if (l >= 1 && l >= l_begin && l <= l_end) { s.wl[l] = o; o += l == F.depth ? h_out_bytes(F) : H_HID_BYTES; }
     }
-    s.w0 = o; o += pad8(P) * TCH * 4;
+    s.w0 = o; o += layer0 ? pad8(P) * TCH * 4 : 0;            // layer-0 weights: only when the pass starts from the state
     s.aff = o; o += (F.depth + 1) * 2 * TCH * 4;
     s.bias = o; o += h_out_rows(F) * 4;
     s.st = o; o += NG * (F.d + 1) * TCM * 4;
     o = (o + 15) & ~15;
     s.sst = o; o += NG * (F.d + 1) * TCM * 4;          // landing zone of the next tile's state rows (bulk copy), per group
     o = (o + 7) & ~7;
-    s.red = o; o += (NG * TCM * 2 + 2 * F.maxW) * 8;
+    s.red = o; o += stats ? (NG * TCM * 2 + 2 * F.maxW) * 8 : 0;   // statistics fold: only in statistics passes
     o = (o + 127) & ~127;
     s.zb = o;                                          // [NG][64][128] floats: stored-activation tile in, then out
     if (zstage) o += NG * TCH * TCM * 4;
@@ -210,10 +211,10 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
     // which slice of the cell this launch computes (same table as flow_tc.cu)
     constexpr bool stats = (MODE & 1) != 0;
     constexpr bool from_z = (MODE & 2) != 0;
-    const int lz = from_z ? (stats ? A.stats_layer - 1 : depth) : 1;      // the first A operand is made of z_{lz}
+    const int lz = from_z ? (A.zin_layer > 0 ? A.zin_layer : (stats ? A.stats_layer - 1 : depth)) : 1;   // first A operand: z_{lz}
     const int l_end = stats ? A.stats_layer - 1 : depth;                   // MMA layers lz .. l_end
     const bool zst = from_z || stats;
-    const HSmem L = h_layout(F, q.P, lz, l_end, zst, NG);
+    const HSmem L = h_layout(F, q.P, lz, l_end, zst, NG, !from_z, stats);
     float* w0s = reinterpret_cast<float*>(sm + L.w0);
     float* affs = reinterpret_cast<float*>(sm + L.aff);
     float* biass = reinterpret_cast<float*>(sm + L.bias);
@@ -568,7 +569,8 @@ static int h_groups(const DevFlow& F) {
             const int P = F.cells[c].P;
             ok = (size_t)h_layout(F, P, 1, F.depth, false, ng).total + 1024 <= lim               // fused eval cell
                  && (size_t)h_layout(F, P, F.depth - 1, F.depth - 1, true, ng).total + 1024 <= lim   // a layer pass
-                 && (size_t)h_layout(F, P, F.depth, F.depth, true, ng).total + 1024 <= lim;      // final pass
+                 && (size_t)h_layout(F, P, F.depth, F.depth, true, ng, false, false).total + 1024 <= lim      // final pass
+                 && (F.depth < 3 || (size_t)h_layout(F, P, F.depth - 1, F.depth, true, ng, false, false).total + 1024 <= lim);   // final pass from z_{depth-1}
         }
         if (ok) return ng;
     }
@@ -632,10 +634,10 @@ int nis_launch_h(const DevFlow& F, const FwdArgs& A, const float* tcpack, cudaSt
         if (sms <= 0) sms = 148;
     }
     const bool stats = A.stats_layer >= 1;
-    const int lz = A.zin ? (stats ? A.stats_layer - 1 : F.depth) : 1;
+    const int lz = A.zin ? (A.zin_layer > 0 ? A.zin_layer : (stats ? A.stats_layer - 1 : F.depth)) : 1;
     const int l_end = stats ? A.stats_layer - 1 : F.depth;
     const int ng = h_groups(F);
-    const size_t smem = (size_t)h_layout(F, F.cells[A.c_begin].P, lz, l_end, A.zin != nullptr || stats, ng).total + 1024;
+    const size_t smem = (size_t)h_layout(F, F.cells[A.c_begin].P, lz, l_end, A.zin != nullptr || stats, ng, A.zin == nullptr, stats).total + 1024;
     const char* hp = reinterpret_cast<const char*>(tcpack);
     if (F.kind == NIS_KIND_PWLIN) {
         switch (ng) {
