@@ -472,7 +472,7 @@ def bench_integrate(world, dev):
     known = 0.06648282151394422
     xq = torch.rand(1 << 22, 8, device=dev, dtype=torch.float32)
     flow_k = flow_launch_times(NF.best_model, xq, dev, 1 << 22, peaks()[0]["hbm_gbs"],
-                               {1: 36, 11: 36 + 256, 13: 256, 12: 256 + 72, 10: 72})
+                               {1: 36, 11: 36 + 256, 13: 512, 12: 256 + 72, 10: 72})
     del xq
     return {"metric": "nis_integrate_points_per_sec", "value": nitn * neval / dt, "unit": "points/s",
             "flow_kernels_at_2p22_points": flow_k,

@@ -456,7 +456,8 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     // pass starts from z_{depth-1} and runs the last hidden layer again (one more MMA block per tile, 256 B/point less traffic
     // per cell); NIS_SKIP_LAST_STORE=0 keeps the store (A/B knob)
     static const int skip_env = [] { const char* e = getenv("NIS_SKIP_LAST_STORE"); return e && e[0] == '0' ? 0 : 1; }();
-    const bool skip_last = hp && !recompute && skip_env && F.depth >= 3;
+    // (PWLin only: measured 7.74 -> 7.29 ms on cfg2; the PWQuad final pass is instruction-bound on its spline and loses 1 %)
+    const bool skip_last = hp && !recompute && skip_env && F.depth >= 3 && F.kind == NIS_KIND_PWLIN;
     if (tc) { rc = hp ? nis_h_pack(F, params, ws.tcpack, s) : nis_tc_pack(F, params, ws.tcpack, s); if (rc) return rc; timing_mark(s, 0); }
     if (wide) { rc = nis_wide_pack(F, params, ws.tcpack, s); if (rc) return rc; }
     const long long rows = (long long)B * (F.d + 1);
