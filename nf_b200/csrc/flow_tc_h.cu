@@ -63,9 +63,10 @@ __host__ __device__ static inline int h_off(int row, int k) {
 __host__ __device__ constexpr uint32_t h_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__host__ __device__ static inline size_t h_cell_bytes(const DevFlow& F) {
-    return (size_t)(F.depth - 1) * H_HID_BYTES + h_out_bytes(F) + 64;      // + the per-layer 1 / (SA * SW) factors
-}
+// a cell's pack: hidden layers 1 .. depth-1 | output layer | layer 0 (K = P <= 16, zero-padded to a 64x64 block: the
+// swizzled rows are 128 bytes whatever K is) | the per-layer 1 / (SA * SW) factors
+__host__ __device__ static inline size_t h_l0_off(const DevFlow& F) { return (size_t)(F.depth - 1) * H_HID_BYTES + h_out_bytes(F); }
+__host__ __device__ static inline size_t h_cell_bytes(const DevFlow& F) { return h_l0_off(F) + H_HID_BYTES + 64; }
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -93,12 +94,13 @@ __global__ void __launch_bounds__(256) flow_h_pack_kernel(DevFlow F, const float
     __shared__ float sw_s;
     const int c = blockIdx.y, li = blockIdx.x, tid = threadIdx.x;
     const DevCell& q = F.cells[c];
-    const bool outl = li == F.depth - 1;
-    const int l = li + 1;                                            // MMA layer 1..depth (depth = output layer)
-    const float* w = params + q.param_off + F.p_lin(c, l);           // hidden: [64][64]; output: [T*K][64] (out, in)
+    const bool outl = li == F.depth - 1, first = li == F.depth;      // (the block of layer 0 comes last in the pack)
+    const int l = first ? 0 : li + 1;                                // MMA layer 0..depth (depth = output layer)
+    const float* w = params + q.param_off + F.p_lin(c, l);           // layer 0: [64][P]; hidden: [64][64]; output: [T*K][64] (out, in)
+    const int kin = first ? q.P : TCH;
     const int rows_src = outl ? q.T * F.K : TCH, rows = outl ? h_out_rows(F) : TCH, slot = h_slot(F);
     float m = 0.f;
-    for (int i = tid; i < rows_src * TCH; i += 256) m = fmaxf(m, fabsf(w[i]));
+    for (int i = tid; i < rows_src * kin; i += 256) m = fmaxf(m, fabsf(w[i]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((tid & 31) == 0) red[tid >> 5] = m;
@@ -113,14 +115,14 @@ __global__ void __launch_bounds__(256) flow_h_pack_kernel(DevFlow F, const float
     __syncthreads();
     const float SW = sw_s;
     char* dst = hpack + (size_t)c * h_cell_bytes(F);
-    char* hi = dst + (size_t)li * H_HID_BYTES;                       // (the output layer follows the depth-1 hidden ones)
+    char* hi = dst + (first ? h_l0_off(F) : (size_t)li * H_HID_BYTES);   // (the output layer follows the depth-1 hidden ones)
     char* lo = hi + (size_t)rows * TCH * 2;
     for (int i = tid; i < rows * TCH; i += 256) {
         const int n = i / TCH, k = i - n * TCH;
         // staged row n = dimension n / slot, logit n % slot (PWLin: slot = K = 32, the torch row order itself)
         const int t = outl ? n / slot : 0, jj = outl ? n - t * slot : n;
-        const bool live = outl ? (t < q.T && jj < F.K) : true;
-        const float v = live ? w[(size_t)(outl ? t * F.K + jj : n) * TCH + k] * SW : 0.f;
+        const bool live = outl ? (t < q.T && jj < F.K) : k < kin;
+        const float v = live ? w[(size_t)(outl ? t * F.K + jj : n) * kin + k] * SW : 0.f;
         const __half h = __float2half_rn(v);
         const int o = h_off(n, k);
         *reinterpret_cast<__half*>(hi + o) = h;
@@ -141,7 +143,8 @@ __host__ __device__ static inline HSmem h_layout(const DevFlow& F, int P, int l_
         s.wl[l] = -1;
         if (l >= 1 && l >= l_begin && l <= l_end) { s.wl[l] = o; o += l == F.depth ? h_out_bytes(F) : H_HID_BYTES; }
     }
-    s.w0 = o; o += layer0 ? pad8(P) * TCH * 4 : 0;            // layer-0 weights: only when the pass starts from the state
+    (void)P;
+    s.w0 = o; o += layer0 ? H_HID_BYTES : 0;                  // layer-0 operand (hi, lo): only when the pass starts from the state
     s.aff = o; o += (F.depth + 1) * 2 * TCH * 4;
     s.bias = o; o += h_out_rows(F) * 4;
     s.st = o; o += NG * (F.d + 1) * TCM * 4;
@@ -215,7 +218,6 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
     const int l_end = stats ? A.stats_layer - 1 : depth;                   // MMA layers lz .. l_end
     const bool zst = from_z || stats;
     const HSmem L = h_layout(F, q.P, lz, l_end, zst, NG, !from_z, stats);
-    float* w0s = reinterpret_cast<float*>(sm + L.w0);
     float* affs = reinterpret_cast<float*>(sm + L.aff);
     float* biass = reinterpret_cast<float*>(sm + L.bias);
     const float* pk = A.wpack + q.pk_off;
@@ -230,17 +232,18 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
         uint4* dst = reinterpret_cast<uint4*>(sm + L.wl[l]);
         for (int i = tid; i < n16; i += NT) dst[i] = src[i];
     }
-    if (!from_z) {
-        const float* s0 = pk + q.wt_off[0];                       // layer 0, [P][64] k-major
-        for (int i = tid; i < q.P * TCH; i += NT) w0s[i] = s0[i];
+    if (!from_z) {                                                // layer 0 (hi, lo): one K = 16 step of a 64x64 block
+        const uint4* src = reinterpret_cast<const uint4*>(cellpack + h_l0_off(F));
+        uint4* dst = reinterpret_cast<uint4*>(sm + L.w0);
+        for (int i = tid; i < H_HID_BYTES / 16; i += NT) dst[i] = src[i];
     }
     for (int l = 0; l <= depth; ++l) {                            // BN scale / shift; layers feeding an MMA carry the SA factor
         const int W = l == 0 ? q.P : TCH, Wp = pad8(W);
         const float* s = pk + q.aff_off[l];
-        const float f = l == 0 ? 1.f : H_SA;
+        const float f = H_SA;
         // a layer fed by the accumulator of the layer below (D = z * SA * SW: chained in this launch, or stored as it is
         // by the statistics pass of that layer) takes that factor into its scale
-        const float fs = (l <= l_end && (l > lz || (from_z && l == lz))) ? f * inv_scale[l - 1] : f;
+        const float fs = (l >= 1 && l >= lz && l <= l_end) ? f * inv_scale[l - 1] : f;
         for (int i = tid; i < W; i += NT) { affs[l * 2 * TCH + i] = fs * s[i]; affs[l * 2 * TCH + TCH + i] = f * s[Wp + i]; }
     }
     const int out_rows = h_out_rows(F);
@@ -327,32 +330,54 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
                 st[d * TCM] = 1.f;
             }
             if (from_z) { mbar_wait(&z_full[g], zph); zph ^= 1; }
+            if (!from_z) {
+                // ---- layer 0 (K = P <= 16): BN_0 of the pass-through columns, split like every other operand, one K = 16
+                //      step (3 instructions) - 4 x 64 multiply-adds per point on the FP32 pipe were 13 % of the fused cell's
+                //      instructions.  Columns beyond P are zero (and so are the weight's).
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int j2 = 0; j2 < 8; ++j2) {
+                    float a0 = 0.f, a1 = 0.f;
+                    if (2 * j2 < q.P) a0 = fmaf(st[q.feed[2 * j2] * TCM], affs[2 * j2], affs[TCH + 2 * j2]);
+                    if (2 * j2 + 1 < q.P) a1 = fmaf(st[q.feed[2 * j2 + 1] * TCM], affs[2 * j2 + 1], affs[TCH + 2 * j2 + 1]);
+                    const uint32_t p01 = h_pack_sat(a0, a1);
+                    const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&p01));
+                    hi[j2] = p01;
+                    lo[j2] = h_pack_sat(a0 - f01.x, a1 - f01.y);
+                }
+                tc_st8(tg + H_COL_AHI, hi);
+                tc_st8(tg + H_COL_ALO, lo);
+                tc_st_wait();
+                tc_fence_before();
+                mbar_arrive(&a_ready[g]);
+                if (gt == 0) {
+                    mbar_wait(&a_ready[g], pa);
+                    tc_fence_after();
+                    const uint32_t whi = smem_u32(sm + L.w0), wlo = whi + TCH * TCH * 2;
+                    const uint32_t tb = tmem_base + g * H_COLS;
+                    h_mma_ts(tb, tb + H_COL_AHI, tc_desc(wlo), idesc, 0);
+                    h_mma_ts(tb, tb + H_COL_ALO, tc_desc(whi), idesc, 1);
+                    h_mma_ts(tb, tb + H_COL_AHI, tc_desc(whi), idesc, 1);
+                    tc_commit(&d_ready[g]);
+                }
+                pa ^= 1;
+                mbar_wait(&d_ready[g], pd);
+                pd ^= 1;
+                tc_fence_after();
+            }
             // ---- MMA layers lz .. l_end: build the A operand of layer l from z_l, 32 features at a time -----------
             for (int l = lz; l <= l_end; ++l) {
                 const float* sc = affs + l * 2 * TCH;
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     float v[32];
-                    if (l > lz) {                                 // chained: the accumulator of layer l-1
+                    if (l > lz || !from_z) {                      // chained: the accumulator of layer l-1
                         tc_ld32(tg + 32 * h, v);
                         tc_ld_wait();
-                    } else if (from_z) {                          // stored pre-BN activations
+                    } else {                                      // stored pre-BN activations
                         const float* zr = zs + (32 * h) * TCM + gt;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = zr[j * TCM];
-                    } else {                                      // layer 0 (K = P) on the FP32 pipe
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                        for (int k = 0; k < q.P; ++k) {
-                            const float a = fmaf(st[q.feed[k] * TCM], affs[k], affs[TCH + k]);
-                            const float4* wr = reinterpret_cast<const float4*>(w0s + k * TCH + 32 * h);
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                const float4 w = wr[j4];
-                                v[4 * j4] = fmaf(a, w.x, v[4 * j4]); v[4 * j4 + 1] = fmaf(a, w.y, v[4 * j4 + 1]);
-                                v[4 * j4 + 2] = fmaf(a, w.z, v[4 * j4 + 2]); v[4 * j4 + 3] = fmaf(a, w.w, v[4 * j4 + 3]);
-                            }
-                        }
                     }
                     h_store_act32(v, sc + 32 * h, sc + TCH + 32 * h, tg + H_COL_AHI + 16 * h, tg + H_COL_ALO + 16 * h);
                 }
@@ -595,7 +620,7 @@ bool nis_h_supported(const DevFlow& F, int64_t B, int bn_mode) {
 }
 
 int nis_h_pack(const DevFlow& F, const float* params, float* tcpack, cudaStream_t s) {
-    flow_h_pack_kernel<<<dim3(F.depth, F.n_cells), 256, 0, s>>>(F, params, reinterpret_cast<char*>(tcpack));
+    flow_h_pack_kernel<<<dim3(F.depth + 1, F.n_cells), 256, 0, s>>>(F, params, reinterpret_cast<char*>(tcpack));
     NIS_CUDA_CHECK_LAUNCH();
     return NIS_OK;
 }

@@ -214,6 +214,11 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* v) {
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
         :: TC_W32(v, 0), TC_W32(v, 8), "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
+        :: TC_W32(v, 0), "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // BN scale/shift + ReLU of this thread's 64 pre-activations, split into TF32 hi / residual lo, written to

@@ -197,9 +197,11 @@ def pwlin_cell(sd, cell, x, P, n_bins, train, stats=None, edges=None, clamp_bins
     return torch.cat((xA, y, J.unsqueeze(-1)), -1), bins.long()
 
 
-def pwquad_cell(sd, cell, x, P, n_bins, train, stats=None, edges=None):
+def pwquad_cell(sd, cell, x, P, n_bins, train, stats=None, edges=None, cond=None):
     """coupling_cells.py:159-228.  Returns (out [B, d+1], bins [B, T]).
-    ``edges`` (list) receives the distance [B, T] of every transformed coordinate to its nearest bin edge."""
+    ``edges`` (list) receives the distance [B, T] of every transformed coordinate to its nearest bin edge; ``cond``
+    (list) the sensitivity [B] of this cell's log-Jacobian to its input coordinates, sum_t |d log f_t / d x_t| =
+    |V_{k+1} - V_k| / (W_k lerp(V_k, V_{k+1}, alpha)): what a rounding error of x is multiplied by inside a narrow bin."""
     d = x.shape[1] - 1
     T = d - P
     nb = n_bins
@@ -226,6 +228,8 @@ def pwquad_cell(sd, cell, x, P, n_bins, train, stats=None, edges=None):
     Vk = torch.gather(V, -1, k).squeeze(-1)
     Vk1 = torch.gather(V, -1, k + 1).squeeze(-1)
     y = alpha ** 2 / 2 * ((Vk1 - Vk) * Wk) + alpha * Vk * Wk + torch.gather(S, -1, k).squeeze(-1)
+    if cond is not None:
+        cond.append(((Vk1 - Vk).abs() / (Wk * torch.lerp(Vk, Vk1, alpha))).sum(-1).detach())
     J = J * torch.prod(torch.lerp(Vk, Vk1, alpha), -1)  # :224-225
     return torch.cat((xA, y, J.unsqueeze(-1)), -1), k.squeeze(-1)
 
@@ -309,10 +313,11 @@ def flow_inverse(layers, sd, yj, kind, n_bins, train=False, stats=None):
 # ----------------------------------------------------------------------------------------------
 # whole flow, layer by layer like the reference Sequential
 # ----------------------------------------------------------------------------------------------
-def flow_forward(layers, sd, xj, kind, n_bins, train=True, stats=None, trace=None, edges=None, clamp_bins=False):
+def flow_forward(layers, sd, xj, kind, n_bins, train=True, stats=None, trace=None, edges=None, clamp_bins=False, cond=None):
     """Run the reference Sequential.  xj: [B, d+1] float64.  Returns (XJ [B, d+1], bins [B, C, T_c]
     as a list of per-cell LongTensors).  ``trace`` (dict) receives each module's output by name, ``edges`` (list)
-    each cell's [B, T_c] distances to the nearest bin edge."""
+    each cell's [B, T_c] distances to the nearest bin edge, ``cond`` (list, PWQuad) each cell's [B] sensitivity of the
+    log-Jacobian to its input coordinates (see pwquad_cell)."""
     d = xj.shape[1] - 1
     cell_fn = pwlin_cell if kind == "lin" else pwquad_cell
     x = xj
@@ -320,7 +325,10 @@ def flow_forward(layers, sd, xj, kind, n_bins, train=True, stats=None, trace=Non
     for L in layers:
         t = L["type"]
         if t == "cell":
-            x, b = cell_fn(sd, L["name"], x, L["P"], n_bins, train, stats, edges, **({"clamp_bins": True} if clamp_bins and kind == "lin" else {}))
+            extra = {"clamp_bins": True} if clamp_bins and kind == "lin" else {}
+            if cond is not None and kind != "lin":
+                extra["cond"] = cond
+            x, b = cell_fn(sd, L["name"], x, L["P"], n_bins, train, stats, edges, **extra)
             all_bins.append(b)
         elif t == "roll":
             x = torch.cat((torch.roll(x[:, :-1], L["shift"], -1), x[:, -1:]), -1)

@@ -82,15 +82,16 @@ def test_forward_matches_oracle_at_size(cfg, mode, max_log_j=None):
     xj = NF.format_input(x, torch.device("cuda"))
     XJ, bins = model.forward_with_bins(xj)
     sd64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}
-    edges = []
+    edges, cond = [], []
     with torch.no_grad():
         ref, ref_bins = oflow.flow_forward(oracle_layers(cfg), sd64, xj.cpu(), cfg["kind"], cfg["n_bins"],
-                                           train=(mode == "train"), edges=edges, clamp_bins=True)
+                                           train=(mode == "train"), edges=edges, clamp_bins=True, cond=cond)
         sd32 = {k: (v.float() if v.dtype.is_floating_point else v) for k, v in sd.items()}
         ref32, _ = oflow.flow_forward(oracle_layers(cfg), sd32, xj.cpu().float(), cfg["kind"], cfg["n_bins"],
                                       train=(mode == "train"), clamp_bins=True)
     compare_flow(XJ.cpu(), bins.cpu(), ref, [b.numpy() for b in ref_bins], "%s/%s" % (cfg["name"], mode),
-                 fp32_yardstick=ref32, ref_edges=[e.numpy() for e in edges], max_log_j=max_log_j)
+                 fp32_yardstick=ref32, ref_edges=[e.numpy() for e in edges], max_log_j=max_log_j,
+                 ref_cond=[c.numpy() for c in cond])
 
 
 @pytest.mark.parametrize("mode", ["eval", "train"])
@@ -153,6 +154,23 @@ WIDE = [
 def test_streamed_weight_kernel_shapes(cfg, mode):
     """flow_wide.cu beyond cfg5_small: width 128 (one round), 192 (one round of N = 192), 256 x 4 layers (two rounds
     per hidden layer), PWLin and PWQuad, bin counts that are not multiples of 16, ragged last tile."""
+    test_forward_matches_oracle_at_size(cfg, mode)
+
+
+MANY_PASS_THROUGH = [
+    dict(name="lin13d_9pass", kind="lin", n_flow=13, n_pass_through=9, n_cells=4, n_bins=32, NN=[64] * 3, roll_step=3, B=2700),
+    dict(name="lin20d_16pass", kind="lin", n_flow=20, n_pass_through=16, n_cells=3, n_bins=32, NN=[64] * 2, roll_step=7, B=1500),
+    dict(name="quad18d", kind="quad", n_flow=18, n_cells=5, n_bins=32, NN=[64] * 3, B=1300),
+    dict(name="lin6d_1layer", kind="lin", n_flow=6, n_pass_through=3, n_cells=4, n_bins=32, NN=[64], roll_step=2, B=2100),
+]
+
+
+@pytest.mark.parametrize("cfg", MANY_PASS_THROUGH, ids=[c["name"] for c in MANY_PASS_THROUGH])
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_fp16_split_kernel_pass_through_counts(cfg, mode):
+    """flow_tc_h.cu with 9 .. 16 pass-through columns: the first linear layer is one K = 16 tensor-core step whatever P
+    is, and beyond 8 columns the statistics of BN_1 come from a layer pass of their own (the one-pass column moments
+    stop at P = 8); a one-hidden-layer conditioner (no chained hidden layer at all)."""
     test_forward_matches_oracle_at_size(cfg, mode)
 
 

@@ -121,6 +121,23 @@ def test_inverse_flow_undoes_the_reference_pinned_forward(golden, case, train):
     assert torch.allclose(xb[:, -1], xj[:, -1], rtol=1e-9)
 
 
+def test_pwquad_condition_output_is_the_derivative_of_the_log_jacobian(golden):
+    """The per-point sensitivity the oracle hands to the GPU parity bound (tests/gpu_util.py COND_K) is what it says:
+    sum_t |d log f_t / d x_t| of one cell in eval mode, checked against autograd on a golden model."""
+    g = golden("flow_quad8d_small")
+    m = g.meta
+    layers = oflow.pwquad_layers(m["n_flow"], m["n_cells"])
+    cell = next(L for L in layers if L["type"] == "cell")
+    sd = g.state_dict()
+    d = m["n_flow"]
+    x = (0.02 + 0.96 * torch.rand(64, d, generator=torch.Generator().manual_seed(9), dtype=torch.float64)).requires_grad_(True)
+    xj = torch.cat((x, torch.ones(64, 1, dtype=torch.float64)), 1)
+    cond = []
+    out, _ = oflow.pwquad_cell(sd, cell["name"], xj, cell["P"], m["n_bins"], False, cond=cond)
+    (grad,) = torch.autograd.grad(torch.log(out[:, -1]).sum(), x)
+    assert torch.allclose(grad[:, cell["P"]:].abs().sum(-1), cond[0], rtol=1e-9)
+
+
 @pytest.mark.parametrize("case", RAMBO_CASES)
 def test_rambo_matches_reference(golden, case):
     g = golden("rambo_" + case)
