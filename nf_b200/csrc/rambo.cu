@@ -9,17 +9,24 @@
 #include "rambo_core.cuh"
 
 #define RAMBO_NT 128
+#ifndef RAMBO_CTAS
+#define RAMBO_CTAS 7
+#endif
 
-// six CTAs per SM (what the shared-memory tile allows): without the bound ptxas takes 255 registers for the four inlined
-// event variants and the kernel runs at half speed
+// doubles of a thread's momenta row: with PDFs the whole event (beams + final state, the beam slots double as the cut
+// scratch); without, the beams are constants the kernel stores itself and the row is [n scratch | 4n final state]
+__host__ __device__ static inline int rambo_row_doubles(int n, bool pdf) { return pdf ? (n + 2) * 4 : 5 * n; }
+
+// seven CTAs per SM (what the shared-memory rows of a 2 -> 4 event allow: 9 + 21 doubles per thread): without the bound
+// ptxas takes 255 registers for the inlined event variants and the kernel runs at half speed
 template <typename RT>
-__global__ void __launch_bounds__(RAMBO_NT, 6) rambo_kernel(const __grid_constant__ RamboConst C, const RT* __restrict__ r,
+__global__ void __launch_bounds__(RAMBO_NT, RAMBO_CTAS) rambo_kernel(const __grid_constant__ RamboConst C, const RT* __restrict__ r,
                                                          double* __restrict__ momenta, double* __restrict__ weight,
                                                          uint8_t* __restrict__ cutmask, long long B) {
     const int ND = 3 * C.n - 4 + (C.pdf_active ? 2 : 0);    // uniforms per event
     const int NDP = ND | 1;                 // odd row stride (doubles): conflict-free per-thread rows
     const int NM = (C.n + 2) * 4;           // momentum components per event
-    const int NMP = NM | 1;
+    const int NMP = rambo_row_doubles(C.n, C.pdf_active != 0) | 1;
     extern __shared__ __align__(16) double smd[];
     double* rs = smd;                       // [NT][NDP]
     double* mo = smd + RAMBO_NT * NDP;      // [NT][NMP]  (scratch even when momenta are not requested)
@@ -53,8 +60,8 @@ __global__ void __launch_bounds__(RAMBO_NT, 6) rambo_kernel(const __grid_constan
             if (C.pdf_active) {
                 if (kin) rambo_event<true, true>(C, row, 1, mo + tid * NMP, 1, w, pass);
                 else rambo_event<false, true>(C, row, 1, mo + tid * NMP, 1, w, pass);
-            } else if (kin) rambo_event<true, false>(C, row, 1, mo + tid * NMP, 1, w, pass);
-            else rambo_event<false, false>(C, row, 1, mo + tid * NMP, 1, w, pass);
+            } else if (kin) rambo_event<true, false, false>(C, row, 1, mo + tid * NMP, 1, w, pass);
+            else rambo_event<false, false, false>(C, row, 1, mo + tid * NMP, 1, w, pass);
             weight[base + tid] = w;
             if (cutmask) cutmask[base + tid] = pass;
         }
@@ -64,7 +71,16 @@ __global__ void __launch_bounds__(RAMBO_NT, 6) rambo_kernel(const __grid_constan
             // no barrier (the cooperative 16-byte copy-out was ~10 % of the kernel's instructions)
             const double* srow = mo + tid * NMP;
             double* dst = momenta + (base + tid) * NM;
-            for (int c = 0; c < NM; c += 4)
+            int c0 = 0;
+            if (!C.pdf_active) {                                   // the beams straight from the launch constants
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
+                             :: "l"(dst), "d"(C.beam[0][0]), "d"(C.beam[0][1]), "d"(C.beam[0][2]), "d"(C.beam[0][3]) : "memory");
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
+                             :: "l"(dst + 4), "d"(C.beam[1][0]), "d"(C.beam[1][1]), "d"(C.beam[1][2]), "d"(C.beam[1][3]) : "memory");
+                srow += C.n - 8;                                   // final state at srow[n ..): component c of the event at srow[c - 8 + n]
+                c0 = 8;
+            }
+            for (int c = c0; c < NM; c += 4)
                 asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
                              :: "l"(dst + c), "d"(srow[c]), "d"(srow[c + 1]), "d"(srow[c + 2]), "d"(srow[c + 3]) : "memory");
         }
@@ -74,11 +90,22 @@ __global__ void __launch_bounds__(RAMBO_NT, 6) rambo_kernel(const __grid_constan
 template <typename RT>
 static int rambo_launch(const RamboConst& C, const void* r, double* momenta, double* weight, uint8_t* cutmask,
                         long long B, cudaStream_t s) {
-    const int NDP = (3 * C.n - 4 + (C.pdf_active ? 2 : 0)) | 1, NMP = ((C.n + 2) * 4) | 1;
+    const int NDP = (3 * C.n - 4 + (C.pdf_active ? 2 : 0)) | 1, NMP = rambo_row_doubles(C.n, C.pdf_active != 0) | 1;
     const size_t smem = sizeof(double) * RAMBO_NT * (NDP + NMP);
     NIS_ENSURE_SMEM((rambo_kernel<RT>), (int)smem);
     long long ntiles = (B + RAMBO_NT - 1) / RAMBO_NT;
-    int grid = (int)(ntiles < 148 * 16 ? ntiles : 148 * 16);
+    // one resident wave: every CTA strides over the same number of tiles (+-1), no partial last wave
+    static int sms = 0;
+    if (sms <= 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rambo_kernel<RT>, RAMBO_NT, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 4;
+    const long long wave = (long long)sms * per_sm;
+    int grid = (int)(ntiles < wave ? ntiles : wave);
     rambo_kernel<RT><<<grid, RAMBO_NT, smem, s>>>(C, (const RT*)r, momenta, weight, cutmask, B);
     NIS_CUDA_CHECK_LAUNCH();
     return NIS_OK;

@@ -310,10 +310,13 @@ NIS_DEV double rambo_pdf_density(const double* grid, int nodes, double lnx_lo, d
 // KIN = false (weight-only call without cuts): only the intermediate masses and the reweighting run.
 // PDF = true: two more uniforms sample the Bjorken x; the event is generated at E = sqrt(x1 x2) E_coll, the cuts see the
 // lab frame (:157-187, 213-219, 283).
-template <bool KIN, bool PDF>
+// BEAMS = false (the CUDA kernel without PDFs, where the beams are launch constants it stores itself): `mo` holds
+// [n scratch slots | 4n final-state components] instead of [8 beam components | 4n final-state components].
+template <bool KIN, bool PDF, bool BEAMS = true>
 NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* mo, int ms, double& weight,
                          uint8_t& pass) {
     const int n = C.n;
+    double* const finw = mo + (BEAMS ? 8 : n) * ms;             // final-state particle j at finw + 4*j*ms
     double K0 = C.K0, wconst = C.wconst, E = C.E_coll, x1 = 1.0, x2 = 1.0;
     if (PDF) {
         const double ra = r[(3 * n - 4) * rs], rb = r[(3 * n - 3) * rs];
@@ -376,7 +379,7 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
         const double coef = (nis_div(pQ, Q0 + Mj) + p0) * iM;
         p1 += coef * Q1; p2 += coef * Q2; p3 += coef * Q3;
         const double e = (Q0 * p0 + pQ) * iM;
-        double* o = mo + (2 + j) * 4 * ms;
+        double* o = finw + j * 4 * ms;
         o[0] = e; o[ms] = p1; o[2 * ms] = p2; o[3 * ms] = p3;
         Q1 -= p1; Q2 -= p2; Q3 -= p3; Q0 -= e;                  // :271-275
         Kj = Kn; Mj = Mn;
@@ -384,7 +387,7 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
     const double w = wconst * nis_div(num, den);
     if (!KIN) { pass = 1; weight = w; return; }
     {
-        double* o = mo + (n + 1) * 4 * ms;                      // :278
+        double* o = finw + (n - 1) * 4 * ms;                    // :278
         o[0] = Q0; o[ms] = Q1; o[2 * ms] = Q2; o[3 * ms] = Q3;
     }
     // ---- cuts (:285-301); x1 = x2 = 1 so the lab frame is the CM frame -------------------------
@@ -408,8 +411,8 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
             lb_gb = lb_g * beta;
         }
     }
-    const double* fin = mo + 8 * ms;                            // final-state particle j at fin + 4*j*ms
-    double* e2 = mo;                                            // exp(2 eta_j), j < n <= 8 (beam slots)
+    const double* fin = finw;
+    double* e2 = mo;                                            // exp(2 eta_j), j < n <= 8 (beam / scratch slots)
     const bool need_eta = C.rap_max > 0.0 || C.dR_min > 0.0;
     if (C.pT_min > 0.0 || need_eta) {
         double pt2min = NIS_HUGE, e2max = 0.0;
@@ -520,7 +523,7 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
         }
         mo[0] = e1; mo[ms] = 0.0; mo[2 * ms] = 0.0; mo[3 * ms] = z;
         mo[4 * ms] = e2_; mo[5 * ms] = 0.0; mo[6 * ms] = 0.0; mo[7 * ms] = -z;
-    } else {
+    } else if (BEAMS) {
 #pragma unroll 1
         for (int i = 0; i < 8; ++i) mo[i * ms] = C.beam[i >> 2][i & 3];
     }
