@@ -193,6 +193,19 @@ LAUNCH_NAMES = {0: "weight packs", 1: "flow_col_moments_kernel", 11: "flow_cell_
                 2: "other"}
 
 
+def count_flow_launches(model, x, dev):
+    """Kernels the library launches for one forward (its own event marks, nis_flow_timing_begin / _end)."""
+    import ctypes
+    from nf_b200 import _cabi
+    lib = _cabi.lib()
+    lib.nis_flow_timing_begin(_cabi.stream_ptr(dev))
+    with torch.no_grad():
+        model(x)
+    lms = (ctypes.c_float * 512)()
+    ltag = (ctypes.c_int32 * 512)()
+    return max(int(lib.nis_flow_timing_end(lms, ltag, 512)), 0)
+
+
 def flow_launch_times(model, x, dev, n_points, hbm_peak, abytes, traffic=None):
     """Per-launch device times of ONE forward, from CUDA events the library records on the launch stream around every
     kernel (nis_flow_timing_begin / _end), grouped by kernel: launches, average ms, share of the step and - with the
@@ -568,8 +581,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = world * N_POINTS / (ms * 1e-3)
     n_cells, depth = 6, 3
-    # pack + tensor-core weight pack + per cell (column moments -> BN0/BN1, depth-1 layer passes, final pass)
-    launches_per_step = 2 + n_cells * (depth + 1) + (1 if world > 1 else 0)
+    # counted, not assumed: the library marks every kernel it launches for one forward (two weight packs, the first cell's
+    # column moments, per cell depth-1 layer passes and the final pass = 21 for cfg2) + the moments reduction at N > 1
+    launches_per_step = count_flow_launches(model, x, dev) + (1 if world > 1 else 0)
 
     # ---- end to end through the public API from pinned host buffers ---------------------------------
     # Every step copies its 2^22 points host->device and its [2^22, 9] result device->host inside the timed
@@ -650,7 +664,9 @@ def main():
         tf32_meas = tensor_peak_tflops(0, 128)
         tfl = N_POINTS * FLOP_PER_POINT / (ms * 1e-3) / 1e12
         # moments pass reads the rows; first layer pass reads rows, writes z2; later passes read+write 256 B; final
-        train_bytes_pt = n_cells * (36 + (36 + 256) + (2 * (depth - 2) - 1) * 256 + (256 + 36 + 36))
+        # first cell: column moments (36); every cell: layer pass from the state (36 + 256), depth-2 layer passes from stored
+        # activations (the last one statistics only: no store), final pass (256 + 36 + 36, it also takes the next cell's moments)
+        train_bytes_pt = 36 + n_cells * ((36 + 256) + (2 * (depth - 2) - 1) * 256 + (256 + 36 + 36))
         gbs_design = N_POINTS * train_bytes_pt / (ms * 1e-3) / 1e9
         gbs = N_POINTS * IO_BYTES_PER_POINT / (ms * 1e-3) / 1e9
         # ---- per-launch device times of one more forward (CUDA events recorded on the launch stream by the library:

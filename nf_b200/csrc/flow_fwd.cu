@@ -442,7 +442,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     A.saved = saved; A.bins = bins_out;
     A.params = params; A.wpack = ws.wpack; A.bn_running = bn_running; A.bn_saved = bn_saved;
     A.partials = ws.partials; A.counter = ws.counter; A.B = B;
-    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr; A.scratch_state = nullptr; A.inverse = 0; A.zin_layer = 0;
+    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr; A.scratch_state = nullptr; A.inverse = 0; A.zin_layer = 0; A.next_moments = 0;
     // per-cell launch sequences: tcgen05 kernel where it applies, else the FP32 register-tiled kernel
     const bool tc = nis_tc_supported(F, B, bn_mode);
     const bool hp = tc && nis_h_supported(F, B, bn_mode);              // fp16-split, four-group kernel (flow_tc_h.cu)
@@ -477,6 +477,10 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
             if (rc == NIS_OK) { timing_mark(s, 2); return NIS_OK; }
         }
     }
+    // fp16-split kernel: the final pass of a train-mode cell also takes the column moments of the next cell (P <= 4) from the
+    // state it writes, so only the first cell runs flow_col_moments_kernel (NIS_FUSE_MOMENTS=0: every cell does, A/B knob)
+    static const int fuse_env = [] { const char* e = getenv("NIS_FUSE_MOMENTS"); return e && e[0] == '0' ? 0 : 1; }();
+    bool moments_ready = false;
     // One launch sequence per cell.  TRAIN: a statistics pass per BN layer, then the full pass.
     // (EVAL reaches here only on the register-tiled path, whose launches are per cell.)
     for (int c = 0; c < F.n_cells; ++c) {
@@ -491,10 +495,12 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
         if (bn_mode == NIS_BN_TRAIN) {
             int l0 = 0;
             if (moments) {
-                A.stats_layer = 0;
-                rc = nis_launch_col_moments(F, A, s);
-                if (rc) return rc;
-                timing_mark(s, 1);
+                if (!moments_ready) {
+                    A.stats_layer = 0;
+                    rc = nis_launch_col_moments(F, A, s);
+                    if (rc) return rc;
+                    timing_mark(s, 1);
+                }
                 l0 = 2;
             }
             for (int l = l0; l <= F.depth; ++l) {
@@ -538,6 +544,9 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
             A.stats_layer = -1; A.no_stats = 0; A.zin = F.depth >= 2 ? zb[F.depth & 1] : nullptr; A.zout = nullptr;
         }
         const bool last = c == F.n_cells - 1;
+        A.next_moments = hp && fuse_env && bn_mode == NIS_BN_TRAIN && !last && A.zin != nullptr
+                         && nis_moments_supported(F, c + 1) && F.cells[c + 1].P <= 4;
+        moments_ready = A.next_moments != 0;
         A.to_out = last;
         A.state_out = saved ? saved + (long long)(c + 1) * rows : (last ? nullptr : ws.state);
         rc = hp ? nis_launch_h(F, A, ws.tcpack, s) : tc ? nis_launch_tc(F, A, ws.tcpack, s) : wide ? nis_launch_wide(F, A, ws.tcpack, s)
@@ -589,7 +598,7 @@ extern "C" int nis_flow_inverse(const NisFlowDesc* desc, const float* params, co
     A.saved = nullptr; A.bins = bins_out;
     A.params = params; A.wpack = ws.wpack; A.bn_running = nullptr; A.bn_saved = nullptr;
     A.partials = ws.partials; A.counter = ws.counter; A.B = B;
-    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr; A.scratch_state = nullptr; A.inverse = 1; A.zin_layer = 0;
+    A.zin = nullptr; A.zout = nullptr; A.no_stats = 0; A.z1out = nullptr; A.scratch_state = nullptr; A.inverse = 1; A.zin_layer = 0; A.next_moments = 0;
     if (bn_mode == NIS_BN_EVAL) {
         A.state_in = nullptr; A.state_out = nullptr; A.from_state = 0; A.to_out = 1;
         A.c_begin = 0; A.c_end = F.n_cells; A.stats_layer = -1;

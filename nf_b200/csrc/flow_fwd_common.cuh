@@ -20,6 +20,8 @@ struct FwdArgs {
     float* scratch_state;                  // cooperative small-batch kernel: fp32 [B][d+1] state between cells when `saved` is null
     int zin_layer;                         // fp16-split kernel: which layer's pre-activations `zin` holds (0: the default,
                                            // stats_layer - 1 for a layer pass, depth for the final pass)
+    int next_moments;                      // fp16-split final pass: also accumulate the column moments of cell c_begin + 1 (its
+                                           // BN_0 / BN_1 statistics) from the state this pass writes - no pass of their own
     int inverse;                           // nis_flow_inverse: cells backwards, inverse splines, J divided (shape-generic kernel only)
 };
 
@@ -108,4 +110,80 @@ __device__ __forceinline__ void bn_stats_finalize(const DevFlow& F, const FwdArg
         aff[Wp + j] = sh;
     }
     if (tid == 0) *A.counter = 0u;
+}
+
+
+// BN_0 and BN_1 of cell c from the first and second moments of its pass-through columns (tot[0..P) = sum x_k,
+// tot[s2i(k, k2)] = sum x_k x_k2 over the batch, in shared memory): BN_0 is per column; layer 0 is linear in BN_0's
+// output, so the batch mean and variance of each of its outputs follow from the covariance matrix - no pass over z_1.
+// Writes scale / shift (wpack), the saved batch statistics (backward) and the running statistics.  Called by every
+// thread of the last CTA (NT threads) after a __syncthreads(); sc0s: P doubles of shared scratch.
+template <int MOM_P>
+__device__ __forceinline__ void moments_finalize(const DevFlow& F, const FwdArgs& A, int c, const double* tot, double* sc0s,
+                                                 int tid, int NT) {
+    const DevCell& q = F.cells[c];
+    const int P = q.P;
+    const double n = (double)A.B, mom = (double)F.momentum, unb = A.B > 1 ? n / (n - 1.0) : 1.0;
+    const float* prm = A.params + q.param_off;
+    float* pk = A.wpack + q.pk_off;
+    const int maxW = F.maxW;
+    // index of S2[k][k2], k <= k2, in the packed upper triangle
+    auto s2i = [](int k, int k2) { return MOM_P + k * MOM_P - k * (k - 1) / 2 + (k2 - k); };
+    // ---- BN0 -------------------------------------------------------------------------------------------
+    if (tid < pad8(P)) {
+        float sc = 0.f, sh = 0.f;
+        if (tid < P) {
+            const double mean = tot[tid] / n;
+            double var = tot[s2i(tid, tid)] / n - mean * mean;
+            var = var > 0.0 ? var : 0.0;
+            const double invstd = 1.0 / sqrt(var + (double)F.eps);
+            const double g = (double)prm[tid], b = (double)prm[P + tid];
+            sc = (float)(g * invstd);
+            sh = (float)(b - mean * g * invstd);
+            sc0s[tid] = g * invstd;
+            if (A.bn_saved) { A.bn_saved[q.sv_off + tid] = (float)mean; A.bn_saved[q.sv_off + maxW + tid] = (float)invstd; }
+            if (A.bn_running) {
+                float* rs = A.bn_running + q.bn_off + F.r_mean(c, 0);
+                rs[tid] = (float)((1.0 - mom) * (double)rs[tid] + mom * mean);
+                rs[P + tid] = (float)((1.0 - mom) * (double)rs[P + tid] + mom * var * unb);
+            }
+        }
+        pk[q.aff_off[0] + tid] = sc;
+        pk[q.aff_off[0] + pad8(P) + tid] = sh;
+    }
+    __syncthreads();
+    // ---- BN1 from the moments ------------------------------------------------------------------------------
+    const int H = F.widths[0], Hp = pad8(H);
+    const float* W0 = prm + F.p_lin(c, 0);                 // [H][P]
+    const float* g1 = prm + F.p_bn_gamma(c, 1);
+    for (int j = tid; j < Hp; j += NT) {
+        float sc = 0.f, sh = 0.f;
+        if (j < H) {
+            double mean1 = 0.0, var1 = 0.0;
+            for (int k = 0; k < P; ++k) {
+                const double wk = (double)W0[j * P + k];
+                mean1 += wk * (double)prm[P + k];
+                const double mk = tot[k] / n;
+                for (int k2 = 0; k2 < P; ++k2) {
+                    const double cov = tot[k <= k2 ? s2i(k, k2) : s2i(k2, k)] / n - mk * (tot[k2] / n);
+                    var1 += wk * sc0s[k] * (double)W0[j * P + k2] * sc0s[k2] * cov;
+                }
+            }
+            var1 = var1 > 0.0 ? var1 : 0.0;
+            const double invstd = 1.0 / sqrt(var1 + (double)F.eps);
+            sc = (float)((double)g1[j] * invstd);
+            sh = (float)((double)g1[H + j] - mean1 * (double)g1[j] * invstd);
+            if (A.bn_saved) {
+                A.bn_saved[q.sv_off + 2 * maxW + j] = (float)mean1;
+                A.bn_saved[q.sv_off + 2 * maxW + maxW + j] = (float)invstd;
+            }
+            if (A.bn_running) {
+                float* rs = A.bn_running + q.bn_off + F.r_mean(c, 1);
+                rs[j] = (float)((1.0 - mom) * (double)rs[j] + mom * mean1);
+                rs[H + j] = (float)((1.0 - mom) * (double)rs[H + j] + mom * var1 * unb);
+            }
+        }
+        pk[q.aff_off[1] + j] = sc;
+        pk[q.aff_off[1] + Hp + j] = sh;
+    }
 }

@@ -194,7 +194,9 @@ __device__ __forceinline__ void h_issue_block(uint32_t tmem_d, uint32_t t_hi, ui
     for (int ks = 0; ks < 4; ++ks) h_mma_ts(tmem_d, t_hi + ks * 8, tc_desc(w_hi + ks * 32), idesc, 1);
 }
 
-// MODE: bit 0 = statistics (layer) pass, bit 1 = the first operand comes from stored activations.  Compile-time, so that
+// MODE: bit 0 = statistics (layer) pass, bit 1 = the first operand comes from stored activations, bit 2 (final pass of a
+// train-mode cell) = the column moments of the NEXT cell's pass-through columns are accumulated from the state this pass
+// writes (14 sums for P <= 4) and folded into that cell's BN_0 / BN_1 by the last CTA.  Compile-time, so that
 // every instantiation carries only its own path: the all-in-one kernel was 64 KB of SASS and its four groups, each in
 // another phase, missed the instruction cache (ncu: `no_instruction` 0.8 stalled warps per issue).
 template <int NG, int KIND, int MODE>
@@ -214,6 +216,11 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
     // which slice of the cell this launch computes (same table as flow_tc.cu)
     constexpr bool stats = (MODE & 1) != 0;
     constexpr bool from_z = (MODE & 2) != 0;
+    constexpr bool nextmom = (MODE & 4) != 0;
+    constexpr int MOM_N = 4 + 4 * 5 / 2;                                    // sum x_k, sum x_k x_k2 (k <= k2), P <= 4
+    float macc[nextmom ? MOM_N : 1];
+#pragma unroll
+    for (int i = 0; i < (nextmom ? MOM_N : 1); ++i) macc[i] = 0.f;
     const int lz = from_z ? (A.zin_layer > 0 ? A.zin_layer : (stats ? A.stats_layer - 1 : depth)) : 1;   // first A operand: z_{lz}
     const int l_end = stats ? A.stats_layer - 1 : depth;                   // MMA layers lz .. l_end
     const bool zst = from_z || stats;
@@ -544,6 +551,20 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
                 }
             }
             st[d * TCM] *= jfac;
+            if (nextmom && valid) {
+                // per-thread float32 partials, like flow_col_moments_kernel (a thread sees ~B / (SMs * 512) points <= 1)
+                const DevCell& qn = F.cells[c + 1];
+                float x[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x[k] = k < qn.P ? st[qn.feed[k] * TCM] : 0.f;
+                int o = 4;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    macc[k] += x[k];
+#pragma unroll
+                    for (int k2 = k; k2 < 4; ++k2) { macc[o] = fmaf(x[k], x[k2], macc[o]); ++o; }
+                }
+            }
             // ---- store ----------------------------------------------------------------------------------
             if (valid) {
                 if (A.state_out) {
@@ -561,6 +582,41 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (nextmom) {
+        // ---- fold the next cell's column moments: warps -> CTA -> (last CTA) grid, in float64 and fixed order ------
+        __shared__ bool s_last_m;
+        __shared__ double sc0s_m[4];
+        double* redm = reinterpret_cast<double*>(sm + L.zb);           // the staging tiles are free now: [NT / 32][MOM_N], then tot
+        double* totm = redm + (NT / 32) * MOM_N;
+#pragma unroll
+        for (int i = 0; i < MOM_N; ++i) {
+            double a = (double)macc[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) redm[warp * MOM_N + i] = a;
+        }
+        __syncthreads();
+        if (tid < MOM_N) {
+            double s_ = 0.0;
+            for (int w = 0; w < NT / 32; ++w) s_ += redm[w * MOM_N + tid];
+            A.partials[(size_t)blockIdx.x * MOM_N + tid] = s_;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last_m = atomicAdd(A.counter, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!s_last_m) return;
+        __threadfence();
+        if (tid < MOM_N) {
+            double s_ = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) s_ += __ldcg(A.partials + (size_t)b * MOM_N + tid);
+            totm[tid] = s_;
+        }
+        __syncthreads();
+        moments_finalize<4>(F, A, c + 1, totm, sc0s_m, tid, NT);
+        if (tid == 0) *A.counter = 0u;
+        return;
+    }
     if (!stats || A.no_stats) return;
     // ---- fold: thread gt of a group holds the sums of feature gt & 63 over half of each of its tiles -----------
     double* red = reinterpret_cast<double*>(sm + L.red);          // [2][NG * 128]: sum / sum of squares per group thread
@@ -645,7 +701,8 @@ static int h_launch(const DevFlow& F, const FwdArgs& A, const char* hpack, size_
     switch ((A.stats_layer >= 1 ? 1 : 0) | (A.zin != nullptr ? 2 : 0)) {
         case 0: return h_launch_mode<NG, KIND, 0>(F, A, hpack, smem, sms, s);
         case 1: return h_launch_mode<NG, KIND, 1>(F, A, hpack, smem, sms, s);
-        case 2: return h_launch_mode<NG, KIND, 2>(F, A, hpack, smem, sms, s);
+        case 2: return A.next_moments ? h_launch_mode<NG, KIND, 6>(F, A, hpack, smem, sms, s)
+                                      : h_launch_mode<NG, KIND, 2>(F, A, hpack, smem, sms, s);
     }
     return h_launch_mode<NG, KIND, 3>(F, A, hpack, smem, sms, s);
 }

@@ -446,69 +446,7 @@ __global__ void __launch_bounds__(256, MOM_P <= 4 ? 4 : 2) flow_col_moments_kern
         tot[tid] = s_;
     }
     __syncthreads();
-    const double n = (double)A.B, mom = (double)F.momentum, unb = A.B > 1 ? n / (n - 1.0) : 1.0;
-    const float* prm = A.params + q.param_off;
-    float* pk = A.wpack + q.pk_off;
-    const int maxW = F.maxW;
-    // index of S2[k][k2], k <= k2, in the packed upper triangle
-    auto s2i = [](int k, int k2) { return MOM_P + k * MOM_P - k * (k - 1) / 2 + (k2 - k); };
-    // ---- BN0 -------------------------------------------------------------------------------------------
-    if (tid < pad8(P)) {
-        float sc = 0.f, sh = 0.f;
-        if (tid < P) {
-            const double mean = tot[tid] / n;
-            double var = tot[s2i(tid, tid)] / n - mean * mean;
-            var = var > 0.0 ? var : 0.0;
-            const double invstd = 1.0 / sqrt(var + (double)F.eps);
-            const double g = (double)prm[tid], b = (double)prm[P + tid];
-            sc = (float)(g * invstd);
-            sh = (float)(b - mean * g * invstd);
-            sc0s[tid] = g * invstd;
-            if (A.bn_saved) { A.bn_saved[q.sv_off + tid] = (float)mean; A.bn_saved[q.sv_off + maxW + tid] = (float)invstd; }
-            if (A.bn_running) {
-                float* rs = A.bn_running + q.bn_off + F.r_mean(c, 0);
-                rs[tid] = (float)((1.0 - mom) * (double)rs[tid] + mom * mean);
-                rs[P + tid] = (float)((1.0 - mom) * (double)rs[P + tid] + mom * var * unb);
-            }
-        }
-        pk[q.aff_off[0] + tid] = sc;
-        pk[q.aff_off[0] + pad8(P) + tid] = sh;
-    }
-    __syncthreads();
-    // ---- BN1 from the moments ------------------------------------------------------------------------------
-    const int H = F.widths[0], Hp = pad8(H);
-    const float* W0 = prm + F.p_lin(c, 0);                 // [H][P]
-    const float* g1 = prm + F.p_bn_gamma(c, 1);
-    for (int j = tid; j < Hp; j += 256) {
-        float sc = 0.f, sh = 0.f;
-        if (j < H) {
-            double mean1 = 0.0, var1 = 0.0;
-            for (int k = 0; k < P; ++k) {
-                const double wk = (double)W0[j * P + k];
-                mean1 += wk * (double)prm[P + k];
-                const double mk = tot[k] / n;
-                for (int k2 = 0; k2 < P; ++k2) {
-                    const double cov = tot[k <= k2 ? s2i(k, k2) : s2i(k2, k)] / n - mk * (tot[k2] / n);
-                    var1 += wk * sc0s[k] * (double)W0[j * P + k2] * sc0s[k2] * cov;
-                }
-            }
-            var1 = var1 > 0.0 ? var1 : 0.0;
-            const double invstd = 1.0 / sqrt(var1 + (double)F.eps);
-            sc = (float)((double)g1[j] * invstd);
-            sh = (float)((double)g1[H + j] - mean1 * (double)g1[j] * invstd);
-            if (A.bn_saved) {
-                A.bn_saved[q.sv_off + 2 * maxW + j] = (float)mean1;
-                A.bn_saved[q.sv_off + 2 * maxW + maxW + j] = (float)invstd;
-            }
-            if (A.bn_running) {
-                float* rs = A.bn_running + q.bn_off + F.r_mean(c, 1);
-                rs[j] = (float)((1.0 - mom) * (double)rs[j] + mom * mean1);
-                rs[H + j] = (float)((1.0 - mom) * (double)rs[H + j] + mom * var1 * unb);
-            }
-        }
-        pk[q.aff_off[1] + j] = sc;
-        pk[q.aff_off[1] + Hp + j] = sh;
-    }
+    moments_finalize<MOM_P>(F, A, c, tot, sc0s, tid, 256);
     if (tid == 0) *A.counter = 0u;
 }
 
