@@ -68,13 +68,15 @@ BIG = [
 
 @pytest.mark.parametrize("cfg", BIG, ids=[c["name"] for c in BIG])
 @pytest.mark.parametrize("mode", ["eval", "train"])
-def test_forward_matches_oracle_at_size(cfg, mode, max_log_j=None):
+def test_forward_matches_oracle_at_size(cfg, mode, max_log_j=None, mutate_sd=None):
     torch.manual_seed(5)
     NF = make_manager(cfg)
     model = NF._model
     cells, out_perm = oflow.compile_layers(oracle_layers(cfg), cfg["n_flow"])
     sd = oflow.init_state_dict(cells, cfg["n_flow"], cfg["kind"], cfg["n_bins"], cfg["NN"], seed=7,
                                dtype=torch.float32, bn_jitter=0.2)
+    if mutate_sd is not None:
+        mutate_sd(sd)
     model.load_state_dict(sd)
     model.train(mode == "train")
     gen = torch.Generator().manual_seed(2026)
