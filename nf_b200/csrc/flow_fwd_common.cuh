@@ -113,11 +113,33 @@ __device__ __forceinline__ void bn_stats_finalize(const DevFlow& F, const FwdArg
 }
 
 
+// Sum of per-CTA partials [nblk][N] (global memory, written by the other CTAs before their counter arrival) into tot[N]
+// (shared), by all NT threads of the last CTA in a fixed order: slices of the CTA list are summed side by side and then
+// combined in slice order.  (N threads walking all nblk partials one dependent L2 latency after the other was a 20-40 us
+// tail on every launch.)  scratch: (NT / W) * N doubles of shared memory, W = 16 for N <= 16, else 64.
+template <int N>
+__device__ __forceinline__ void fold_partials(const double* partials, unsigned nblk, double* scratch, double* tot, int tid, int NT) {
+    constexpr int W = N <= 16 ? 16 : 64;
+    const int slices = NT / W, sl = tid / W, i = tid - sl * W;
+    if (i < N && sl < slices) {
+        double s_ = 0.0;
+        for (unsigned b = sl; b < nblk; b += slices) s_ += __ldcg(partials + (size_t)b * N + i);
+        scratch[sl * N + i] = s_;
+    }
+    __syncthreads();
+    if (tid < N) {
+        double s_ = 0.0;
+        for (int k = 0; k < slices; ++k) s_ += scratch[k * N + tid];
+        tot[tid] = s_;
+    }
+    __syncthreads();
+}
+
 // BN_0 and BN_1 of cell c from the first and second moments of its pass-through columns (tot[0..P) = sum x_k,
 // tot[s2i(k, k2)] = sum x_k x_k2 over the batch, in shared memory): BN_0 is per column; layer 0 is linear in BN_0's
 // output, so the batch mean and variance of each of its outputs follow from the covariance matrix - no pass over z_1.
 // Writes scale / shift (wpack), the saved batch statistics (backward) and the running statistics.  Called by every
-// thread of the last CTA (NT threads) after a __syncthreads(); sc0s: P doubles of shared scratch.
+// thread of the last CTA (NT threads) after a __syncthreads(); sc0s: MOM_P + MOM_P^2 doubles of shared scratch.
 template <int MOM_P>
 __device__ __forceinline__ void moments_finalize(const DevFlow& F, const FwdArgs& A, int c, const double* tot, double* sc0s,
                                                  int tid, int NT) {
@@ -152,6 +174,13 @@ __device__ __forceinline__ void moments_finalize(const DevFlow& F, const FwdArgs
         pk[q.aff_off[0] + pad8(P) + tid] = sh;
     }
     __syncthreads();
+    // covariance of BN_0's outputs (without the shift), once: sc_k sc_k2 (E[x_k x_k2] - E[x_k] E[x_k2])
+    double* covs = sc0s + MOM_P;                                    // [P][P]
+    for (int i = tid; i < P * P; i += NT) {
+        const int k = i / P, k2 = i - k * P;
+        covs[i] = sc0s[k] * sc0s[k2] * (tot[k <= k2 ? s2i(k, k2) : s2i(k2, k)] / n - (tot[k] / n) * (tot[k2] / n));
+    }
+    __syncthreads();
     // ---- BN1 from the moments ------------------------------------------------------------------------------
     const int H = F.widths[0], Hp = pad8(H);
     const float* W0 = prm + F.p_lin(c, 0);                 // [H][P]
@@ -163,11 +192,7 @@ __device__ __forceinline__ void moments_finalize(const DevFlow& F, const FwdArgs
             for (int k = 0; k < P; ++k) {
                 const double wk = (double)W0[j * P + k];
                 mean1 += wk * (double)prm[P + k];
-                const double mk = tot[k] / n;
-                for (int k2 = 0; k2 < P; ++k2) {
-                    const double cov = tot[k <= k2 ? s2i(k, k2) : s2i(k2, k)] / n - mk * (tot[k2] / n);
-                    var1 += wk * sc0s[k] * (double)W0[j * P + k2] * sc0s[k2] * cov;
-                }
+                for (int k2 = 0; k2 < P; ++k2) var1 += wk * (double)W0[j * P + k2] * covs[k * P + k2];
             }
             var1 = var1 > 0.0 ? var1 : 0.0;
             const double invstd = 1.0 / sqrt(var1 + (double)F.eps);

@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
     if (nextmom) {
         // ---- fold the next cell's column moments: warps -> CTA -> (last CTA) grid, in float64 and fixed order ------
         __shared__ bool s_last_m;
-        __shared__ double sc0s_m[4];
+        __shared__ double sc0s_m[4 + 16];
         double* redm = reinterpret_cast<double*>(sm + L.zb);           // the staging tiles are free now: [NT / 32][MOM_N], then tot
         double* totm = redm + (NT / 32) * MOM_N;
 #pragma unroll
@@ -607,12 +607,7 @@ __global__ void __launch_bounds__(NG * TCM, 1) flow_cell_h_kernel(const __grid_c
         __syncthreads();
         if (!s_last_m) return;
         __threadfence();
-        if (tid < MOM_N) {
-            double s_ = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) s_ += __ldcg(A.partials + (size_t)b * MOM_N + tid);
-            totm[tid] = s_;
-        }
-        __syncthreads();
+        fold_partials<MOM_N>(A.partials, gridDim.x, totm + MOM_N, totm, tid, NT);
         moments_finalize<4>(F, A, c + 1, totm, sc0s_m, tid, NT);
         if (tid == 0) *A.counter = 0u;
         return;

@@ -386,7 +386,8 @@ __global__ void __launch_bounds__(256, MOM_P <= 4 ? 4 : 2) flow_col_moments_kern
     constexpr int MOM_N = MOM_P + MOM_P * (MOM_P + 1) / 2;
     __shared__ double red[8][MOM_N];
     __shared__ double tot[MOM_N];
-    __shared__ double sc0s[MOM_P];
+    __shared__ double fold_s[(256 / (MOM_N <= 16 ? 16 : 64)) * MOM_N];
+    __shared__ double sc0s[MOM_P + MOM_P * MOM_P];
     __shared__ bool s_last;
     const int c = A.c_begin;
     const DevCell& q = F.cells[c];
@@ -440,12 +441,7 @@ __global__ void __launch_bounds__(256, MOM_P <= 4 ? 4 : 2) flow_col_moments_kern
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (tid < MOM_N) {
-        double s_ = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) s_ += __ldcg(A.partials + (size_t)b * MOM_N + tid);
-        tot[tid] = s_;
-    }
-    __syncthreads();
+    fold_partials<MOM_N>(A.partials, gridDim.x, fold_s, tot, tid, 256);
     moments_finalize<MOM_P>(F, A, c, tot, sc0s, tid, 256);
     if (tid == 0) *A.counter = 0u;
 }
