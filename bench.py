@@ -485,7 +485,8 @@ def bench_integrate(world, dev):
     known = 0.06648282151394422
     xq = torch.rand(1 << 22, 8, device=dev, dtype=torch.float32)
     flow_k = flow_launch_times(NF.best_model, xq, dev, 1 << 22, peaks()[0]["hbm_gbs"],
-                               {1: 36, 11: 36 + 256, 13: 512, 12: 256 + 72, 10: 72})
+                               {1: 36, 11: 36 + 256, 13: 512, 12: 256 + 72, 10: 72},       # PWQuad keeps the z_3 store
+                               {11: 1175477000, 13: 2294614000, 12: 1374712000})           # profiles/r02_ncu_h_quad.md
     del xq
     return {"metric": "nis_integrate_points_per_sec", "value": nitn * neval / dt, "unit": "points/s",
             "flow_kernels_at_2p22_points": flow_k,
@@ -521,8 +522,8 @@ def bench_rambo(steps, warmup, world, hbm_peak, peak_kind):
             "dtype": "f64",
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^24 events from the committed
-                         # ncu --set full capture (profiles/r01_ncu_rambo.md: 1.074 GB + 3.300 GB); not re-measured per run
-                         "traffic": 4374426000 if RAMBO_EVENTS == 1 << 24 else None,
+                         # ncu --set full capture (profiles/r02_ncu_rambo.md: 1.074 GB + 3.304 GB); not re-measured per run
+                         "traffic": 4378114000 if RAMBO_EVENTS == 1 << 24 else None,
                          "peak_kind": peak_kind, "algorithmic_bytes_per_event": RAMBO_BYTES_PER_EVENT},
             "weight_only": {"value": world * RAMBO_EVENTS / (ms_w * 1e-3), "unit": "events/s", "ms_per_step": ms_w}}
 
@@ -675,7 +676,7 @@ def main():
         # (the last layer pass only takes statistics: it reads its 256 B/point tile and stores nothing)
         abytes = {1: 36, 11: 36 + 256, 13: 256, 12: 256 + 36 + 36, 10: 36 + 36}
         # dram__bytes_read.sum + dram__bytes_write.sum per launch at 2^22 points, ncu --set full (profiles/r02_ncu_h_kernel.md)
-        traffic = {11: 1176675000, 13: 2407364000, 12: 1378160000, 10: 264708000} if N_POINTS == 1 << 22 else None
+        traffic = {11: 1177050000, 13: 1239061000, 12: 1377346000, 10: 257961000} if N_POINTS == 1 << 22 else None
         kernels = flow_launch_times(model, x, dev, N_POINTS, pk["hbm_gbs"], abytes, traffic)
         dom = next((k for k in kernels if "achieved_gbs" in k), None)
         line["roofline"] = {
