@@ -16,6 +16,7 @@ from pinned host buffers, H2D/D2H inside the timed region), ``eval_mode`` (BN fo
 ``rambo`` (BASELINE.json configs[2]: events/s of the fused RAMBO+cuts kernel against the HBM roofline).
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -376,7 +377,7 @@ def bench_train_step(steps, warmup, world, dev, log2n=16):
     f = torch.exp(-((x - 0.5) ** 2).sum(-1) / 0.2)
 
     def step():
-        model.zero_grad(set_to_none=False)
+        model.zero_grad()                 # set_to_none, as the training loop does (manager.py): gradients land as views of one flat buffer
         XJ = model(x)
         torch.var(f * XJ[:, -1]).backward()
         if world > 1:
@@ -399,20 +400,30 @@ def bench_readme(dev):
         return torch.exp(-((x[:, 0] - 0.75) ** 2 + (x[:, 1] - 0.75) ** 2) / (0.2 ** 2)) + \
             torch.exp(-((x[:, 0] - 0.25) ** 2 + (x[:, 1] - 0.25) ** 2) / (0.2 ** 2))
 
-    torch.manual_seed(0)
-    NF = PWQuadManager(n_flow=2)
-    NF.create_model(2, 4, [3] * 3, dev=dev.index or 0)
-    optim = torch.optim.Adamax(NF._model.parameters(), lr=2e-3, weight_decay=1e-04)
-    torch.cuda.synchronize()
-    t0 = time.time()
-    NF._train_variance_forward_seq(camel, optim, True, tempfile.mkdtemp(), 10000, 300, dev.index or 0, False, True, preburn_time=50)
-    torch.cuda.synchronize()
-    t1 = time.time()
-    sig, err = NF.integrate(camel, 10, 10000, dev.index or 0)
-    torch.cuda.synchronize()
-    return {"metric": "readme_example_wall_seconds", "value": t1 - t0, "unit": "s", "higher_is_better": False,
-            "integrate_seconds": time.time() - t1, "estimate": float(sig), "reported_error": float(err),
-            "analytic": 0.232322, "best_loss": float(NF.best_loss), "int_loss": float(NF.int_loss),
+    # twice: the first run of a process also pays for loading the kernels and the optimizer's / integrand's torch kernels
+    # it is the first to use (CUDA loads modules lazily) - reported as first_run_seconds; `value` is the second run
+    gc.collect()
+    torch.cuda.empty_cache()                  # cached blocks of the previous (GB-sized) workloads
+    runs = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        NF = PWQuadManager(n_flow=2)
+        NF.create_model(2, 4, [3] * 3, dev=dev.index or 0)
+        optim = torch.optim.Adamax(NF._model.parameters(), lr=2e-3, weight_decay=1e-04)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        NF._train_variance_forward_seq(camel, optim, True, tempfile.mkdtemp(), 10000, 300, dev.index or 0, False, True, preburn_time=50)
+        torch.cuda.synchronize()
+        t1 = time.time()
+        sig, err = NF.integrate(camel, 10, 10000, dev.index or 0)
+        torch.cuda.synchronize()
+        runs.append((t1 - t0, time.time() - t1, float(sig), float(err), float(NF.best_loss), float(NF.int_loss)))
+    w = runs[1]
+    return {"metric": "readme_example_wall_seconds", "value": w[0], "unit": "s", "higher_is_better": False,
+            "first_run_seconds": runs[0][0], "us_per_minibatch_step": w[0] / (300 * 5) * 1e6,
+            "integrate_seconds": w[1], "estimate": w[2], "reported_error": w[3],
+            "analytic": 0.232322, "best_loss": w[4], "int_loss": w[5],
+            "same_result_both_runs": runs[0][2:] == runs[1][2:],
             "reference": "368 s on 8 CPU cores, best_loss 0.024 from int_loss 0.071 (BASELINE.md)"}
 
 
@@ -436,7 +447,7 @@ def bench_wide(steps, warmup, world, dev):
             model(x)
 
     def step():
-        model.zero_grad(set_to_none=False)
+        model.zero_grad()
         XJ = model(x)
         torch.var(f * XJ[:, -1]).backward()
         if world > 1:
@@ -528,6 +539,36 @@ def bench_rambo(steps, warmup, world, hbm_peak, peak_kind):
             "weight_only": {"value": world * RAMBO_EVENTS / (ms_w * 1e-3), "unit": "events/s", "ms_per_step": ms_w}}
 
 
+def bind_to_gpu_numa(local):
+    """Host side of the end-to-end path: run this rank (and so first-touch its pinned staging buffers) on the CPUs of the
+    NUMA node its GPU hangs off, as `numactl --cpunodebind` would.  With every rank on the default node the eight
+    GPUs' copies share one socket's memory controllers.  Returns what it found (reported in the JSON line);
+    BENCH_NUMA_BIND=0 turns it off."""
+    info = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        info["pci"] = bdf
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as fh:
+            node = int(fh.read().strip())
+        info["numa_node"] = node
+        info["nodes_online"] = open("/sys/devices/system/node/online").read().strip()
+        if node < 0 or os.environ.get("BENCH_NUMA_BIND", "1") == "0":
+            return info
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["cpus"] = len(cpus)
+            info["bound"] = True
+    except Exception as e:                                      # sysfs not there (container): leave the affinity alone
+        info["error"] = repr(e)[:120]
+    return info
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -545,6 +586,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local) if args.impl == "ours" else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # stdout carries exactly one JSON line: NCCL's banner / debug output goes to stderr
@@ -645,6 +687,12 @@ def main():
            "api": "FlowSequential.__call__ (PWLinManager._model); pinned host float32 points in, pinned host "
                   "[N,9] result out, copies on a side stream inside the timed region"}
     del xh, oh, xd
+    if world > 1:
+        topo = [None] * world
+        dist.all_gather_object(topo, numa)
+    else:
+        topo = [numa]
+    e2e["host_topology"] = topo                                    # per rank: GPU PCI address, its NUMA node, CPUs bound to
     if rank == 0:
         e2e["pcie"] = pcie_probe(dev)
         e2e["pcie_bound_ms_per_step"] = (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) / \
