@@ -16,6 +16,7 @@
  *   nis_rambo_generate    <- FlatInvertiblePhasespace.generateKinematics_batch, pdf inactive and pdf active
  *                            (nisrep/PhaseSpace/flat_phase_space_generator.py:81-137, 139-308, 313-441;
  *                             PhaseSpace/utils.py:5-146, 151-187)
+ *   nis_rambo_invert      <- (no reference body: README.md:68-69 "inverse phase space" to do) the inverse of the map above
  *   nis_uniform_fill      <- torch.nn.init.uniform_(w) (manager.py:222,395)
  *
  * Conventions: plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
@@ -182,6 +183,12 @@ typedef struct NisRamboDesc {
  * r must be 16-byte and momenta 32-byte aligned (rows are moved as 16- / 32-byte vectors). */
 int nis_rambo_generate(const NisRamboDesc* desc, const void* r, int32_t r_dtype, double* momenta,
                        double* weight, uint8_t* cutmask, int64_t B, void* stream);
+
+/* Inverse of the pdf-inactive map (the reference lists it as to do, README.md:68-69): momenta[B, 2+n, 4]
+ * float64 as nis_rambo_generate writes them (CM frame; the two beam rows are skipped) -> r[B, 3n-4] float64, the uniforms
+ * generateKinematics_batch maps to these momenta, and weight[B] float64 = the weight of that point WITHOUT cuts (optional).
+ * desc->pdf_active must be 0 (NIS_EUNSUPPORTED otherwise). */
+int nis_rambo_invert(const NisRamboDesc* desc, const double* momenta, double* r, double* weight, int64_t B, void* stream);
 
 /* Philox4x32-10 uniforms in [0,1): out[n] of dtype; element i is a pure function of (seed, offset+i),
  * so ranks draw disjoint streams by offsetting. */

@@ -154,3 +154,35 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
         if return_cutmask:
             return mom, weight, mask
         return mom, weight
+
+    def invertKinematics_batch(self, E_cm, momenta):
+        """momenta[B, 2+n_final, 4] (as ``generateKinematics_batch`` returns them: CM frame, two beam rows first) ->
+        (random_variables[B, 3 n_final - 4] float64, weight[B] float64): the uniforms the generator maps to these momenta and
+        the flat weight x massive Jacobian / (2 s) of that point, WITHOUT cuts.  The reference lists the inverse as to do
+        (README.md:68-69): this is the algebraic inverse of :139-308 (masses of the remaining system ->
+        K ratios -> the mass polynomial evaluated forward; decay angles in the parent rest frame).  pdf-inactive only.
+        """
+        if self.pdf_active:
+            raise NotImplementedError("invertKinematics_batch: the pdf-active map (tau / y_cm) is not inverted")
+        mom = momenta if torch.is_tensor(momenta) else torch.as_tensor(momenta, dtype=torch.double)
+        assert mom.dim() == 3 and mom.shape[1] == 2 + self.n_final and mom.shape[2] == 4
+        if torch.is_tensor(E_cm):
+            raise TypeError("E_cm is the (scalar) centre-of-mass energy")
+        lib = _cabi.lib()
+        home = mom.device
+        dev = home if home.type == "cuda" else self.masses_t.device
+        md = mom.detach().to(dev, torch.double).contiguous()
+        if md.data_ptr() % 32:                     # events are read 32 bytes at a time
+            md = md.clone()
+        B = md.shape[0]
+        desc = self._desc(E_cm, -1, -1, -1)
+        with torch.cuda.device(dev):
+            r = torch.empty(B, self.nDimPhaseSpace(), dtype=torch.double, device=dev)
+            weight = torch.empty(B, dtype=torch.double, device=dev)
+            rc = lib.nis_rambo_invert(ctypes.byref(desc), _cabi.ptr(md), _cabi.ptr(r), _cabi.ptr(weight), B,
+                                      _cabi.stream_ptr(dev))
+            _cabi.check(rc, "nis_rambo_invert")
+        if home != dev:
+            r, weight = r.to(home), weight.to(home)
+        return r, weight
+

@@ -73,6 +73,7 @@ _PROTOS = {
                                         ctypes.c_size_t, _P]),
     "nis_rambo_generate": (ctypes.c_int, [ctypes.POINTER(NisRamboDesc), _P, ctypes.c_int32, _P, _P, _P,
                                           ctypes.c_int64, _P]),
+    "nis_rambo_invert": (ctypes.c_int, [ctypes.POINTER(NisRamboDesc), _P, _P, _P, ctypes.c_int64, _P]),
     "nis_uniform_fill": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, _P]),
     "nis_probe_fp32_fma": (ctypes.c_int64, [_P, ctypes.c_int32, _P]),
     "nis_probe_tensor": (ctypes.c_int64, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P]),

@@ -125,3 +125,39 @@ extern "C" int nis_rambo_generate(const NisRamboDesc* desc, const void* r, int32
     return r_dtype == NIS_F64 ? rambo_launch<double>(C, r, momenta, weight, cutmask, B, s)
                               : rambo_launch<float>(C, r, momenta, weight, cutmask, B, s);
 }
+
+
+// ---- inverse map: one thread per event, momenta read straight from global memory (32-byte vectors), the recovered
+//      uniforms kept in a local row until the weight is evaluated on them ---------------------------------------------
+__global__ void __launch_bounds__(128) rambo_invert_kernel(const __grid_constant__ RamboConst C, const double* __restrict__ momenta,
+                                                           double* __restrict__ r, double* __restrict__ weight, long long B) {
+    const int n = C.n, ND = 3 * n - 4, NM = (n + 2) * 4;
+    for (long long ev = (long long)blockIdx.x * blockDim.x + threadIdx.x; ev < B; ev += (long long)gridDim.x * blockDim.x) {
+        double fin[NIS_MAX_FINAL * 4], row[3 * NIS_MAX_FINAL - 4];
+        const double* src = momenta + ev * NM + 8;                 // final state after the two beams
+        for (int i = 0; i < 4 * n; i += 4) {
+            double a, b, c, d;
+            asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(src + i));
+            fin[i] = a; fin[i + 1] = b; fin[i + 2] = c; fin[i + 3] = d;
+        }
+        double w;
+        rambo_invert_event(C, fin, 1, row, 1, w);
+        for (int i = 0; i < ND; ++i) r[ev * ND + i] = row[i];
+        if (weight) weight[ev] = w;
+    }
+}
+
+extern "C" int nis_rambo_invert(const NisRamboDesc* desc, const double* momenta, double* r, double* weight, int64_t B, void* stream) {
+    if (!desc || B < 0 || (B > 0 && (!momenta || !r))) return NIS_EINVAL;
+    if (desc->pdf_active) return NIS_EUNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(momenta) & 31) return NIS_EINVAL;      // events are read 32 bytes at a time
+    RamboConst C;
+    int rc = rambo_fill_const(desc, &C);
+    if (rc) return rc;
+    if (B == 0) return NIS_OK;
+    const long long blocks = (B + 127) / 128;
+    const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+    rambo_invert_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(C, momenta, r, weight, B);
+    NIS_CUDA_CHECK_LAUNCH();
+    return NIS_OK;
+}

@@ -530,3 +530,46 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
     pass = ok ? 1 : 0;
     weight = ok ? w : 0.0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Inverse map (the reference lists it as to do, README.md:68-69): final-state momenta in the CM frame ->
+// the 3n-4 uniforms generateKinematics_batch would have produced them from, and the weight of that point.
+// fin: n x 4 components (E, px, py, pz) at stride ms, r: 3n-4 values at stride rs.  pdf-inactive map only.
+//   Q_j = sum_{i >= j} p_i,  M_j = sqrt(Q_j^2) (M_0 = E_cm, M_{n-1} = m_{n-1}),  K_j = M_j - sum_{i >= j} m_i,
+//   u_j = (K_{j+1} / K_j)^2,  r_j = (e+1) u^e - e u^{e+1}, e = n-2-j  (the polynomial the forward inverts, :101-105);
+//   p_j boosted into the rest frame of Q_j (the forward's boost with Q -> (Q0, -Q)) gives cos(theta) = 2 r - 1 and
+//   phi = 2 pi r (:233-243).
+// The weight is the forward's own arithmetic on the recovered uniforms (rambo_event<false, false>).
+NIS_DEV void rambo_invert_event(const RamboConst& C, const double* fin, int ms, double* r, int rs, double& weight) {
+    const int n = C.n;
+    double Mj = C.K0 + C.msum[0], Kj = C.K0;                    // M_0 = E_cm: the momenta are CM-frame momenta, Q_0 = (E_cm, 0)
+    double Q0 = Mj, Q1 = 0.0, Q2 = 0.0, Q3 = 0.0;
+    for (int j = 0; j < n - 1; ++j) {
+        const double e = fin[(4 * j) * ms], p1 = fin[(4 * j + 1) * ms], p2 = fin[(4 * j + 2) * ms], p3 = fin[(4 * j + 3) * ms];
+        // the angles of p_j in the rest frame of Q_j: the forward's boost with Q -> (Q0, -Q)
+        const double pQ = -(p1 * Q1 + p2 * Q2 + p3 * Q3);
+        const double coef = nis_div(nis_div(pQ, Q0 + Mj) + e, Mj);
+        const double x = p1 - coef * Q1, y = p2 - coef * Q2, z = p3 - coef * Q3;
+        const double pm = nis_sqrt(x * x + y * y + z * z);
+        double ct = pm > 0.0 ? nis_div(z, pm) : 1.0;
+        ct = ct > 1.0 ? 1.0 : (ct < -1.0 ? -1.0 : ct);
+        double phi = atan2(y, x) * 0.15915494309189535;         // / (2 pi)
+        if (phi < 0.0) phi += 1.0;
+        r[(n - 2 + 2 * j) * rs] = 0.5 * (ct + 1.0);
+        r[(n - 1 + 2 * j) * rs] = phi;
+        if (j < n - 2) {                                        // the mass of what is left, and the uniform behind it
+            Q0 -= e; Q1 -= p1; Q2 -= p2; Q3 -= p3;
+            const double Mn = nis_sqrt(Q0 * Q0 - (Q1 * Q1 + Q2 * Q2 + Q3 * Q3));
+            const double Kn = Mn - C.msum[j + 1];
+            double u = nis_div(Kn, Kj);
+            u = u * u;
+            u = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+            const int ex = n - 2 - j;
+            const double ue1 = ex == 1 ? 1.0 : rambo_pow_em1(u, ex);          // u^(e-1)
+            r[j * rs] = ue1 * u * ((double)(ex + 1) - (double)ex * u);
+            Kj = Kn; Mj = Mn;
+        }
+    }
+    uint8_t pass;
+    rambo_event<false, false>(C, r, rs, nullptr, 1, weight, pass);
+}

@@ -258,3 +258,52 @@ def generate_kinematics(E_cm, r, initial_masses, final_masses,
     if return_parts:
         return cm, weight, w, cut
     return cm, weight
+
+
+# ----------------------------------------------------------------------------------------------
+# inverse map.  The reference has none (README.md:68-69: to do); this is the algebraic inverse of
+# generate_kinematics above, pinned by round trips through the reference's own golden momenta (tests/test_oracle_golden.py).
+# ----------------------------------------------------------------------------------------------
+def invert_kinematics(E_cm, momenta, initial_masses, final_masses):
+    """momenta [B, 2+n, 4] (E,px,py,pz; CM frame, beams first) -> (r [B, 3n-4], weight [B] without cuts).
+
+    Written independently of the forward's arrangement: the parent system Q_j = sum_{i>=j} p_i, its mass from the
+    Minkowski square, the daughter brought to the parent's rest frame by the textbook boost with beta = -Q/Q0,
+    gamma = Q0/M, and the mass uniforms from the polynomial the forward inverts (massless_map, :101-105)."""
+    mom = torch.as_tensor(momenta, dtype=torch.float64)
+    n = len(final_masses)
+    B = mom.shape[0]
+    m = torch.tensor(final_masses, dtype=torch.float64)
+    fin = mom[:, 2:, :]
+    r = torch.zeros(B, 3 * n - 4, dtype=torch.float64)
+    msum = torch.flip(torch.cumsum(torch.flip(m, (-1,)), -1), (-1,))           # msum[j] = sum_{i>=j} m_i
+    Q = torch.zeros(B, 4, dtype=torch.float64)
+    Q[:, 0] = E_cm                                                  # the sum of the final state, exactly (E_cm, 0, 0, 0)
+    K = torch.full((B,), float(E_cm) - float(m.sum()), dtype=torch.float64)
+    for j in range(n - 1):
+        p = fin[:, j, :]
+        M = torch.sqrt((Q[:, 0] ** 2 - (Q[:, 1:] ** 2).sum(-1)).clamp_min(0.0))
+        beta = -Q[:, 1:] / Q[:, :1]
+        gamma = (Q[:, 0] / M).unsqueeze(-1)
+        bp = (beta * p[:, 1:]).sum(-1, keepdim=True)
+        b2 = (beta ** 2).sum(-1, keepdim=True)
+        # p' = p + [(gamma - 1) (beta.p) / beta^2 + gamma E] beta   (boost of the frame by velocity -beta ... applied with beta = -Q/Q0)
+        fac = torch.where(b2 > 0, (gamma - 1.0) * bp / b2.clamp_min(1e-300), torch.zeros_like(bp)) + gamma * p[:, :1]
+        prest = p[:, 1:] + fac * beta
+        pm = torch.sqrt((prest ** 2).sum(-1))
+        ct = torch.where(pm > 0, prest[:, 2] / pm.clamp_min(1e-300), torch.ones_like(pm)).clamp(-1.0, 1.0)
+        phi = torch.atan2(prest[:, 1], prest[:, 0]) / (2.0 * math.pi)
+        phi = torch.where(phi < 0, phi + 1.0, phi)
+        r[:, n - 2 + 2 * j] = 0.5 * (ct + 1.0)
+        r[:, n - 1 + 2 * j] = phi
+        if j < n - 2:
+            Q = Q - p
+            Mn = torch.sqrt((Q[:, 0] ** 2 - (Q[:, 1:] ** 2).sum(-1)).clamp_min(0.0))
+            Kn = Mn - msum[j + 1]
+            u = ((Kn / K) ** 2).clamp(0.0, 1.0)
+            e = n - 2 - j
+            r[:, j] = (e + 1) * u ** e - e * u ** (e + 1)          # massless_map, :101-105
+            K = Kn
+    _, w = generate_kinematics(E_cm, r, initial_masses, final_masses)
+    return r, w
+

@@ -50,5 +50,16 @@ int host_rambo(const NisRamboDesc* d, long long B, const double* r, double* mom,
     return 0;
 }
 
+// inverse map: mom [B][n+2][4] -> r [B][3n-4], w [B] (no cuts)
+int host_rambo_invert(const NisRamboDesc* d, long long B, const double* mom, double* r, double* w) {
+    RamboConst C;
+    int rc = rambo_fill_const(d, &C);
+    if (rc) return rc;
+    if (d->pdf_active) return NIS_EUNSUPPORTED;
+    const int n = d->n_final, nd = 3 * n - 4, nm = (n + 2) * 4;
+    for (long long i = 0; i < B; ++i) rambo_invert_event(C, mom + i * nm + 8, 1, r + i * nd, 1, w[i]);
+    return 0;
+}
+
 double host_rambo_root(int e, double r) { return rambo_root_dyn(e, r); }
 }

@@ -160,3 +160,51 @@ def test_cut_masks_bit_exact_at_a_million_events(masses, E):
     _, rw = orambo.generate_kinematics(E, r, [masses] * 2, [masses] * 4, **cuts)
     assert np.array_equal(mask.cpu().numpy().astype(bool), (rw != 0).numpy())
     assert 0.3 < float(mask.float().mean()) < 0.99
+
+
+# ---- inverse phase space (the reference has none: README.md:68-69) ---------------------------------------
+@pytest.mark.parametrize("case", RAMBO_CASES)
+@pytest.mark.parametrize("where", ["cuda", "cpu"])
+def test_inverse_recovers_the_reference_uniforms(golden, case, where):
+    """nis_rambo_invert on the momenta the REFERENCE produced returns the uniforms the reference was given and, where no
+    cut removed the event, the reference's weight; it agrees with the float64 oracle inverse."""
+    g = golden("rambo_" + case)
+    m = g.meta
+    ps = FlatInvertiblePhasespace(m["initial"], m["final"], pdf=None, pdf_active=False)
+    r, w = ps.invertKinematics_batch(m["E_cm"], g.t("momenta").to(where))
+    assert r.device.type == where and r.dtype == torch.float64 and r.shape == g.t("r").shape
+    assert torch.allclose(r.cpu(), g.t("r"), rtol=0, atol=2e-9)
+    kept = g.t("weight") != 0
+    assert torch.allclose(w.cpu()[kept], g.t("weight")[kept], rtol=1e-7)
+    ro, wo = orambo.invert_kinematics(m["E_cm"], g.t("momenta"), m["initial"], m["final"])
+    assert torch.allclose(r.cpu(), ro, rtol=0, atol=1e-10) and torch.allclose(w.cpu(), wo, rtol=1e-8)
+
+
+@pytest.mark.parametrize("masses", [[100.0] * 4, [0.0] * 4, [0.0, 0.0], [10.0, 20.0, 30.0], [0.0, 5.0, 0.0, 80.0, 1.0],
+                                    [1.0] * 8], ids=["m4", "m0_4", "n2", "mixed3", "mixed5", "n8"])
+def test_inverse_round_trip_at_size(masses):
+    """generate -> invert -> generate on 2^18 events for every multiplicity 2..8: the uniforms come back to 1e-9 (the
+    azimuth modulo 1), the weight to 1e-9, and regenerating from the recovered uniforms reproduces the momenta."""
+    n = len(masses)
+    ps = FlatInvertiblePhasespace([0.0, 0.0], masses)
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    r = torch.rand(1 << 18, 3 * n - 4, device="cuda", dtype=torch.float64, generator=gen)
+    mom, w = ps.generateKinematics_batch(1000.0, r)
+    r2, w2 = ps.invertKinematics_batch(1000.0, mom)
+    d = (r2 - r).abs()
+    d = torch.minimum(d, 1.0 - d)                              # phi = 0 and phi = 1 are the same direction
+    # a uniform is recovered through K_{j+1} / K_j and a polynomial with slope e (e + 1) u^(e-1) (1 - u): 1e-9 leaves room
+    # for the cancellation in M = sqrt(Q^2) when the remaining system is light
+    assert float(torch.quantile(d.reshape(-1)[:: 7], 0.9999)) < 1e-10 and float(d.max()) < 1e-6, float(d.max())
+    assert torch.allclose(w2, w, rtol=1e-7)
+    mom2, _ = ps.generateKinematics_batch(1000.0, r2)
+    assert torch.allclose(mom2, mom, rtol=1e-7, atol=1e-7 * 1000.0)
+
+
+def test_inverse_argument_errors():
+    ps = FlatInvertiblePhasespace([0.0, 0.0], [100.0] * 4)
+    with pytest.raises(AssertionError):
+        ps.invertKinematics_batch(1000.0, torch.zeros(5, 4, 4, dtype=torch.float64, device="cuda"))
+    r, w = ps.invertKinematics_batch(1000.0, torch.zeros(0, 6, 4, dtype=torch.float64, device="cuda"))
+    assert r.shape == (0, 8) and w.shape == (0,)
+

@@ -176,6 +176,28 @@ def test_rambo_event_matches_reference_golden(host, golden, case):
     np.testing.assert_allclose(mom, ref_mom, rtol=1e-9, atol=1e-9 * m["E_cm"])
 
 
+@pytest.mark.parametrize("case", RAMBO_CASES)
+def test_rambo_inverse_recovers_the_reference_uniforms(host, golden, case):
+    """SURVEY 8 f4 (the reference has no inverse, README.md:68-69): the kernel source's inverse map, fed the momenta the
+    REFERENCE produced, returns the uniforms the reference was given and - where no cut removed the event - its weight."""
+    g = golden("rambo_" + case)
+    m = g.meta
+    n = len(m["final"])
+    d = RamboDesc(n, (ctypes.c_double * 2)(*m["initial"]), (ctypes.c_double * 8)(*(m["final"] + [0.0] * (8 - n))),
+                  m["E_cm"], -1.0, -1.0, -1.0)
+    mom = np.ascontiguousarray(g["momenta"])
+    B = mom.shape[0]
+    r = np.zeros((B, 3 * n - 4))
+    w = np.zeros(B)
+    assert host.host_rambo_invert(ctypes.byref(d), ctypes.c_longlong(B), fp(mom, D), fp(r, D), fp(w, D)) == 0
+    np.testing.assert_allclose(r, g["r"], rtol=0, atol=2e-9)
+    kept = g["weight"] != 0
+    np.testing.assert_allclose(w[kept], g["weight"][kept], rtol=1e-7)
+    r2, w2 = orambo.invert_kinematics(m["E_cm"], torch.as_tensor(mom), m["initial"], m["final"])
+    np.testing.assert_allclose(r, r2.numpy(), rtol=0, atol=1e-10)
+    np.testing.assert_allclose(w, w2.numpy(), rtol=1e-8)
+
+
 def _host_rambo_case(host, g):
     m = g.meta
     n = len(m["final"])

@@ -149,6 +149,19 @@ def test_rambo_matches_reference(golden, case):
     assert torch.allclose(mom, ref_mom, rtol=1e-12, atol=1e-10 * m["E_cm"] * 1e-3)
 
 
+@pytest.mark.parametrize("case", RAMBO_CASES)
+def test_rambo_inverse_is_pinned_by_the_reference_momenta(golden, case):
+    """SURVEY 8 f4.  The reference has no inverse phase space (README.md:68-69), so the oracle's is pinned through what the
+    reference did produce: its golden momenta go back to the uniforms it was given (2e-9) and to its weight where no cut
+    removed the event."""
+    g = golden("rambo_" + case)
+    m = g.meta
+    r, w = orambo.invert_kinematics(m["E_cm"], g.t("momenta"), m["initial"], m["final"])
+    assert torch.allclose(r, g.t("r"), rtol=0, atol=2e-9)
+    kept = g.t("weight") != 0
+    assert torch.allclose(w[kept], g.t("weight")[kept], rtol=1e-7)
+
+
 @pytest.mark.parametrize("case", RAMBO_EDGE_CASES)
 def test_rambo_edges_match_reference(golden, case):
     """r on the ends of [0,1]: the oracle follows the reference bit for bit, including where the reference's momenta
