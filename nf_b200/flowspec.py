@@ -156,6 +156,11 @@ class FlowSpec:
         self.n_params = poff
         self._ws = {}
         self._checked = False
+        # Set by the training loop around a forward that runs concurrently with other minibatches (manager.py): the running
+        # statistics of THAT forward go into this private float32 buffer (bn_arena layout) instead of the shared one, and
+        # the loop folds the private buffers back in minibatch order afterwards (BatchNorm's update is a sequential
+        # recurrence; concurrent read-modify-writes of the shared buffer would lose updates).
+        self.bn_override = None
 
     # ---- C-ABI plumbing -------------------------------------------------------------------------
     def _self_check(self, lib):
@@ -202,7 +207,8 @@ class FlowSpec:
             raise ValueError("Expected more than 1 value per channel when training, got input size [1, %d]" % d)
         with torch.cuda.device(dev):
             params = self.param_arena.get(dev)
-            bn = self.bn_arena.get(dev)
+            private = self.bn_override if train else None
+            bn = private if private is not None else self.bn_arena.get(dev)
             out = torch.empty(B, d + 1, dtype=out_dtype or xj.dtype, device=dev)
             saved = torch.empty(self.n_cells + 1, B, d + 1, dtype=torch.float32, device=dev) if want_saved else None
             bn_saved = torch.empty(self.bn_saved_count(lib), dtype=torch.float32, device=dev) \
@@ -215,7 +221,7 @@ class FlowSpec:
                                       _cabi.BN_TRAIN if train else _cabi.BN_EVAL, _cabi.ptr(ws), ws.numel(), B,
                                       _cabi.stream_ptr(dev))
             _cabi.check(rc, "nis_flow_forward")
-            if train:
+            if train and private is None:
                 self.bn_arena.write_back(bn)
                 nbt = self.nbt_arena.get(dev)
                 nbt += 1

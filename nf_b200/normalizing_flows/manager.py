@@ -268,30 +268,79 @@ class BasicManager(ModelAPI):
         state = EpochState(self.int_loss, preburn_time, kill_counter, impr_ratio)
         params = [p for p in self.model.parameters() if p.requires_grad]
         i = epoch_start - 1
+        # Small minibatches leave most of the GPU idle (a 2000-point minibatch of the README example occupies 16 CTAs), and the
+        # minibatches of an epoch are independent (fresh points, own BatchNorm statistics, one backward of their mean): they
+        # run side by side on a few streams - forwards and, since autograd replays a node on the stream of its forward, the
+        # backwards too.  BatchNorm's running statistics are a sequential recurrence, so every concurrent forward writes
+        # its update into a private zeroed buffer (FlowSpec.bn_override: m * batch statistic) and the buffers are folded
+        # back in minibatch order afterwards: rs <- (1-m)^n rs + sum_k (1-m)^(n-1-k) priv_k - what n sequential forwards
+        # produce.  NIS_TRAIN_STREAMS=0 (or ``minibatch_streams = 0`` on the manager) keeps the minibatches in sequence.
+        n_par = int(os.environ.get("NIS_TRAIN_STREAMS", getattr(self, "minibatch_streams", 8)))
+        par_streams = None
+        fold_weights = {}                              # minibatch count -> (1-m)^(n-1-k), made outside any graph capture
+        if n_par > 1 and hasattr(self.model, "spec") and len(my_minibatches) > 1 and mini_batch_size <= 16384 and dev.type == "cuda":
+            par_streams = [torch.cuda.Stream(device=dev) for _ in range(min(n_par, len(my_minibatches)))]
+
+        def one_minibatch(preburn, w):
+            XJ = self.model(self.format_input(w, dev))
+            X = XJ[:, :-1].detach()                 # the sample is fixed, the Jacobian is optimised
+            if preburn:
+                fres = f(w)
+                fXJ = torch.mul(fres, XJ[:, -1]) / maxf
+                integ_k = torch.mean(fres) / n_minibatches
+                err_k = torch.var(fres) / n_minibatches
+            else:
+                fres = torch.mul(f(X), XJ[:, -1])
+                fXJ = fres / maxf
+                integ_k = torch.mean(fres.detach()) / n_minibatches
+                err_k = torch.var(fres.detach()) / n_minibatches
+            loss_k = torch.var(fXJ) if loss_mode == "var" else torch.mean((fXJ * maxf) ** 2)
+            var_k = torch.var(fXJ.detach() ** 2) / mini_batch_size
+            return loss_k, var_k, integ_k, err_k
+
         def epoch_body(preburn, batches):
             """One epoch up to and including backward (manager.py:219-278): fresh uniform minibatches, the variance of
             f J / maxf per minibatch, one backward of their mean.  Returns (loss, var, integ, err) tensors."""
+            ws = [self._uniform(mini_batch_size, dev, generator=gen) for _ in batches]     # drawn in minibatch order
+            parts = []
+            if par_streams is not None and len(ws) > 1:
+                spec = self.model.spec()
+                cur = torch.cuda.current_stream(dev)
+                bn_flat = spec.bn_arena.get(dev)
+                priv = torch.zeros(len(ws), bn_flat.numel(), dtype=bn_flat.dtype, device=dev)
+                used = par_streams[:min(len(par_streams), len(ws))]
+                for st_ in used:
+                    st_.wait_stream(cur)
+                try:
+                    for k, w in enumerate(ws):
+                        with torch.cuda.stream(used[k % len(used)]):
+                            spec.bn_override = priv[k]
+                            parts.append(one_minibatch(preburn, w))
+                finally:
+                    spec.bn_override = None
+                for st_ in used:
+                    cur.wait_stream(st_)
+                # fold the private running-statistics updates back, in minibatch order
+                keep = 1.0 - float(spec.desc.bn_momentum)
+                wts = fold_weights.get(len(ws))
+                if wts is None:                        # (first reached in an eager warm-up epoch, never under capture)
+                    wts = torch.tensor([keep ** (len(ws) - 1 - k) for k in range(len(ws))], dtype=bn_flat.dtype, device=dev)
+                    fold_weights[len(ws)] = wts
+                with torch.no_grad():
+                    bn_flat.mul_(keep ** len(ws)).add_(torch.matmul(wts, priv))
+                    spec.bn_arena.write_back(bn_flat)
+                    nbt = spec.nbt_arena.get(dev)
+                    nbt += len(ws)
+                    spec.nbt_arena.write_back(nbt)
+            else:
+                for w in ws:
+                    parts.append(one_minibatch(preburn, w))
             loss, var, integ_e, err_e = 0, 0, 0, 0
-            for _ in batches:
-                w = self._uniform(mini_batch_size, dev, generator=gen)
-                XJ = self.model(self.format_input(w, dev))
-                X = XJ[:, :-1].detach()                 # the sample is fixed, the Jacobian is optimised
-                if preburn:
-                    fres = f(w)
-                    fXJ = torch.mul(fres, XJ[:, -1]) / maxf
-                    integ_e = integ_e + torch.mean(fres) / n_minibatches
-                    err_e = err_e + torch.var(fres) / n_minibatches
-                else:
-                    fres = torch.mul(f(X), XJ[:, -1])
-                    fXJ = fres / maxf
-                    integ_e = integ_e + torch.mean(fres.detach()) / n_minibatches
-                    err_e = err_e + torch.var(fres.detach()) / n_minibatches
-                if loss_mode == "var":
-                    loss = loss + torch.var(fXJ)
-                else:
-                    loss = loss + torch.mean((fXJ * maxf) ** 2)
-                var = var + (torch.var(fXJ.detach() ** 2) / mini_batch_size)
-                del X, fXJ, XJ
+            for loss_k, var_k, integ_k, err_k in parts:
+                loss = loss + loss_k
+                var = var + var_k
+                integ_e = integ_e + integ_k
+                err_e = err_e + err_k
             if torch.is_tensor(loss):
                 loss = loss / n_minibatches
                 loss.backward()

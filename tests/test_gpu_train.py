@@ -49,6 +49,36 @@ def test_readme_example_trains_and_integrates(tmp_path):
     assert float(err) < 0.8 * float(err0)            # the trained flow integrates with a smaller error
 
 
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
+def test_concurrent_minibatches_equal_sequential_ones(tmp_path, graph):
+    """The minibatches of an epoch run side by side on streams (manager.minibatch_streams, default 8) with private
+    BatchNorm running-statistics buffers folded back in minibatch order.  Same seed, same draws: after a few epochs the
+    weights, the running statistics, num_batches_tracked and the losses equal those of minibatches run one after the
+    other (up to the order in which the five gradient contributions are added)."""
+    out = []
+    for streams in (0, 8):
+        torch.manual_seed(3)
+        NF = PWQuadManager(n_flow=2)
+        NF.create_model(2, 4, [3] * 3)
+        NF.minibatch_streams = streams
+        NF.cuda_graph_epochs = graph
+        optim = torch.optim.Adamax(NF._model.parameters(), lr=2e-3, weight_decay=1e-04)
+        NF._train_variance_forward_seq(camel, optim, False, str(tmp_path), 10000, 8, 0, False, True, preburn_time=3)
+        torch.cuda.synchronize()
+        out.append(({k: v.detach().cpu().clone() for k, v in NF._model.state_dict().items()},
+                    [float(h) for h in NF.history], float(NF.best_loss)))
+    (sd0, h0, b0), (sd1, h1, b1) = out
+    assert len(h0) == len(h1) == 8
+    assert torch.allclose(torch.tensor(h0), torch.tensor(h1), rtol=2e-4), (h0, h1)
+    assert abs(b0 - b1) <= 2e-4 * abs(b0)
+    for k in sd0:
+        if k.endswith("num_batches_tracked"):
+            assert int(sd0[k]) == int(sd1[k]) > 0, k
+        else:
+            scale = float(sd0[k].abs().max()) + 1e-12
+            assert float((sd0[k] - sd1[k]).abs().max()) <= 2e-4 * scale + 1e-7, (k, float((sd0[k] - sd1[k]).abs().max()), scale)
+
+
 def test_tail_integration_est_loss_and_unknown_loss(tmp_path, capsys):
     torch.manual_seed(1)
     NF = PWLinManager(n_flow=2)
