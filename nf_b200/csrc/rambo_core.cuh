@@ -19,8 +19,12 @@
 
 #ifdef __CUDACC__
 #define nis_fdiv(a, b) __fdividef((a), (b))       /* 2-ulp float division: only steers a Newton iterate */
+#define nis_fpow(a, b) __powf((a), (b))           /* ex2.approx(b * lg2.approx(a)) */
+#define nis_fsqrt(a) __fsqrt_rn(a)
 #else
 #define nis_fdiv(a, b) ((a) / (b))
+#define nis_fpow(a, b) powf((a), (b))
+#define nis_fsqrt(a) sqrtf(a)
 #endif
 #ifndef __CUDACC__
 // host build (tests only): glibc has no sincospi
@@ -105,6 +109,7 @@ struct RamboConst {
     double cos_dR;                // cos(min(dR_min, pi))
     int dR_ge_pi;                 // dR_min >= pi: the d-phi quick reject never fires
     double u_one[NIS_MAX_FINAL];  // u_one[e]: what the reference's lattice bisection returns for r == 1
+    float rstar[NIS_MAX_FINAL];   // rstar[e]: rambo_rstar(e)
     // parton-density mode (flat_phase_space_generator.py:157-187): per-event partonic energy
     int pdf_active, tau_mode;
     double E_coll, tau_min, x_cut;
@@ -124,6 +129,18 @@ struct RamboConst {
 //     handed to the kernel as a per-exponent constant.
 // With these two values the weight stays finite wherever the reference's is (massless: the rho ratio is 1).
 #define NIS_U_FLOOR 8.673617379884035e-19   /* 2^-60 */
+// r at the inflection point u* = (e-1)/e of the map: which asymptote the Newton start is taken from
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline float rambo_rstar(int e) {
+    const float ef = (float)e;
+    const float ustar = (ef - 1.f) / ef;
+    float us = 1.f;
+    for (int i = 0; i < e; ++i) us *= ustar;
+    return us * ((ef + 1.f) - ef * ustar);
+}
+
 static inline double rambo_lattice_at_one(int e) {
     double left = 0.0, right = 1.0, u = 1.0, scale = 0.5;
     for (int level = 0; level < 60; ++level, scale *= 0.5) {
@@ -184,6 +201,8 @@ static inline int rambo_fill_const(const NisRamboDesc* d, RamboConst* C) {
     C->cos_dR = cos(d->delR_mincut < NIS_PI ? d->delR_mincut : NIS_PI);
     C->u_one[0] = 1.0;
     for (int e = 1; e < NIS_MAX_FINAL; ++e) C->u_one[e] = rambo_lattice_at_one(e);
+    C->rstar[0] = 0.f;
+    for (int e = 1; e < NIS_MAX_FINAL; ++e) C->rstar[e] = rambo_rstar(e);
     return NIS_OK;
 }
 
@@ -222,22 +241,20 @@ double rambo_root_slow(int e, double r, double X) {
     return X;
 }
 
-NIS_DEV double rambo_root(int e, double r, double u_one) {
+
+NIS_DEV double rambo_root(int e, double r, double u_one, float rstar) {
     if (r >= 1.0) return u_one;                                // see NIS_U_FLOOR above
     if (e == 1) return fmax(nis_div(r, 1.0 + nis_sqrt(1.0 - r)), NIS_U_FLOOR);   // u = 1 - sqrt(1-r), stable form
     if (r <= 0.0) return NIS_U_FLOOR;
     const float ef = (float)e;
-    const float ustar = (ef - 1.f) / ef;                      // inflection point of the map
-    float us = 1.f;
-    for (int i = 0; i < e; ++i) us *= ustar;
-    const float rstar = us * ((ef + 1.f) - ef * ustar);
     const float rf = (float)r;
     // start on the asymptote of the side the root is on, then four plain float32 Newton steps (a step that
     // leaves (0,1) is dropped).  No bracket: a bracket narrowed with float32 function values ends up one ulp
-    // wide, and the bisection fallback then throws a converged iterate far away.
+    // wide, and the bisection fallback then throws a converged iterate far away.  The start only steers the
+    // iteration: fast lg2 / ex2 / rsqrt on the device.
     float x;
-    if (rf < rstar) x = exp2f(log2f(fmaxf(rf, 1e-37f) / (ef + 1.f)) / ef);
-    else x = 1.f - sqrtf(2.f * fmaxf(1.f - rf, 0.f) / (ef * (ef + 1.f)));
+    if (rf < rstar) x = nis_fpow(nis_fdiv(fmaxf(rf, 1e-37f), ef + 1.f), nis_fdiv(1.f, ef));
+    else x = 1.f - nis_fsqrt(nis_fdiv(2.f * fmaxf(1.f - rf, 0.f), ef * (ef + 1.f)));
     x = fminf(fmaxf(x, 0.f), 1.f);
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
@@ -267,7 +284,7 @@ NIS_DEV double rambo_root(int e, double r, double u_one) {
     return fmax(X, NIS_U_FLOOR);
 }
 
-NIS_DEV double rambo_root_dyn(int e, double r) { return rambo_root(e, r, rambo_lattice_at_one(e)); }
+NIS_DEV double rambo_root_dyn(int e, double r) { return rambo_root(e, r, rambo_lattice_at_one(e), rambo_rstar(e)); }
 
 // x f(x) from the caller's grid (nodes uniform in ln x over [lnx_lo, 0]) by 4-point Lagrange interpolation in ln x,
 // divided by x: the density get_pdfQ2 returns (flat_phase_space_generator.py:120-137).  NULL grid: 1.
@@ -347,7 +364,7 @@ NIS_DEV void rambo_event(const RamboConst& C, const double* r, int rs, double* m
         double Kn = 0.0, Mn = C.m[n - 1];
         const double mj = C.m[j];
         if (j < n - 2) {                                        // :363-370, :391-392
-            const double u = rambo_root(n - 2 - j, r[j * rs], C.u_one[n - 2 - j]);
+            const double u = rambo_root(n - 2 - j, r[j * rs], C.u_one[n - 2 - j], C.rstar[n - 2 - j]);
             Kn = nis_sqrt(u) * Kj;
             Mn = Kn + C.msum[j + 1];
         }
