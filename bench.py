@@ -534,7 +534,7 @@ def bench_rambo(steps, warmup, world, hbm_peak, peak_kind):
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^24 events from the committed
                          # ncu --set full capture (profiles/r02_ncu_rambo.md: 1.074 GB + 3.304 GB); not re-measured per run
-                         "traffic": 4378114000 if RAMBO_EVENTS == 1 << 24 else None,
+                         "traffic": 4376176000 if RAMBO_EVENTS == 1 << 24 else None,
                          "peak_kind": peak_kind, "algorithmic_bytes_per_event": RAMBO_BYTES_PER_EVENT},
             "weight_only": {"value": world * RAMBO_EVENTS / (ms_w * 1e-3), "unit": "events/s", "ms_per_step": ms_w}}
 

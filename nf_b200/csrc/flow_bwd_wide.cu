@@ -570,20 +570,35 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_bwd_wide_dgrad_kernel(cons
                     tc_ld32(tg + 64 * jb, dv);
                     tc_ld32(tg + 64 * jb + 32, dv + 32);
                     tc_ld_wait();
+                    // z_lam comes from global memory: 32 loads are issued before the first use (interleaved with the stores
+                    // of dL/dh the compiler has to keep every load behind the previous store - the two pointers may alias for
+                    // all it knows - and the loop ran at one DRAM latency per feature: 53 % of this kernel's stall samples)
+                    float zn[32];
 #pragma unroll
-                    for (int x = 0; x < TCH; ++x) {
-                        const int r = 64 * jb + x;
-                        const bool on = fmaf(zp[(size_t)r * TCM], scp[r], shp[r]) > 0.f;
-                        dv[x] = on ? dv[x] : 0.f;
-                        out[(size_t)r * TCM] = dv[x];
+                    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) zn[x] = __ldg(zp + (size_t)(64 * jb + 32 * hh + x) * TCM);
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) {
+                            const int r = 64 * jb + 32 * hh + x;
+                            const bool on = fmaf(zn[x], scp[r], shp[r]) > 0.f;
+                            dv[32 * hh + x] = on ? dv[32 * hh + x] : 0.f;
+                        }
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) out[(size_t)(64 * jb + 32 * hh + x) * TCM] = dv[32 * hh + x];
                     }
                     // per-warp sums in float32 (32 addends), float64 across tiles: ample for gradients
                     float a[2], b[2];
                     tc_warp_feature_sums(dv, lane, a[0], a[1]);
 #pragma unroll
-                    for (int x = 0; x < TCH; ++x) {
-                        const int r = 64 * jb + x;
-                        dv[x] *= (zp[(size_t)r * TCM] - mup[r]) * rsp[r];
+                    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) zn[x] = __ldg(zp + (size_t)(64 * jb + 32 * hh + x) * TCM);
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) {
+                            const int r = 64 * jb + 32 * hh + x;
+                            dv[32 * hh + x] *= (zn[x] - mup[r]) * rsp[r];
+                        }
                     }
                     tc_warp_feature_sums(dv, lane, b[0], b[1]);
 #pragma unroll
