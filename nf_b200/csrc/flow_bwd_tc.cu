@@ -628,14 +628,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_layer_kernel(const 
                 if (lam > 0) {
                     const float* zp = A.zbuf + ((size_t)(lam - 1) * ntiles + tile) * BT_TILE + (size_t)f0 * TCM + gt;
                     float dv[32], pr[32];
+                    // z_lam from global memory, all 32 loads ahead of the stores below (interleaved, every load has to stay
+                    // behind the previous store - the pointers may alias - and the loop runs at one memory latency per feature)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) pr[j] = __ldg(zp + (size_t)j * TCM);
                     tc_ld32(tg + BT_COL_D + f0, dv);
                     tc_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         dv[j] = ((mask >> j) & 1u) ? dv[j] : 0.f;
-                        out[(size_t)(f0 + j) * TCM] = dv[j];
-                        pr[j] = dv[j] * (zp[(size_t)j * TCM] - mup[f0 + j]) * rsp[f0 + j];
+                        pr[j] = dv[j] * (pr[j] - mup[f0 + j]) * rsp[f0 + j];
                     }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) out[(size_t)(f0 + j) * TCM] = dv[j];
                     acc1 += (double)bt_warp_feature_sums32(dv, lane);
                     acc2 += (double)bt_warp_feature_sums32(pr, lane);
                 } else if (sub == 0) {
