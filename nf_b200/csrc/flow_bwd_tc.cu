@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_bwd_tc_head_kernel(const _
                     float S = 0.f, C = 0.f, ek = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float e = expf(z[j] - m);
+                        const float e = __expf(z[j] - m);          // ex2.approx, like the forward (flow_tc_h.cu); the accurate expf was 16 % of this kernel
                         z[j] = e;
                         S += e;
                         C += j < kb ? e : 0.f;
