@@ -44,7 +44,9 @@ extern "C" {
 #define NIS_MAX_WIDTH 512  /* max hidden width */
 #define NIS_MAX_FINAL 8    /* max final-state particles of the phase-space generator */
 
-enum { NIS_KIND_PWLIN = 0, NIS_KIND_PWQUAD = 1 };
+enum { NIS_KIND_PWLIN = 0, NIS_KIND_PWQUAD = 1,
+       NIS_KIND_AFFINE = 2 /* AffineCoupling (layers/coupling_cells.py:6-70): two conditioner outputs per transformed
+                              dimension in Reshape(2, T) row order; n_bins is ignored; shape-generic kernels only */ };
 enum { NIS_F32 = 0, NIS_F64 = 1 };
 enum { NIS_BN_EVAL = 0, NIS_BN_TRAIN = 1 };
 

@@ -16,7 +16,7 @@ NIS_MAX_CELLS = 32
 NIS_MAX_HIDDEN = 8
 NIS_MAX_WIDTH = 512
 NIS_MAX_FINAL = 8
-KIND_PWLIN, KIND_PWQUAD = 0, 1
+KIND_PWLIN, KIND_PWQUAD, KIND_AFFINE = 0, 1, 2
 F32, F64 = 0, 1
 BN_EVAL, BN_TRAIN = 0, 1
 

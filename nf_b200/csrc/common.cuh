@@ -56,6 +56,9 @@ struct DevFlow {
     DevCell cells[NIS_MAX_CELLS];
 
     __host__ __device__ int W(int c, int l) const { return l == 0 ? cells[c].P : widths[l - 1]; }
+    // row of output j of transformed dimension t in the output layer's torch weight: Reshape(T, K) for the spline cells,
+    // Reshape(2, T) for the affine cell (coupling_cells.py:46)
+    __host__ __device__ int out_row(int c, int t, int j) const { return kind == NIS_KIND_AFFINE ? j * cells[c].T + t : t * K + j; }
     __host__ __device__ int Wp(int c, int l) const { return pad8(W(c, l)); }
     // offsets inside a cell's torch-layout parameter block
     __host__ __device__ long long p_bn_gamma(int c, int l) const {

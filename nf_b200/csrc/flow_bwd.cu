@@ -74,7 +74,9 @@ __global__ void flow_bwd_pack_kernel(DevFlow F, const float* __restrict__ params
         float* dst = o + wb_layer_off(F, c, l);
         for (int i = tid; i < rows * inp; i += nth) {
             const int j = i / inp, k = i - j * inp;
-            dst[i] = k < in ? w[(long long)j * in + k] : 0.f;
+            // (output layer: staged per transformed dimension, [t][K][inp], whatever the torch row order is)
+            const int src = l < F.depth ? j : F.out_row(c, j / F.K, j % F.K);
+            dst[i] = k < in ? w[(long long)src * in + k] : 0.f;
         }
         if (l < F.depth) in = F.widths[l];
     }
@@ -272,7 +274,18 @@ __device__ __forceinline__ void bwd_generic_body(const DevFlow& F, const BwdArgs
                     const float x = st[col * NT];
                     const float gy = g[col * NT];
                     float dx;
-                    if (F.kind == NIS_KIND_PWLIN) {
+                    if (F.kind == NIS_KIND_AFFINE) {
+                        // v = s0 x + s1, s0 = 20 e^{Z0}, s1 = relu(Z1); y = (2/pi) atan v; log f = log s0 - log(1 + v^2)
+                        const float z1 = lg[NT];
+                        const float s0 = 20.f * expf(lg[0]), s1 = fmaxf(z1, 0.f);
+                        const float v = fmaf(s0, x, s1);
+                        const float iv = 1.f / (v * v + 1.f);
+                        const float dv = gy * 0.6366197723675814f * iv - gJJ * 2.f * v * iv;
+                        lg[0] = dv * s0 * x + gJJ;
+                        lg[NT] = z1 > 0.f ? dv : 0.f;
+                        dx = dv * s0;
+                        Fprod *= s0 * iv;
+                    } else if (F.kind == NIS_KIND_PWLIN) {
                         float f, S, al;
                         int k;
                         const float y = pwlin_fwd(lg, NT, F.nb, x, f, k, S, al);
@@ -291,10 +304,19 @@ __device__ __forceinline__ void bwd_generic_body(const DevFlow& F, const BwdArgs
                     dense8b<NT, false>(wbc + wb_layer_off(F, c, depth) + (size_t)t * F.K * inp, F.K, inp, lg,
                                 [&](int k, float v) { if (k < in_last) GA[k * NT] += v; });
                     __syncthreads();
-                    outer_accum<NT>(lg0, F.K, (sm + acto[depth]), in_last, gp + F.p_out_w(c) + (size_t)t * F.K * in_last, depth > 0);
-                    rowsum_accum<NT>(lg0, F.K, gp + F.p_out_b(c) + t * F.K);
+                    if (F.kind == NIS_KIND_AFFINE) {           // rows j T + t of the torch weight (Reshape(2, T))
+                        for (int j = 0; j < 2; ++j) {
+                            outer_accum<NT>(lg0 + j * NT, 1, (sm + acto[depth]), in_last,
+                                            gp + F.p_out_w(c) + (size_t)F.out_row(c, t, j) * in_last, depth > 0);
+                            rowsum_accum<NT>(lg0 + j * NT, 1, gp + F.p_out_b(c) + F.out_row(c, t, j));
+                        }
+                    } else {
+                        outer_accum<NT>(lg0, F.K, (sm + acto[depth]), in_last, gp + F.p_out_w(c) + (size_t)t * F.K * in_last, depth > 0);
+                        rowsum_accum<NT>(lg0, F.K, gp + F.p_out_b(c) + t * F.K);
+                    }
                     __syncthreads();
                 }
+                if (F.kind == NIS_KIND_AFFINE) Fprod *= 0.6366197723675814f;    // 1 / (pi/2), once per cell
                 g[d * NT] = gJ * Fprod;
             } else {
                 // ================= BatchNorm (+ReLU) backward of layer `step` =================

@@ -2,7 +2,9 @@
 #include <string.h>
 #include "common.cuh"
 
-static int cond_out(const NisFlowDesc* d) { return d->kind == NIS_KIND_PWLIN ? d->n_bins : 2 * d->n_bins + 1; }
+static int cond_out(const NisFlowDesc* d) {
+    return d->kind == NIS_KIND_PWLIN ? d->n_bins : (d->kind == NIS_KIND_AFFINE ? 2 : 2 * d->n_bins + 1);
+}
 
 extern "C" int64_t nis_flow_cell_param_count(const NisFlowDesc* d, int32_t c) {
     if (!d || c < 0 || c >= d->n_cells) return NIS_EINVAL;
@@ -24,7 +26,7 @@ int nis_build_dev_flow(const NisFlowDesc* d, DevFlow* F) {
     if (!d || !F) return NIS_EINVAL;
     if (d->n_flow < 2 || d->n_flow > NIS_MAX_DIM) return NIS_EINVAL;
     if (d->n_cells < 1 || d->n_cells > NIS_MAX_CELLS) return NIS_EINVAL;
-    if (d->kind != NIS_KIND_PWLIN && d->kind != NIS_KIND_PWQUAD) return NIS_EINVAL;
+    if (d->kind != NIS_KIND_PWLIN && d->kind != NIS_KIND_PWQUAD && d->kind != NIS_KIND_AFFINE) return NIS_EINVAL;
     if (d->n_bins < 1 || d->n_bins > 512) return NIS_EINVAL;
     if (d->depth < 0 || d->depth > NIS_MAX_HIDDEN) return NIS_EINVAL;
     memset(F, 0, sizeof(*F));

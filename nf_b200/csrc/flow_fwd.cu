@@ -60,11 +60,11 @@ __global__ void flow_pack_kernel(DevFlow F, const float* __restrict__ params, co
     const int K = F.K, Kp = F.Kpad;
     for (int i = tid; i < q.T * in * Kp; i += nth) {
         const int t = i / (in * Kp), r = i - t * in * Kp, k = r / Kp, j = r - k * Kp;
-        pk[q.wo_off + i] = j < K ? wo[((long long)t * K + j) * in + k] : 0.f;
+        pk[q.wo_off + i] = j < K ? wo[(long long)F.out_row(c, t, j) * in + k] : 0.f;
     }
     for (int i = tid; i < q.T * Kp; i += nth) {
         const int t = i / Kp, j = i - t * Kp;
-        pk[q.bo_off + i] = j < K ? bo[t * K + j] : 0.f;
+        pk[q.bo_off + i] = j < K ? bo[F.out_row(c, t, j)] : 0.f;
     }
 }
 
@@ -191,7 +191,21 @@ __device__ __forceinline__ void fwd_generic_body(const DevFlow& F, const FwdArgs
                 const float x = st[col * NT];
                 float y, f;
                 int k;
-                if (A.inverse) {
+                if (F.kind == NIS_KIND_AFFINE) {
+                    // AffineCoupling (coupling_cells.py:49-68): y = atan(20 e^{Z0} x + relu(Z1)) / (pi/2); the Jacobian takes
+                    // 20 e^{Z0} / (v^2 + 1) per dimension and 1/(pi/2) ONCE per cell (as the reference writes it)
+                    const float s0 = 20.f * expf(nxt[0]), s1 = fmaxf(nxt[NT], 0.f);
+                    k = 0;
+                    if (A.inverse) {
+                        const float v = tanf(x * 1.5707963267948966f);
+                        y = (v - s1) / s0;
+                        f = (v * v + 1.f) / s0;
+                    } else {
+                        const float v = fmaf(s0, x, s1);
+                        y = atanf(v) * 0.6366197723675814f;
+                        f = s0 / (v * v + 1.f);
+                    }
+                } else if (A.inverse) {
                     y = F.kind == NIS_KIND_PWLIN ? pwlin_inv(nxt, NT, F.nb, x, f, k) : pwquad_inv(nxt, NT, F.nb, x, f, k);
                     f = 1.f / f;
                 } else if (F.kind == NIS_KIND_PWLIN) {
@@ -206,6 +220,7 @@ __device__ __forceinline__ void fwd_generic_body(const DevFlow& F, const FwdArgs
                 jfac *= f;
                 if (A.bins && valid) A.bins[((long long)c * A.B + pt) * d + t] = k;
             }
+            if (F.kind == NIS_KIND_AFFINE) jfac *= A.inverse ? 1.5707963267948966f : 0.6366197723675814f;
             st[d * NT] *= jfac;
         }
         if (stats || !valid) continue;

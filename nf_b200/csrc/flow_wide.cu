@@ -374,7 +374,7 @@ int64_t nis_tc_min_batch(int64_t dflt);
 bool nis_wide_supported(const DevFlow& F, int64_t B, int bn_mode) {
     const char* off = getenv("NIS_TC");                   // NIS_TC=0 forces the FP32-pipe kernels (test knob)
     if (off && off[0] == '0') return false;
-    if (F.depth < 1 || B < nis_tc_min_batch(256)) return false;
+    if (F.depth < 1 || B < nis_tc_min_batch(256) || F.kind == NIS_KIND_AFFINE) return false;
     const int W = F.widths[0];
     if (W < 64 || W > 256 || (W & 63)) return false;          // (width 64 with 32 bins is taken by flow_tc.cu first)
     for (int l = 0; l < F.depth; ++l) if (F.widths[l] != W) return false;

@@ -29,6 +29,14 @@ def _cell_tensors(cell):
     return params, bns
 
 
+def _hidden_biases(cell):
+    """Biases of the hidden Linear layers (AffineCoupling only), layer by layer.  They stay outside the kernels' parameter
+    block: in front of a BatchNorm a bias only moves the mean, so it is folded into the running mean the kernels see
+    (FlowSpec._bn_for_kernel) and gets its gradient from the BatchNorm shift's (FlowSpec._hidden_bias_grads)."""
+    nn_ = cell.NN
+    return [nn_[1 + 3 * l].bias for l in range(len(cell.hidden)) if nn_[1 + 3 * l].bias is not None]
+
+
 class _Arena:
     """A flat tensor whose slices back a list of tensors (``t.data`` is re-pointed at its slice)."""
 
@@ -129,11 +137,34 @@ class FlowSpec:
         for bn in bns:
             rstats += [bn.running_mean, bn.running_var]
         self.bn_arena = _Arena(rstats, torch.float32)
+        # hidden-layer biases (affine cells): where the running mean / variance of the BatchNorm behind each of them sits in
+        # the bn arena, and where that BatchNorm's weight / bias sit in the parameter arena
+        self.hidden_biases = []
+        hb_mean, hb_var, hb_gamma, hb_beta = [], [], [], []
+        bn_i = 0
+        for _, c, _, _ in cells:
+            hbs = _hidden_biases(c)
+            cell_bns = _cell_tensors(c)[1]
+            for l, b in enumerate(hbs):
+                bn = cell_bns[1 + l]
+                k = self.bn_modules.index(bn)
+                m0 = self.bn_arena.offsets[2 * k]
+                v0 = self.bn_arena.offsets[2 * k + 1]
+                g0 = self.param_arena.offsets[[id(t) for t in params].index(id(bn.weight))]
+                b0 = self.param_arena.offsets[[id(t) for t in params].index(id(bn.bias))]
+                n = b.numel()
+                self.hidden_biases.append(b)
+                hb_mean += list(range(m0, m0 + n)); hb_var += list(range(v0, v0 + n))
+                hb_gamma += list(range(g0, g0 + n)); hb_beta += list(range(b0, b0 + n))
+            bn_i += len(cell_bns)
+        self._hb_idx = None
+        if self.hidden_biases:
+            self._hb_idx = tuple(torch.tensor(v, dtype=torch.long) for v in (hb_mean, hb_var, hb_gamma, hb_beta))
         self.nbt_arena = _Arena([bn.num_batches_tracked for bn in bns], torch.long)
 
         desc = _cabi.NisFlowDesc()
         desc.n_flow, desc.n_cells = d, len(cells)
-        desc.kind = _cabi.KIND_PWLIN if self.kind == "lin" else _cabi.KIND_PWQUAD
+        desc.kind = {"lin": _cabi.KIND_PWLIN, "quad": _cabi.KIND_PWQUAD, "affine": _cabi.KIND_AFFINE}[self.kind]
         desc.n_bins, desc.depth = self.n_bins, len(self.hidden)
         for i, h in enumerate(self.hidden):
             desc.widths[i] = h
@@ -183,6 +214,49 @@ class FlowSpec:
             self._ws[key] = ws
         return ws
 
+    # ---- hidden-layer biases (affine cells) -----------------------------------------------------------
+    def _hb(self, device):
+        """(index tensors on ``device``, concatenated biases as float32) or None."""
+        if not self.hidden_biases:
+            return None
+        if self._hb_idx[0].device != device:
+            self._hb_idx = tuple(t.to(device) for t in self._hb_idx)
+        return self._hb_idx, torch.cat([b.detach().reshape(-1).to(device, torch.float32) for b in self.hidden_biases])
+
+    def _bn_for_kernel(self, bn, train, device):
+        """The running statistics the kernels should see.  BN(z + b) with running statistics equals BN(z) with the
+        running mean lowered by b: eval mode hands the kernel such a copy; train mode (batch statistics: the bias cancels)
+        hands it the buffer itself and `_after_train_forward` adds what the bias contributes to the update."""
+        hb = self._hb(device)
+        if hb is None or train:
+            return bn
+        eff = bn.clone()
+        eff.index_add_(0, hb[0][0], -hb[1])
+        return eff
+
+    def _after_train_forward(self, bn, device):
+        hb = self._hb(device)
+        if hb is not None:                   # running_mean <- (1-m) rm + m (mean(z) + b): the kernel added m mean(z)
+            bn.index_add_(0, hb[0][0], float(self.desc.bn_momentum) * hb[1])
+
+    def _hidden_bias_grads(self, gparams, train, device):
+        """Gradients of the hidden biases, one tensor per bias.  Train mode: exactly zero (BatchNorm with batch statistics
+        removes any constant added in front of it).  Eval mode: y = gamma (z + b - rm) / sqrt(rv + eps) + beta, so
+        dL/db = dL/dbeta * gamma / sqrt(rv + eps)."""
+        if not self.hidden_biases:
+            return []
+        if train:
+            return [torch.zeros_like(b) for b in self.hidden_biases]
+        (_, iv, ig, ib), _ = self._hb(device)
+        params = self.param_arena.get(device)
+        bn = self.bn_arena.get(device)
+        flat = gparams[ib] * params[ig] / torch.sqrt(bn[iv] + float(self.desc.bn_eps))
+        out, off = [], 0
+        for b in self.hidden_biases:
+            out.append(flat[off:off + b.numel()].view(b.shape).to(b.dtype))
+            off += b.numel()
+        return out
+
     def bn_saved_count(self, lib):
         return lib.nis_flow_bn_saved_count(ctypes.byref(self.desc))
 
@@ -208,7 +282,8 @@ class FlowSpec:
         with torch.cuda.device(dev):
             params = self.param_arena.get(dev)
             private = self.bn_override if train else None
-            bn = private if private is not None else self.bn_arena.get(dev)
+            bn_home = private if private is not None else self.bn_arena.get(dev)
+            bn = self._bn_for_kernel(bn_home, train, dev)
             out = torch.empty(B, d + 1, dtype=out_dtype or xj.dtype, device=dev)
             saved = torch.empty(self.n_cells + 1, B, d + 1, dtype=torch.float32, device=dev) if want_saved else None
             bn_saved = torch.empty(self.bn_saved_count(lib), dtype=torch.float32, device=dev) \
@@ -221,6 +296,8 @@ class FlowSpec:
                                       _cabi.BN_TRAIN if train else _cabi.BN_EVAL, _cabi.ptr(ws), ws.numel(), B,
                                       _cabi.stream_ptr(dev))
             _cabi.check(rc, "nis_flow_forward")
+            if train:
+                self._after_train_forward(bn_home, dev)
             if train and private is None:
                 self.bn_arena.write_back(bn)
                 nbt = self.nbt_arena.get(dev)
@@ -250,7 +327,7 @@ class FlowSpec:
             raise ValueError("Expected more than 1 value per channel when training, got input size [1, %d]" % d)
         with torch.cuda.device(dev):
             params = self.param_arena.get(dev)
-            bn = self.bn_arena.get(dev)
+            bn = self._bn_for_kernel(self.bn_arena.get(dev), train, dev)
             out = torch.empty(B, d + 1, dtype=out_dtype or yj.dtype, device=dev)
             bins = torch.full((self.n_cells, B, d), -1, dtype=torch.int32, device=dev) if want_bins else None
             ws = self.workspace(lib, B, dev)
@@ -271,7 +348,7 @@ class FlowSpec:
             grad_out = grad_out.double()
         with torch.cuda.device(dev):
             params = self.param_arena.get(dev)
-            bn = self.bn_arena.get(dev)
+            bn = self._bn_for_kernel(self.bn_arena.get(dev), train, dev)
             gparams = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
             gin = torch.empty(B, d + 1, dtype=grad_out.dtype, device=dev) if need_grad_in else None
             ws = self.workspace(lib, B, dev)
@@ -309,6 +386,7 @@ class _FlowFn(torch.autograd.Function):
         grads = []
         for p, off, need in zip(spec.params, spec.param_arena.offsets, ctx.needs_input_grad[4:]):
             grads.append(gparams[off:off + p.numel()].view(p.shape).to(p.dtype) if need else None)
+        grads += spec._hidden_bias_grads(gparams, ctx.train, saved.device)
         return (gin, None, None, None) + tuple(grads)
 
 
@@ -319,8 +397,9 @@ def flow_apply(spec, xj, train):
         # before autograd records them as inputs, or the first backward after a device change sees gradients
         # on another device than the one it noted for the parameters.
         spec.param_arena.get(xj.device)
-    need = torch.is_grad_enabled() and (xj.requires_grad or any(p.requires_grad for p in spec.params))
-    return _FlowFn.apply(xj, spec, bool(train), need, *spec.params)
+    need = torch.is_grad_enabled() and (xj.requires_grad or any(p.requires_grad for p in spec.params)
+                                        or any(p.requires_grad for p in spec.hidden_biases))
+    return _FlowFn.apply(xj, spec, bool(train), need, *spec.params, *spec.hidden_biases)
 
 
 class FlowSequential(torch.nn.Sequential):

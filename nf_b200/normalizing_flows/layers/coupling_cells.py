@@ -13,13 +13,14 @@ import torch
 from .layers import Reshape
 
 
-def conditioner_stack(pass_through_size, sizes, reshape):
+def conditioner_stack(pass_through_size, sizes, reshape, hidden_bias=False):
     """coupling_cells.py:84-104 / :230-254: BN(P) -> [Linear(no bias) -> BN -> ReLU] * depth ->
-    Linear(bias) -> Reshape(T, K).  ``sizes`` = hidden widths + [T*K]."""
+    Linear(bias) -> Reshape(T, K).  ``sizes`` = hidden widths + [T*K].  ``hidden_bias``: the affine cell's hidden
+    Linear layers carry a bias (coupling_cells.py:27-38 uses the torch default)."""
     mods = [torch.nn.BatchNorm1d(pass_through_size)]
     fan_in = pass_through_size
     for width in sizes[:-1]:
-        mods += [torch.nn.Linear(fan_in, width, bias=False), torch.nn.BatchNorm1d(width), torch.nn.ReLU()]
+        mods += [torch.nn.Linear(fan_in, width, bias=hidden_bias), torch.nn.BatchNorm1d(width), torch.nn.ReLU()]
         fan_in = width
     mods += [torch.nn.Linear(fan_in, sizes[-1]), Reshape(reshape[0], reshape[1])]
     return torch.nn.Sequential(*mods)
@@ -75,3 +76,25 @@ class PWQuad(_CouplingCell):
 
     def outputs_per_dim(self):
         return 2 * self.n_bins + 1
+
+
+class AffineCoupling(_CouplingCell):
+    """coupling_cells.py:6-70 — affine coupling squashed back into the unit interval: the conditioner returns
+    (Z0, Z1) per transformed dimension (``Reshape(2, T)``), y = atan(20 e^{Z0} x + relu(Z1)) / (pi/2), and the Jacobian
+    takes 20 e^{Z0} / (v^2 + 1) per dimension and 1/(pi/2) once per cell.  Hidden Linear layers have a bias."""
+    kind = "affine"
+
+    def __init__(self, flow_size, pass_through_size, NN_layers):
+        torch.nn.Module.__init__(self)
+        self.pass_through_size = pass_through_size
+        self.flow_size = flow_size
+        self.transform_size = flow_size - pass_through_size
+        self.n_bins = 1
+        self.hidden = list(NN_layers)
+        self.NN = conditioner_stack(pass_through_size, self.hidden + [2 * self.transform_size],
+                                    (2, self.transform_size), hidden_bias=True)
+        self._solo = None
+
+    def outputs_per_dim(self):
+        return 2
+

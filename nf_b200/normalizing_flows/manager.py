@@ -30,7 +30,7 @@ from tqdm.autonotebook import tqdm
 
 from .. import _cabi
 from ..flowspec import FlowSequential
-from .layers.coupling_cells import PWLin, PWQuad
+from .layers.coupling_cells import AffineCoupling, PWLin, PWQuad
 from .layers.layers import AddJacobian, DeMaskLayer, MaskLayer, RollLayer
 from .misc import tqdm_recycled
 
@@ -162,6 +162,8 @@ class BasicManager(ModelAPI):
                 with torch.no_grad():
                     for fb, fa in pairs:
                         fb.copy_(fa)
+                    for hb, ha in zip(ds.hidden_biases, ss.hidden_biases):      # affine cells: biases outside the arenas
+                        hb.copy_(ha)
                 return
             except Exception:
                 pass
@@ -609,6 +611,23 @@ class PWLinManager(BasicManager):
                                                 n_bins=n_bins, NN_layers=NN))
             # The reference registers every roll under the one name "roll" (manager.py:492): add_module
             # replaces it in place, so a single roll survives, right after cell 0.  Reproduced as is.
+            model.add_module("roll", RollLayer(roll_step))
+        _finish_model(self, model, 0)
+
+
+class AffineManager(BasicManager):
+    """Affine coupling cells with cyclic roll layers (manager.py:411-453).  Same topology as PWLinManager -
+    the reference registers every roll under the one name "roll", so a single roll survives right after cell 0.
+
+    Hyperparameters: n_pass_through, n_cells, NN (hidden widths), roll_step.  (The reference's create_model raises torch's
+    mixed-dtype error in its trial pass on current torch, after ``_model`` is set - the same quirk as PWLinManager's; this
+    one runs the trial pass.)"""
+
+    def create_model(self, n_pass_through, n_cells, NN, roll_step):
+        model = FlowSequential(self.n_flow)
+        for i_cell in range(n_cells):
+            model.add_module(str(i_cell), AffineCoupling(flow_size=self.n_flow, pass_through_size=n_pass_through,
+                                                         NN_layers=NN))
             model.add_module("roll", RollLayer(roll_step))
         _finish_model(self, model, 0)
 

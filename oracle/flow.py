@@ -159,6 +159,8 @@ def rectnn(sd, cell, xA, train, stats=None):
     h = _bn(xA, sd, pre + "0", train, stats)
     for l in range(depth):
         h = h @ sd[pre + "%d.weight" % (1 + 3 * l)].T
+        if pre + "%d.bias" % (1 + 3 * l) in sd:         # AffineCoupling: torch-default Linear (coupling_cells.py:27-38)
+            h = h + sd[pre + "%d.bias" % (1 + 3 * l)]
         h = torch.relu(_bn(h, sd, pre + "%d" % (2 + 3 * l), train, stats))
     last = pre + "%d" % (1 + 3 * depth)
     return h @ sd[last + ".weight"].T + sd[last + ".bias"]
@@ -234,6 +236,37 @@ def pwquad_cell(sd, cell, x, P, n_bins, train, stats=None, edges=None, cond=None
     return torch.cat((xA, y, J.unsqueeze(-1)), -1), k.squeeze(-1)
 
 
+def affine_cell(sd, cell, x, P, n_bins, train, stats=None, edges=None):
+    """AffineCoupling.forward, coupling_cells.py:49-70.  Returns (out [B, d+1], bins [B, T] of zeros).
+    Z = NN(xA) reshaped (2, T); s0 = exp(Z[:, 0]); s1 = relu(Z[:, 1]); yB = atan(20 s0 xB + s1) / (pi/2);
+    J *= prod(20 s0) * (1 / (pi/2)) * prod(1 / (v^2 + 1)) - the 1/(pi/2) ONCE per cell, as the reference writes it."""
+    d = x.shape[1] - 1
+    T = d - P
+    xA, xB, J = x[:, :P], x[:, P:d], x[:, d]
+    Z = rectnn(sd, cell, xA, train, stats).reshape(-1, 2, T)
+    s0 = torch.exp(Z[:, 0])
+    s1 = torch.where(Z[:, 1] > 0, Z[:, 1], torch.zeros_like(Z[:, 1]))
+    v = xB * (20 * s0) + s1
+    diff = 1 / (v ** 2 + 1)
+    y = torch.atan(v) / (math.pi / 2)
+    J = J * torch.prod(20 * s0, 1) * (1 / (math.pi / 2)) * torch.prod(diff, 1)
+    return torch.cat((xA, y, J.unsqueeze(-1)), -1), torch.zeros(x.shape[0], T, dtype=torch.long)
+
+
+def affine_cell_inverse(sd, cell, yj, P, n_bins, train, stats=None):
+    """Inverse of affine_cell: yj = (xA, y, J) -> (xA, x, J / (cell Jacobian))."""
+    d = yj.shape[1] - 1
+    T = d - P
+    xA, yB, J = yj[:, :P], yj[:, P:d], yj[:, d]
+    Z = rectnn(sd, cell, xA, train, stats).reshape(-1, 2, T)
+    s0 = torch.exp(Z[:, 0])
+    s1 = torch.relu(Z[:, 1])
+    v = torch.tan(yB * (math.pi / 2))
+    x = (v - s1) / (20 * s0)
+    J = J / (torch.prod(20 * s0, 1) * (1 / (math.pi / 2)) * torch.prod(1 / (v ** 2 + 1), 1))
+    return torch.cat((xA, x, J.unsqueeze(-1)), -1), torch.zeros(yj.shape[0], T, dtype=torch.long)
+
+
 # ----------------------------------------------------------------------------------------------
 # inverse cells (SURVEY 8 f4).  The reference has no inverse (its README lists it as to do, README.md:68-69); these are
 # the algebraic inverses of the two maps above, validated by round trips against the reference-pinned forward.
@@ -291,7 +324,7 @@ def flow_inverse(layers, sd, yj, kind, n_bins, train=False, stats=None):
     """Inverse of flow_forward: the Sequential backwards (inverse rolls / masks, inverse cells).  yj: [B, d+1] in
     the reference's output column order; returns (XJ, bins) with XJ[:, -1] = J_in / prod f, so that
     flow_inverse(flow_forward(x)) = x with Jacobian 1."""
-    cell_fn = pwlin_cell_inverse if kind == "lin" else pwquad_cell_inverse
+    cell_fn = {"lin": pwlin_cell_inverse, "quad": pwquad_cell_inverse, "affine": affine_cell_inverse}[kind]
     x = yj
     all_bins = []
     for L in reversed(layers):
@@ -319,14 +352,14 @@ def flow_forward(layers, sd, xj, kind, n_bins, train=True, stats=None, trace=Non
     each cell's [B, T_c] distances to the nearest bin edge, ``cond`` (list, PWQuad) each cell's [B] sensitivity of the
     log-Jacobian to its input coordinates (see pwquad_cell)."""
     d = xj.shape[1] - 1
-    cell_fn = pwlin_cell if kind == "lin" else pwquad_cell
+    cell_fn = {"lin": pwlin_cell, "quad": pwquad_cell, "affine": affine_cell}[kind]
     x = xj
     all_bins = []
     for L in layers:
         t = L["type"]
         if t == "cell":
             extra = {"clamp_bins": True} if clamp_bins and kind == "lin" else {}
-            if cond is not None and kind != "lin":
+            if cond is not None and kind == "quad":
                 extra["cond"] = cond
             x, b = cell_fn(sd, L["name"], x, L["P"], n_bins, train, stats, edges, **extra)
             all_bins.append(b)
@@ -347,7 +380,7 @@ def flow_forward_compiled(cells, out_perm, sd, xj, kind, n_bins, train=True, sta
     """Same map, but in the index-table form the CUDA kernels use (state never moves; each cell
     reads/writes physical columns).  Used to check that folding Roll/Mask/DeMask is exact."""
     d = xj.shape[1] - 1
-    cell_fn = pwlin_cell if kind == "lin" else pwquad_cell
+    cell_fn = {"lin": pwlin_cell, "quad": pwquad_cell, "affine": affine_cell}[kind]
     state = xj.clone()
     all_bins = []
     for c in cells:
@@ -384,12 +417,14 @@ def init_state_dict(cells, d, kind, n_bins, NN, seed, dtype=torch.float64, bn_ji
     for c in cells:
         P = c["P"]
         T = d - P
-        out = T * (n_bins if kind == "lin" else 2 * n_bins + 1)
+        out = T * {"lin": n_bins, "quad": 2 * n_bins + 1, "affine": 2}[kind]
         pre = "%s.NN." % c["name"]
         bn(pre + "0", P)
         fan = P
         for l, h in enumerate(NN):
             sd[pre + "%d.weight" % (1 + 3 * l)] = U((h, fan), 1 / math.sqrt(fan))
+            if kind == "affine":
+                sd[pre + "%d.bias" % (1 + 3 * l)] = U((h,), 1 / math.sqrt(fan))
             bn(pre + "%d" % (2 + 3 * l), h)
             fan = h
         sd[pre + "%d.weight" % (1 + 3 * len(NN))] = U((out, fan), 1 / math.sqrt(fan))

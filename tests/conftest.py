@@ -31,6 +31,8 @@ class Golden:
     def __init__(self, fname):
         self.z = np.load(os.path.join(GOLDEN, fname))
         self.meta = json.loads(str(self.z["meta"])) if "meta" in self.z.files else {}
+        if self.meta.get("kind") == "affine":
+            self.meta.setdefault("n_bins", 1)            # (no bins; the kernels' descriptor carries 1)
 
     def __getitem__(self, k):
         return self.z[k]
@@ -50,8 +52,8 @@ class Golden:
 
 
 FLOW_CASES = ["quad2d", "quad3d", "quad7d", "quad8d", "quad8d_small", "quad9d_extra", "quad16d",
-              "lin8d", "lin4d", "lin5d"]
-GRAD_CASES = ["quad2d", "quad3d", "quad8d_small", "lin4d"]
+              "lin8d", "lin4d", "lin5d", "affine4d", "affine6d"]
+GRAD_CASES = ["quad2d", "quad3d", "quad8d_small", "lin4d", "affine4d"]
 RAMBO_CASES = ["m4_cuts", "m4_nocuts", "m0_4", "m2", "mixed3", "m5_cuts", "m0_6", "readme"]
 # uniforms on the ends of [0,1] (0, denormal, 2^-24, 1-2^-24, 1) in every column; edge0 = with 0 / denormal rows
 # (the reference then stops its lattice bisection after 60 levels), edge1 = without

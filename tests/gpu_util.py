@@ -4,7 +4,7 @@ import torch
 
 from oracle import flow as oflow
 
-from nf_b200.normalizing_flows.manager import PWLinManager, PWQuadManager
+from nf_b200.normalizing_flows.manager import AffineManager, PWLinManager, PWQuadManager
 
 RTOL, ATOL_Y = 1e-5, 1e-6          # north_star: 1e-5 relative on points and log-Jacobians, in fp32
 
@@ -13,6 +13,9 @@ def make_manager(meta):
     if meta["kind"] == "quad":
         NF = PWQuadManager(n_flow=meta["n_flow"])
         NF.create_model(meta["n_cells"], meta["n_bins"], meta["NN"])
+    elif meta["kind"] == "affine":
+        NF = AffineManager(n_flow=meta["n_flow"])
+        NF.create_model(meta["n_pass_through"], meta["n_cells"], meta["NN"], meta["roll_step"])
     else:
         NF = PWLinManager(n_flow=meta["n_flow"])
         NF.create_model(meta["n_pass_through"], meta["n_cells"], meta["n_bins"], meta["NN"], meta["roll_step"])

@@ -80,6 +80,8 @@ BIG = [
     dict(name="cfg4", kind="quad", n_flow=8, n_cells=6, n_bins=32, NN=[64] * 3, B=3000),
     dict(name="cfg1", kind="quad", n_flow=2, n_cells=2, n_bins=4, NN=[3] * 3, B=2000),
     dict(name="cfg5_small", kind="quad", n_flow=16, n_cells=8, n_bins=16, NN=[128] * 2, B=1500),
+    # AffineCoupling: biased hidden layers folded into the running mean, Reshape(2, T) output rows
+    dict(name="affine8d", kind="affine", n_flow=8, n_pass_through=4, n_cells=4, n_bins=1, NN=[64] * 2, roll_step=4, B=3000),
 ]
 
 

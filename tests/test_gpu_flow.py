@@ -23,13 +23,17 @@ def test_forward_matches_reference_golden(golden, case, mode, io):
     xj = g.t("xj").to(io).cuda()
     XJ, bins = model.forward_with_bins(xj)
     assert XJ.dtype == io and XJ.shape == xj.shape
-    ref_bins = [g["%s/bins/%d" % (mode, i)] for i in range(model.spec().n_cells)]
+    if g.meta["kind"] == "affine":           # no bins: the kernel reports 0 for every transformed dimension
+        T = g.meta["n_flow"] - g.meta["n_pass_through"]
+        ref_bins = [np.zeros((xj.shape[0], T), np.int32) for _ in range(model.spec().n_cells)]
+    else:
+        ref_bins = [g["%s/bins/%d" % (mode, i)] for i in range(model.spec().n_cells)]
     edges = []                              # distances to the nearest bin edge, from the oracle (== reference to 1e-12)
     with torch.no_grad():
         oflow.flow_forward(oracle_layers(g.meta), g.state_dict(), g.t("xj"), g.meta["kind"], g.meta["n_bins"],
                            train=(mode == "train"), edges=edges)
     compare_flow(XJ.cpu(), bins.cpu(), g.t(mode + "/XJ"), ref_bins, "%s/%s" % (case, mode),
-                 ref_edges=[e.numpy() for e in edges])
+                 ref_edges=[e.numpy() for e in edges] if edges else None)
     if mode == "train":                      # running statistics updated like torch BatchNorm1d
         sd = model.state_dict()
         for k in g.keys("train/stats/"):
@@ -159,6 +163,22 @@ def test_streamed_weight_kernel_shapes(cfg, mode):
     test_forward_matches_oracle_at_size(cfg, mode)
 
 
+AFFINE = [
+    dict(name="affine8d_wide", kind="affine", n_flow=8, n_pass_through=4, n_cells=4, n_bins=1, NN=[64] * 2, roll_step=4, B=5000),
+    dict(name="affine3d", kind="affine", n_flow=3, n_pass_through=1, n_cells=5, n_bins=1, NN=[8, 8, 8], roll_step=1, B=777),
+]
+
+
+@pytest.mark.parametrize("cfg", AFFINE, ids=[c["name"] for c in AFFINE])
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_affine_coupling_flow_matches_oracle_at_size(cfg, mode):
+    """AffineCoupling / AffineManager (coupling_cells.py:6-70, manager.py:411-453) on the shape-generic kernels:
+    y = atan(20 e^{Z0} x + relu(Z1)) / (pi/2), 1/(pi/2) once per cell in the Jacobian, hidden layers WITH bias (folded into
+    the running mean the kernels see), Reshape(2, T) row order of the output layer; a 64-wide conditioner must not be
+    taken by the tensor-core paths."""
+    test_forward_matches_oracle_at_size(cfg, mode)
+
+
 MANY_PASS_THROUGH = [
     dict(name="lin13d_9pass", kind="lin", n_flow=13, n_pass_through=9, n_cells=4, n_bins=32, NN=[64] * 3, roll_step=3, B=2700),
     dict(name="lin20d_16pass", kind="lin", n_flow=20, n_pass_through=16, n_cells=3, n_bins=32, NN=[64] * 2, roll_step=7, B=1500),
@@ -190,6 +210,7 @@ INV = [
     dict(name="quad2d", kind="quad", n_flow=2, n_cells=2, n_bins=4, NN=[3] * 3, B=2000),
     dict(name="quad9d_extra", kind="quad", n_flow=9, n_cells=10, n_bins=6, NN=[16, 16], B=777),
     dict(name="lin5d", kind="lin", n_flow=5, n_pass_through=1, n_cells=4, n_bins=7, NN=[12], roll_step=2, B=1025),
+    dict(name="affine6d", kind="affine", n_flow=6, n_pass_through=3, n_cells=4, n_bins=1, NN=[16], roll_step=2, B=1500),
 ]
 
 
@@ -220,12 +241,32 @@ def test_inverse_flow(cfg, mode):
     for c, rb in enumerate(ref_bins):
         same &= (bins[c, :, :rb.shape[1]].long() == rb).all(1)
     assert float(same.float().mean()) > 0.995, float(same.float().mean())
-    # |dx| = |dy| / density: compare in units of the local stretch (the Jacobian column holds 1 / prod density)
-    stretch = ref[:, -1].clamp_min(1.0)
-    err = ((X[:, :-1] - ref[:, :-1]).abs().max(1).values / stretch)[same]
-    assert float(err.max()) < 2e-5, float(err.max())
-    lj = (torch.log(X[:, -1]) - torch.log(ref[:, -1])).abs()[same]
-    assert float(torch.quantile(lj, 0.99)) < 1e-4 and float(lj.median()) < 1e-5, (float(lj.median()), float(lj.max()))
+    if cfg["kind"] == "affine":
+        # The affine flow maps the unit cube INTO a subset of itself, and inverting the atan squashing multiplies an error
+        # by (pi/2)(1 + v^2) / s0 (up to ~1e3) in EVERY cell: for a y outside the image the next conditioner sees
+        # pass-through values like -30 or 200, and even on image points two float32 evaluations of a four-cell inverse agree
+        # only to ~1e-2.  The kernel is therefore checked in the well-conditioned direction, on image points (y = forward(x)
+        # from the oracle): the float64 FORWARD of what the kernel returned - points and Jacobian column - must give y back;
+        # then through the CUDA round trip below.
+        xs = (0.002 + 0.996 * torch.rand(cfg["B"], cfg["n_flow"], generator=gen, dtype=torch.float32)).double()
+        with torch.no_grad():
+            img, _ = oflow.flow_forward(oracle_layers(cfg), sd64, torch.cat((xs, torch.ones(cfg["B"], 1, dtype=torch.float64)), 1),
+                                        cfg["kind"], cfg["n_bins"], train=(mode == "train"))
+        img32 = img.float().double()
+        Xi = model.spec().inverse(img32.cuda(), model.training)[0].cpu().double()
+        with torch.no_grad():
+            fw, _ = oflow.flow_forward(oracle_layers(cfg), sd64, Xi, cfg["kind"], cfg["n_bins"], train=(mode == "train"))
+        dp = (fw[:, :-1] - img32[:, :-1]).abs().max(1).values
+        assert float(torch.quantile(dp, 0.999)) < 2e-5, (float(torch.quantile(dp, 0.999)), float(dp.max()))
+        lj = (torch.log(fw[:, -1]) - torch.log(img32[:, -1])).abs()
+        assert float(torch.quantile(lj, 0.99)) < 2e-4 and float(lj.median()) < 2e-5, (float(lj.median()), float(lj.max()))
+    else:
+        # |dx| = |dy| / density: compare in units of the local stretch (the Jacobian column holds 1 / prod density)
+        stretch = ref[:, -1].clamp_min(1.0)
+        err = ((X[:, :-1] - ref[:, :-1]).abs().max(1).values / stretch)[same]
+        assert float(err.max()) < 2e-5, float(err.max())
+        lj = (torch.log(X[:, -1]) - torch.log(ref[:, -1])).abs()[same]
+        assert float(torch.quantile(lj, 0.99)) < 1e-4 and float(lj.median()) < 1e-5, (float(lj.median()), float(lj.max()))
     # round trip through the CUDA forward
     x = (0.002 + 0.996 * torch.rand(cfg["B"], cfg["n_flow"], generator=gen, dtype=torch.float32)).double().cuda()
     with torch.no_grad():
@@ -233,4 +274,5 @@ def test_inverse_flow(cfg, mode):
         back = model.inverse(Y)
     rt = (back[:, :-1] - x).abs().max(1).values * Y[:, -1].clamp_max(1.0)      # stretch of the inverse = 1 / J
     assert float(torch.quantile(rt, 0.999)) < 2e-5, float(rt.max())
-    assert float(torch.quantile((torch.log(back[:, -1])).abs(), 0.99)) < 2e-4
+    if cfg["kind"] != "affine":              # (affine: the Jacobian along a path that float32 rounding has moved by ~1e-2 in latent
+        assert float(torch.quantile((torch.log(back[:, -1])).abs(), 0.99)) < 2e-4      # space is not 1 to 2e-4; see above)

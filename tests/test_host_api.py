@@ -14,7 +14,7 @@ from oracle import nis as onis
 
 from nf_b200 import _cabi
 from nf_b200.flowspec import FlowSequential
-from nf_b200.normalizing_flows.manager import EpochState, PWLinManager, PWQuadManager, get_bin
+from nf_b200.normalizing_flows.manager import AffineManager, EpochState, PWLinManager, PWQuadManager, get_bin
 from nf_b200.PhaseSpace.flat_phase_space_generator import FlatInvertiblePhasespace, PhaseSpaceGeneratorError
 
 
@@ -23,6 +23,9 @@ def make_manager(meta):
     if meta["kind"] == "quad":
         NF = PWQuadManager(n_flow=meta["n_flow"])
         NF.create_model(meta["n_cells"], meta["n_bins"], meta["NN"])
+    elif meta["kind"] == "affine":
+        NF = AffineManager(n_flow=meta["n_flow"])
+        NF.create_model(meta["n_pass_through"], meta["n_cells"], meta["NN"], meta["roll_step"])
     else:
         NF = PWLinManager(n_flow=meta["n_flow"])
         NF.create_model(meta["n_pass_through"], meta["n_cells"], meta["n_bins"], meta["NN"], meta["roll_step"])
@@ -43,7 +46,9 @@ def test_create_model_reproduces_reference_topology_and_schema(golden, case):
         assert tuple(sd[k].shape) == tuple(ref_sd[k].shape), k
     model.load_state_dict(ref_sd)            # reference checkpoints load unchanged (float64 -> float32)
     assert NF.best_model is NF.model
-    assert sum(p.numel() for p in model.parameters()) == model.spec().n_params
+    # (the affine cell's hidden-layer biases stay outside the kernels' parameter block: flowspec._hidden_biases)
+    assert sum(p.numel() for p in model.parameters()) == \
+        model.spec().n_params + sum(b.numel() for b in model.spec().hidden_biases)
 
 
 @pytest.mark.parametrize("case", FLOW_CASES)
