@@ -400,12 +400,14 @@ def bench_readme(dev):
         return torch.exp(-((x[:, 0] - 0.75) ** 2 + (x[:, 1] - 0.75) ** 2) / (0.2 ** 2)) + \
             torch.exp(-((x[:, 0] - 0.25) ** 2 + (x[:, 1] - 0.25) ** 2) / (0.2 ** 2))
 
-    # twice: the first run of a process also pays for loading the kernels and the optimizer's / integrand's torch kernels
-    # it is the first to use (CUDA loads modules lazily) - reported as first_run_seconds; `value` is the second run
+    # four runs: the first run of a process also pays for loading the kernels and the optimizer's / integrand's torch kernels
+    # it is the first to use (CUDA loads modules lazily) - reported as first_run_seconds; `value` is the median of the
+    # three warm runs (the example is host-latency sensitive - 300 epochs of ~1 ms with a loss read-back each - and single
+    # runs on a shared VM scatter by a factor of two; all four are listed in runs_seconds)
     gc.collect()
     torch.cuda.empty_cache()                  # cached blocks of the previous (GB-sized) workloads
     runs = []
-    for _ in range(2):
+    for _ in range(4):
         torch.manual_seed(0)
         NF = PWQuadManager(n_flow=2)
         NF.create_model(2, 4, [3] * 3, dev=dev.index or 0)
@@ -418,12 +420,15 @@ def bench_readme(dev):
         sig, err = NF.integrate(camel, 10, 10000, dev.index or 0)
         torch.cuda.synchronize()
         runs.append((t1 - t0, time.time() - t1, float(sig), float(err), float(NF.best_loss), float(NF.int_loss)))
-    w = runs[1]
+        del NF, optim
+    warm = sorted(runs[1:], key=lambda r: r[0])
+    w = warm[len(warm) // 2]
     return {"metric": "readme_example_wall_seconds", "value": w[0], "unit": "s", "higher_is_better": False,
-            "first_run_seconds": runs[0][0], "us_per_minibatch_step": w[0] / (300 * 5) * 1e6,
+            "first_run_seconds": runs[0][0], "runs_seconds": [r[0] for r in runs],
+            "us_per_minibatch_step": w[0] / (300 * 5) * 1e6,
             "integrate_seconds": w[1], "estimate": w[2], "reported_error": w[3],
             "analytic": 0.232322, "best_loss": w[4], "int_loss": w[5],
-            "same_result_both_runs": runs[0][2:] == runs[1][2:],
+            "same_result_every_run": all(r[2:] == runs[0][2:] for r in runs),
             "reference": "368 s on 8 CPU cores, best_loss 0.024 from int_loss 0.071 (BASELINE.md)"}
 
 
