@@ -116,6 +116,27 @@ int nis_flow_forward(const NisFlowDesc* desc, const float* params, float* bn_run
                      float* saved, float* bn_saved, int32_t bn_mode,
                      void* workspace, size_t workspace_bytes, int64_t B, void* stream);
 
+/* Activation cache for training (round 2).  Where both the forward and the backward of a shape run the streamed-weights
+ * tcgen05 kernels (wide conditioners such as BASELINE configs[4]: [256]*4), the backward needs the pre-BatchNorm
+ * activations z_1..z_depth of every cell.  nis_flow_forward_cached writes them to act_saved
+ * (float32 [nis_flow_act_saved_count(desc, B)], layout [cell][layer][tile][width][128]) and nis_flow_backward_cached reads
+ * them instead of running the layer passes again (what torch.autograd does for the reference's loss.backward(),
+ * manager.py:278: it keeps every intermediate of the forward).  nis_flow_act_saved_count returns 0 for shapes / batch sizes
+ * that have no use for the cache; act_saved == NULL (or the plain entry points) keeps the recomputing backward (its z is
+ * rebuilt from the saved float32 batch statistics: the two gradients agree to float32 rounding, tested at 1e-5 of the
+ * gradient scale). */
+int64_t nis_flow_act_saved_count(const NisFlowDesc* desc, int64_t B);
+int nis_flow_forward_cached(const NisFlowDesc* desc, const float* params, float* bn_running,
+                            const void* xj_in, int32_t in_dtype, int32_t in_cols,
+                            void* xj_out, int32_t out_dtype, int32_t* bins_out,
+                            float* saved, float* bn_saved, float* act_saved, int32_t bn_mode,
+                            void* workspace, size_t workspace_bytes, int64_t B, void* stream);
+int nis_flow_backward_cached(const NisFlowDesc* desc, const float* params, const float* bn_running,
+                             const float* saved, const float* bn_saved, const float* act_saved,
+                             const void* grad_out, int32_t grad_dtype,
+                             float* grad_params, void* grad_in, int32_t bn_mode,
+                             void* workspace, size_t workspace_bytes, int64_t B, void* stream);
+
 /* Inverse flow (the reference lists it as to do, README.md:68-69): yj_in [B, n_flow(+1)] in the flow's OUTPUT
  * column order -> xj_out [B, n_flow+1] with column n_flow = J_in / prod of the densities, so that
  * nis_flow_inverse(nis_flow_forward(x)) == x with Jacobian 1 (away from PWQuad's clamp at 1 - 1e-6).  EVAL: running

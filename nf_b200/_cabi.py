@@ -62,6 +62,12 @@ _PROTOS = {
     "nis_flow_forward": (ctypes.c_int, [ctypes.POINTER(NisFlowDesc), _P, _P, _P, ctypes.c_int32, ctypes.c_int32,
                                         _P, ctypes.c_int32, _P, _P, _P, ctypes.c_int32, _P, ctypes.c_size_t,
                                         ctypes.c_int64, _P]),
+    "nis_flow_act_saved_count": (ctypes.c_int64, [ctypes.POINTER(NisFlowDesc), ctypes.c_int64]),
+    "nis_flow_forward_cached": (ctypes.c_int, [ctypes.POINTER(NisFlowDesc), _P, _P, _P, ctypes.c_int32, ctypes.c_int32,
+                                               _P, ctypes.c_int32, _P, _P, _P, _P, ctypes.c_int32, _P, ctypes.c_size_t,
+                                               ctypes.c_int64, _P]),
+    "nis_flow_backward_cached": (ctypes.c_int, [ctypes.POINTER(NisFlowDesc), _P, _P, _P, _P, _P, _P, ctypes.c_int32, _P, _P,
+                                                ctypes.c_int32, _P, ctypes.c_size_t, ctypes.c_int64, _P]),
     "nis_flow_inverse": (ctypes.c_int, [ctypes.POINTER(NisFlowDesc), _P, _P, _P, ctypes.c_int32, ctypes.c_int32,
                                         _P, ctypes.c_int32, _P, ctypes.c_int32, _P, ctypes.c_size_t, ctypes.c_int64, _P]),
     "nis_flow_backward": (ctypes.c_int, [ctypes.POINTER(NisFlowDesc), _P, _P, _P, _P, _P, ctypes.c_int32, _P, _P,

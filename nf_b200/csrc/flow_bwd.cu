@@ -568,8 +568,9 @@ int nis_flow_backward_tc(const DevFlow& F, const FlowWorkspace& ws, const float*
 // wide-conditioner train-mode backward (flow_bwd_wide.cu)
 bool nis_bwd_wide_supported(const DevFlow& F, int64_t B, int bn_mode);
 int nis_flow_backward_wide(const DevFlow& F, const FlowWorkspace& ws, const float* params, const float* bn_running,
-                           const float* saved, const float* bn_saved, const void* grad_out, int grad_dtype,
+                           const float* saved, const float* bn_saved, const float* act_saved, const void* grad_out, int grad_dtype,
                            float* grad_params, void* grad_in, int64_t B, cudaStream_t s);
+size_t nis_act_cache_floats(const DevFlow& F, int64_t B);
 
 static int launch_bwd_any(const DevFlow& F, const BwdArgs& A, int NT, int grid, cudaStream_t s) {
     switch (NT) {
@@ -584,6 +585,14 @@ extern "C" int nis_flow_backward(const NisFlowDesc* desc, const float* params, c
                                  const float* saved, const float* bn_saved, const void* grad_out,
                                  int32_t grad_dtype, float* grad_params, void* grad_in, int32_t bn_mode,
                                  void* workspace, size_t workspace_bytes, int64_t B, void* stream) {
+    return nis_flow_backward_cached(desc, params, bn_running, saved, bn_saved, nullptr, grad_out, grad_dtype, grad_params,
+                                    grad_in, bn_mode, workspace, workspace_bytes, B, stream);
+}
+
+extern "C" int nis_flow_backward_cached(const NisFlowDesc* desc, const float* params, const float* bn_running,
+                                        const float* saved, const float* bn_saved, const float* act_saved,
+                                        const void* grad_out, int32_t grad_dtype, float* grad_params, void* grad_in,
+                                        int32_t bn_mode, void* workspace, size_t workspace_bytes, int64_t B, void* stream) {
     DevFlow F;
     int rc = nis_build_dev_flow(desc, &F);
     if (rc) return rc;
@@ -600,7 +609,8 @@ extern "C" int nis_flow_backward(const NisFlowDesc* desc, const float* params, c
     if (nis_bwd_tc_supported(F, B, bn_mode))
         return nis_flow_backward_tc(F, ws, params, bn_running, saved, bn_saved, grad_out, grad_dtype, grad_params, grad_in, B, s);
     if (nis_bwd_wide_supported(F, B, bn_mode))
-        return nis_flow_backward_wide(F, ws, params, bn_running, saved, bn_saved, grad_out, grad_dtype, grad_params, grad_in, B, s);
+        return nis_flow_backward_wide(F, ws, params, bn_running, saved, bn_saved,
+                                      nis_act_cache_floats(F, B) ? act_saved : nullptr, grad_out, grad_dtype, grad_params, grad_in, B, s);
     bool rotate = false;
     const int NT = bwd_pick_nt(F, train != 0, &rotate);
     if (!NT) return NIS_EUNSUPPORTED;

@@ -936,7 +936,7 @@ size_t nis_bwd_wide_scratch_floats(const DevFlow& F, int64_t B) {
 }
 
 int nis_flow_backward_wide(const DevFlow& F, const FlowWorkspace& ws, const float* params, const float* bn_running,
-                           const float* saved, const float* bn_saved, const void* grad_out, int grad_dtype,
+                           const float* saved, const float* bn_saved, const float* act_saved, const void* grad_out, int grad_dtype,
                            float* grad_params, void* grad_in, int64_t B, cudaStream_t s) {
     BwScratch sc;
     bw_carve(F, B, ws.bwd, &sc);
@@ -977,8 +977,11 @@ int nis_flow_backward_wide(const DevFlow& F, const FlowWorkspace& ws, const floa
     for (int c = F.n_cells - 1; c >= 0; --c) {
         const DevCell& q = F.cells[c];
         A.c = c; A.first = c == F.n_cells - 1;
-        // ---- recompute: z_1 .. z_depth with the forward's layer passes (BN from the saved batch statistics) --------
-        {
+        // ---- z_1 .. z_depth: kept by nis_flow_forward_cached, or recomputed with the forward's layer passes (BN from the
+        //      saved batch statistics) ------------------------------------------------------------------------------------
+        if (act_saved) {
+            A.zbuf = act_saved + (size_t)c * depth * ntiles * tile_fl;
+        } else {
             FwdArgs Fa;
             Fa.in = nullptr; Fa.in_dtype = NIS_F32; Fa.in_cols = F.d + 1;
             Fa.state_in = saved + (long long)c * rows; Fa.state_out = nullptr; Fa.out = nullptr; Fa.out_dtype = NIS_F32;

@@ -420,11 +420,37 @@ static int launch_fwd_any(const DevFlow& F, const FwdArgs& A, cudaStream_t s) {
     return NIS_EUNSUPPORTED;
 }
 
+// Activation cache of the streamed-weights path (cfg5-like shapes): a train-mode forward that a backward will follow can
+// keep z_1..z_depth of every cell ([cell][layer][tile][W][128] float32) so that the backward does not run the layer passes
+// again.  Nonzero only where both the forward and the backward take the wide kernels.
+size_t nis_act_cache_floats(const DevFlow& F, int64_t B) {
+    if (B <= 0 || F.depth < 2) return 0;
+    if (nis_tc_supported(F, B, NIS_BN_TRAIN) || !nis_wide_supported(F, B, NIS_BN_TRAIN)) return 0;
+    if (nis_bwd_tc_supported(F, B, NIS_BN_TRAIN) || !nis_bwd_wide_supported(F, B, NIS_BN_TRAIN)) return 0;
+    const size_t tiles = (size_t)((B + 127) / 128);
+    return (size_t)F.n_cells * F.depth * tiles * F.widths[0] * 128;
+}
+
+extern "C" int64_t nis_flow_act_saved_count(const NisFlowDesc* desc, int64_t B) {
+    DevFlow F;
+    if (nis_build_dev_flow(desc, &F) != NIS_OK || B < 0) return 0;
+    return (int64_t)nis_act_cache_floats(F, B);
+}
+
 extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, float* bn_running,
                                 const void* xj_in, int32_t in_dtype, int32_t in_cols,
                                 void* xj_out, int32_t out_dtype, int32_t* bins_out,
                                 float* saved, float* bn_saved, int32_t bn_mode,
                                 void* workspace, size_t workspace_bytes, int64_t B, void* stream) {
+    return nis_flow_forward_cached(desc, params, bn_running, xj_in, in_dtype, in_cols, xj_out, out_dtype, bins_out, saved,
+                                   bn_saved, nullptr, bn_mode, workspace, workspace_bytes, B, stream);
+}
+
+extern "C" int nis_flow_forward_cached(const NisFlowDesc* desc, const float* params, float* bn_running,
+                                       const void* xj_in, int32_t in_dtype, int32_t in_cols,
+                                       void* xj_out, int32_t out_dtype, int32_t* bins_out,
+                                       float* saved, float* bn_saved, float* act_saved, int32_t bn_mode,
+                                       void* workspace, size_t workspace_bytes, int64_t B, void* stream) {
     DevFlow F;
     int rc = nis_build_dev_flow(desc, &F);
     if (rc) return rc;
@@ -496,6 +522,10 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
     // state it writes, so only the first cell runs flow_col_moments_kernel (NIS_FUSE_MOMENTS=0: every cell does, A/B knob)
     static const int fuse_env = [] { const char* e = getenv("NIS_FUSE_MOMENTS"); return e && e[0] == '0' ? 0 : 1; }();
     bool moments_ready = false;
+    // activation cache (nis_flow_forward_cached): the wide layer passes write z_1..z_depth of every cell there instead of the
+    // two rotating workspace buffers
+    float* acts = (wide && bn_mode == NIS_BN_TRAIN && act_saved && saved && nis_act_cache_floats(F, B)) ? act_saved : nullptr;
+    const size_t act_layer = (size_t)((B + 127) / 128) * (size_t)F.widths[0] * 128;
     // One launch sequence per cell.  TRAIN: a statistics pass per BN layer, then the full pass.
     // (EVAL reaches here only on the register-tiled path, whose launches are per cell.)
     for (int c = 0; c < F.n_cells; ++c) {
@@ -504,6 +534,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
         A.state_in = c > 0 ? (saved ? saved + (long long)c * rows : ws.state) : nullptr;
         A.state_out = nullptr; A.to_out = 0;
         float* zb[2] = {ws.bwd, ws.bwd + zbuf_floats(F, B)};
+        float* const acell = acts ? acts + (size_t)c * F.depth * act_layer : nullptr;
         // BN0 + BN1 from one streaming pass over the pass-through columns (flow_col_moments_kernel), then
         // the layer passes start at layer 2 (recomputing the K=P layer 0 on the way)
         const bool moments = tiled && bn_mode == NIS_BN_TRAIN && nis_moments_supported(F, c);
@@ -524,6 +555,11 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
                     // layer pass: reads the pre-BN activations of layer l-1, writes those of layer l
                     A.zin = (l >= 2 && !(moments && l == 2) && !recompute) ? zb[(l - 1) & 1] : nullptr;
                     A.zout = (recompute || (skip_last && moments && l == F.depth)) ? nullptr : zb[l & 1];
+                    if (acell) {
+                        if (A.zin) A.zin = acell + (size_t)(l - 2) * act_layer;
+                        A.zout = acell + (size_t)(l - 1) * act_layer;
+                        A.z1out = (!A.zin && l == 2) ? acell : nullptr;
+                    }
                     rc = hp ? nis_launch_h(F, A, ws.tcpack, s) : tc ? nis_launch_tc(F, A, ws.tcpack, s)
                             : wide ? nis_launch_wide(F, A, ws.tcpack, s) : nis_launch_tiled(F, A, s);
                 } else if (tiled && l == 0) {
@@ -538,6 +574,7 @@ extern "C" int nis_flow_forward(const NisFlowDesc* desc, const float* params, fl
         A.stats_layer = -1;
         A.zin = (tiled && bn_mode == NIS_BN_TRAIN && !(moments && F.depth == 1) && !recompute) ? zb[F.depth & 1] : nullptr;
         A.zout = nullptr;
+        if (acell) { A.zin = acell + (size_t)(F.depth - 1) * act_layer; A.z1out = nullptr; }
         if (skip_last && moments && bn_mode == NIS_BN_TRAIN) { A.zin = zb[(F.depth - 1) & 1]; A.zin_layer = F.depth - 1; }
         if (tc && !hp && bn_mode == NIS_BN_EVAL && nis_tc_split_eval(F)) {
             // eval, PWQuad: hidden layers in one launch (activations of the last hidden layer to HBM), then the final pass

@@ -7,6 +7,7 @@ into the ``NisFlowDesc`` of include/nis_b200.h and keeps the cells' parameters i
 needed per call) plus one arena for the BatchNorm running statistics.
 """
 import ctypes
+import os
 
 import torch
 
@@ -260,8 +261,17 @@ class FlowSpec:
     def bn_saved_count(self, lib):
         return lib.nis_flow_bn_saved_count(ctypes.byref(self.desc))
 
+    def act_saved_count(self, lib, B):
+        """Floats of the activation cache a train-mode forward may keep for its backward (0: none).  The cache costs
+        cells * depth * width * 4 bytes per point (cfg5: 32 KB); NIS_ACT_CACHE_MAX_BYTES (default 8 GiB) bounds it --
+        above the bound the backward recomputes the activations."""
+        n = lib.nis_flow_act_saved_count(ctypes.byref(self.desc), B)
+        limit = int(os.environ.get("NIS_ACT_CACHE_MAX_BYTES", str(8 << 30)))
+        return n if 0 < 4 * n <= limit else 0
+
     def forward(self, xj, train, want_saved=False, want_bins=False, out_dtype=None):
-        """Runs nis_flow_forward.  Returns (XJ, saved, bn_saved, bins)."""
+        """Runs nis_flow_forward(_cached).  Returns (XJ, saved, bn_saved, bins); ``saved`` is a tuple
+        (states, activation cache) when the shape keeps one."""
         lib = _cabi.lib()
         self._self_check(lib)
         if xj.dim() != 2 or xj.shape[1] not in (self.n_flow, self.n_flow + 1):
@@ -289,13 +299,17 @@ class FlowSpec:
             bn_saved = torch.empty(self.bn_saved_count(lib), dtype=torch.float32, device=dev) \
                 if (want_saved and train) else None
             bins = torch.full((self.n_cells, B, d), -1, dtype=torch.int32, device=dev) if want_bins else None
+            n_act = self.act_saved_count(lib, B) if (want_saved and train) else 0
+            acts = torch.empty(n_act, dtype=torch.float32, device=dev) if n_act else None
             ws = self.workspace(lib, B, dev)
-            rc = lib.nis_flow_forward(ctypes.byref(self.desc), _cabi.ptr(params), _cabi.ptr(bn), _cabi.ptr(xj),
-                                      _cabi.dtype_code(xj), xj.shape[1], _cabi.ptr(out), _cabi.dtype_code(out),
-                                      _cabi.ptr(bins), _cabi.ptr(saved), _cabi.ptr(bn_saved),
-                                      _cabi.BN_TRAIN if train else _cabi.BN_EVAL, _cabi.ptr(ws), ws.numel(), B,
-                                      _cabi.stream_ptr(dev))
-            _cabi.check(rc, "nis_flow_forward")
+            rc = lib.nis_flow_forward_cached(ctypes.byref(self.desc), _cabi.ptr(params), _cabi.ptr(bn), _cabi.ptr(xj),
+                                             _cabi.dtype_code(xj), xj.shape[1], _cabi.ptr(out), _cabi.dtype_code(out),
+                                             _cabi.ptr(bins), _cabi.ptr(saved), _cabi.ptr(bn_saved), _cabi.ptr(acts),
+                                             _cabi.BN_TRAIN if train else _cabi.BN_EVAL, _cabi.ptr(ws), ws.numel(), B,
+                                             _cabi.stream_ptr(dev))
+            _cabi.check(rc, "nis_flow_forward_cached")
+            if acts is not None:
+                saved = (saved, acts)
             if train:
                 self._after_train_forward(bn_home, dev)
             if train and private is None:
@@ -339,8 +353,11 @@ class FlowSpec:
         return out, bins
 
     def backward(self, saved, bn_saved, grad_out, train, need_grad_in):
-        """Runs nis_flow_backward.  Returns (grad_params flat float32, grad_in or None)."""
+        """Runs nis_flow_backward(_cached).  Returns (grad_params flat float32, grad_in or None)."""
         lib = _cabi.lib()
+        acts = None
+        if isinstance(saved, tuple):
+            saved, acts = saved
         dev = saved.device
         B, d = saved.shape[1], self.n_flow
         grad_out = grad_out.contiguous()
@@ -352,12 +369,12 @@ class FlowSpec:
             gparams = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
             gin = torch.empty(B, d + 1, dtype=grad_out.dtype, device=dev) if need_grad_in else None
             ws = self.workspace(lib, B, dev)
-            rc = lib.nis_flow_backward(ctypes.byref(self.desc), _cabi.ptr(params), _cabi.ptr(bn), _cabi.ptr(saved),
-                                       _cabi.ptr(bn_saved), _cabi.ptr(grad_out), _cabi.dtype_code(grad_out),
-                                       _cabi.ptr(gparams), _cabi.ptr(gin),
-                                       _cabi.BN_TRAIN if train else _cabi.BN_EVAL, _cabi.ptr(ws), ws.numel(), B,
-                                       _cabi.stream_ptr(dev))
-            _cabi.check(rc, "nis_flow_backward")
+            rc = lib.nis_flow_backward_cached(ctypes.byref(self.desc), _cabi.ptr(params), _cabi.ptr(bn), _cabi.ptr(saved),
+                                              _cabi.ptr(bn_saved), _cabi.ptr(acts), _cabi.ptr(grad_out),
+                                              _cabi.dtype_code(grad_out), _cabi.ptr(gparams), _cabi.ptr(gin),
+                                              _cabi.BN_TRAIN if train else _cabi.BN_EVAL, _cabi.ptr(ws), ws.numel(), B,
+                                              _cabi.stream_ptr(dev))
+            _cabi.check(rc, "nis_flow_backward_cached")
         return gparams, gin
 
 
@@ -368,10 +385,14 @@ class _FlowFn(torch.autograd.Function):
         # ctx.needs_input_grad only reflects requires_grad, so under torch.no_grad() (integrate, the tail
         # integration, create_model's trial pass) neither can tell that no backward will follow
         out, saved, bn_saved, _ = spec.forward(xj, train, want_saved=need)
+        acts = None
+        if isinstance(saved, tuple):
+            saved, acts = saved
         ctx.spec, ctx.train = spec, train
         ctx.in_cols, ctx.in_dtype, ctx.in_device = xj.shape[1], xj.dtype, xj.device
-        ctx.save_for_backward(*[t for t in (saved, bn_saved) if t is not None])
+        ctx.save_for_backward(*[t for t in (saved, bn_saved, acts) if t is not None])
         ctx.has_bn_saved = bn_saved is not None
+        ctx.has_acts = acts is not None
         return out
 
     @staticmethod
@@ -380,13 +401,15 @@ class _FlowFn(torch.autograd.Function):
         tensors = ctx.saved_tensors
         saved = tensors[0]
         bn_saved = tensors[1] if ctx.has_bn_saved else None
+        if ctx.has_acts:
+            saved = (saved, tensors[-1])
         gparams, gin = spec.backward(saved, bn_saved, grad_out, ctx.train, ctx.needs_input_grad[0])
         if gin is not None:
             gin = gin[:, :ctx.in_cols].to(device=ctx.in_device, dtype=ctx.in_dtype)
         grads = []
         for p, off, need in zip(spec.params, spec.param_arena.offsets, ctx.needs_input_grad[4:]):
             grads.append(gparams[off:off + p.numel()].view(p.shape).to(p.dtype) if need else None)
-        grads += spec._hidden_bias_grads(gparams, ctx.train, saved.device)
+        grads += spec._hidden_bias_grads(gparams, ctx.train, tensors[0].device)
         return (gin, None, None, None) + tuple(grads)
 
 

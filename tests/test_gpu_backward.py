@@ -212,6 +212,56 @@ def test_tensor_core_backward_at_large_batch_matches_generic(monkeypatch, which,
     print("tc vs generic backward at 2^%d points: worst |diff| / model gradient scale = %.2e" % (log2b, worst))
 
 
+@pytest.mark.parametrize("which,B", [(3, 3000), (3, 1 << 14)], ids=["cfg5_small_3000", "cfg5_small_2p14"])
+def test_activation_cache_backward_equals_recomputing_backward(monkeypatch, which, B):
+    """nis_flow_forward_cached keeps z_1..z_depth of the streamed-weights layer passes and nis_flow_backward_cached reads them;
+    with NIS_ACT_CACHE_MAX_BYTES=0 the backward runs the layer passes again (BatchNorm scale / shift rebuilt from the saved
+    float32 batch statistics, so z differs from the forward's by a rounding).  Forward outputs are bit-identical, the
+    gradients agree to 1e-5 of the model's gradient scale."""
+    import ctypes
+    from nf_b200 import _cabi
+    cfg = dict(BIG[which], B=B)
+    layers = oracle_layers(cfg)
+    cells, _ = oflow.compile_layers(layers, cfg["n_flow"])
+    sd = oflow.init_state_dict(cells, cfg["n_flow"], cfg["kind"], cfg["n_bins"], cfg["NN"], seed=35,
+                               dtype=torch.float32, bn_jitter=0.2)
+    gen = torch.Generator().manual_seed(8)
+    x = torch.rand(cfg["B"], cfg["n_flow"], generator=gen, dtype=torch.float32)
+    fres = torch.exp(-((x - 0.5) ** 2).sum(-1) / 0.2).cuda()
+    res = {}
+    for mode, env in (("cached", None), ("recompute", "0")):
+        monkeypatch.delenv("NIS_ACT_CACHE_MAX_BYTES", raising=False)
+        if env is not None:
+            monkeypatch.setenv("NIS_ACT_CACHE_MAX_BYTES", env)
+        NF = make_manager(cfg)
+        model = NF._model
+        model.load_state_dict(sd)
+        model.train()
+        spec = model.spec()
+        n = spec.act_saved_count(_cabi.lib(), B)
+        assert (n > 0) == (mode == "cached"), (mode, n)
+        xin = x.cuda().requires_grad_(True)
+        XJ = model(xin)
+        torch.var(fres * XJ[:, -1]).backward()
+        res[mode] = (XJ.detach().clone(), xin.grad.clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters()})
+    assert torch.equal(res["cached"][0], res["recompute"][0])
+    gscale = max(float(g.abs().max()) for g in res["recompute"][2].values())
+    xscale = float(res["recompute"][1].abs().max())
+    assert gscale > 0 and xscale > 0
+    # a z within a rounding of 0 may land on the other side of the ReLU in the recomputation: that point's dL/dx then
+    # differs by one hidden unit's contribution -- allow a handful of such rows
+    rowdiff = (res["cached"][1] - res["recompute"][1]).abs().amax(dim=1) / xscale
+    bad_rows = int((rowdiff > 1e-5).sum())
+    print("rows of dL/dx beyond 1e-5 of the scale: %d of %d (max %.2e)" % (bad_rows, B, float(rowdiff.max())))
+    assert bad_rows <= max(2, B // 1000), bad_rows
+    worst = 0.0
+    for k, g in res["cached"][2].items():
+        assert torch.isfinite(g).all(), k
+        worst = max(worst, float((g - res["recompute"][2][k]).abs().max()) / gscale)
+    print("activation cache vs recomputing backward: worst |diff| / gradient scale = %.2e" % worst)
+    assert worst <= 1e-4, worst
+
+
 WIDE_BWD = [
     dict(name="wide_lin128", kind="lin", n_flow=8, n_pass_through=4, n_cells=4, n_bins=48, NN=[128] * 3, roll_step=4, B=2400),
     dict(name="quad64_20bins", kind="quad", n_flow=8, n_cells=6, n_bins=20, NN=[64] * 2, B=2600),

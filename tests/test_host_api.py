@@ -1,6 +1,7 @@
 """CPU tests of the host layer: the reference-facing API mirror, topology folding, state_dict schema,
 the epoch state machine and the C-ABI library's symbols (no compute: this box has no GPU)."""
 import ctypes
+import os
 import math
 import re
 
@@ -166,6 +167,36 @@ def test_cabi_library_exports_every_declared_symbol():
     bad = _cabi.NisFlowDesc()
     assert lib.nis_flow_workspace_bytes(ctypes.byref(bad), 10) == 0       # invalid descriptor rejected on the host
     assert lib.nis_flow_cell_param_count(ctypes.byref(bad), 0) == -1
+
+
+def test_activation_cache_count_is_host_code():
+    """nis_flow_act_saved_count: cells * depth * width floats per point (tiles of 128) for the shape whose forward AND backward
+    run the streamed-weights kernels (cfg5), 0 for the resident-weights shapes (cfg2, cfg4), for a batch below the
+    tensor-core threshold and for a single hidden layer; FlowSpec.act_saved_count applies NIS_ACT_CACHE_MAX_BYTES."""
+    from nf_b200.normalizing_flows.manager import PWLinManager, PWQuadManager
+    lib = _cabi.load()
+    NF = PWQuadManager(n_flow=16)
+    NF.create_model(8, 64, [256] * 4)
+    spec = NF._model.spec()
+    B = (1 << 14) + 5
+    tiles = (B + 127) // 128
+    assert lib.nis_flow_act_saved_count(ctypes.byref(spec.desc), B) == 8 * 4 * tiles * 256 * 128
+    assert lib.nis_flow_act_saved_count(ctypes.byref(spec.desc), 100) == 0
+    assert spec.act_saved_count(lib, B) == 8 * 4 * tiles * 256 * 128
+    os.environ["NIS_ACT_CACHE_MAX_BYTES"] = "1000"
+    try:
+        assert spec.act_saved_count(lib, B) == 0
+    finally:
+        del os.environ["NIS_ACT_CACHE_MAX_BYTES"]
+    NF = PWLinManager(n_flow=8)
+    NF.create_model(4, 6, 32, [64] * 3, 4)
+    assert lib.nis_flow_act_saved_count(ctypes.byref(NF._model.spec().desc), 1 << 16) == 0
+    NF = PWQuadManager(n_flow=8)
+    NF.create_model(6, 32, [64] * 3)
+    assert lib.nis_flow_act_saved_count(ctypes.byref(NF._model.spec().desc), 1 << 16) == 0
+    NF = PWQuadManager(n_flow=6)
+    NF.create_model(6, 12, [128])
+    assert lib.nis_flow_act_saved_count(ctypes.byref(NF._model.spec().desc), 1 << 14) == 0
 
 
 @pytest.mark.parametrize("kind,n_flow,args,scratch_per_point", [
