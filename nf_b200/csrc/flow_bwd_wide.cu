@@ -675,7 +675,8 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_bwd_wide_dgrad_kernel(cons
 // ===================================================================================================
 // wgrad of linear layer lam
 // ===================================================================================================
-#define BWW_THREADS 288       // 8 point warps (two threads per point, each fills half of the operand rows) + MMA issuer
+#define BWW_THREADS 256       // 8 point warps, two threads per point (each fills half of the operand rows); thread 0 issues the MMAs
+                              // (a ninth warp would put three warps on one scheduler: 168 registers per thread instead of 255)
 #define BWW_FLUSH 8
 
 // grid = (row blocks of 64 upstream features) x (column blocks of 128 features of h_lam) x nparts
@@ -708,7 +709,7 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
         mbar_init(&a_ready, 2 * TCM); mbar_init(&done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -720,12 +721,93 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
     const long long ntiles = A.ntiles, rowlen = d + 1;
     float* slice = A.slices + ((((size_t)rb * gridDim.y + nh) * gridDim.z + part) * 128) * 128;
 
-    if (warp == 8) {
-        if ((tid & 31) == 0) {
-            const uint32_t idesc = tc_idesc(TCM, N);
-            const uint32_t sA = smem_u32(slabA), sBh = smem_u32(slabBh), sBl = smem_u32(slabBl);
-            unsigned n = 0;
-            for (long long tile = part; tile < ntiles; tile += gridDim.z, ++n) {
+    {
+        // two threads per point: `half` 0 / 1 fills rows [0,32) / [32,64) of the upstream block and the lower / upper half of
+        // the h block, all of a thread's loads of a round issued before the first shared-memory store (the stores are
+        // generic, so the compiler keeps later global loads behind them)
+        const int gt = tid & 127, half = tid >> 7;
+        const uint32_t idesc = tc_idesc(TCM, N);
+        const uint32_t sA = smem_u32(slabA), sBh = smem_u32(slabBh), sBl = smem_u32(slabBl);
+        const uint32_t tg = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        unsigned n = 0;
+        int nflush = 0;
+        // A: 64 upstream features [64 rb, 64 rb + 64), 32 per thread; B: h_lam features [128 nh, 128 nh + N), nb = N / 2 per
+        // thread (lam = 0: the normalised pass-through columns, 16 rows, by half 0).  The operand values of the NEXT tile
+        // are loaded into registers before the wait for this tile's MMAs, so their latency hides behind the tensor work.
+        const int nb = N >> 1;
+        const bool two = lam > 0 && nb > 32;
+        float v[32], w[32], w2[32];
+        auto load_tile = [&](long long tile) {
+            const float* up = (OUTL ? A.dl + (size_t)tile * nlog * TCM : A.dz + (size_t)tile * W * TCM) + (size_t)(64 * rb + 32 * half) * TCM + gt;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 64 * rb + 32 * half + j < nrows ? up[(size_t)j * TCM] : 0.f;
+            if (lam > 0) {
+                const float* zp = A.zbuf + (((size_t)(lam - 1) * ntiles + tile) * W + 128 * nh + nb * half) * TCM + gt;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) w[j] = zp[(size_t)j * TCM];
+                if (two) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) w2[j] = zp[(size_t)(32 + j) * TCM];
+                }
+            }
+        };
+        if (part < ntiles) load_tile(part);
+        for (long long tile = part; tile < ntiles; tile += gridDim.z, ++n) {
+            const long long pt = tile * TCM + gt;
+            const bool valid = pt < A.B;
+            // pull the tile after the next one into L2 (its operand blocks are contiguous in the tile-blocked buffers)
+            if (tid == 0 && tile + 2 * gridDim.z < ntiles) {
+                const long long tn = tile + 2 * gridDim.z;
+                const int rows_here = nrows - 64 * rb < 64 ? nrows - 64 * rb : 64;
+                if (rows_here > 0)
+                    bulk_prefetch_l2((OUTL ? A.dl + (size_t)tn * nlog * TCM : A.dz + (size_t)tn * W * TCM) + (size_t)(64 * rb) * TCM,
+                                     (uint32_t)rows_here * TCM * 4);
+                if (lam > 0) bulk_prefetch_l2(A.zbuf + (((size_t)(lam - 1) * ntiles + tn) * W + 128 * nh) * TCM, (uint32_t)N * TCM * 4);
+            }
+            // hi rounded to nearest; the residual is exact in float32 and left as it is (the MMA truncates it: 2^-22 of the value)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int r = 32 * half + j;
+                const float hi = tf32_rn(v[j]);
+                *reinterpret_cast<float*>(slabA + tc_slab_off(128, r, gt)) = hi;
+                *reinterpret_cast<float*>(slabA + tc_slab_off(128, 64 + r, gt)) = v[j] - hi;
+            }
+            if (lam > 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int r = nb * half + j;
+                    const float h = fmaxf(fmaf(w[j], coef[r], coef[128 + r]), 0.f);
+                    const float hi = tf32_rn(h);
+                    *reinterpret_cast<float*>(slabBh + tc_slab_off(N, r, gt)) = hi;
+                    *reinterpret_cast<float*>(slabBl + tc_slab_off(N, r, gt)) = h - hi;
+                }
+                if (two) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int r = nb * half + 32 + j;
+                        const float h = fmaxf(fmaf(w2[j], coef[r], coef[128 + r]), 0.f);
+                        const float hi = tf32_rn(h);
+                        *reinterpret_cast<float*>(slabBh + tc_slab_off(N, r, gt)) = hi;
+                        *reinterpret_cast<float*>(slabBl + tc_slab_off(N, r, gt)) = h - hi;
+                    }
+                }
+            }
+            if (lam == 0 && half == 0) {
+                const float* xs = A.saved + ((long long)c * A.B + (valid ? pt : 0)) * rowlen;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float a = k < q.P ? fmaf(xs[q.feed[k]], coef[k], coef[128 + k]) : 0.f;
+                    const float hi = tf32_rn(a);
+                    *reinterpret_cast<float*>(slabBh + tc_slab_off(16, k, gt)) = hi;
+                    *reinterpret_cast<float*>(slabBl + tc_slab_off(16, k, gt)) = a - hi;
+                }
+            }
+            proxy_fence();
+            tc_fence_before();
+            mbar_arrive(&a_ready);
+            const bool lastt = tile + gridDim.z >= ntiles;
+            if (!lastt) load_tile(tile + gridDim.z);
+            if (tid == 0) {
                 mbar_wait(&a_ready, n & 1);
                 tc_fence_after();
                 uint32_t acc = (n % BWW_FLUSH) != 0;
@@ -739,89 +821,9 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
                 }
                 tc_commit(&done);
             }
-        }
-    } else {
-        // two threads per point: `half` 0 / 1 fills rows [0,32) / [32,64) of the upstream block and the lower / upper half of
-        // the h block, all of a thread's loads of a round issued before the first shared-memory store (the stores are
-        // generic, so the compiler keeps later global loads behind them)
-        const int gt = tid & 127, half = tid >> 7;
-        const uint32_t tg = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        unsigned n = 0;
-        int nflush = 0;
-        for (long long tile = part; tile < ntiles; tile += gridDim.z, ++n) {
-            const long long pt = tile * TCM + gt;
-            const bool valid = pt < A.B;
-            // the kernel is latency-bound (5 warps per SM, operands loaded in dependent batches of 32 values): pull the next
-            // tile's two operand blocks (contiguous in the tile-blocked buffers) into L2 while this one is processed
-            if (tid == 0 && tile + gridDim.z < ntiles) {
-                const long long tn = tile + gridDim.z;
-                const int rows_here = nrows - 64 * rb < 64 ? nrows - 64 * rb : 64;
-                if (rows_here > 0)
-                    bulk_prefetch_l2((OUTL ? A.dl + (size_t)tn * nlog * TCM : A.dz + (size_t)tn * W * TCM) + (size_t)(64 * rb) * TCM,
-                                     (uint32_t)rows_here * TCM * 4);
-                if (lam > 0) bulk_prefetch_l2(A.zbuf + (((size_t)(lam - 1) * ntiles + tn) * W + 128 * nh) * TCM, (uint32_t)N * TCM * 4);
-            }
-            // A: 64 upstream features [64 rb, 64 rb + 64), 32 per thread; B: h_lam features [128 nh, 128 nh + N), N / 2 per thread
-            // (lam = 0: the normalised pass-through columns, 16 rows, by half 0)
-            {
-                const float* up = (OUTL ? A.dl + (size_t)tile * nlog * TCM : A.dz + (size_t)tile * W * TCM) + (size_t)(64 * rb + 32 * half) * TCM + gt;
-                const int nb = N >> 1;                          // h rows of this thread: [nb half, nb half + nb), nb = 64 or 32
-                const float* zp = lam > 0 ? A.zbuf + (((size_t)(lam - 1) * ntiles + tile) * W + 128 * nh + nb * half) * TCM + gt : nullptr;
-                float v[32], w[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 64 * rb + 32 * half + j < nrows ? up[(size_t)j * TCM] : 0.f;
-                if (lam > 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) w[j] = zp[(size_t)j * TCM];
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int r = 32 * half + j;
-                    const float hi = tf32_rn(v[j]);
-                    *reinterpret_cast<float*>(slabA + tc_slab_off(128, r, gt)) = hi;
-                    *reinterpret_cast<float*>(slabA + tc_slab_off(128, 64 + r, gt)) = tf32_rn(v[j] - hi);
-                }
-                if (lam > 0) {
-                    if (nb > 32) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = zp[(size_t)(32 + j) * TCM];
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int r = nb * half + j;
-                        const float h = fmaxf(fmaf(w[j], coef[r], coef[128 + r]), 0.f);
-                        const float hi = tf32_rn(h);
-                        *reinterpret_cast<float*>(slabBh + tc_slab_off(N, r, gt)) = hi;
-                        *reinterpret_cast<float*>(slabBl + tc_slab_off(N, r, gt)) = tf32_rn(h - hi);
-                    }
-                    if (nb > 32) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int r = nb * half + 32 + j;
-                            const float h = fmaxf(fmaf(v[j], coef[r], coef[128 + r]), 0.f);
-                            const float hi = tf32_rn(h);
-                            *reinterpret_cast<float*>(slabBh + tc_slab_off(N, r, gt)) = hi;
-                            *reinterpret_cast<float*>(slabBl + tc_slab_off(N, r, gt)) = tf32_rn(h - hi);
-                        }
-                    }
-                }
-            }
-            if (lam == 0 && half == 0) {
-                const float* xs = A.saved + ((long long)c * A.B + (valid ? pt : 0)) * rowlen;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const float a = k < q.P ? fmaf(xs[q.feed[k]], coef[k], coef[128 + k]) : 0.f;
-                    const float hi = tf32_rn(a);
-                    *reinterpret_cast<float*>(slabBh + tc_slab_off(16, k, gt)) = hi;
-                    *reinterpret_cast<float*>(slabBl + tc_slab_off(16, k, gt)) = tf32_rn(a - hi);
-                }
-            }
-            proxy_fence();
-            tc_fence_before();
-            mbar_arrive(&a_ready);
+            __syncwarp();
             mbar_wait(&done, n & 1);
             tc_fence_after();
-            const bool lastt = tile + gridDim.z >= ntiles;
             if ((n % BWW_FLUSH) == BWW_FLUSH - 1 || lastt) {
                 // accumulator -> slice (fp32, round to nearest); the next tile starts a new accumulation
                 float* sl = slice + (size_t)gt * 128;
@@ -849,7 +851,7 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
 }
 
 // grad_params[layer lam of cell c] += slices (fixed order)
