@@ -685,7 +685,8 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
     extern __shared__ char smraw[];
     __shared__ uint64_t a_ready, done;
     __shared__ uint32_t tmem_base_s;
-    char* sm = smem_align1024_generic(smraw);
+    __shared__ float coef[256];                             // sc[128] sh[128] of this column block
+    char* sm = smem_align1024(smraw);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int c = A.c, lam = A.lam;
     const DevCell& q = F.cells[c];
@@ -697,7 +698,6 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
     char* slabA = sm;                                       // [128: dz hi (64) ; dz lo (64)][128 points]
     char* slabBh = sm + 65536;                              // [N][128 points]
     char* slabBl = sm + 65536 + 65536;
-    float* coef = reinterpret_cast<float*>(sm + 196608);    // sc[128] sh[128] of this column block
     const float* pk = A.wpack + q.pk_off;
     for (int j = tid; j < 128; j += BWW_THREADS) {
         const int f = 128 * nh + j;
@@ -736,6 +736,17 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
         // are loaded into registers before the wait for this tile's MMAs, so their latency hides behind the tensor work.
         const int nb = N >> 1;
         const bool two = lam > 0 && nb > 32;
+        // K-major 128B-swizzled slab address of (row, point gt) = base[row & 7] + (row >> 3) * 1024: eight bases per operand,
+        // this thread's first row folded in, so that every store is base + immediate
+        char* pA[8];
+        char* pB[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int sw = i * 128 + (((((gt & 31) >> 2) ^ i) << 4) | ((gt & 3) << 2));
+            pA[i] = slabA + (gt >> 5) * 128 * 128 + (32 * half >> 3) * 1024 + sw;
+            pB[i] = slabBh + (gt >> 5) * N * 128 + (lam > 0 ? (nb * half >> 3) * 1024 : 0) + sw;
+        }
+        const float* cf = coef + nb * half;
         float v[32], w[32], w2[32];
         auto load_tile = [&](long long tile) {
             const float* up = (OUTL ? A.dl + (size_t)tile * nlog * TCM : A.dz + (size_t)tile * W * TCM) + (size_t)(64 * rb + 32 * half) * TCM + gt;
@@ -767,28 +778,25 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
             // hi rounded to nearest; the residual is exact in float32 and left as it is (the MMA truncates it: 2^-22 of the value)
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const int r = 32 * half + j;
                 const float hi = tf32_rn(v[j]);
-                *reinterpret_cast<float*>(slabA + tc_slab_off(128, r, gt)) = hi;
-                *reinterpret_cast<float*>(slabA + tc_slab_off(128, 64 + r, gt)) = v[j] - hi;
+                *reinterpret_cast<float*>(pA[j & 7] + (j >> 3) * 1024) = hi;
+                *reinterpret_cast<float*>(pA[j & 7] + (8 + (j >> 3)) * 1024) = v[j] - hi;
             }
             if (lam > 0) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int r = nb * half + j;
-                    const float h = fmaxf(fmaf(w[j], coef[r], coef[128 + r]), 0.f);
+                    const float h = fmaxf(fmaf(w[j], cf[j], cf[128 + j]), 0.f);
                     const float hi = tf32_rn(h);
-                    *reinterpret_cast<float*>(slabBh + tc_slab_off(N, r, gt)) = hi;
-                    *reinterpret_cast<float*>(slabBl + tc_slab_off(N, r, gt)) = h - hi;
+                    *reinterpret_cast<float*>(pB[j & 7] + (j >> 3) * 1024) = hi;
+                    *reinterpret_cast<float*>(pB[j & 7] + (j >> 3) * 1024 + 65536) = h - hi;
                 }
                 if (two) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const int r = nb * half + 32 + j;
-                        const float h = fmaxf(fmaf(w2[j], coef[r], coef[128 + r]), 0.f);
+                        const float h = fmaxf(fmaf(w2[j], cf[32 + j], cf[160 + j]), 0.f);
                         const float hi = tf32_rn(h);
-                        *reinterpret_cast<float*>(slabBh + tc_slab_off(N, r, gt)) = hi;
-                        *reinterpret_cast<float*>(slabBl + tc_slab_off(N, r, gt)) = h - hi;
+                        *reinterpret_cast<float*>(pB[j & 7] + (4 + (j >> 3)) * 1024) = hi;
+                        *reinterpret_cast<float*>(pB[j & 7] + (4 + (j >> 3)) * 1024 + 65536) = h - hi;
                     }
                 }
             }
@@ -798,8 +806,8 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
                 for (int k = 0; k < 16; ++k) {
                     const float a = k < q.P ? fmaf(xs[q.feed[k]], coef[k], coef[128 + k]) : 0.f;
                     const float hi = tf32_rn(a);
-                    *reinterpret_cast<float*>(slabBh + tc_slab_off(16, k, gt)) = hi;
-                    *reinterpret_cast<float*>(slabBl + tc_slab_off(16, k, gt)) = a - hi;
+                    *reinterpret_cast<float*>(pB[k & 7] + (k >> 3) * 1024) = hi;
+                    *reinterpret_cast<float*>(pB[k & 7] + (k >> 3) * 1024 + 65536) = a - hi;
                 }
             }
             proxy_fence();
@@ -832,12 +840,16 @@ __global__ void __launch_bounds__(BWW_THREADS, 1) flow_bwd_wide_wgrad_kernel(con
                     float r[16];
                     tc_ld16(tg + j0, r);
                     tc_ld_wait();
+                    // the first flush stores, the later ones add with vector reductions (no round trip to wait for; every
+                    // element belongs to this thread alone, so the order of the additions is fixed)
                     float4* o4 = reinterpret_cast<float4*>(sl + j0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float4 v = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-                        if (nflush) { const float4 o = o4[j]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                        o4[j] = v;
+                        if (nflush)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o4 + j), "f"(r[4 * j]), "f"(r[4 * j + 1]),
+                                         "f"(r[4 * j + 2]), "f"(r[4 * j + 3]) : "memory");
+                        else
+                            o4[j] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                     }
                 }
                 ++nflush;
@@ -988,8 +1000,8 @@ int nis_flow_backward_wide(const DevFlow& F, const FlowWorkspace& ws, const floa
     const size_t tile_fl = (size_t)W * TCM;
     const long long rows = (long long)B * (F.d + 1);
     auto headk = F.kind == NIS_KIND_PWLIN ? flow_bwd_wide_head_kernel<NIS_KIND_PWLIN> : flow_bwd_wide_head_kernel<NIS_KIND_PWQUAD>;
-    NIS_ENSURE_SMEM((flow_bwd_wide_wgrad_kernel<true>), 196608 + 1024 + 1024);
-    NIS_ENSURE_SMEM((flow_bwd_wide_wgrad_kernel<false>), 196608 + 1024 + 1024);
+    NIS_ENSURE_SMEM((flow_bwd_wide_wgrad_kernel<true>), 196608 + 1024);
+    NIS_ENSURE_SMEM((flow_bwd_wide_wgrad_kernel<false>), 196608 + 1024);
     for (int c = F.n_cells - 1; c >= 0; --c) {
         const DevCell& q = F.cells[c];
         A.c = c; A.first = c == F.n_cells - 1;
@@ -1045,7 +1057,7 @@ int nis_flow_backward_wide(const DevFlow& F, const FlowWorkspace& ws, const floa
             if (nparts > ntiles) nparts = (int)ntiles;
             if (nparts < 1) return NIS_EUNSUPPORTED;
             A.nparts = nparts;
-            const size_t wsm = 196608 + 1024 + 1024;
+            const size_t wsm = 196608 + 1024;
             if (lam == depth) flow_bwd_wide_wgrad_kernel<true><<<dim3(nrb, nnh, nparts), BWW_THREADS, wsm, s>>>(F, A);
             else flow_bwd_wide_wgrad_kernel<false><<<dim3(nrb, nnh, nparts), BWW_THREADS, wsm, s>>>(F, A);
             NIS_CUDA_CHECK_LAUNCH();
