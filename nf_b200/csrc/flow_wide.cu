@@ -129,9 +129,11 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
     const long long rowlen = d + 1;
     const int kpanels = kc;                                 // K-panels of 32 per round (one per A chunk)
     const size_t panel_floats = (size_t)npanel * 64;
-    double dsum[4][2], dsq[4][2];
+    // BatchNorm statistics of a hidden pass: thread t of the point warps owns feature 64 j + (t >> 1) of every 64-feature block j
+    // (both threads of a pair hold the same sums)
+    double dsum[4], dsq[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { dsum[j][0] = dsum[j][1] = dsq[j][0] = dsq[j][1] = 0.0; }
+    for (int j = 0; j < 4; ++j) { dsum[j] = dsq[j] = 0.0; }
 
     if (warp == 5) {
         // ===================== weight producer: panels in consumption order through the ring ===============
@@ -283,12 +285,30 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
                             zo[(size_t)(64 * j + x) * TCM] = v[x];
                         }
                         if (!A.no_stats) {
-                            double s[2], s2[2];
-                            wd_warp_feature_sums64(v, lane, s, s2);
+                            // per-feature sums over the tile: the 64 x 128 block goes through shared memory (conflict-free
+                            // column writes), then two threads per feature add half a row each with rotated 16-byte loads
+                            // (float32 over the 128 points of the tile, float64 across tiles -- as flow_tc_h.cu does); the
+                            // float64 shuffle tree this replaces was a third of the pass
+#pragma unroll
+                            for (int x = 0; x < TCH; ++x) stg[x * TCM] = v[x];
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            const float4* row = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sm + L.stg) + (gt >> 1) * TCM + (gt & 1) * 64);
+                            float s_ = 0.f, q_ = 0.f, q1 = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float4 x = row[(i + lane) & 15];
+                                s_ += (x.x + x.y) + (x.z + x.w);
+                                q_ = fmaf(x.x, x.x, fmaf(x.y, x.y, q_));
+                                q1 = fmaf(x.z, x.z, fmaf(x.w, x.w, q1));
+                            }
+                            q_ += q1;
+                            s_ += __shfl_xor_sync(0xffffffffu, s_, 1);
+                            q_ += __shfl_xor_sync(0xffffffffu, q_, 1);
                             const int fb = (r * npanel >> 6) + j;          // 64-feature block of the layer
 #pragma unroll
                             for (int y = 0; y < 4; ++y)
-                                if (y == fb) { dsum[y][0] += s[0]; dsum[y][1] += s[1]; dsq[y][0] += s2[0]; dsq[y][1] += s2[1]; }
+                                if (y == fb) { dsum[y] += (double)s_; dsq[y] += (double)q_; }
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
                         }
                     }
                     tc_fence_before();
@@ -344,25 +364,15 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
     __syncthreads();
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     if (!stats || A.no_stats) return;
-    // ---- fold the per-lane sums: lane i of a warp holds features 64 j + 2 i, 64 j + 2 i + 1 ---------------------
-    double* red = reinterpret_cast<double*>(sm + L.ring);            // [4 warps][32 lanes][16]   (the ring is idle now)
+    // ---- this CTA's sums: the even thread of a pair publishes feature 64 j + (tid >> 1) -------------------------------
     double* sacc = reinterpret_cast<double*>(sm + L.red);            // [2 * maxW]
-    if (warp < 4) {
-        double* r = red + ((size_t)warp * 32 + lane) * 16;
+    for (int f = W + tid; f < F.maxW; f += WD_THREADS) { sacc[f] = 0.0; sacc[F.maxW + f] = 0.0; }
+    if (warp < 4 && !(tid & 1)) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { r[4 * j] = dsum[j][0]; r[4 * j + 1] = dsum[j][1]; r[4 * j + 2] = dsq[j][0]; r[4 * j + 3] = dsq[j][1]; }
-    }
-    __syncthreads();
-    for (int f = tid; f < F.maxW; f += WD_THREADS) {
-        double s = 0.0, s2 = 0.0;
-        if (f < W) {
-            const int j = f >> 6, ln = (f & 63) >> 1, ix = f & 1;
-            for (int w = 0; w < 4; ++w) {
-                s += red[((size_t)w * 32 + ln) * 16 + 4 * j + ix];
-                s2 += red[((size_t)w * 32 + ln) * 16 + 4 * j + 2 + ix];
-            }
+        for (int j = 0; j < 4; ++j) {
+            const int f = 64 * j + (tid >> 1);
+            if (f < W) { sacc[f] = dsum[j]; sacc[F.maxW + f] = dsq[j]; }
         }
-        sacc[f] = s; sacc[F.maxW + f] = s2;
     }
     bn_stats_finalize(F, A, sacc, WD_THREADS);
 }

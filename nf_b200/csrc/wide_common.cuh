@@ -67,7 +67,7 @@ __host__ __device__ static inline WdSmem wd_layout(const DevFlow& F, int P, bool
     const int affb = (2 * 16 + 2 * W) * 4;
     const int biasb = final_pass ? T * Kp * 4 : 0;
     const int stb = (F.d + 1) * TCM * 4;
-    const int stgb = final_pass ? Kp * TCM * 4 : 0;
+    const int stgb = final_pass ? Kp * TCM * 4 : 64 * TCM * 4;    // logits of one dimension / statistics staging tile [64][128]
     const int redb = 2 * W * 8;
     other = w0b + affb + biasb + stb + stgb + redb + 256;
     int slots = (226 * 1024 - other) / s.slot_bytes;
