@@ -879,10 +879,23 @@ __global__ void flow_bwd_wide_reduce_kernel(DevFlow F, const float* __restrict__
         int row = o;                                         // row of the upstream tile
         if (lam == F.depth) { const int t = o / F.K, j = o - t * F.K; row = t * Kp + j; }
         const int rb = row >> 6, r = row & 63, nh = lam == 0 ? 0 : k >> 7, col = lam == 0 ? k : k & 127;
+        // eight slices' loads in flight at a time, added in slice order (the sum is the same as one slice after the other)
+        const float* sl0 = slices + (((size_t)rb * nnh + nh) * nparts * 128) * 128 + (size_t)r * 128 + col;
         float s = 0.f;
-        for (int p = 0; p < nparts; ++p) {
-            const float* sl = slices + ((((size_t)rb * nnh + nh) * nparts + p) * 128) * 128;
-            s += sl[(size_t)r * 128 + col] + sl[(size_t)(64 + r) * 128 + col];
+        int p = 0;
+        for (; p + 8 <= nparts; p += 8) {
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float* sl = sl0 + (size_t)(p + u) * 128 * 128;
+                t[u] = __ldcg(sl) + __ldcg(sl + 64 * 128);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += t[u];
+        }
+        for (; p < nparts; ++p) {
+            const float* sl = sl0 + (size_t)p * 128 * 128;
+            s += __ldcg(sl) + __ldcg(sl + 64 * 128);
         }
         gw[i] += s;
     }
