@@ -785,20 +785,44 @@ __global__ void __launch_bounds__(256) flow_bwd_tc_tail_kernel(const __grid_cons
 
 // grad_params[cell] += per-CTA slices (fixed order).  blockIdx.y = linear layer.
 __global__ void flow_bwd_tc_reduce_kernel(DevFlow F, const float* __restrict__ slices, int grid, int c, float* __restrict__ grad_params) {
+    // four lanes per weight: lane g adds the slices of CTAs [g * chunk, (g + 1) * chunk) in CTA order (eight loads in flight),
+    // the four partial sums are combined as (s0 + s1) + (s2 + s3): fixed order, no atomics
     const int lam = blockIdx.y;
     const DevCell& q = F.cells[c];
     const int in = lam == 0 ? q.P : TCH;
     const int nout = lam == F.depth ? q.T * F.K : TCH;
     float* gw = grad_params + q.param_off + F.p_lin(c, lam);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nout * in; i += gridDim.x * blockDim.x) {
-        const int o = i / in, k = i - o * in;
-        const int h = o >> 6, r = o & 63;
+    const int lane = threadIdx.x & 31, g = lane >> 3;
+    const int chunk = (grid + 3) >> 2;
+    const int b0 = g * chunk, b1 = b0 + chunk < grid ? b0 + chunk : grid;
+    const int total = nout * in, per_block = blockDim.x >> 2;
+    for (int base = blockIdx.x * per_block; base < ((total + per_block - 1) / per_block) * per_block; base += gridDim.x * per_block) {
+        const int i = base + (threadIdx.x >> 5) * 8 + (lane & 7);
         float s = 0.f;
-        for (int b = 0; b < grid; ++b) {
-            const float* sl = slices + ((((size_t)lam * grid + b) * 2 + h) * 128) * TCH;
-            s += sl[(size_t)r * TCH + k] + sl[(size_t)(TCH + r) * TCH + k];
+        if (i < total) {
+            const int o = i / in, k = i - o * in;
+            const int h = o >> 6, r = o & 63;
+            const float* sl0 = slices + ((((size_t)lam * grid) * 2 + h) * 128) * TCH + (size_t)r * TCH + k;
+            const size_t step = (size_t)2 * 128 * TCH;
+            int b = b0;
+            for (; b + 8 <= b1; b += 8) {
+                float t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float* sl = sl0 + (size_t)(b + u) * step;
+                    t[u] = __ldcg(sl) + __ldcg(sl + TCH * TCH);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += t[u];
+            }
+            for (; b < b1; ++b) {
+                const float* sl = sl0 + (size_t)b * step;
+                s += __ldcg(sl) + __ldcg(sl + TCH * TCH);
+            }
         }
-        gw[i] += s;
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        if (i < total && g == 0) gw[i] += s;
     }
 }
 
@@ -915,7 +939,7 @@ int nis_flow_backward_tc(const DevFlow& F, const FlowWorkspace& ws, const float*
         flow_bwd_tc_tail_kernel<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, s>>>(F, A);
         NIS_CUDA_CHECK_LAUNCH();
         A.grad_in = nullptr;
-        flow_bwd_tc_reduce_kernel<<<dim3(32, F.depth + 1), 256, 0, s>>>(F, sc.slices, lgrid, c, grad_params);
+        flow_bwd_tc_reduce_kernel<<<dim3(128, F.depth + 1), 256, 0, s>>>(F, sc.slices, lgrid, c, grad_params);
         NIS_CUDA_CHECK_LAUNCH();
     }
     return NIS_OK;
