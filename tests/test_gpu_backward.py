@@ -178,13 +178,14 @@ def test_full_size_cfg5_gradients(monkeypatch, backend):
     test_gradients_match_oracle_autograd_at_size(cfg, "train")
 
 
-@pytest.mark.parametrize("which,log2b", [(0, 19), (3, 15)], ids=["cfg2_2p19", "cfg5_small_2p15"])
+@pytest.mark.parametrize("which,log2b", [(0, 19), (3, 15), (3, 18)], ids=["cfg2_2p19", "cfg5_small_2p15", "cfg5_small_2p18"])
 def test_tensor_core_backward_at_large_batch_matches_generic(monkeypatch, which, log2b):
-    """Many tiles per CTA (cfg2: 2^19 points = 28 tiles per CTA; the 128-wide cfg5_small: 2^15 points): the
-    weight-gradient accumulators in tensor memory are flushed to the CTA's slice every 16 (8) tiles because
-    tcgen05 accumulation truncates; the result must agree with the FP32 generic kernel (itself pinned against the
-    oracle above)."""
-    cfg = dict(BIG[which], B=1 << log2b)
+    """Many tiles per CTA (cfg2: 2^19 points = 28 tiles per CTA; the 128-wide cfg5_small: 2^15 points, and 2^18 points =
+    14 tiles per hidden-layer CTA / 42 per output-layer CTA of the streamed-weights wgrad kernel, so that its second and
+    later accumulator flushes -- vector reductions onto the slice -- run): the weight-gradient accumulators in tensor
+    memory are flushed to the CTA's slice every 16 (8) tiles because tcgen05 accumulation truncates; the result must
+    agree with the FP32 generic kernel (itself pinned against the oracle above)."""
+    cfg = dict(which if isinstance(which, dict) else BIG[which], B=1 << log2b)
     layers = oracle_layers(cfg)
     cells, _ = oflow.compile_layers(layers, cfg["n_flow"])
     sd = oflow.init_state_dict(cells, cfg["n_flow"], cfg["kind"], cfg["n_bins"], cfg["NN"], seed=33,
@@ -260,6 +261,14 @@ def test_activation_cache_backward_equals_recomputing_backward(monkeypatch, whic
         worst = max(worst, float((g - res["recompute"][2][k]).abs().max()) / gscale)
     print("activation cache vs recomputing backward: worst |diff| / gradient scale = %.2e" % worst)
     assert worst <= 1e-4, worst
+
+
+def test_full_cfg5_backward_with_several_flushes_matches_generic(monkeypatch):
+    """BASELINE configs[4] at its full shape (width 256: two column blocks per weight-gradient row block) on 2^14 points:
+    16 tiles per output-layer CTA of the streamed-weights wgrad kernel = two accumulator flushes, the second a vector
+    reduction onto the slice."""
+    cfg = dict(name="cfg5", kind="quad", n_flow=16, n_cells=8, n_bins=64, NN=[256] * 4)
+    test_tensor_core_backward_at_large_batch_matches_generic(monkeypatch, cfg, 14)
 
 
 WIDE_BWD = [
