@@ -436,6 +436,7 @@ def bench_wide(steps, warmup, world, dev):
     """BASELINE configs[4]: 16-D PWQuad flow, 8 mask cells, 64 bins, MLP [256]*4 (the tensor-core conditioner path:
     flow_wide.cu / flow_bwd_wide.cu) — forward + log-det with train-mode BN, and one variance-loss training step
     (forward + backward + gradient all-reduce), 2^16 points per rank per step."""
+    from nf_b200 import _cabi
     from nf_b200.normalizing_flows.manager import BasicManager, PWQuadManager
     torch.manual_seed(1234)
     NF = PWQuadManager(n_flow=16)
@@ -470,7 +471,8 @@ def bench_wide(steps, warmup, world, dev):
                          "peak_kind": "tcgen05.mma kind::tf32 M128 N128 K8 back to back on every SM, measured in this run",
                          "note": "3xTF32: three tensor MACs per conditioner MAC"},
             "train_step": {"metric": "nis_train_step_points_per_sec", "value": world * n / (ms_s * 1e-3), "unit": "points/s",
-                           "ms_per_step": ms_s}}
+                           "ms_per_step": ms_s,
+                           "activation_cache_bytes_per_rank": 4 * model.spec().act_saved_count(_cabi.lib(), n)}}
 
 
 def bench_integrate(world, dev):
