@@ -79,6 +79,41 @@ def test_concurrent_minibatches_equal_sequential_ones(tmp_path, graph):
             assert float((sd0[k] - sd1[k]).abs().max()) <= 2e-4 * scale + 1e-7, (k, float((sd0[k] - sd1[k]).abs().max()), scale)
 
 
+def gauss6(x):
+    return torch.exp(-((x - 0.5) ** 2).sum(-1) / 0.2)
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
+def test_wide_conditioner_trains_through_the_manager_with_the_activation_cache(tmp_path, graph):
+    """A 128-wide PWQuad flow (streamed-weights tcgen05 forward and backward) through the training loop with minibatches of
+    1024 points side by side on streams, eager and with the epoch replayed from a CUDA graph: every forward keeps its
+    activation cache (allocated inside the capture like the saved states), the variance loss comes down, and the run with
+    NIS_ACT_CACHE_MAX_BYTES=0 (recomputing backward) sees the same losses to float32 rounding."""
+    from nf_b200 import _cabi
+    hist = {}
+    for cache in ("on", "off"):
+        if cache == "off":
+            os.environ["NIS_ACT_CACHE_MAX_BYTES"] = "0"
+        try:
+            torch.manual_seed(5)
+            NF = PWQuadManager(n_flow=6)
+            NF.create_model(6, 12, [128] * 2)
+            NF.cuda_graph_epochs = graph
+            n_act = NF._model.spec().act_saved_count(_cabi.lib(), 1024)
+            assert (n_act > 0) == (cache == "on")
+            optim = torch.optim.Adamax(NF._model.parameters(), lr=2e-3, weight_decay=1e-04)
+            NF._train_variance_forward_seq(gauss6, optim, False, str(tmp_path), 4096, 12, 0, False, True,
+                                           mini_batch_size=1024, preburn_time=3)
+            torch.cuda.synchronize()
+            hist[cache] = [float(h) for h in NF.history]
+        finally:
+            os.environ.pop("NIS_ACT_CACHE_MAX_BYTES", None)
+    assert len(hist["on"]) == len(hist["off"]) >= 6
+    assert all(math.isfinite(h) for h in hist["on"])
+    assert min(hist["on"][3:]) < hist["on"][0]
+    assert torch.allclose(torch.tensor(hist["on"]), torch.tensor(hist["off"]), rtol=5e-3), (hist["on"], hist["off"])
+
+
 def test_affine_manager_trains_and_snapshots_its_hidden_biases(tmp_path):
     """AffineManager (manager.py:411-453) through the same training loop: the variance loss comes down, the
     best-model snapshot carries the hidden-layer biases (they live outside the kernels' arenas) and the checkpoint has the
