@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_bwd_wide_head_kernel(const
                     dx = pwlin_bwd(stg, TCM, F.nb, kbin, S, al, y, f, gy, gJJ);
                 } else {
                     QuadCtx qc;
-                    pwquad_fwd(stg, TCM, F.nb, xv, qc);
+                    pwquad_fwd<true>(stg, TCM, F.nb, xv, qc);
                     f = qc.f;
                     dx = pwquad_bwd(stg, TCM, F.nb, qc, gy, gJJ / qc.f);
                 }

@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_wide_tc_kernel(const __gri
                         y = pwlin_fwd(stg, TCM, F.nb, xv, f, kbin, S, al);
                     } else {
                         QuadCtx qc;
-                        pwquad_fwd(stg, TCM, F.nb, xv, qc);
+                        pwquad_fwd<true>(stg, TCM, F.nb, xv, qc);
                         y = qc.y; f = qc.f; kbin = qc.k;
                     }
                     st[col * TCM] = y;

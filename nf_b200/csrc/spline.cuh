@@ -97,6 +97,17 @@ struct QuadCtx {
 
 // z[0..nb] raw heights, z[nb+1..2nb] raw widths.  Overwrites with v_j = exp(. - max) and
 // w_j = exp(. - max).  Fills ctx.
+// FAST: exponentials as ex2.approx(x log2 e) (__expf; arguments are <= 0 after the max shift) instead of the accurate expf --
+// the streamed-weights kernels (flow_wide.cu final pass, flow_bwd_wide.cu head), like the resident-weights tensor-core kernels.
+template <bool FAST = false>
+NIS_DEV float nis_spline_exp(float x) {
+#ifdef __CUDA_ARCH__
+    if (FAST) return __expf(x);
+#endif
+    return expf(x);
+}
+
+template <bool FAST = false>
 NIS_DEV void pwquad_fwd(float* z, int zs, int nb, float x, QuadCtx& c) {
     float* zv = z;
     float* zw = z + (nb + 1) * zs;
@@ -106,12 +117,12 @@ NIS_DEV void pwquad_fwd(float* z, int zs, int nb, float x, QuadCtx& c) {
     // The cumulative sums that locate x inside its bin are kept in float64: alpha = (x - E_k)/W_k
     // amplifies their rounding by 1/W_k, and a float64 add per bin is free next to the conditioner.
     double Sw = 0.0;
-    for (int j = 0; j < nb; ++j) { float e = expf(zw[j * zs] - mw); zw[j * zs] = e; Sw += (double)e; }
-    float vprev = expf(zv[0] - mv);
+    for (int j = 0; j < nb; ++j) { float e = nis_spline_exp<FAST>(zw[j * zs] - mw); zw[j * zs] = e; Sw += (double)e; }
+    float vprev = nis_spline_exp<FAST>(zv[0] - mv);
     zv[0] = vprev;
     double Araw = 0.0;      // sum (v_j + v_{j+1})/2 * w_j  (unnormalised widths)
     for (int j = 0; j < nb; ++j) {
-        float vn = expf(zv[(j + 1) * zs] - mv);
+        float vn = nis_spline_exp<FAST>(zv[(j + 1) * zs] - mv);
         zv[(j + 1) * zs] = vn;
         Araw += 0.5 * ((double)vprev + (double)vn) * (double)zw[j * zs];
         vprev = vn;
