@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_bwd_wide_head_kernel(const
                     QuadCtx qc;
                     pwquad_fwd<true>(stg, TCM, F.nb, xv, qc);
                     f = qc.f;
-                    dx = pwquad_bwd(stg, TCM, F.nb, qc, gy, gJJ / qc.f);
+                    dx = pwquad_bwd<true>(stg, TCM, F.nb, qc, gy, gJJ / qc.f);
                 }
                 gr[col * TCM] = dx;
                 Fprod *= f;

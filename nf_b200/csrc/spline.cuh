@@ -111,16 +111,22 @@ template <bool FAST = false>
 NIS_DEV void pwquad_fwd(float* z, int zs, int nb, float x, QuadCtx& c) {
     float* zv = z;
     float* zw = z + (nb + 1) * zs;
+    // (FAST also unrolls the read-only loops by 8: with one thread per point and one warp per scheduler the streamed-weights
+    //  kernels otherwise wait one shared-memory latency per bin)
     float mv = zv[0], mw = zw[0];
+#pragma unroll(FAST ? 8 : 1)
     for (int j = 1; j <= nb; ++j) mv = fmaxf(mv, zv[j * zs]);
+#pragma unroll(FAST ? 8 : 1)
     for (int j = 1; j < nb; ++j) mw = fmaxf(mw, zw[j * zs]);
     // The cumulative sums that locate x inside its bin are kept in float64: alpha = (x - E_k)/W_k
     // amplifies their rounding by 1/W_k, and a float64 add per bin is free next to the conditioner.
     double Sw = 0.0;
+#pragma unroll(FAST ? 8 : 1)
     for (int j = 0; j < nb; ++j) { float e = nis_spline_exp<FAST>(zw[j * zs] - mw); zw[j * zs] = e; Sw += (double)e; }
     float vprev = nis_spline_exp<FAST>(zv[0] - mv);
     zv[0] = vprev;
     double Araw = 0.0;      // sum (v_j + v_{j+1})/2 * w_j  (unnormalised widths)
+#pragma unroll(FAST ? 8 : 1)
     for (int j = 0; j < nb; ++j) {
         float vn = nis_spline_exp<FAST>(zv[(j + 1) * zs] - mv);
         zv[(j + 1) * zs] = vn;
@@ -194,6 +200,7 @@ NIS_DEV float pwquad_inv(float* z, int zs, int nb, float y, float& f, int& kout)
 
 // z holds v_j / w_j (after pwquad_fwd).  Overwrites with dL/dz.  Returns dL/dx.
 //   gy = dL/dy, gf = dL/df
+template <bool FAST = false>
 NIS_DEV float pwquad_bwd(float* z, int zs, int nb, const QuadCtx& c, float gy, float gf) {
     float* zv = z;
     float* zw = z + (nb + 1) * zs;
@@ -203,6 +210,7 @@ NIS_DEV float pwquad_bwd(float* z, int zs, int nb, const QuadCtx& c, float gy, f
     const float galpha = gy * c.f * c.Wk + gf * D;
     // pass 1: R = sum_j GV_j V_j ; Q = sum_j GWdirect_j W_j ; Abar = sum_j (V_j+V_{j+1})/2 W_j = 1
     float R = 0.f, Q = 0.f;
+#pragma unroll(FAST ? 8 : 1)
     for (int j = 0; j <= nb; ++j) {
         float Vj = zv[j * zs] * invA;
         float gv = 0.f;
@@ -213,6 +221,7 @@ NIS_DEV float pwquad_bwd(float* z, int zs, int nb, const QuadCtx& c, float gy, f
         if (j == k + 1) gv += gy * 0.5f * c.alpha * c.alpha * c.Wk + gf * c.alpha;
         R += gv * Vj;
     }
+#pragma unroll(FAST ? 8 : 1)
     for (int j = 0; j <= k; ++j) {
         float Wj = zw[j * zs] * invSw;
         float trap = 0.5f * (zv[j * zs] + zv[(j + 1) * zs]) * invA;
