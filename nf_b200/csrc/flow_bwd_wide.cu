@@ -355,9 +355,15 @@ __global__ void __launch_bounds__(WD_THREADS, 1) flow_bwd_wide_head_kernel(const
                 // output-layer bias gradient: row sums of the staged tile (thread j owns logits j, j + 128)
                 group_sync(0);
                 for (int j = gt; j < F.K; j += TCM) {
-                    float s = 0.f;
-                    for (int i = 0; i < TCM; ++i) s += stg0[j * TCM + ((i + gt) & (TCM - 1))];
-                    bacc[t * Kp + j] += (double)s;
+                    const float4* row = reinterpret_cast<const float4*>(stg0 + j * TCM);     // rotated 16-byte loads: conflict-free
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+                    for (int i = 0; i < TCM / 4; ++i) {
+                        const float4 x = row[(i + gt) & (TCM / 4 - 1)];
+                        s0 += x.x + x.y;
+                        s1 += x.z + x.w;
+                    }
+                    bacc[t * Kp + j] += (double)(s0 + s1);
                 }
                 group_sync(0);
             }
