@@ -3,7 +3,8 @@
 // Same cut of the autograd chain as flow_bwd_tc.cu (one launch per BatchNorm reduction), with the GEMMs in the
 // streamed-weights form of flow_wide.cu because neither the weights nor the gradient accumulators of a
 // 256-wide layer fit an SM:
-//   recompute : the forward's wide layer passes (flow_wide_tc_kernel, no statistics) store z_1..z_depth
+//   z_1..z_depth : kept by the forward (nis_flow_forward_cached: the activation cache), or recomputed by the forward's
+//               wide layer passes (flow_wide_tc_kernel, no statistics) when the caller passed no cache
 //   head      : output layer per transformed dimension (streamed panels, A chunks in tensor memory), logits
 //               staged in shared memory, spline forward + hand-derived backward of spline.cuh in place ->
 //               dL/dlogits tile, dL/dx of the transformed columns, dL/dJ, output-layer bias gradient
@@ -13,9 +14,11 @@
 //               of dL/dh and dL/dh * xhat (last CTA finalises: dL/dbeta, dL/dgamma, means for the next launch)
 //   wgrad     : dL/dW_lam = dz^T h_lam as SS-mode MMAs with K = the tile's 128 points.  One CTA owns a
 //               64-row block of dz (hi and lo stacked to M = 128) x a 128-column block of h_lam and a slice of
-//               the tiles; the point threads write both operands into a K-major swizzled slab; the accumulator
-//               lives in tensor memory and is flushed to the CTA's slice every 8 tiles (tcgen05 accumulation
-//               truncates); a fixed-order reduce adds the slices.
+//               the tiles; eight point warps (two threads per point, half of the operand rows each) write both operands
+//               into a K-major swizzled slab from values loaded while the previous tile's MMAs ran, thread 0 issues the
+//               MMAs; the accumulator lives in tensor memory and is flushed to the CTA's slice every 8 tiles (tcgen05
+//               accumulation truncates; the first flush stores, the later ones are vector reductions); a fixed-order
+//               reduce adds the slices.
 //   tail      : BatchNorm backward of the input normalisation (flow_bwd_tc.cu's kernel).
 #include <stdlib.h>
 #include "common.cuh"

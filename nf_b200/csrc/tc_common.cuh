@@ -24,12 +24,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // 1024-byte aligned start inside the dynamic shared-memory window, formed as base + offset: a pointer rebuilt from an
 // integer loses its address space and every access through it becomes a generic LD / ST instead of LDS / STS
 __device__ __forceinline__ char* smem_align1024(char* smraw) { return smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u); }
-// The same through an integer (generic LD / ST).  Measured A/B per kernel (insitu_step.py): every tensor-core kernel is
-// faster with LDS / STS (cfg2 backward layer kernel 445 -> 329 us) EXCEPT the wide weight-gradient kernel, whose 384 operand-
-// slab stores per thread and tile run 283 us generic against 380 us as STS (output layer 1.54 against 2.20 ms); it keeps this form.
-__device__ __forceinline__ char* smem_align1024_generic(char* smraw) {
-    return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
-}
+// (Until the last session of round 2 the wide weight-gradient kernel rebuilt its base through an integer on purpose: generic
+// stores measured faster there, 283 against 380 us -- they only kept the compiler from reordering the kernel's load batches.
+// With the loads issued explicitly ahead of the stores it runs LDS / STS like every other kernel: 127 us.)
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
