@@ -169,6 +169,34 @@ def test_cabi_library_exports_every_declared_symbol():
     assert lib.nis_flow_cell_param_count(ctypes.byref(bad), 0) == -1
 
 
+def test_entry_points_validate_their_arguments_on_the_host():
+    """Argument checks of the forward / backward entry points (plain and _cached) run before any CUDA call: a missing
+    parameter pack is NIS_EINVAL (-1), a short workspace NIS_EWORKSPACE (-2), an empty batch NIS_OK -- no GPU needed."""
+    from nf_b200.normalizing_flows.manager import PWQuadManager
+    lib = _cabi.load()
+    NF = PWQuadManager(n_flow=4)
+    NF.create_model(4, 8, [16, 16])
+    d = NF._model.spec().desc
+    dp = ctypes.byref(d)
+    buf = (ctypes.c_float * 64)()
+    ptr = ctypes.cast(buf, ctypes.c_void_p)
+    need = lib.nis_flow_workspace_bytes(dp, 0)
+    assert need > 0
+    F32, TRAIN = 0, _cabi.BN_TRAIN
+    # forward: params missing -> EINVAL; workspace too small -> EWORKSPACE; B == 0 -> OK
+    for fn, extra in ((lib.nis_flow_forward, ()), (lib.nis_flow_forward_cached, (None,))):
+        args = lambda params, wsb, B: (dp, params, None, ptr, F32, 4, ptr, F32, None, None, None) + extra + (TRAIN, ptr, wsb, B, None)
+        assert fn(*args(None, need, 0)) == -1
+        assert fn(*args(ptr, need - 1, 0)) == -2
+        assert fn(*args(ptr, need, 0)) == 0
+    # backward: saved states missing -> EINVAL; B == 0 -> OK
+    for fn, extra in ((lib.nis_flow_backward, ()), (lib.nis_flow_backward_cached, (None,))):
+        args = lambda saved, wsb, B: (dp, ptr, None, saved, ptr) + extra + (ptr, F32, ptr, None, TRAIN, ptr, wsb, B, None)
+        assert fn(*args(None, need, 0)) == -1
+        assert fn(*args(ptr, need - 1, 0)) == -2
+        assert fn(*args(ptr, need, 0)) == 0
+
+
 def test_activation_cache_count_is_host_code():
     """nis_flow_act_saved_count: cells * depth * width floats per point (tiles of 128) for the shape whose forward AND backward
     run the streamed-weights kernels (cfg5), 0 for the resident-weights shapes (cfg2, cfg4), for a batch below the
